@@ -1,0 +1,359 @@
+// The three dense contractions of the margin-softmax head on tcgen05 (see pfc_umma.cuh for the pipeline)
+// and their C-ABI launchers (declared in include/pfc.h).
+//
+// Numerics of the forward epilogue (reference: nets/PartialFC.py:198-207, nets/ArcFace.py:76-91,
+// nets/PartialFC.py:442-461).  All logits are bounded, |z| <= s, so instead of an online row maximum the
+// epilogue uses one fixed shift:   e = 2^(log2e*(z - s) + PFC_EXP_TOP).   With PFC_EXP_TOP = 64 and s <= 64
+// every term is a normal fp32/bf16 number (2^-121 .. 2^64) and a row sum over <= 2^21 classes cannot
+// overflow, so no term is ever flushed and the softmax is exact up to fp32 rounding.  e is therefore final
+// the moment it is produced; it is spilled once as bf16 (E') and both gradient GEMMs read it back:
+//   dXn_i = c_i * sum_c E'_ic Wn_c,    dWn_c = sum_i E'_ic (c_i Xn_i),    c_i = g*s / (B * L_i)
+// where L_i is the global row sum and the target column of E' is patched to -dm_i*mask_i*Lothers_i
+// (pfc_backward_prepare) so that the one-hot term needs no separate pass.
+#include "pfc_umma.cuh"
+#include "pfc_internal.h"
+
+namespace pfc {
+
+// ============================================================================ G1: forward
+struct FwdPolicy {
+    static constexpr bool A_MN = false;
+    static constexpr bool B_MN = false;
+    struct Params {
+        int num_tiles;
+        int B, n, n_pad, B_pad;
+        int m_tiles, k_stages;
+        const int32_t* labels;   // [B] shard-local class id (after sampling remap) or -1
+        float k1, k2;            // e = exp2(clamp(cos) * k1 - k2)
+        float cos_m, sin_m, theta, sinmm, m3;
+        int margin_kind;         // 0 = ArcFace-style (cos(theta+m)), 1 = CosFace-style (t - m3)
+        float filter_thr;        // CombinedMarginLoss.interclass_filtering_threshold (0 = off)
+        __nv_bfloat16* E;        // [B, n_pad]
+        float* part_sum;         // [n_tiles_n, B_pad] sum of non-target e over this class tile
+        float* tgt_raw;          // [B] raw (unclamped) target cosine, written by the owning tile only
+        float* tgt_e;            // [B] e of the margin-adjusted target logit
+        float* tgt_z;            // [B] margin-adjusted target logit (already * s)
+        float s;
+    };
+    __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
+        TileCoord tc;
+        const int ct = t / p.m_tiles;
+        tc.m0 = (t - ct * p.m_tiles) * BM;   // sample tile fastest: CTAs running together share the W tile in L2
+        tc.n0 = ct * BN;
+        tc.k0 = 0;
+        tc.k1 = p.k_stages;
+        tc.aux = ct;
+        return tc;
+    }
+
+    template <bool kHasTarget, bool kTail, bool kFilter>
+    __device__ static __forceinline__ float chunk(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[16],
+                                                  int col_base, int jt) {
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            float e2[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float raw = __uint_as_float(v[j + u]);
+                float cl = fminf(fmaxf(raw, -1.f), 1.f);
+                bool keep = fabsf(raw) <= 1.f;           // clamp backward passes gradient only inside [-1, 1]
+                if (kFilter) {
+                    if (cl > p.filter_thr) { cl = 0.f; keep = false; }
+                }
+                float e = fast_exp2(fmaf(cl, p.k1, -p.k2));
+                if (kTail) {
+                    if (col_base + j + u >= p.n) e = 0.f;
+                }
+                if (kHasTarget) {
+                    if (j + u == jt) e = 0.f;            // the target column is accounted separately
+                }
+                sum += e;
+                e2[u] = keep ? e : 0.f;
+            }
+            o[j >> 1] = pack_bf16x2(e2[0], e2[1]);
+        }
+        return sum;
+    }
+
+    __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr,
+                                                    int row_in_tile, int lane) {
+        const int row = tc.m0 + row_in_tile;
+        const bool row_ok = row < p.B;
+        const int lbl = row_ok ? p.labels[row] : -1;
+        const int tgt_off = (lbl >= tc.n0 && lbl < tc.n0 + BN) ? (lbl - tc.n0) : -1;
+        float sum = 0.f;
+        __nv_bfloat16* erow = p.E + static_cast<size_t>(row_ok ? row : 0) * p.n_pad;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            const int col_base = tc.n0 + c * 32;
+            if (col_base >= p.n) break;                  // warp-uniform: nothing valid from here on
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+            tmem_ld_wait();
+            uint32_t o[16];
+            const bool has_t = (tgt_off >= 0) && ((tgt_off >> 5) == c);
+            const bool tail = col_base + 32 > p.n;
+            const bool filt = p.filter_thr > 0.f;
+            const int jt = tgt_off & 31;
+            if (!has_t && !tail && !filt) {
+                sum += chunk<false, false, false>(p, v, o, col_base, jt);
+            } else if (!filt) {
+                sum += chunk<true, true, false>(p, v, o, col_base, has_t ? jt : -1);
+            } else {
+                sum += chunk<true, true, true>(p, v, o, col_base, has_t ? jt : -1);
+            }
+            if (has_t) {
+                float raw = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) raw = (j == jt) ? __uint_as_float(v[j]) : raw;
+                const float t = fminf(fmaxf(raw, -1.f), 1.f);
+                float fin;
+                if (p.margin_kind == 0) {
+                    const float sin_t = sqrtf(fmaxf(1.f - t * t, 0.f));
+                    const float ctm = t * p.cos_m - sin_t * p.sin_m;
+                    fin = (t > p.theta) ? ctm : (t - p.sinmm);
+                } else {
+                    fin = t - p.m3;
+                }
+                p.tgt_raw[row] = raw;
+                p.tgt_e[row] = fast_exp2(fmaf(fin, p.k1, -p.k2));
+                p.tgt_z[row] = fin * p.s;
+            }
+            if (row_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(erow + col_base);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (col_base + q * 8 + 8 <= p.n_pad)
+                        dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                }
+            }
+        }
+        if (row_ok) p.part_sum[static_cast<size_t>(tc.aux) * p.B_pad + row] = sum;
+    }
+};
+
+// ============================================================================ G2 / G3: fp32 tile store
+// out[aux][row][col] = accumulator, rows < rows_valid, cols < cols_valid.
+struct StoreParams {
+    int num_tiles;
+    int m_tiles, n_tiles, splits;
+    int k_stages_total, k_stages_per_split;
+    int n_fastest;
+    int rows_valid, cols_valid;
+    int ld;                 // row stride of out (elements)
+    size_t split_stride;    // elements between split slabs
+    float* out;
+};
+
+template <bool kAMN>
+struct StorePolicy {
+    static constexpr bool A_MN = kAMN;
+    static constexpr bool B_MN = true;
+    using Params = StoreParams;
+    __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
+        // n_fastest=0: m fastest (CTAs running together share the B stage in L2);
+        // n_fastest=1: the N tiles of one M tile run side by side (they share the A stage in L2)
+        TileCoord tc;
+        const int z = t / (p.m_tiles * p.n_tiles);
+        const int r = t - z * (p.m_tiles * p.n_tiles);
+        int mt, nt;
+        if (p.n_fastest) { mt = r / p.n_tiles; nt = r - mt * p.n_tiles; }
+        else             { nt = r / p.m_tiles; mt = r - nt * p.m_tiles; }
+        tc.m0 = mt * BM;
+        tc.n0 = nt * BN;
+        tc.k0 = z * p.k_stages_per_split;
+        tc.k1 = min(tc.k0 + p.k_stages_per_split, p.k_stages_total);
+        tc.aux = z;
+        return tc;
+    }
+    __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr,
+                                                    int row_in_tile, int lane) {
+        const int row = tc.m0 + row_in_tile;
+        const bool row_ok = row < p.rows_valid;
+        float* orow = p.out + static_cast<size_t>(tc.aux) * p.split_stride +
+                      static_cast<size_t>(row_ok ? row : 0) * p.ld;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            const int col_base = tc.n0 + c * 32;
+            if (col_base >= p.cols_valid) break;
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c * 32, v);
+            tmem_ld_wait();
+            if (row_ok) {
+                float4* dst = reinterpret_cast<float4*>(orow + col_base);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (col_base + q * 4 + 4 <= p.cols_valid)
+                        dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                             __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                }
+            }
+        }
+    }
+};
+
+// ============================================================================ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// bf16 row-major [outer, inner] tensor, box = box_inner x box_outer, 128-byte swizzle, OOB reads give zero.
+static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                     uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return PFC_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_elems * 2) % 16) return PFC_ERR_ALIGNMENT;
+    cuuint64_t gdim[2] = {inner, outer};
+    cuuint64_t gstr[1] = {row_stride_elems * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PFC_OK : PFC_ERR_TENSORMAP;
+}
+
+static int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+    }
+    return sms;
+}
+
+template <class P>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const typename P::Params& prm,
+                       cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             GEMM_SMEM_BYTES);
+        if (e != cudaSuccess) return PFC_ERR_CUDA;
+        attr_set = true;
+    }
+    const int sms = num_sms();
+    if (sms <= 0) return PFC_ERR_CUDA;
+    const int grid = prm.num_tiles < sms ? prm.num_tiles : sms;
+    if (grid <= 0) return PFC_OK;
+    umma_gemm_kernel<P><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, prm);
+    return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
+}
+
+}  // namespace pfc
+
+using namespace pfc;
+
+extern "C" {
+
+int pfc_exp_top(void) { return PFC_EXP_TOP; }
+
+int pfc_padded_classes(int n) { return (n + 63) / 64 * 64; }
+int pfc_num_class_tiles(int n) { return (n + BN - 1) / BN; }
+int pfc_padded_batch(int B) { return (B + BM - 1) / BM * BM; }
+
+int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int B, int n, int d, float s,
+                int margin_kind, float m2, float m3, float filter_thr, void* E, int n_pad, float* part_sum,
+                float* tgt_raw, float* tgt_e, float* tgt_z, void* stream) {
+    if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 8 || n_pad < n) return PFC_ERR_SHAPE;
+    const float log2e = 1.4426950408889634f;
+    // every representable term must stay a normal bf16/fp32 number: 2*s*log2e <= TOP + 126
+    if (!(s > 0.f) || 2.f * s * log2e > PFC_EXP_TOP + 126.f) return PFC_ERR_SCALE_RANGE;
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, xn, d, B, d, BK, BM);
+    if (rc) return rc;
+    rc = make_tmap(&tb, wn, d, n, d, BK, BN);
+    if (rc) return rc;
+    FwdPolicy::Params p;
+    p.B = B; p.n = n; p.n_pad = n_pad; p.B_pad = pfc_padded_batch(B);
+    p.m_tiles = (B + BM - 1) / BM;
+    p.k_stages = (d + BK - 1) / BK;
+    p.num_tiles = p.m_tiles * pfc_num_class_tiles(n);
+    p.labels = labels_local;
+    p.k1 = s * log2e;
+    p.k2 = s * log2e - (float)PFC_EXP_TOP;
+    {   // same double-precision constants the reference computes with math.cos/sin (nets/ArcFace.py:69-72)
+        const double pi = 3.14159265358979323846;
+        p.cos_m = (float)cos((double)m2); p.sin_m = (float)sin((double)m2);
+        p.theta = (float)cos(pi - (double)m2);
+        p.sinmm = (float)(sin(pi - (double)m2) * (double)m2);
+    }
+    p.m3 = m3; p.margin_kind = margin_kind; p.filter_thr = filter_thr;
+    p.E = reinterpret_cast<__nv_bfloat16*>(E);
+    p.part_sum = part_sum; p.tgt_raw = tgt_raw; p.tgt_e = tgt_e; p.tgt_z = tgt_z; p.s = s;
+    return launch_gemm<FwdPolicy>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Number of class splits the dX contraction uses for a given shape (callers size `partial` with it).
+int pfc_dx_splits(int B, int n, int d) {
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    const int base = ((B + BM - 1) / BM) * ((d + BN - 1) / BN);
+    const int k_total = (n + BK - 1) / BK;
+    int splits = sms / base;
+    if (splits < 1) splits = 1;
+    if (splits > k_total) splits = k_total;
+    const int per = (k_total + splits - 1) / splits;
+    return (k_total + per - 1) / per;   // no empty split
+}
+
+// partial[z][B][d] (fp32) = E'[:, classes of split z] . Wn[classes of split z, :]
+int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int d, float* partial, int splits,
+                    void* stream) {
+    if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 8 || splits <= 0) return PFC_ERR_SHAPE;
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, E, n, B, n_pad, BK, BM);       // A: [B, n] K-major (K = classes)
+    if (rc) return rc;
+    rc = make_tmap(&tb, wn, d, n, d, 64, BK);              // B: Wn [n(K), d(N)] MN-major boxes 64(N) x 64(K)
+    if (rc) return rc;
+    StoreParams p;
+    p.m_tiles = (B + BM - 1) / BM;
+    p.n_tiles = (d + BN - 1) / BN;
+    p.k_stages_total = (n + BK - 1) / BK;
+    p.k_stages_per_split = (p.k_stages_total + splits - 1) / splits;
+    p.splits = (p.k_stages_total + p.k_stages_per_split - 1) / p.k_stages_per_split;
+    if (p.splits != splits) return PFC_ERR_SHAPE;
+    p.num_tiles = p.m_tiles * p.n_tiles * p.splits;
+    p.n_fastest = 0;
+    p.rows_valid = B; p.cols_valid = d; p.ld = d;
+    p.split_stride = static_cast<size_t>(B) * d;
+    p.out = partial;
+    return launch_gemm<StorePolicy<false>>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// dwn[n][d] (fp32) = E'^T . Xs,   Xs = c_i * Xn_i (bf16, [B, d])
+int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int d, float* dwn, void* stream) {
+    if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 8) return PFC_ERR_SHAPE;
+    CUtensorMap ta, tb;
+    int rc = make_tmap(&ta, E, n, B, n_pad, 64, BK);       // A: E' [B(K), n(M)] MN-major boxes 64(M) x 64(K)
+    if (rc) return rc;
+    rc = make_tmap(&tb, xs, d, B, d, 64, BK);              // B: Xs [B(K), d(N)] MN-major
+    if (rc) return rc;
+    StoreParams p;
+    p.m_tiles = (n + BM - 1) / BM;
+    p.n_tiles = (d + BN - 1) / BN;
+    p.splits = 1;
+    p.k_stages_total = (B + BK - 1) / BK;
+    p.k_stages_per_split = p.k_stages_total;
+    p.num_tiles = p.m_tiles * p.n_tiles;
+    p.n_fastest = 1;
+    p.rows_valid = n; p.cols_valid = d; p.ld = d;
+    p.split_stride = 0;
+    p.out = dwn;
+    return launch_gemm<StorePolicy<true>>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

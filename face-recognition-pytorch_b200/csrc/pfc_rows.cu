@@ -1,0 +1,467 @@
+// HBM-bound row kernels of the head: fused L2-normalise (fp32 -> bf16 + 1/norm), label localisation,
+// row-statistics / loss reduction, backward coefficient + target patch, normalise-backward for dX and dW,
+// fused SGD / AdamW update that also emits the next step's normalised bf16 shard, and row gather / scatter
+// for the sampled (PartialFC r<1) path.
+//
+// Layout: every matrix is row-major with d (embedding size) contiguous; one warp owns one row and moves it
+// with 16-byte loads (lane l handles float4 #l, #l+32, ...), reductions are warp shuffles.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <math.h>
+#include "pfc_internal.h"
+
+namespace pfc {
+
+constexpr int ROW_WARPS = 8;           // rows per CTA
+constexpr int MAXV = 8;                // float4 per lane -> d <= 1024
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ld4_stream(const float* p) {   // read-once data: do not keep in L1
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 pack4_bf16(float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    return r;
+}
+__device__ __forceinline__ float4 unpack4_bf16(uint2 r) {
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x), b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// xn = x / max(||x||, 1e-12) as bf16, inv = 1 / max(||x||, 1e-12)          (nets/PartialFC.py:199-200)
+// optional gather: row r reads x[index[r]]                                   (nets/PartialFC.py:120)
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+l2norm_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ index, int rows, int d,
+                   __nv_bfloat16* __restrict__ xn, float* __restrict__ inv_norm) {
+    const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int64_t src = index ? index[row] : row;
+    const float* xr = x + src * d;
+    const int nv = d >> 2;
+    float4 v[MAXV];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nv) {
+            v[j] = ld4_stream(xr + 4 * c);
+            ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+        }
+    }
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    __nv_bfloat16* o = xn + static_cast<size_t>(row) * d;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nv) {
+            const float4 q = make_float4(v[j].x / denom, v[j].y / denom, v[j].z / denom, v[j].w / denom);
+            *reinterpret_cast<uint2*>(o + 4 * c) = pack4_bf16(q);
+        }
+    }
+    if (lane == 0) inv_norm[row] = 1.f / denom;
+}
+
+// labels -> shard-local ids, -1 for classes owned by another rank           (nets/PartialFC.py:188-193)
+__global__ void localize_labels_kernel(const int64_t* __restrict__ labels, int B, int64_t class_start,
+                                       int num_local, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int64_t l = labels[i] - class_start;
+    out[i] = (l >= 0 && l < num_local) ? static_cast<int32_t>(l) : -1;
+}
+
+// stats[i] = { sum over class tiles of part_sum[t][i],  target e (0 when the target lives on another rank) }
+// Fixed summation order -> bit-reproducible.  CTA = 32 rows x 8 tile groups.
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
+                 const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* __restrict__ stats) {
+    __shared__ float red[8][33];
+    const int r = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + r;
+    float s = 0.f;
+    if (row < B)
+        for (int t = g; t < n_tiles; t += 8) s += part_sum[static_cast<size_t>(t) * B_pad + row];
+    red[g][r] = s;
+    __syncthreads();
+    if (g == 0 && row < B) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += red[k][r];
+        stats[2 * row] = tot;
+        stats[2 * row + 1] = (labels[row] >= 0) ? tgt_e[row] : 0.f;
+    }
+}
+
+// loss = -mean_i log(max(p_i, 1e-30)),  p_i = target e / row sum             (nets/PartialFC.py:454-461)
+// stats is the (all-reduced) [B][2] array; also emits L_i = stats[i][0] + stats[i][1].
+__global__ void __launch_bounds__(1024)
+loss_kernel(const float* __restrict__ stats, int B, float* __restrict__ row_L, float* __restrict__ loss) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < B; i += 1024) {
+        const float others = stats[2 * i], te = stats[2 * i + 1];
+        const float L = others + te;
+        row_L[i] = L;
+        const float p = fmaxf(te / L, 1e-30f);
+        acc -= logf(p);
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = red[threadIdx.x];
+        v = warp_sum(v);
+        if (threadIdx.x == 0) loss[0] = v / static_cast<float>(B);
+    }
+}
+
+// Backward coefficients (nets/PartialFC.py:464-484 and the autograd of nets/ArcFace.py:80-91, :204):
+//   c_i = g * s / (B * L_i);  Xs_i = c_i * Xn_i (bf16);  E'[i, y_i] = -dm_i * mask_i * Lothers_i
+//   dm_i = d(margin)/dt = cos m + sin m * t / sqrt(1 - t^2)  if t > cos(pi - m) else 1   (CosFace: 1)
+//   mask_i = 1 if -1 <= raw <= 1 (clamp backward) else 0
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict__ row_L,
+                        const float* __restrict__ grad_loss, float s, int B, int d,
+                        const int32_t* __restrict__ labels, const float* __restrict__ tgt_raw, int margin_kind,
+                        float cos_m, float sin_m, float theta, const __nv_bfloat16* __restrict__ xn,
+                        __nv_bfloat16* __restrict__ xs, float* __restrict__ coef, __nv_bfloat16* __restrict__ E,
+                        int n_pad) {
+    const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float g = grad_loss ? grad_loss[0] : 1.f;
+    const float c = g * s / (static_cast<float>(B) * row_L[row]);
+    const int nv = d >> 2;
+    for (int k = lane; k < nv; k += 32) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(xn + static_cast<size_t>(row) * d + 4 * k);
+        float4 v = unpack4_bf16(raw);
+        v.x *= c; v.y *= c; v.z *= c; v.w *= c;
+        *reinterpret_cast<uint2*>(xs + static_cast<size_t>(row) * d + 4 * k) = pack4_bf16(v);
+    }
+    if (lane == 0) {
+        coef[row] = c;
+        const int lbl = labels[row];
+        if (lbl >= 0) {
+            const float raw = tgt_raw[row];
+            const float mask = (fabsf(raw) <= 1.f) ? 1.f : 0.f;
+            const float t = fminf(fmaxf(raw, -1.f), 1.f);
+            float dm = 1.f;
+            if (margin_kind == 0 && t > theta) dm = cos_m + sin_m * t / sqrtf(fmaxf(1.f - t * t, 1e-12f));
+            E[static_cast<size_t>(row) * n_pad + lbl] = __float2bfloat16_rn(-dm * mask * stats[2 * row]);
+        }
+    }
+}
+
+// dX: sum the class-split partials, scale by c_i, and (when x is given) apply the normalise backward
+//   dx = scale * (dxn - xn (xn . dxn)) / ||x||,   xn = x * inv_norm          (autograd of F.normalize)
+// scale = world_size reproduces AllGatherFunc.backward's "grad_out *= len(grad_list)" (nets/PartialFC.py:521).
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+dx_finalize_kernel(const float* __restrict__ partial, int splits, size_t split_stride, const float* __restrict__ coef,
+                   const float* __restrict__ x, const float* __restrict__ inv_norm, float scale, int rows, int d,
+                   float* __restrict__ out) {
+    const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = d >> 2;
+    const float c = coef ? coef[row] : 1.f;
+    float4 g[MAXV], xv[MAXV];
+    float dot = 0.f;
+    const float inv = x ? inv_norm[row] : 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int k = lane + 32 * j;
+        if (k < nv) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < splits; ++z) {
+                const float4 p = ld4(partial + z * split_stride + static_cast<size_t>(row) * d + 4 * k);
+                a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+            }
+            a.x *= c; a.y *= c; a.z *= c; a.w *= c;
+            g[j] = a;
+            if (x) {
+                float4 q = ld4(x + static_cast<size_t>(row) * d + 4 * k);
+                q.x *= inv; q.y *= inv; q.z *= inv; q.w *= inv;
+                xv[j] = q;
+                dot += q.x * a.x + q.y * a.y + q.z * a.z + q.w * a.w;
+            }
+        }
+    }
+    if (x) dot = warp_sum(dot);
+    const float m = x ? scale * inv : scale;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int k = lane + 32 * j;
+        if (k < nv) {
+            float4 a = g[j];
+            if (x) {
+                a.x -= xv[j].x * dot; a.y -= xv[j].y * dot; a.z -= xv[j].z * dot; a.w -= xv[j].w * dot;
+            }
+            a.x *= m; a.y *= m; a.z *= m; a.w *= m;
+            st4(out + static_cast<size_t>(row) * d + 4 * k, a);
+        }
+    }
+}
+
+// dW normalise-backward (+ optional fused optimiser step, + next step's bf16 normalised shard).
+//   dw  = (dwn - wn (wn . dwn)) / ||w||
+//   SGD   (torch.optim.SGD, dampening 0, no nesterov):  g = dw + wd w;  buf = mu buf + g;  w -= lr buf
+//   AdamW (torch.optim.AdamW):  w *= 1 - lr wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+//                               w -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+enum { OPT_NONE = 0, OPT_SGD = 1, OPT_ADAMW = 2, OPT_ADAM = 3 };
+struct OptArgs {
+    int kind;
+    float lr, momentum, wd;         // SGD
+    float beta1, beta2, eps, bc1, bc2_sqrt;   // Adam(W): bc1 = 1-b1^t, bc2_sqrt = sqrt(1-b2^t)
+    float inv_grad_scale;           // multiplies dw first (GradScaler unscale); 1 otherwise
+};
+
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const float* __restrict__ inv_norm_w,
+                   int rows, int d, OptArgs opt, float* __restrict__ dw_out, float* __restrict__ st1,
+                   float* __restrict__ st2, __nv_bfloat16* __restrict__ wn_next, float* __restrict__ inv_norm_next) {
+    const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int nv = d >> 2;
+    const float inv = inv_norm_w[row];
+    const size_t base = static_cast<size_t>(row) * d;
+    float4 g[MAXV], wv[MAXV];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int k = lane + 32 * j;
+        if (k < nv) {
+            g[j] = ld4_stream(dwn + base + 4 * k);
+            wv[j] = ld4(w + base + 4 * k);
+            dot += wv[j].x * g[j].x + wv[j].y * g[j].y + wv[j].z * g[j].z + wv[j].w * g[j].w;
+        }
+    }
+    dot = warp_sum(dot) * inv;                       // wn . dwn
+    const float wscale = dot * inv;                  // (wn . dwn) * wn = w * (dot * inv)
+    const float gs = inv * opt.inv_grad_scale;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int k = lane + 32 * j;
+        if (k < nv) {
+            float4 a;
+            a.x = (g[j].x - wv[j].x * wscale) * gs;
+            a.y = (g[j].y - wv[j].y * wscale) * gs;
+            a.z = (g[j].z - wv[j].z * wscale) * gs;
+            a.w = (g[j].w - wv[j].w * wscale) * gs;
+            if (opt.kind == OPT_NONE) {
+                st4(dw_out + base + 4 * k, a);
+                continue;
+            }
+            float4 wq = wv[j];
+            if (opt.kind == OPT_SGD) {
+                a.x += opt.wd * wq.x; a.y += opt.wd * wq.y; a.z += opt.wd * wq.z; a.w += opt.wd * wq.w;
+                float4 b = a;
+                if (opt.momentum != 0.f) {
+                    b = ld4(st1 + base + 4 * k);
+                    b.x = opt.momentum * b.x + a.x; b.y = opt.momentum * b.y + a.y;
+                    b.z = opt.momentum * b.z + a.z; b.w = opt.momentum * b.w + a.w;
+                    st4(st1 + base + 4 * k, b);
+                }
+                wq.x -= opt.lr * b.x; wq.y -= opt.lr * b.y; wq.z -= opt.lr * b.z; wq.w -= opt.lr * b.w;
+            } else {
+                if (opt.kind == OPT_ADAMW) {
+                    const float dec = 1.f - opt.lr * opt.wd;
+                    wq.x *= dec; wq.y *= dec; wq.z *= dec; wq.w *= dec;
+                } else {
+                    a.x += opt.wd * wq.x; a.y += opt.wd * wq.y; a.z += opt.wd * wq.z; a.w += opt.wd * wq.w;
+                }
+                float4 m = ld4(st1 + base + 4 * k), v = ld4(st2 + base + 4 * k);
+                const float b1 = opt.beta1, b2 = opt.beta2;
+                m.x = b1 * m.x + (1.f - b1) * a.x; m.y = b1 * m.y + (1.f - b1) * a.y;
+                m.z = b1 * m.z + (1.f - b1) * a.z; m.w = b1 * m.w + (1.f - b1) * a.w;
+                v.x = b2 * v.x + (1.f - b2) * a.x * a.x; v.y = b2 * v.y + (1.f - b2) * a.y * a.y;
+                v.z = b2 * v.z + (1.f - b2) * a.z * a.z; v.w = b2 * v.w + (1.f - b2) * a.w * a.w;
+                st4(st1 + base + 4 * k, m);
+                st4(st2 + base + 4 * k, v);
+                const float step = opt.lr / opt.bc1;
+                wq.x -= step * m.x / (sqrtf(v.x) / opt.bc2_sqrt + opt.eps);
+                wq.y -= step * m.y / (sqrtf(v.y) / opt.bc2_sqrt + opt.eps);
+                wq.z -= step * m.z / (sqrtf(v.z) / opt.bc2_sqrt + opt.eps);
+                wq.w -= step * m.w / (sqrtf(v.w) / opt.bc2_sqrt + opt.eps);
+            }
+            st4(w + base + 4 * k, wq);
+            wv[j] = wq;
+            ss += wq.x * wq.x + wq.y * wq.y + wq.z * wq.z + wq.w * wq.w;
+        }
+    }
+    if (opt.kind == OPT_NONE || wn_next == nullptr) return;
+    // next step's normalised operand straight from the registers: saves re-reading the fp32 shard
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+        const int k = lane + 32 * j;
+        if (k < nv) {
+            const float4 q = make_float4(wv[j].x / denom, wv[j].y / denom, wv[j].z / denom, wv[j].w / denom);
+            *reinterpret_cast<uint2*>(wn_next + base + 4 * k) = pack4_bf16(q);
+        }
+    }
+    if (lane == 0) inv_norm_next[row] = 1.f / denom;
+}
+
+// dst[r] = src[index[r]]  /  dst[index[r]] = src[r]   (nets/PartialFC.py:120-121, :142-143), up to 3 tensors at once
+struct RowSet { const float* src[3]; float* dst[3]; int count; };
+
+template <bool kScatter>
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+move_rows_kernel(RowSet set, const int64_t* __restrict__ index, int rows, int d) {
+    const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int64_t other = index[row];
+    const int nv = d >> 2;
+    for (int t = 0; t < set.count; ++t) {
+        const float* s = set.src[t] + (kScatter ? static_cast<int64_t>(row) : other) * d;
+        float* o = set.dst[t] + (kScatter ? other : static_cast<int64_t>(row)) * d;
+        for (int k = lane; k < nv; k += 32) st4(o + 4 * k, ld4_stream(s + 4 * k));
+    }
+}
+
+static inline int row_grid(int rows) { return (rows + ROW_WARPS - 1) / ROW_WARPS; }
+static inline int check_launch() { return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH; }
+static inline bool bad_d(int d) { return d <= 0 || (d & 7) || d > 128 * MAXV; }
+
+}  // namespace pfc
+
+using namespace pfc;
+
+extern "C" {
+
+int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void* xn, float* inv_norm, void* stream) {
+    if (rows < 0 || bad_d(d)) return PFC_ERR_SHAPE;
+    if (rows == 0) return PFC_OK;
+    l2norm_rows_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        x, index, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm);
+    return check_launch();
+}
+
+int pfc_localize_labels(const int64_t* labels, int B, int64_t class_start, int num_local, int32_t* labels_local,
+                        void* stream) {
+    if (B <= 0) return PFC_ERR_SHAPE;
+    localize_labels_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(labels, B, class_start, num_local,
+                                                                              labels_local);
+    return check_launch();
+}
+
+int pfc_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
+                  float* stats, void* stream) {
+    if (B <= 0 || n_tiles <= 0) return PFC_ERR_SHAPE;
+    const int B_pad = (B + 127) / 128 * 128;
+    row_stats_kernel<<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(part_sum, n_tiles, B, B_pad, labels_local,
+                                                                     tgt_e, stats);
+    return check_launch();
+}
+
+int pfc_loss(const float* stats, int B, float* row_L, float* loss, void* stream) {
+    if (B <= 0) return PFC_ERR_SHAPE;
+    loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(stats, B, row_L, loss);
+    return check_launch();
+}
+
+int pfc_backward_prepare(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
+                         const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
+                         const void* xn, void* xs, float* coef, void* E, int n_pad, void* stream) {
+    if (B <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
+    const double pi = 3.14159265358979323846;
+    backward_prepare_kernel<<<row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
+        (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
+        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad);
+    return check_launch();
+}
+
+int pfc_dx_finalize(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
+                    float scale, int rows, int rows_total, int d, float* out, void* stream) {
+    if (rows <= 0 || bad_d(d) || splits <= 0 || rows_total < rows) return PFC_ERR_SHAPE;
+    dx_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, d, out);
+    return check_launch();
+}
+
+int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, int rows, int d, float inv_grad_scale,
+                    float* dw, void* stream) {
+    if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
+    OptArgs o = {};
+    o.kind = OPT_NONE;
+    o.inv_grad_scale = inv_grad_scale;
+    dw_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        dwn, const_cast<float*>(w), inv_norm_w, rows, d, o, dw, nullptr, nullptr, nullptr, nullptr);
+    return check_launch();
+}
+
+int pfc_dw_sgd(const float* dwn, float* w, float* mom, const float* inv_norm_w, int rows, int d, float lr,
+               float momentum, float weight_decay, float inv_grad_scale, void* wn_next, float* inv_norm_next,
+               void* stream) {
+    if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
+    OptArgs o = {};
+    o.kind = OPT_SGD;
+    o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.inv_grad_scale = inv_grad_scale;
+    dw_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        dwn, w, inv_norm_w, rows, d, o, nullptr, mom, nullptr, reinterpret_cast<__nv_bfloat16*>(wn_next),
+        inv_norm_next);
+    return check_launch();
+}
+
+int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
+                int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
+                float inv_grad_scale, void* wn_next, float* inv_norm_next, void* stream) {
+    if (rows <= 0 || bad_d(d) || step <= 0) return PFC_ERR_SHAPE;
+    OptArgs o = {};
+    o.kind = decoupled ? OPT_ADAMW : OPT_ADAM;
+    o.lr = lr; o.wd = weight_decay; o.beta1 = beta1; o.beta2 = beta2; o.eps = eps;
+    o.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    o.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    o.inv_grad_scale = inv_grad_scale;
+    dw_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        dwn, w, inv_norm_w, rows, d, o, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(wn_next),
+        inv_norm_next);
+    return check_launch();
+}
+
+int pfc_gather_rows(const float* const* src, float* const* dst, int count, const int64_t* index, int rows, int d,
+                    void* stream) {
+    if (rows < 0 || count < 1 || count > 3 || d <= 0 || (d & 3)) return PFC_ERR_SHAPE;
+    if (rows == 0) return PFC_OK;
+    RowSet s = {};
+    s.count = count;
+    for (int i = 0; i < count; ++i) { s.src[i] = src[i]; s.dst[i] = dst[i]; }
+    move_rows_kernel<false><<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(s, index, rows, d);
+    return check_launch();
+}
+
+int pfc_scatter_rows(const float* const* src, float* const* dst, int count, const int64_t* index, int rows, int d,
+                     void* stream) {
+    if (rows < 0 || count < 1 || count > 3 || d <= 0 || (d & 3)) return PFC_ERR_SHAPE;
+    if (rows == 0) return PFC_OK;
+    RowSet s = {};
+    s.count = count;
+    for (int i = 0; i < count; ++i) { s.src[i] = src[i]; s.dst[i] = dst[i]; }
+    move_rows_kernel<true><<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(s, index, rows, d);
+    return check_launch();
+}
+
+}  // extern "C"

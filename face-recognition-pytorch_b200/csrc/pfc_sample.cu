@@ -1,0 +1,283 @@
+// PartialFC negative-class sampling (reference: nets/PartialFC.py:92-121) as a radix select.
+//
+// Reference semantics: perm = rand(num_local); perm[positive] = 2.0; index = sort(topk(perm, num_sample).indices);
+// if there are more positives than num_sample the index list is the sorted positives.  Both cases are
+// "the k_eff = max(num_sample, n_pos) largest keys, emitted in ascending index order", because the forced
+// 2.0 is larger than any draw.  Keys are the IEEE bit patterns mapped to an order-preserving uint32; the
+// k_eff-th largest key T is found with three MSB-first histogram passes (11 + 11 + 10 bits); elements
+// with key > T are taken, elements with key == T are taken lowest-index-first until k_eff is reached
+// (the tie rule is ours: torch.topk leaves it implementation-defined), and an ordered stream compaction writes
+// the ascending index list and, for positives, their slot (= searchsorted(index, label), :118).
+//
+// The draw itself stays an input (the reference draws on the CPU generator, :110), so the selected set can be
+// compared bit-for-bit with the reference given the same draw.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pfc_internal.h"
+
+namespace pfc {
+
+constexpr int SEL_THREADS = 1024;
+constexpr int SEL_ITEMS = 8;
+constexpr int SEL_TILE = SEL_THREADS * SEL_ITEMS;
+__host__ __device__ constexpr int radix_bits(int pass) { return pass == 2 ? 10 : 11; }
+__host__ __device__ constexpr int radix_shift(int pass) { return pass == 0 ? 21 : (pass == 1 ? 10 : 0); }
+constexpr int MAX_BINS = 2048;
+
+struct SelState {
+    uint32_t prefix;      // bits of T decided so far
+    uint32_t k_rem;       // how many still to take among keys matching the prefix
+    uint32_t n_pos;       // number of distinct positive classes
+    uint32_t k_eff;       // max(num_sample, n_pos)
+    uint32_t hist[3][MAX_BINS];
+};
+
+__device__ __forceinline__ uint32_t sortable(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ uint32_t key_of(const float* perm, const uint8_t* flags, int i) {
+    return flags[i] ? sortable(2.0f) : sortable(perm[i]);
+}
+
+__global__ void mark_positive_kernel(const int32_t* __restrict__ labels, int B, uint8_t* __restrict__ flags) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < B && labels[j] >= 0) flags[labels[j]] = 1;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(SEL_THREADS)
+hist_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, SelState* st) {
+    __shared__ uint32_t h[MAX_BINS];
+    __shared__ uint32_t npos_s;
+    for (int b = threadIdx.x; b < MAX_BINS; b += SEL_THREADS) h[b] = 0;
+    if (threadIdx.x == 0) npos_s = 0;
+    __syncthreads();
+    const uint32_t prefix = PASS ? st->prefix : 0;
+    constexpr uint32_t hi_mask = PASS == 0 ? 0u : (PASS == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+    constexpr uint32_t dmask = (1u << radix_bits(PASS)) - 1;
+    uint32_t np = 0;
+    for (int i = blockIdx.x * SEL_THREADS + threadIdx.x; i < nl; i += gridDim.x * SEL_THREADS) {
+        const uint32_t k = key_of(perm, flags, i);
+        if (PASS == 0) np += flags[i];
+        if ((k & hi_mask) == prefix) atomicAdd(&h[(k >> radix_shift(PASS)) & dmask], 1u);
+    }
+    if (PASS == 0 && np) atomicAdd(&npos_s, np);
+    __syncthreads();
+    for (int b = threadIdx.x; b < MAX_BINS; b += SEL_THREADS)
+        if (h[b]) atomicAdd(&st->hist[PASS][b], h[b]);
+    if (PASS == 0 && threadIdx.x == 0 && npos_s) atomicAdd(&st->n_pos, npos_s);
+}
+
+// single warp: walk the bins from the top until the running count reaches k_rem
+template <int PASS>
+__global__ void pick_kernel(SelState* st, int num_sample, int nl) {
+    if (threadIdx.x != 0) return;
+    if (PASS == 0) {
+        uint32_t k = st->n_pos > (uint32_t)num_sample ? st->n_pos : (uint32_t)num_sample;
+        if (k > (uint32_t)nl) k = nl;
+        st->k_eff = k;
+        st->k_rem = k;
+        st->prefix = 0;
+    }
+    uint32_t rem = st->k_rem;
+    const int bins = 1 << radix_bits(PASS);
+    int b = bins - 1;
+    if (rem == 0) {   // nothing to select: threshold above every key
+        st->prefix = 0xFFFFFFFFu;
+        return;
+    }
+    for (; b > 0; --b) {
+        const uint32_t c = st->hist[PASS][b];
+        if (c >= rem) break;
+        rem -= c;
+    }
+    st->prefix |= static_cast<uint32_t>(b) << radix_shift(PASS);
+    st->k_rem = rem;
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t& total) {
+    // exclusive scan over the 1024 threads of the CTA (thread order)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = warp_tot[lane];
+        uint32_t ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += n;
+        }
+        warp_tot[lane] = ti - t;           // exclusive warp offsets
+        if (lane == 31) warp_tot[32] = ti;  // grand total
+    }
+    __syncthreads();
+    total = warp_tot[32];
+    const uint32_t r = warp_tot[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// per-tile counts of (key > T) and (key == T)
+__global__ void __launch_bounds__(SEL_THREADS)
+count_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, const SelState* st,
+             uint32_t* __restrict__ gt_cnt, uint32_t* __restrict__ eq_cnt) {
+    __shared__ uint32_t sg, se;
+    if (threadIdx.x == 0) { sg = 0; se = 0; }
+    __syncthreads();
+    const uint32_t T = st->prefix;
+    const bool none = st->k_eff == 0;
+    uint32_t g = 0, e = 0;
+    const int base = blockIdx.x * SEL_TILE + threadIdx.x * SEL_ITEMS;
+#pragma unroll
+    for (int u = 0; u < SEL_ITEMS; ++u) {
+        const int i = base + u;
+        if (i < nl && !none) {
+            const uint32_t k = key_of(perm, flags, i);
+            g += k > T;
+            e += k == T;
+        }
+    }
+    g = __reduce_add_sync(0xffffffffu, g);
+    e = __reduce_add_sync(0xffffffffu, e);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&sg, g); atomicAdd(&se, e); }
+    __syncthreads();
+    if (threadIdx.x == 0) { gt_cnt[blockIdx.x] = sg; eq_cnt[blockIdx.x] = se; }
+}
+
+// exclusive scan of the per-tile counts (tiles <= a few hundred: one CTA, serial chunks of 1024)
+__global__ void __launch_bounds__(SEL_THREADS)
+scan_tiles_kernel(uint32_t* __restrict__ gt_cnt, uint32_t* __restrict__ eq_cnt, int tiles) {
+    __shared__ uint32_t wt[33];
+    uint32_t carry_g = 0, carry_e = 0;
+    for (int b0 = 0; b0 < tiles; b0 += SEL_THREADS) {
+        const int i = b0 + threadIdx.x;
+        const uint32_t g = i < tiles ? gt_cnt[i] : 0, e = i < tiles ? eq_cnt[i] : 0;
+        uint32_t tg, te;
+        const uint32_t xg = block_excl_scan(g, wt, tg);
+        const uint32_t xe = block_excl_scan(e, wt, te);
+        if (i < tiles) { gt_cnt[i] = carry_g + xg; eq_cnt[i] = carry_e + xe; }
+        carry_g += tg;
+        carry_e += te;
+    }
+}
+
+// ordered compaction: ascending index list + slot of every positive class
+__global__ void __launch_bounds__(SEL_THREADS)
+compact_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, const SelState* st,
+               const uint32_t* __restrict__ gt_off, const uint32_t* __restrict__ eq_off,
+               int64_t* __restrict__ index_out, int32_t* __restrict__ slot_of, int32_t* __restrict__ n_out) {
+    __shared__ uint32_t wt[33];
+    const uint32_t T = st->prefix;
+    const uint32_t need_eq = st->k_rem;
+    const bool none = st->k_eff == 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_out[0] = static_cast<int32_t>(st->k_eff);
+    const int base = blockIdx.x * SEL_TILE + threadIdx.x * SEL_ITEMS;
+    uint32_t isgt = 0, iseq = 0;   // bit u = item u
+    uint32_t ng = 0, ne = 0;
+#pragma unroll
+    for (int u = 0; u < SEL_ITEMS; ++u) {
+        const int i = base + u;
+        if (i < nl && !none) {
+            const uint32_t k = key_of(perm, flags, i);
+            if (k > T) { isgt |= 1u << u; ++ng; }
+            if (k == T) { iseq |= 1u << u; ++ne; }
+        }
+    }
+    uint32_t tot;
+    const uint32_t eq_before_blk = eq_off[blockIdx.x];
+    uint32_t eq_rank = eq_before_blk + block_excl_scan(ne, wt, tot);
+    // selected flags now known per item
+    uint32_t sel = isgt, nsel = ng;
+#pragma unroll
+    for (int u = 0; u < SEL_ITEMS; ++u) {
+        if (iseq & (1u << u)) {
+            if (eq_rank < need_eq) { sel |= 1u << u; ++nsel; }
+            ++eq_rank;
+        }
+    }
+    const uint32_t sel_before_blk = gt_off[blockIdx.x] + min(eq_before_blk, need_eq);
+    uint32_t pos = sel_before_blk + block_excl_scan(nsel, wt, tot);
+#pragma unroll
+    for (int u = 0; u < SEL_ITEMS; ++u) {
+        if (sel & (1u << u)) {
+            const int i = base + u;
+            index_out[pos] = i;
+            if (flags[i]) slot_of[i] = static_cast<int32_t>(pos);
+            ++pos;
+        }
+    }
+}
+
+__global__ void remap_labels_kernel(const int32_t* __restrict__ labels, int B, const int32_t* __restrict__ slot_of,
+                                    int32_t* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= B) return;
+    const int l = labels[j];
+    out[j] = l >= 0 ? slot_of[l] : -1;
+}
+
+struct SelLayout {
+    size_t flags, state, gt, eq, slot, total;
+    int tiles;
+};
+static SelLayout sel_layout(int nl) {
+    SelLayout L;
+    L.tiles = (nl + SEL_TILE - 1) / SEL_TILE;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    L.flags = take(static_cast<size_t>(nl));
+    L.state = take(sizeof(SelState));
+    L.gt = take(sizeof(uint32_t) * L.tiles);
+    L.eq = take(sizeof(uint32_t) * L.tiles);
+    L.slot = take(sizeof(int32_t) * static_cast<size_t>(nl));
+    L.total = off;
+    return L;
+}
+
+}  // namespace pfc
+
+using namespace pfc;
+
+extern "C" {
+
+size_t pfc_sample_workspace_bytes(int num_local) { return num_local > 0 ? sel_layout(num_local).total : 0; }
+
+int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_local, int num_sample,
+               int64_t* index_out, int32_t* n_out, int32_t* labels_remapped, void* workspace,
+               size_t workspace_bytes, void* stream_) {
+    if (B <= 0 || num_local <= 0 || num_sample < 0) return PFC_ERR_SHAPE;
+    const SelLayout L = sel_layout(num_local);
+    if (workspace_bytes < L.total) return PFC_ERR_WORKSPACE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    uint8_t* flags = ws + L.flags;
+    SelState* st = reinterpret_cast<SelState*>(ws + L.state);
+    uint32_t* gt = reinterpret_cast<uint32_t*>(ws + L.gt);
+    uint32_t* eq = reinterpret_cast<uint32_t*>(ws + L.eq);
+    int32_t* slot = reinterpret_cast<int32_t*>(ws + L.slot);
+    // flags and the selection state are contiguous at the front of the workspace
+    if (cudaMemsetAsync(ws, 0, L.gt, stream) != cudaSuccess) return PFC_ERR_CUDA;
+    mark_positive_kernel<<<(B + 255) / 256, 256, 0, stream>>>(labels_local, B, flags);
+    int hb = L.tiles;   // one CTA per SEL_TILE keys keeps every SM busy for the big shards, 1 CTA for small ones
+    hist_kernel<0><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
+    pick_kernel<0><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    hist_kernel<1><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
+    pick_kernel<1><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    hist_kernel<2><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
+    pick_kernel<2><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    count_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq);
+    scan_tiles_kernel<<<1, SEL_THREADS, 0, stream>>>(gt, eq, L.tiles);
+    compact_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq, index_out, slot, n_out);
+    remap_labels_kernel<<<(B + 255) / 256, 256, 0, stream>>>(labels_local, B, slot, labels_remapped);
+    return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// Warp-specialised persistent tcgen05 GEMM skeleton shared by the three dense contractions of the head:
+//   G1  logits tile  S  = Xn  . Wn^T      (A K-major,  B K-major,  epilogue = margin/exp/row-sum/bf16 spill)
+//   G2  dXn          += E' . Wn           (A K-major,  B MN-major, split over classes, epilogue = fp32 partial)
+//   G3  dWn           = E'^T . Xs         (A MN-major, B MN-major, epilogue = fp32 tile store)
+// One CTA per SM: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+// warps 2..5 = epilogue (one per TMEM lane quarter).  Three pipelines: smem full/empty (TMA<->MMA),
+// TMEM full/empty (MMA<->epilogue, two 256-column accumulators), and the static persistent tile loop.
+//
+// Tile = 128 (TMEM lanes) x 256 (TMEM columns) fp32, K consumed in 64-element (128-byte, SWIZZLE_128B)
+// stages, 4 stages x (16 KB A + 32 KB B) = 192 KB of shared memory.
+#pragma once
+#include "pfc_ptx.cuh"
+
+namespace pfc {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int B_STAGE_BYTES = BN * BK * 2;
+constexpr int MN_BOX_BYTES = 64 * BK * 2;   // one 64(MN) x 64(K) box of an MN-major operand
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024;   // +1024: manual alignment
+constexpr int TMEM_COLS = 512;
+
+struct TileCoord {
+    int m0;    // first row of the A-side (TMEM lane) dimension
+    int n0;    // first row of the B-side (TMEM column) dimension
+    int k0;    // first K stage (units of BK)
+    int k1;    // one past the last K stage
+    int aux;   // policy-defined (e.g. split index / class-tile index)
+};
+
+// Policy contract:
+//   static constexpr bool A_MN, B_MN;           operand major-ness in shared memory
+//   struct Params { int num_tiles; ... };
+//   static TileCoord tile(const Params&, int t);
+//   static void epilogue(const Params&, const TileCoord&, uint32_t taddr, int row_in_tile, int lane);
+//        taddr = TMEM address of this warp's lane quarter, column 0 of the tile's accumulator.
+template <class P>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const typename P::Params prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);   // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = blockIdx.x; t < prm.num_tiles; t += gridDim.x) {
+                const TileCoord tc = P::tile(prm, t);
+                for (int kc = tc.k0; kc < tc.k1; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+                    uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+                    uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
+                    const int kel = kc * BK;
+                    if constexpr (P::A_MN) {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_2d(a_dst + j * MN_BOX_BYTES, &tma_a, &full_bar[stage], tc.m0 + j * 64, kel);
+                    } else {
+                        tma_load_2d(a_dst, &tma_a, &full_bar[stage], kel, tc.m0);
+                    }
+                    if constexpr (P::B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_2d(b_dst + j * MN_BOX_BYTES, &tma_b, &full_bar[stage], tc.n0 + j * 64, kel);
+                    } else {
+                        tma_load_2d(b_dst, &tma_b, &full_bar[stage], kel, tc.n0);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
+            uint32_t stage = 0, phase = 0;
+            int tl = 0;
+            for (int t = blockIdx.x; t < prm.num_tiles; t += gridDim.x, ++tl) {
+                const TileCoord tc = P::tile(prm, t);
+                const int acc = tl & 1;
+                const uint32_t acc_phase = (tl >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kc = tc.k0; kc < tc.k1; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
+                    const uint32_t b_base = smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per 16-element K step.
+                        // MN-major: 64(MN) x 8(K) atoms of 1024 B; next 64-wide MN block one box (8 KB) further,
+                        //           next 8 K rows 1024 B further; +2048 B per 16-row K step.
+                        const uint64_t adesc = P::A_MN ? umma_smem_desc_sw128(a_base + k * 2048, MN_BOX_BYTES, 1024)
+                                                       : umma_smem_desc_sw128(a_base + k * 32, 16, 1024);
+                        const uint64_t bdesc = P::B_MN ? umma_smem_desc_sw128(b_base + k * 2048, MN_BOX_BYTES, 1024)
+                                                       : umma_smem_desc_sw128(b_base + k * 32, 16, 1024);
+                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc > tc.k0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full_bar[acc]);     // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (4 warps)
+        const int quarter = warp & 3;                  // TMEM lanes [32q, 32q+32) are the only ones this warp may read
+        const int row_in_tile = quarter * 32 + lane;
+        int tl = 0;
+        for (int t = blockIdx.x; t < prm.num_tiles; t += gridDim.x, ++tl) {
+            const TileCoord tc = P::tile(prm, t);
+            const int acc = tl & 1;
+            const uint32_t acc_phase = (tl >> 1) & 1;
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+            P::epilogue(prm, tc, taddr, row_in_tile, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace pfc

@@ -1,0 +1,149 @@
+/* libpfc_b200 -- C ABI of the B200-native margin-softmax head (ArcFace + PartialFC) and pair-verification scorer.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, caller-owned device memory, an explicit CUDA stream,
+ * no allocation, no host synchronisation, no exceptions.  Every function returns PFC_OK (0) or a negative
+ * PFC_ERR_* code; nothing is launched when an error is returned.  All pointers are DEVICE pointers unless
+ * stated otherwise; `stream` is a cudaStream_t (NULL = default stream).  Matrices are row-major with the
+ * embedding dimension d contiguous; d must be a multiple of 8 and <= 1024; bf16 buffers are 16-byte aligned.
+ *
+ * The reference is pure Python (aanna0701/face-recognition-pytorch); each entry point names the reference
+ * code it replaces as file:line.  The Python binding a maintainer would add is shown in INTEGRATION.md.
+ */
+#ifndef PFC_B200_H
+#define PFC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFC_OK 0
+#define PFC_ERR_CUDA (-1)        /* a CUDA runtime call failed */
+#define PFC_ERR_LAUNCH (-2)      /* kernel launch failed */
+#define PFC_ERR_SHAPE (-3)       /* invalid / unsupported shape argument */
+#define PFC_ERR_ALIGNMENT (-4)   /* pointer or stride not 16-byte aligned */
+#define PFC_ERR_DRIVER (-5)      /* cuTensorMapEncodeTiled not available from the driver */
+#define PFC_ERR_TENSORMAP (-6)   /* tensor-map encoding rejected */
+#define PFC_ERR_SCALE_RANGE (-7) /* logit scale s outside the fixed-shift exponent range (s <= ~65.8) */
+#define PFC_ERR_WORKSPACE (-8)   /* workspace too small */
+
+#define PFC_MARGIN_ARCFACE 0     /* nets/ArcFace.py:63-91 and CombinedMarginLoss with m1 == 1, m3 == 0 (:42-52) */
+#define PFC_MARGIN_COSFACE 1     /* nets/ArcFace.py:94-106 and CombinedMarginLoss with m3 > 0 (:54-57) */
+
+int pfc_version(void);
+const char* pfc_error_string(int code);           /* host string */
+
+/* ---- shape helpers (host only, no CUDA calls except pfc_dx_splits' SM-count query) ---------------------- */
+int pfc_exp_top(void);                            /* exponent offset of the spilled e terms (see pfc_forward) */
+int pfc_padded_classes(int n);                    /* row stride (elements) of the E' spill for n active classes */
+int pfc_padded_batch(int B);                      /* row count the part_sum slabs are padded to */
+int pfc_num_class_tiles(int n);                   /* number of 256-class tiles = leading dim of part_sum */
+int pfc_dx_splits(int B, int n, int d);           /* class splits pfc_backward_dx will use for this shape */
+
+/* ---- (1) fused L2 normalise: F.normalize of embeddings / of the classifier shard, nets/PartialFC.py:199-200.
+ * xn[r,:] = bf16(x[src,:] / max(||x[src,:]||, 1e-12)), inv_norm[r] = 1/max(||.||, 1e-12), src = index ? index[r] : r
+ * (the optional gather is the `self.weight[self.weight_index]` of nets/PartialFC.py:120 fused in). */
+int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void* xn_bf16, float* inv_norm,
+                    void* stream);
+
+/* ---- label localisation, nets/PartialFC.py:188-193: out[i] = labels[i]-class_start if owned by this rank else -1 */
+int pfc_localize_labels(const int64_t* labels, int B, int64_t class_start, int num_local, int32_t* labels_local,
+                        void* stream);
+
+/* ---- (2) negative-class sampling, nets/PartialFC.py:92-121 (sample()).
+ * perm: the rank's uniform draw [num_local] (the reference draws it with torch.rand on the CPU generator, :110).
+ * index_out [max(num_sample, #positives)] ascending int64 (== self.weight_index), n_out[0] its length,
+ * labels_remapped[i] = searchsorted(index_out, labels_local[i]) for owned rows, -1 otherwise (:118).
+ * Ties at the k-th value are resolved lowest-index-first. */
+size_t pfc_sample_workspace_bytes(int num_local);
+int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_local, int num_sample,
+               int64_t* index_out, int32_t* n_out, int32_t* labels_remapped, void* workspace,
+               size_t workspace_bytes, void* stream);
+
+/* rows of up to 3 fp32 matrices at once: dst[t][r,:] = src[t][index[r],:]  (nets/PartialFC.py:120-121)
+ * and dst[t][index[r],:] = src[t][r,:] (update(), nets/PartialFC.py:133-143).  src/dst are HOST arrays of device
+ * pointers. */
+int pfc_gather_rows(const float* const* src, float* const* dst, int count, const int64_t* index, int rows, int d,
+                    void* stream);
+int pfc_scatter_rows(const float* const* src, float* const* dst, int count, const int64_t* index, int rows, int d,
+                     void* stream);
+
+/* ---- (3) forward: cosine-logit GEMM + clamp + margin + scale + softmax terms, nets/PartialFC.py:201-207,
+ * nets/ArcFace.py:76-91 (or :100-105), nets/PartialFC.py:446-458.  tcgen05 GEMM Xn[B,d] . Wn[n,d]^T whose epilogue
+ * never writes logits: for every (sample i, class c) it forms e_ic = 2^(log2e*(z_ic - s) + pfc_exp_top()) with
+ * z = s*clamp(cos,-1,1) (margin applied on the target column), accumulates the per-row sum of the NON-target terms
+ * per 256-class tile into part_sum[tile][i] and spills e (zeroed where the clamp blocks the gradient) as bf16
+ * into E[i*n_pad + c].  For rows whose target class is local it also writes the raw target cosine, the target's
+ * e term and the target logit.  labels_local: -1 = target on another rank. */
+int pfc_forward(const void* xn_bf16, const void* wn_bf16, const int32_t* labels_local, int B, int n, int d, float s,
+                int margin_kind, float m2, float m3, float interclass_filtering_threshold, void* E_bf16, int n_pad,
+                float* part_sum, float* tgt_raw, float* tgt_e, float* tgt_z, void* stream);
+
+/* ---- (4) row statistics and loss, nets/PartialFC.py:446-461 (DistCrossEntropyFunc.forward).
+ * pfc_row_stats: stats[i] = { sum_tiles part_sum[.][i], target e or 0 } -- the [B,2] array ranks all-reduce (SUM),
+ * replacing the reference's three all-reduces (:448, :453, :459).
+ * pfc_loss: row_L[i] = stats[i][0]+stats[i][1]; loss[0] = -mean_i log(max(stats[i][1]/row_L[i], 1e-30)). */
+int pfc_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
+                  float* stats, void* stream);
+int pfc_loss(const float* stats, int B, float* row_L, float* loss, void* stream);
+
+/* ---- (5) backward, nets/PartialFC.py:464-484 (DistCrossEntropyFunc.backward) + autograd of :199-206.
+ * pfc_backward_prepare: coef[i] = g*s/(B*row_L[i]) (g = grad_loss[0], device scalar, NULL = 1), xs = bf16(coef*xn),
+ *   and the target column of E is patched to -dm_i*mask_i*stats[i][0] (dm = margin derivative, mask = clamp gate).
+ * pfc_backward_dx: partial[z] = E[:, split z] . Wn[split z, :]   (tcgen05, `splits` = pfc_dx_splits(B,n,d) slabs [B,d])
+ * pfc_dx_finalize: out = scale * normalize_backward(coef * sum_z partial[z]); with x == NULL only the scaled sum is
+ *   formed (the array ranks reduce-scatter, replacing AllGatherFunc.backward :505-522; `scale` = world size, :521).
+ * pfc_backward_dw: dwn[n,d] = E^T . xs   (tcgen05)
+ * pfc_dw_finalize: dw = normalize_backward(dwn) * inv_grad_scale (un-fused: hand dw to any torch optimizer)
+ * pfc_dw_sgd / pfc_dw_adam: the same plus the optimizer step fused (torch.optim.SGD / Adam / AdamW semantics,
+ *   driven from model/FR_PartialFC.py:182-188), also emitting the next step's bf16 normalised shard. */
+int pfc_backward_prepare(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
+                         const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
+                         const void* xn_bf16, void* xs_bf16, float* coef, void* E_bf16, int n_pad, void* stream);
+int pfc_backward_dx(const void* E_bf16, int n_pad, const void* wn_bf16, int B, int n, int d, float* partial,
+                    int splits, void* stream);
+int pfc_dx_finalize(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
+                    float scale, int rows, int rows_total, int d, float* out, void* stream);
+int pfc_backward_dw(const void* E_bf16, int n_pad, const void* xs_bf16, int B, int n, int d, float* dwn,
+                    void* stream);
+int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, int rows, int d, float inv_grad_scale,
+                    float* dw, void* stream);
+int pfc_dw_sgd(const float* dwn, float* w, float* momentum_buf, const float* inv_norm_w, int rows, int d, float lr,
+               float momentum, float weight_decay, float inv_grad_scale, void* wn_next_bf16, float* inv_norm_next,
+               void* stream);
+int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
+                int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
+                float inv_grad_scale, void* wn_next_bf16, float* inv_norm_next, void* stream);
+
+/* ---- (6) pair verification, utils/eval.py.
+ * fr_pair_score  (:68-99): scores[i] = 1 - ||e1_i - e2_i||^2/4 (fp32 difference, fp64 accumulation), optional
+ *   dist[i] = ||.||^2, and the 100001-bin genuine / imposter histograms (uint64 counts; zeroed by the call).
+ * fr_roc         (:7-51, :140-144): EER threshold + FRR at FAR = 10^-k for k in [min_level, max_level].
+ * fr_acc_counts  (:54-66): fr_fa = { #(score <= threshold & label == 1), #(score > threshold & label == 0) }.
+ * fr_kfold_acc: standard LFW protocol -- `folds` contiguous folds, thresholds t*step on dist, best-train threshold
+ *   applied to the held-out fold (not in the reference; BASELINE.json config 5). correct_ws: folds*n_thr uint32. */
+typedef struct {
+    int32_t eer_threshold;
+    int32_t pad;
+    double eer;
+    double total_genuine, total_imposter;
+    double frr_at[16];   /* NaN where the reference would leave None */
+    int32_t th_at[16];   /* -1 where the reference would leave None */
+} fr_roc_out_t;
+
+int pfc_eval_hist_bins(void);
+int fr_pair_score(const float* e1, const float* e2, const uint8_t* labels, int N, int d, double* scores, double* dist,
+                  unsigned long long* hist_genuine, unsigned long long* hist_imposter, void* stream);
+int fr_roc(const unsigned long long* hist_genuine, const unsigned long long* hist_imposter, int min_level,
+           int max_level, void* roc_out /* fr_roc_out_t, device */, void* stream);
+int fr_acc_counts(const double* scores, const uint8_t* labels, int N, double threshold, unsigned long long* fr_fa,
+                  void* stream);
+int fr_kfold_acc(const double* dist, const uint8_t* labels, int N, int folds, int n_thr, double step,
+                 unsigned int* correct_ws, double* acc, int* best_idx, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFC_B200_H */
