@@ -1,0 +1,113 @@
+"""Pins the oracle: every function of oracle/ against fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import HEAD_CASES, load_case, case_inputs, case_margin, case_perms
+from inputs import eval_inputs_cfg5
+from oracle import head_oracle as ho
+from oracle import eval_oracle as eo
+
+
+def _close(got, ref, tol):
+    """fp64 oracle vs the reference's fp32 run: max abs error relative to the largest reference entry."""
+    got = got.numpy() if hasattr(got, "numpy") else np.asarray(got)
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64)).max()
+    assert err <= tol * max(np.abs(ref).max(), 1e-12), (err, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", HEAD_CASES)
+def test_head_steps_match_reference(name):
+    cfg, z = load_case(name)
+    weights, xs, ls = case_inputs(cfg)
+    W, b = cfg["W"], cfg["b"]
+    orc = ho.PartialFCOracle(weights, cfg["C"], case_margin(cfg), cfg["sample_rate"], cfg["lr"], cfg["momentum"],
+                             cfg["wd"])
+    for s in range(cfg["steps"]):
+        xl = [xs[s][r * b:(r + 1) * b] for r in range(W)]
+        ll = [ls[s][r * b:(r + 1) * b] for r in range(W)]
+        res = orc.step(xl, ll, case_perms(cfg, z, s))
+        for r in range(W):
+            ref_loss = float(z[f"r{r}_loss_{s}"])
+            assert abs(float(res.loss) - ref_loss) <= 2e-6 * max(1.0, abs(ref_loss))
+            _close(res.dx_local[r], z[f"r{r}_dx_{s}"], 5e-5)
+            _close(res.dw[r], z[f"r{r}_dw_{s}"], 5e-5)
+            if cfg["sample_rate"] < 1:
+                assert np.array_equal(res.index[r].numpy(), z[f"r{r}_index_{s}"])   # bit-exact index set
+    wf, mf = orc.full_weights()
+    for r in range(W):
+        _close(wf[r], z[f"r{r}_weight_final"], 5e-5)
+        _close(mf[r], z[f"r{r}_mom_final"], 2e-4)
+
+
+def test_shard_arithmetic_covers_all_classes():
+    for C in (10, 301, 93431, 360232):
+        for W in (1, 2, 3, 8):
+            spans = [ho.shard_range(C, r, W) for r in range(W)]
+            assert sum(n for n, _ in spans) == C
+            pos = 0
+            for n, start in spans:
+                assert start == pos
+                pos += n
+    assert ho.shard_range(93431, 0, 8) == (11679, 0)
+    assert ho.shard_range(93431, 7, 8)[0] == 11678
+
+
+@pytest.mark.parametrize("key,kind,s,m,thr", [
+    ("arcface", "arcface", 64.0, 0.5, 0.0), ("arcface_30", "arcface", 30.0, 0.35, 0.0),
+    ("cosface", "cosface", 64.0, 0.4, 0.0), ("combined_arc", "arcface", 64.0, 0.5, 0.0),
+    ("combined_cos", "cosface", 64.0, 0.4, 0.0), ("combined_filter", "arcface", 64.0, 0.5, 0.5)])
+def test_margin_modules(key, kind, s, m, thr):
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "margins.npz"))
+    logits = torch.from_numpy(z["logits"]).double()
+    labels = torch.from_numpy(z["labels"]).reshape(-1)
+    mg = ho.Margin(kind=kind, s=s, m=m, filter_thr=thr)
+    # rank_logits works on cosines produced by a GEMM; feed the fixture logits through an identity "GEMM"
+    n = logits.shape[1]
+    f = ho.rank_logits(logits, torch.eye(n, dtype=torch.float64), labels, mg)
+    np.testing.assert_allclose(f.z.numpy(), z[key], rtol=1e-5, atol=1e-5)
+    # d sum(z) / d logits == grad_gate (identity weight => wn = I)
+    np.testing.assert_allclose(f.grad_gate.numpy(), z[key + "_grad"], rtol=1e-5, atol=1e-5)
+
+
+def _hist(z, prefix, which):
+    h = np.zeros(eo.HIST_BINS)
+    h[z[f"{prefix}_{which}_nz"]] = z[f"{prefix}_{which}_val"]
+    return h
+
+
+def test_eval_small_case():
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "eval.npz"))
+    hg, hi, sc = eo.pair_score(z["small_e1"], z["small_e2"], z["small_lab"])
+    assert np.array_equal(hg, _hist(z, "small", "hg")) and np.array_equal(hi, _hist(z, "small", "hi"))
+    np.testing.assert_allclose(sc, z["small_scores"], rtol=0, atol=4e-16)
+    rep, th = eo.performance_roc(hg, hi, 1, 3)
+    assert th == int(z["small_th"]) and rep == str(z["small_report"])
+    assert eo.performance_acc(sc, z["small_lab"], th) == float(z["small_acc"])
+
+
+def test_eval_cfg5_bit_exact_accuracy():
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "eval.npz"))
+    a, b, lab = eval_inputs_cfg5()
+    chk = z["cfg5_input_checksum"]
+    assert float(a.astype(np.float64).sum()) == chk[0] and float(b.astype(np.float64).sum()) == chk[1]
+    hg, hi, sc = eo.pair_score(a, b, lab)
+    assert np.array_equal(hg, _hist(z, "cfg5", "hg")) and np.array_equal(hi, _hist(z, "cfg5", "hi"))
+    rep, th = eo.performance_roc(hg, hi)
+    assert th == 63399 == int(z["cfg5_th"])
+    assert rep == str(z["cfg5_report"])
+    acc = eo.performance_acc(sc, lab, th)
+    assert acc == float(z["cfg5_acc"]) and abs(acc - 94.66666666666667) < 1e-12
+
+
+def test_kfold_protocol_properties():
+    a, b, lab = eval_inputs_cfg5()
+    _, _, sc = eo.pair_score(a, b, lab)
+    dist = 4.0 * (1.0 - sc)
+    acc, best = eo.kfold_accuracy(dist, lab)
+    assert acc.shape == (10,) and 0.9 < acc.mean() < 0.97
+    # perfectly separable data -> 100 %
+    d2 = np.where(lab, 0.5, 2.5)
+    acc2, _ = eo.kfold_accuracy(d2, lab)
+    assert np.all(acc2 == 1.0)
