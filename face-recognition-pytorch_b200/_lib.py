@@ -1,0 +1,96 @@
+"""ctypes binding of libpfc_b200.so -- the only way the Python host code reaches the CUDA kernels.
+
+There is no fallback: if the library is missing and cannot be built, importing this module raises.
+Signatures mirror include/pfc.h one to one.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint, c_void_p
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class PfcError(RuntimeError):
+    def __init__(self, code, where):
+        self.code = code
+        super().__init__(f"{where}: libpfc_b200 error {code} ({error_string(code)})")
+
+
+def _load():
+    path = _build.LIB
+    if not os.path.exists(path) or (os.environ.get("PFC_REBUILD") == "1"):
+        # first use in a fresh checkout: compile in-tree (needs nvcc); failure here is fatal by design
+        _build.build(force=True)
+    try:
+        return ctypes.CDLL(path)
+    except OSError as e:   # pragma: no cover
+        raise ImportError(f"cannot load {path}: {e}. The CUDA extension is mandatory (no CPU fallback).") from e
+
+
+lib = _load()
+
+p = c_void_p
+_SIGS = {
+    "pfc_version": (c_int, []),
+    "pfc_error_string": (c_char_p, [c_int]),
+    "pfc_exp_top": (c_int, []),
+    "pfc_padded_classes": (c_int, [c_int]),
+    "pfc_padded_batch": (c_int, [c_int]),
+    "pfc_num_class_tiles": (c_int, [c_int]),
+    "pfc_dx_splits": (c_int, [c_int, c_int, c_int]),
+    "pfc_dx_max_splits": (c_int, [c_int, c_int]),
+    "pfc_l2norm_rows": (c_int, [p, p, c_int, c_int, p, p, p]),
+    "pfc_localize_labels": (c_int, [p, c_int, c_int64, c_int, p, p]),
+    "pfc_sample_workspace_bytes": (c_size_t, [c_int]),
+    "pfc_sample": (c_int, [p, p, c_int, c_int, c_int, p, p, p, p, c_size_t, p]),
+    "pfc_gather_rows": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, p, c_int, c_int, p]),
+    "pfc_scatter_rows": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, p, c_int, c_int, p]),
+    "pfc_forward": (c_int, [p, p, p, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float, p, c_int, p, p,
+                            p, p, p]),
+    "pfc_margin_apply": (c_int, [p, p, c_int, c_int, c_int, c_float, c_float, c_float, c_float, p, p, p]),
+    "pfc_row_stats": (c_int, [p, c_int, c_int, p, p, p, p]),
+    "pfc_loss": (c_int, [p, c_int, p, p, p]),
+    "pfc_backward_prepare": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, c_int, p]),
+    "pfc_backward_dx": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
+    "pfc_dx_finalize": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p]),
+    "pfc_backward_dw": (c_int, [p, c_int, p, c_int, c_int, c_int, p, p]),
+    "pfc_dw_finalize": (c_int, [p, p, p, c_int, c_int, c_float, p, p]),
+    "pfc_dw_sgd": (c_int, [p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, p, p, p]),
+    "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int,
+                            c_float, p, p, p]),
+    "pfc_eval_hist_bins": (c_int, []),
+    "fr_pair_score": (c_int, [p, p, p, c_int, c_int, p, p, p, p, p]),
+    "fr_roc": (c_int, [p, p, c_int, c_int, p, p]),
+    "fr_acc_counts": (c_int, [p, p, c_int, c_double, p, p]),
+    "fr_kfold_acc": (c_int, [p, p, c_int, c_int, c_int, c_double, p, p, p, p]),
+}
+EXPORTS = tuple(_SIGS)
+
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)      # AttributeError here == header / library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def error_string(code):
+    return lib.pfc_error_string(int(code)).decode()
+
+
+def check(code, where):
+    if code != 0:
+        raise PfcError(code, where)
+
+
+class RocOut(ctypes.Structure):
+    """fr_roc_out_t of include/pfc.h."""
+    _fields_ = [("eer_threshold", c_int32), ("pad", c_int32), ("eer", c_double), ("total_genuine", c_double),
+                ("total_imposter", c_double), ("frr_at", c_double * 16), ("th_at", c_int32 * 16)]
+
+
+def ptr_array(ptrs):
+    arr = (c_void_p * len(ptrs))()
+    for i, v in enumerate(ptrs):
+        arr[i] = v
+    return arr

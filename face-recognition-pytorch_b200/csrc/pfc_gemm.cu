@@ -35,6 +35,7 @@ struct FwdPolicy {
         float* tgt_z;            // [B] margin-adjusted target logit (already * s)
         float s;
     };
+    __device__ static __forceinline__ DescCfg desc(const Params&) { return default_desc_cfg(false, false); }
     __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
         TileCoord tc;
         const int ct = t / p.m_tiles;
@@ -144,6 +145,7 @@ struct StoreParams {
     int ld;                 // row stride of out (elements)
     size_t split_stride;    // elements between split slabs
     float* out;
+    DescCfg dc;             // descriptor geometry (runtime so that tools/gpu_probe.py can try alternatives)
 };
 
 template <bool kAMN>
@@ -151,6 +153,7 @@ struct StorePolicy {
     static constexpr bool A_MN = kAMN;
     static constexpr bool B_MN = true;
     using Params = StoreParams;
+    __device__ static __forceinline__ DescCfg desc(const Params& p) { return p.dc; }
     __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
         // n_fastest=0: m fastest (CTAs running together share the B stage in L2);
         // n_fastest=1: the N tiles of one M tile run side by side (they share the A stage in L2)
@@ -236,6 +239,16 @@ static int num_sms() {
     return sms;
 }
 
+// Debug hook (tools/gpu_probe.py): override the MN-major descriptor geometry. 0 = keep default.
+static uint32_t g_dbg_mn_lbo = 0, g_dbg_mn_sbo = 0, g_dbg_mn_kstep = 0;
+static DescCfg store_desc_cfg(bool a_mn) {
+    DescCfg dc = default_desc_cfg(a_mn, true);
+    if (g_dbg_mn_lbo) { dc.b_lbo = g_dbg_mn_lbo; if (a_mn) dc.a_lbo = g_dbg_mn_lbo; }
+    if (g_dbg_mn_sbo) { dc.b_sbo = g_dbg_mn_sbo; if (a_mn) dc.a_sbo = g_dbg_mn_sbo; }
+    if (g_dbg_mn_kstep) { dc.b_kstep = g_dbg_mn_kstep; if (a_mn) dc.a_kstep = g_dbg_mn_kstep; }
+    return dc;
+}
+
 template <class P>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const typename P::Params& prm,
                        cudaStream_t stream) {
@@ -261,6 +274,11 @@ using namespace pfc;
 extern "C" {
 
 int pfc_exp_top(void) { return PFC_EXP_TOP; }
+
+// not part of the public header: descriptor-geometry override for the MN-major operands (0 = default)
+void pfc_debug_mn_desc(unsigned lbo, unsigned sbo, unsigned kstep) {
+    g_dbg_mn_lbo = lbo; g_dbg_mn_sbo = sbo; g_dbg_mn_kstep = kstep;
+}
 
 int pfc_padded_classes(int n) { return (n + 63) / 64 * 64; }
 int pfc_num_class_tiles(int n) { return (n + BN - 1) / BN; }
@@ -310,6 +328,13 @@ int pfc_dx_splits(int B, int n, int d) {
     return (k_total + per - 1) / per;   // no empty split
 }
 
+// Upper bound of pfc_dx_splits over every n (callers size the partial buffer with it).
+int pfc_dx_max_splits(int B, int d) {
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    const int base = ((B + BM - 1) / BM) * ((d + BN - 1) / BN);
+    return sms / base > 1 ? sms / base : 1;
+}
+
 // partial[z][B][d] (fp32) = E'[:, classes of split z] . Wn[classes of split z, :]
 int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int d, float* partial, int splits,
                     void* stream) {
@@ -331,6 +356,7 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     p.rows_valid = B; p.cols_valid = d; p.ld = d;
     p.split_stride = static_cast<size_t>(B) * d;
     p.out = partial;
+    p.dc = store_desc_cfg(false);
     return launch_gemm<StorePolicy<false>>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -353,6 +379,7 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.rows_valid = n; p.cols_valid = d; p.ld = d;
     p.split_stride = 0;
     p.out = dwn;
+    p.dc = store_desc_cfg(true);
     return launch_gemm<StorePolicy<true>>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 

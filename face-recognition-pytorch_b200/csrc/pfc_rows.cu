@@ -234,9 +234,9 @@ struct OptArgs {
 };
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
-dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const float* __restrict__ inv_norm_w,
+dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const float* inv_norm_w,
                    int rows, int d, OptArgs opt, float* __restrict__ dw_out, float* __restrict__ st1,
-                   float* __restrict__ st2, __nv_bfloat16* __restrict__ wn_next, float* __restrict__ inv_norm_next) {
+                   float* __restrict__ st2, __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -339,6 +339,35 @@ move_rows_kernel(RowSet set, const int64_t* __restrict__ index, int rows, int d)
         float* o = set.dst[t] + (kScatter ? other : static_cast<int64_t>(row)) * d;
         for (int k = lane; k < nv; k += 32) st4(o + 4 * k, ld4_stream(s + 4 * k));
     }
+}
+
+// Stand-alone margin module (nets/ArcFace.py:76-91, :100-105, :27-61): out = s * margin(logits), gate = d out / d in.
+__global__ void margin_apply_kernel(const float* __restrict__ in, const int64_t* __restrict__ labels, int B, int n,
+                                    int margin_kind, float s, float cos_m, float sin_m, float theta, float sinmm,
+                                    float m3, float thr, float* __restrict__ out, float* __restrict__ gate) {
+    const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= static_cast<size_t>(B) * n) return;
+    const int i = static_cast<int>(idx / n), c = static_cast<int>(idx - static_cast<size_t>(i) * n);
+    const float t = in[idx];
+    float v = t, g = 1.f;
+    if (labels[i] == c) {
+        if (margin_kind == 0) {
+            if (t > theta) {
+                const float st = sqrtf(1.f - t * t);
+                v = t * cos_m - st * sin_m;
+                g = cos_m + sin_m * t / st;
+            } else {
+                v = t - sinmm;
+            }
+        } else {
+            v = t - m3;
+        }
+    } else if (thr > 0.f && t > thr) {
+        v = 0.f;
+        g = 0.f;
+    }
+    out[idx] = v * s;
+    if (gate) gate[idx] = g * s;
 }
 
 static inline int row_grid(int rows) { return (rows + ROW_WARPS - 1) / ROW_WARPS; }
@@ -461,6 +490,18 @@ int pfc_scatter_rows(const float* const* src, float* const* dst, int count, cons
     s.count = count;
     for (int i = 0; i < count; ++i) { s.src[i] = src[i]; s.dst[i] = dst[i]; }
     move_rows_kernel<true><<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(s, index, rows, d);
+    return check_launch();
+}
+
+int pfc_margin_apply(const float* logits, const int64_t* labels, int B, int n, int margin_kind, float s, float m2,
+                     float m3, float interclass_filtering_threshold, float* out, float* gate, void* stream) {
+    if (B <= 0 || n <= 0) return PFC_ERR_SHAPE;
+    const double pi = 3.14159265358979323846;
+    const size_t total = static_cast<size_t>(B) * n;
+    margin_apply_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        logits, labels, B, n, margin_kind, s, (float)cos((double)m2), (float)sin((double)m2),
+        (float)cos(pi - (double)m2), (float)(sin(pi - (double)m2) * (double)m2), m3, interclass_filtering_threshold,
+        out, gate);
     return check_launch();
 }
 

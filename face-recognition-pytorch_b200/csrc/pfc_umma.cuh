@@ -33,9 +33,20 @@ struct TileCoord {
     int aux;   // policy-defined (e.g. split index / class-tile index)
 };
 
+// Shared-memory descriptor geometry of one operand stage (bytes).
+struct DescCfg {
+    uint32_t a_lbo, a_sbo, a_kstep;
+    uint32_t b_lbo, b_sbo, b_kstep;
+};
+__host__ __device__ constexpr DescCfg default_desc_cfg(bool a_mn, bool b_mn) {
+    return DescCfg{a_mn ? (uint32_t)MN_BOX_BYTES : 16u, 1024u, a_mn ? 2048u : 32u,
+                   b_mn ? (uint32_t)MN_BOX_BYTES : 16u, 1024u, b_mn ? 2048u : 32u};
+}
+
 // Policy contract:
 //   static constexpr bool A_MN, B_MN;           operand major-ness in shared memory
 //   struct Params { int num_tiles; ... };
+//   static DescCfg desc(const Params&);         smem descriptor geometry (default_desc_cfg(A_MN, B_MN))
 //   static TileCoord tile(const Params&, int t);
 //   static void epilogue(const Params&, const TileCoord&, uint32_t taddr, int row_in_tile, int lane);
 //        taddr = TMEM address of this warp's lane quarter, column 0 of the tile's accumulator.
@@ -126,15 +137,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
                     const uint32_t b_base = smem_u32(sB + stage * B_STAGE_BYTES);
+                    // K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per 16-element K step.
+                    // MN-major: 64(MN) x 8(K) atoms of 1024 B; next 64-wide MN block one box (8 KB) further,
+                    //           next 8 K rows 1024 B further; +2048 B per 16-row K step.
+                    const DescCfg dc = P::desc(prm);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per 16-element K step.
-                        // MN-major: 64(MN) x 8(K) atoms of 1024 B; next 64-wide MN block one box (8 KB) further,
-                        //           next 8 K rows 1024 B further; +2048 B per 16-row K step.
-                        const uint64_t adesc = P::A_MN ? umma_smem_desc_sw128(a_base + k * 2048, MN_BOX_BYTES, 1024)
-                                                       : umma_smem_desc_sw128(a_base + k * 32, 16, 1024);
-                        const uint64_t bdesc = P::B_MN ? umma_smem_desc_sw128(b_base + k * 2048, MN_BOX_BYTES, 1024)
-                                                       : umma_smem_desc_sw128(b_base + k * 32, 16, 1024);
+                        const uint64_t adesc = umma_smem_desc_sw128(a_base + k * dc.a_kstep, dc.a_lbo, dc.a_sbo);
+                        const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * dc.b_kstep, dc.b_lbo, dc.b_sbo);
                         umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc > tc.k0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire

@@ -1,0 +1,156 @@
+"""Torch-tensor level wrappers over the C ABI (include/pfc.h).
+
+Every function takes CUDA tensors, passes raw device pointers plus the current CUDA stream to libpfc_b200 and
+returns nothing (outputs are caller-allocated).  No host synchronisation, no allocation, no fallback: a CPU tensor
+is an error.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+MARGIN_ARCFACE, MARGIN_COSFACE = 0, 1
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("libpfc_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("libpfc_b200 kernels need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+F32, BF16, I32, I64, U8, F64 = torch.float32, torch.bfloat16, torch.int32, torch.int64, torch.uint8, torch.float64
+
+exp_top = lib.pfc_exp_top
+padded_classes = lib.pfc_padded_classes
+padded_batch = lib.pfc_padded_batch
+num_class_tiles = lib.pfc_num_class_tiles
+dx_splits = lib.pfc_dx_splits
+dx_max_splits = lib.pfc_dx_max_splits
+sample_workspace_bytes = lib.pfc_sample_workspace_bytes
+hist_bins = lib.pfc_eval_hist_bins
+
+
+def l2norm_rows(x, index, rows, xn, inv_norm):
+    d = x.shape[1]
+    check(lib.pfc_l2norm_rows(_p(x, F32), _p(index, I64), rows, d, _p(xn, BF16), _p(inv_norm, F32), _stream()),
+          "pfc_l2norm_rows")
+
+
+def localize_labels(labels, class_start, num_local, out):
+    check(lib.pfc_localize_labels(_p(labels, I64), labels.numel(), class_start, num_local, _p(out, I32), _stream()),
+          "pfc_localize_labels")
+
+
+def sample(perm, labels_local, num_local, num_sample, index_out, n_out, labels_remapped, workspace):
+    check(lib.pfc_sample(_p(perm, F32), _p(labels_local, I32), labels_local.numel(), num_local, num_sample,
+                         _p(index_out, I64), _p(n_out, I32), _p(labels_remapped, I32), _p(workspace, U8),
+                         workspace.numel(), _stream()), "pfc_sample")
+
+
+def gather_rows(srcs, dsts, index, rows):
+    d = srcs[0].shape[1]
+    check(lib.pfc_gather_rows(_lib.ptr_array([_p(s, F32).value for s in srcs]),
+                              _lib.ptr_array([_p(t, F32).value for t in dsts]), len(srcs), _p(index, I64), rows, d,
+                              _stream()), "pfc_gather_rows")
+
+
+def scatter_rows(srcs, dsts, index, rows):
+    d = srcs[0].shape[1]
+    check(lib.pfc_scatter_rows(_lib.ptr_array([_p(s, F32).value for s in srcs]),
+                               _lib.ptr_array([_p(t, F32).value for t in dsts]), len(srcs), _p(index, I64), rows, d,
+                               _stream()), "pfc_scatter_rows")
+
+
+def forward(xn, wn, labels_local, B, n, d, s, margin_kind, m2, m3, filter_thr, E, n_pad, part_sum, tgt_raw, tgt_e,
+            tgt_z):
+    check(lib.pfc_forward(_p(xn, BF16), _p(wn, BF16), _p(labels_local, I32), B, n, d, s, margin_kind, m2, m3,
+                          filter_thr, _p(E, BF16), n_pad, _p(part_sum, F32), _p(tgt_raw, F32), _p(tgt_e, F32),
+                          _p(tgt_z, F32), _stream()), "pfc_forward")
+
+
+def margin_apply(logits, labels, margin_kind, s, m2, m3, filter_thr, out, gate):
+    B, n = logits.shape
+    check(lib.pfc_margin_apply(_p(logits, F32), _p(labels, I64), B, n, margin_kind, s, m2, m3, filter_thr,
+                               _p(out, F32), _p(gate, F32), _stream()), "pfc_margin_apply")
+
+
+def row_stats(part_sum, n_tiles, B, labels_local, tgt_e, stats):
+    check(lib.pfc_row_stats(_p(part_sum, F32), n_tiles, B, _p(labels_local, I32), _p(tgt_e, F32), _p(stats, F32),
+                            _stream()), "pfc_row_stats")
+
+
+def loss(stats, B, row_L, out):
+    check(lib.pfc_loss(_p(stats, F32), B, _p(row_L, F32), _p(out, F32), _stream()), "pfc_loss")
+
+
+def backward_prepare(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E,
+                     n_pad):
+    check(lib.pfc_backward_prepare(_p(stats, F32), _p(row_L, F32), _p(grad_loss, F32), s, B, d, _p(labels_local, I32),
+                                   _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16), _p(xs, BF16), _p(coef, F32),
+                                   _p(E, BF16), n_pad, _stream()), "pfc_backward_prepare")
+
+
+def backward_dx(E, n_pad, wn, B, n, d, partial, splits):
+    check(lib.pfc_backward_dx(_p(E, BF16), n_pad, _p(wn, BF16), B, n, d, _p(partial, F32), splits, _stream()),
+          "pfc_backward_dx")
+
+
+def dx_finalize(partial, splits, coef, x, inv_norm, scale, rows, rows_total, d, out):
+    check(lib.pfc_dx_finalize(_p(partial, F32), splits, _p(coef, F32), _p(x, F32), _p(inv_norm, F32), scale, rows,
+                              rows_total, d, _p(out, F32), _stream()), "pfc_dx_finalize")
+
+
+def backward_dw(E, n_pad, xs, B, n, d, dwn):
+    check(lib.pfc_backward_dw(_p(E, BF16), n_pad, _p(xs, BF16), B, n, d, _p(dwn, F32), _stream()),
+          "pfc_backward_dw")
+
+
+def dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, dw):
+    check(lib.pfc_dw_finalize(_p(dwn, F32), _p(w, F32), _p(inv_norm_w, F32), rows, d, inv_grad_scale, _p(dw, F32),
+                              _stream()), "pfc_dw_finalize")
+
+
+def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, inv_grad_scale, wn_next, inv_norm_next):
+    check(lib.pfc_dw_sgd(_p(dwn, F32), _p(w, F32), _p(mom, F32), _p(inv_norm_w, F32), rows, d, lr, momentum,
+                         weight_decay, inv_grad_scale, _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()),
+          "pfc_dw_sgd")
+
+
+def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, weight_decay, step, decoupled,
+            inv_grad_scale, wn_next, inv_norm_next):
+    check(lib.pfc_dw_adam(_p(dwn, F32), _p(w, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), _p(inv_norm_w, F32), rows,
+                          d, lr, beta1, beta2, eps, weight_decay, step, int(decoupled), inv_grad_scale,
+                          _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()), "pfc_dw_adam")
+
+
+# ---- verification scorer
+def pair_score(e1, e2, labels_u8, scores, dist, hist_g, hist_i):
+    N, d = e1.shape
+    check(lib.fr_pair_score(_p(e1, F32), _p(e2, F32), _p(labels_u8, U8), N, d, _p(scores, F64), _p(dist, F64),
+                            _p(hist_g, I64), _p(hist_i, I64), _stream()), "fr_pair_score")
+
+
+def roc(hist_g, hist_i, min_level, max_level, out_bytes):
+    check(lib.fr_roc(_p(hist_g, I64), _p(hist_i, I64), min_level, max_level, _p(out_bytes, U8), _stream()), "fr_roc")
+
+
+def acc_counts(scores, labels_u8, threshold, fr_fa):
+    check(lib.fr_acc_counts(_p(scores, F64), _p(labels_u8, U8), scores.numel(), threshold, _p(fr_fa, I64), _stream()),
+          "fr_acc_counts")
+
+
+def kfold_acc(dist, labels_u8, folds, n_thr, step, correct_ws, acc, best_idx):
+    check(lib.fr_kfold_acc(_p(dist, F64), _p(labels_u8, U8), dist.numel(), folds, n_thr, step, _p(correct_ws, I32),
+                           _p(acc, F64), _p(best_idx, I32), _stream()), "fr_kfold_acc")

@@ -1,0 +1,412 @@
+"""PartialFC / PartialFCAdamW with the reference's nn.Module interface (nets/PartialFC.py), backed by libpfc_b200.
+
+Same constructor, same `forward(local_embeddings, local_labels, optimizer) -> loss`, same attributes
+(rank, world_size, num_local, class_start, num_sample, weight, weight_mom, weight_activated, weight_activated_mom,
+weight_index ...), same `{"weight": [num_local, d]}` per-rank state_dict, same optimizer patching when
+sample_rate < 1 -- so `importlib.import_module(f"nets.{conf.loss}").PartialFC(conf=..., num_classes=...)`
+(model/FR_PartialFC.py:102-109) keeps working when `nets` resolves to this package's shim.
+
+What changes underneath (one rank = one GPU, all work enqueued on the current CUDA stream, no host syncs except
+the data-dependent sampled size when num_sample < global batch):
+  forward : l2norm(x)->bf16 | all-gather(bf16 x, labels) | localise labels | [sample + gather rows] | l2norm(W)->bf16
+            | tcgen05 GEMM with margin/exp/row-sum epilogue spilling bf16 E' | row stats | ONE all-reduce [B,2] | loss
+  backward: coefficients + target patch | tcgen05 dX GEMM (class-split) | scale [+ reduce-scatter] + normalise-bwd
+            | tcgen05 dW GEMM | normalise-bwd (+ fused SGD / AdamW step and next step's bf16 shard)
+The collectives are the naturally sharded ones issued through torch.distributed.
+
+Optional keys read from `conf` beyond the reference's five (emd_size, sample_rate, mixed_precision, loss_s, loss_m):
+  conf.fused_optimizer (bool, default False): run the SGD / AdamW update of the head inside the backward and leave
+      weight_activated.grad = None so optimizer.step() skips it.  Hyper-parameters are re-read from
+      optimizer.param_groups[-1] every step (the scheduler mutates lr, utils/scheduler.py:87-88).  Not valid together
+      with a GradScaler (inf-skipping cannot be honoured); the un-fused default is.
+"""
+import collections
+from typing import Callable
+
+import torch
+from torch import distributed
+
+from . import kernels as K
+from .arcface import ArcFace
+
+
+def shard_range(num_classes: int, rank: int, world_size: int):
+    """nets/PartialFC.py:57-62."""
+    num_local = num_classes // world_size + int(rank < num_classes % world_size)
+    class_start = num_classes // world_size * rank + min(rank, num_classes % world_size)
+    return num_local, class_start
+
+
+class _Workspace:
+    """Persistent device buffers for one (global batch, max active classes, d) shape -- allocated once so that the
+    whole step is CUDA-graph capturable and nothing is allocated in the hot loop."""
+
+    def __init__(self, dev, b, W, n_max, nl, d, sampled):
+        B = b * W
+        f32, bf16, i32, i64 = torch.float32, torch.bfloat16, torch.int32, torch.int64
+        z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)   # noqa: E731
+        self.B, self.b, self.n_max = B, b, n_max
+        self.n_pad_max = K.padded_classes(n_max)
+        self.B_pad = K.padded_batch(B)
+        self.xn_local = z(b, d, dt=bf16)
+        self.inv_x = z(b)
+        self.xn_all = z(B, d, dt=bf16) if W > 1 else self.xn_local
+        self.labels_all = z(B, dt=i64)
+        self.labels_local = z(B, dt=i32)
+        self.labels_act = z(B, dt=i32) if sampled else self.labels_local
+        self.wn = z(n_max, d, dt=bf16)
+        self.inv_w = z(n_max)
+        self.E = z(B * self.n_pad_max, dt=bf16)
+        self.part_sum = z(K.num_class_tiles(n_max) * self.B_pad)
+        self.tgt_raw, self.tgt_e, self.tgt_z = z(B), z(B), z(B)
+        self.stats = z(B, 2)
+        self.row_L = z(B)
+        self.loss = z(1)
+        self.coef = z(B)
+        self.xs = z(B, d, dt=bf16)
+        self.max_splits = max(1, K.dx_max_splits(B, d))
+        self.dx_partial = z(self.max_splits * B * d)
+        self.dxn_all = z(B, d) if W > 1 else None
+        self.dxn_local = z(b, d) if W > 1 else None
+        self.dwn = z(n_max, d)
+        if sampled:
+            self.perm = z(nl)
+            self.index = z(n_max, dt=i64)
+            self.n_out = z(1, dt=i32)
+            self.sample_ws = z(K.sample_workspace_bytes(nl), dt=torch.uint8)
+
+
+class _HeadFunction(torch.autograd.Function):
+    """loss = head(local_embeddings, weight_activated); backward delivers W * dL/d local_embeddings
+    (nets/PartialFC.py:521) and dL/d weight_activated (or None when the optimizer step is fused)."""
+
+    @staticmethod
+    def forward(ctx, local_embeddings, weight_activated, head):
+        ctx.head = head
+        ctx.x = local_embeddings
+        ctx.step_id = head._step_id
+        return head._forward_impl(local_embeddings)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        head = ctx.head
+        if ctx.step_id != head._step_id:
+            raise RuntimeError("PartialFC backward called after a newer forward: the head keeps one step of state")
+        dx, dw = head._backward_impl(ctx.x, grad_loss)
+        return dx, dw, None
+
+
+class _PartialFCBase(torch.nn.Module):
+    _version = 1
+    _optimizer_kind = "sgd"
+
+    def __init__(self, conf, num_classes, margin_loss: Callable = ArcFace):
+        super().__init__()
+        assert distributed.is_initialized(), "must initialize distributed before create this"
+        self.rank = distributed.get_rank()
+        self.world_size = distributed.get_world_size()
+
+        self.embedding_size = conf.emd_size
+        self.sample_rate: float = conf.sample_rate
+        self.fp16 = conf.mixed_precision           # kept for interface parity; the kernels always run bf16-in / fp32-acc
+        self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
+        self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
+        self.num_sample: int = int(self.sample_rate * self.num_local)
+        self.last_batch_size: int = 0
+        self.is_updated: bool = True
+        self.init_weight_update: bool = True
+        self._state_names = self._optimizer_state_names()
+
+        d = self.embedding_size
+        if self.sample_rate < 1:
+            self.register_buffer("weight", tensor=torch.normal(0, 0.01, (self.num_local, d)))
+            for nm in self._state_names:
+                self.register_buffer("weight_" + nm, tensor=torch.zeros(self.num_local, d))
+                self.register_buffer("weight_activated_" + nm, tensor=torch.empty(0, 0))
+            self.register_parameter("weight_activated", param=torch.nn.Parameter(torch.empty(0, 0)))
+            self.register_buffer("weight_index", tensor=torch.empty(0, 0))
+        else:
+            self.weight_activated = torch.nn.Parameter(torch.normal(0, 0.01, (self.num_local, d)))
+
+        if isinstance(margin_loss, Callable):
+            self.margin_softmax = margin_loss(conf.loss_s, conf.loss_m)
+        else:
+            raise RuntimeError("margin_loss must be callable")
+        if not hasattr(self.margin_softmax, "margin_spec"):
+            raise TypeError("the fused head needs a margin from this package (ArcFace, CosFace, CombinedMarginLoss): "
+                            "the margin is applied inside the GEMM epilogue, not by calling the module")
+        self.step = 0
+        self._ws = None
+        self._step_id = 0
+        self._wn_valid = False          # wn / inv_w in the workspace match weight_activated
+        self._act_store = None          # persistent storage behind weight_activated / its optimizer state (r < 1)
+        self._fused_state = None        # optimizer state for the fused step when sample_rate == 1
+        self._n = self.num_local        # active classes this step
+        self._opt_args = None
+
+    # ------------------------------------------------------------------ reference-visible helpers
+    def _optimizer_state_names(self):
+        return ["mom"]
+
+    def _patch_optimizer(self, optimizer):
+        raise NotImplementedError
+
+    @torch.no_grad()
+    def sample(self, labels_local: torch.Tensor, index_positive, optimizer: torch.optim.Optimizer,
+               perm: torch.Tensor = None):
+        """nets/PartialFC.py:92-131.  labels_local: int32 shard-local ids with -1 for foreign rows (index_positive
+        is implied by it and only kept for signature parity).  `perm` defaults to torch.rand on the CPU generator exactly like the reference
+        (:110) -- one H2D copy per step; pass a device tensor to replay a recorded draw."""
+        ws = self._ws
+        if perm is None:
+            perm = torch.rand(size=[self.num_local])
+        ws.perm.copy_(perm, non_blocking=True)
+        K.sample(ws.perm, labels_local, self.num_local, self.num_sample, ws.index, ws.n_out, ws.labels_act,
+                 ws.sample_ws)
+        if self.num_sample >= ws.B:
+            n = self.num_sample                      # positives (<= B distinct) always fit: no host sync needed
+        else:
+            n = int(ws.n_out.item())                 # data-dependent: more positives than num_sample (:114-115)
+        self._n = n
+        self.weight_index = ws.index[:n]
+        names = self._state_names
+        srcs = [self.weight] + [getattr(self, "weight_" + nm) for nm in names]
+        dsts = [self._act_store[0][:n]] + [self._act_store[1 + i][:n] for i in range(len(names))]
+        K.gather_rows(srcs, dsts, self.weight_index, n)                          # :120-121
+        self.weight_activated = torch.nn.Parameter(dsts[0])
+        for i, nm in enumerate(names):
+            setattr(self, "weight_activated_" + nm, dsts[1 + i])
+        self._wn_valid = False
+        self._patch_optimizer(optimizer)                                         # :123-131
+
+    @torch.no_grad()
+    def update(self):
+        """partial weight to global, nets/PartialFC.py:133-143."""
+        if self.init_weight_update:
+            self.init_weight_update = False
+            return
+        if self.sample_rate < 1:
+            names = self._state_names
+            n = self.weight_activated.shape[0]
+            if n == 0:
+                return
+            srcs = [self.weight_activated.data] + [getattr(self, "weight_activated_" + nm) for nm in names]
+            dsts = [self.weight] + [getattr(self, "weight_" + nm) for nm in names]
+            K.scatter_rows(srcs, dsts, self.weight_index, n)
+
+    # ------------------------------------------------------------------ forward / backward
+    def _ensure_workspace(self, b, dev):
+        d = self.embedding_size
+        sampled = self.sample_rate < 1
+        B = b * self.world_size
+        n_max = self.num_local if not sampled else max(self.num_sample, min(B, self.num_local))
+        if self._ws is None or self._ws.b != b or self._ws.xn_local.device != dev:
+            self._ws = _Workspace(dev, b, self.world_size, n_max, self.num_local, d, sampled)
+            self._wn_valid = False
+            if sampled:
+                k = 1 + len(self._state_names)
+                self._act_store = [torch.zeros(n_max, d, device=dev) for _ in range(k)]
+        return self._ws
+
+    def forward(self, local_embeddings: torch.Tensor, local_labels: torch.Tensor, optimizer: torch.optim.Optimizer,
+                perm: torch.Tensor = None):
+        local_labels.squeeze_()                                       # in place on the caller's tensor, :164
+        local_labels = local_labels.long()
+        self.update()
+
+        batch_size = local_embeddings.size(0)
+        if self.last_batch_size == 0:
+            self.last_batch_size = batch_size
+        assert self.last_batch_size == batch_size, (
+            "last batch size do not equal current batch size: {} vs {}".format(self.last_batch_size, batch_size))
+        if local_embeddings.dtype != torch.float32:
+            local_embeddings = local_embeddings.float()
+        ws = self._ensure_workspace(batch_size, local_embeddings.device)
+        self._labels_in = local_labels.contiguous()
+        self._optimizer = optimizer
+        self._perm = perm
+        self._step_id += 1
+        return _HeadFunction.apply(local_embeddings, self.weight_activated, self)
+
+    def _read_optimizer(self, optimizer):
+        raise NotImplementedError
+
+    def _forward_impl(self, local_embeddings):
+        ws, W, d = self._ws, self.world_size, self.embedding_size
+        b, B = ws.b, ws.B
+        x = local_embeddings.detach().contiguous()
+        self._x_local = x
+        K.l2norm_rows(x, None, b, ws.xn_local, ws.inv_x)
+        if W > 1:
+            distributed.all_gather_into_tensor(ws.xn_all, ws.xn_local)            # :182 (bf16: half the bytes)
+            distributed.all_gather_into_tensor(ws.labels_all, self._labels_in)    # :183
+            labels_all = ws.labels_all
+        else:
+            labels_all = self._labels_in
+        K.localize_labels(labels_all, self.class_start, self.num_local, ws.labels_local)   # :188-193
+        if self.sample_rate < 1:
+            self.sample(ws.labels_local, None, self._optimizer, self._perm)             # :195-196
+        else:
+            self._n = self.num_local
+        n = self._n
+        w = self.weight_activated.data
+        if not self._wn_valid:
+            K.l2norm_rows(w, None, n, ws.wn, ws.inv_w)                            # :200
+            self._wn_valid = True
+        kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
+        self._n_pad = K.padded_classes(n)
+        K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
+                  ws.tgt_raw, ws.tgt_e, ws.tgt_z)                                 # :201-207
+        K.row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats)
+        if W > 1:
+            distributed.all_reduce(ws.stats, distributed.ReduceOp.SUM)            # replaces :448, :453, :459
+        K.loss(ws.stats, B, ws.row_L, ws.loss)                                    # :461
+        if self.fused_optimizer:
+            self._opt_args = self._read_optimizer(self._optimizer)
+        return ws.loss[0].clone()
+
+    def _backward_impl(self, x_in, grad_loss):
+        ws, W, d = self._ws, self.world_size, self.embedding_size
+        b, B, n, n_pad = ws.b, ws.B, self._n, self._n_pad
+        kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
+        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
+                           ws.coef, ws.E, n_pad)
+        dx = None
+        if x_in.requires_grad:
+            splits = K.dx_splits(B, n, d)
+            K.backward_dx(ws.E, n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
+            dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
+            if W == 1:
+                K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
+            else:
+                K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
+                distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM)   # :505-519
+                K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)    # :521
+        K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, ws.dwn)
+        w = self.weight_activated.data
+        if self.fused_optimizer:
+            self._fused_step(w, n, d)
+            return dx, None
+        dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
+        K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
+        self._wn_valid = False            # an external optimizer is about to change the weights
+        return dx, dw
+
+    def _fused_step(self, w, n, d):
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ checkpoint layout (nets/PartialFC.py:210-232)
+    def state_dict(self, destination=None, prefix="", keep_vars=False):
+        if destination is None:
+            destination = collections.OrderedDict()
+            destination._metadata = collections.OrderedDict()
+        for name, module in self._modules.items():
+            if module is not None:
+                module.state_dict(destination, prefix + name + ".", keep_vars=keep_vars)
+        if self.sample_rate < 1:
+            destination["weight"] = self.weight.detach()
+        else:
+            destination["weight"] = self.weight_activated.data.detach()
+        return destination
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        self._wn_valid = False
+        if self.sample_rate < 1:
+            self.weight = state_dict["weight"].to(self.weight.device)
+            for nm in self._state_names:
+                getattr(self, "weight_" + nm).zero_()
+                getattr(self, "weight_activated_" + nm).zero_()
+            self.weight_activated.data.zero_()
+            if self._state_names == ["mom"]:
+                self.weight_index.zero_()
+        else:
+            self.weight_activated.data = state_dict["weight"].to(self.weight_activated.data.device)
+            self._fused_state = None
+
+
+class PartialFC(_PartialFCBase):
+    """Class-sharded margin-softmax head driven by torch.optim.SGD (nets/PartialFC.py:10-232)."""
+    _optimizer_kind = "sgd"
+
+    def _optimizer_state_names(self):
+        return ["mom"]
+
+    def _patch_optimizer(self, optimizer):
+        if isinstance(optimizer, torch.optim.SGD):
+            # the params of partial fc must be last in the params list (:124)
+            optimizer.state.pop(optimizer.param_groups[-1]["params"][0], None)
+            optimizer.param_groups[-1]["params"][0] = self.weight_activated
+            optimizer.state[self.weight_activated]["momentum_buffer"] = self.weight_activated_mom
+        else:
+            raise RuntimeError("PartialFC needs torch.optim.SGD (nets/PartialFC.py:130-131)")
+
+    def _read_optimizer(self, optimizer):
+        if not isinstance(optimizer, torch.optim.SGD):
+            raise RuntimeError("fused_optimizer: PartialFC needs torch.optim.SGD")
+        g = optimizer.param_groups[-1]
+        if g.get("dampening", 0) != 0 or g.get("nesterov", False) or g.get("maximize", False):
+            raise RuntimeError("fused SGD supports dampening=0, nesterov=False, maximize=False")
+        return dict(lr=float(g["lr"]), momentum=float(g["momentum"]), wd=float(g["weight_decay"]))
+
+    def _fused_step(self, w, n, d):
+        ws, o = self._ws, self._opt_args
+        if self.sample_rate < 1:
+            mom = self.weight_activated_mom
+        else:
+            if self._fused_state is None:
+                self._fused_state = torch.zeros_like(w)
+                self.weight_activated_mom = self._fused_state
+            mom = self._fused_state
+        K.dw_sgd(ws.dwn, w, mom, ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], 1.0, ws.wn, ws.inv_w)
+        self._wn_valid = True             # the update wrote next step's normalised bf16 rows and 1/norm in place
+
+
+class PartialFCAdamW(_PartialFCBase):
+    """Same head with Adam / AdamW state (nets/PartialFC.py:235-432)."""
+    _optimizer_kind = "adamw"
+
+    def _optimizer_state_names(self):
+        return ["exp_avg", "exp_avg_sq"]
+
+    @torch.no_grad()
+    def sample(self, labels_local, index_positive, optimizer, perm=None):
+        self.step += 1                                                            # :306
+        super().sample(labels_local, index_positive, optimizer, perm)
+
+    def _patch_optimizer(self, optimizer):
+        if isinstance(optimizer, (torch.optim.Adam, torch.optim.AdamW)):
+            optimizer.state.pop(optimizer.param_groups[-1]["params"][0], None)
+            optimizer.param_groups[-1]["params"][0] = self.weight_activated
+            st = optimizer.state[self.weight_activated]
+            st["exp_avg"] = self.weight_activated_exp_avg
+            st["exp_avg_sq"] = self.weight_activated_exp_avg_sq
+            # the reference stores a Python int (:327); current torch expects a tensor step for Adam/AdamW
+            st["step"] = torch.tensor(float(self.step))
+        else:
+            raise RuntimeError("PartialFCAdamW needs torch.optim.Adam or AdamW (nets/PartialFC.py:328-329)")
+
+    def _read_optimizer(self, optimizer):
+        if not isinstance(optimizer, (torch.optim.Adam, torch.optim.AdamW)):
+            raise RuntimeError("fused_optimizer: PartialFCAdamW needs torch.optim.Adam / AdamW")
+        g = optimizer.param_groups[-1]
+        if g.get("amsgrad", False) or g.get("maximize", False):
+            raise RuntimeError("fused Adam supports amsgrad=False, maximize=False")
+        decoupled = isinstance(optimizer, torch.optim.AdamW) or bool(g.get("decoupled_weight_decay", False))
+        return dict(lr=float(g["lr"]), beta1=float(g["betas"][0]), beta2=float(g["betas"][1]), eps=float(g["eps"]),
+                    wd=float(g["weight_decay"]), decoupled=decoupled)
+
+    def _fused_step(self, w, n, d):
+        ws, o = self._ws, self._opt_args
+        if self.sample_rate < 1:
+            m, v = self.weight_activated_exp_avg, self.weight_activated_exp_avg_sq
+            step = self.step
+        else:
+            if self._fused_state is None:
+                self._fused_state = (torch.zeros_like(w), torch.zeros_like(w))
+            m, v = self._fused_state
+            self.step += 1
+            step = self.step
+        K.dw_adam(ws.dwn, w, m, v, ws.inv_w, n, d, o["lr"], o["beta1"], o["beta2"], o["eps"], o["wd"], step,
+                  o["decoupled"], 1.0, ws.wn, ws.inv_w)
+        self._wn_valid = True

@@ -41,6 +41,7 @@ int pfc_padded_classes(int n);                    /* row stride (elements) of th
 int pfc_padded_batch(int B);                      /* row count the part_sum slabs are padded to */
 int pfc_num_class_tiles(int n);                   /* number of 256-class tiles = leading dim of part_sum */
 int pfc_dx_splits(int B, int n, int d);           /* class splits pfc_backward_dx will use for this shape */
+int pfc_dx_max_splits(int B, int d);              /* upper bound of pfc_dx_splits over all n (sizes `partial`) */
 
 /* ---- (1) fused L2 normalise: F.normalize of embeddings / of the classifier shard, nets/PartialFC.py:199-200.
  * xn[r,:] = bf16(x[src,:] / max(||x[src,:]||, 1e-12)), inv_norm[r] = 1/max(||.||, 1e-12), src = index ? index[r] : r
@@ -80,6 +81,12 @@ int pfc_scatter_rows(const float* const* src, float* const* dst, int count, cons
 int pfc_forward(const void* xn_bf16, const void* wn_bf16, const int32_t* labels_local, int B, int n, int d, float s,
                 int margin_kind, float m2, float m3, float interclass_filtering_threshold, void* E_bf16, int n_pad,
                 float* part_sum, float* tgt_raw, float* tgt_e, float* tgt_z, void* stream);
+
+/* ---- stand-alone margin module, nets/ArcFace.py:76-91 (ArcFace.forward), :100-105 (CosFace), :27-61 (Combined):
+ * out[i,c] = s * margin(logits[i,c]) on the target column labels[i] (int64, -1 = none), s * logits elsewhere
+ * (0 where the inter-class filter fires); gate (nullable) = d out / d logits for the backward. */
+int pfc_margin_apply(const float* logits, const int64_t* labels, int B, int n, int margin_kind, float s, float m2,
+                     float m3, float interclass_filtering_threshold, float* out, float* gate, void* stream);
 
 /* ---- (4) row statistics and loss, nets/PartialFC.py:446-461 (DistCrossEntropyFunc.forward).
  * pfc_row_stats: stats[i] = { sum_tiles part_sum[.][i], target e or 0 } -- the [B,2] array ranks all-reduce (SUM),

@@ -1,0 +1,161 @@
+"""Parity of the CUDA head (through the nn.Module -> C ABI -> kernels) against the oracle and against the
+golden fixtures produced by the reference.  Tolerances are BASELINE.json's: loss within 1e-3 relative,
+dX / dW cosine similarity >= 0.999 (bf16 operands, fp32 accumulation), sampled index set bit-exact."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_case, case_inputs, case_margin, case_perms, cosine
+from oracle import head_oracle as ho
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-3
+COS_MIN = 0.999
+
+
+@pytest.fixture(scope="module")
+def pfc():
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29711", rank=0, world_size=1)
+    torch.cuda.set_device(0)
+    import face_recognition_pytorch_b200 as m
+    return m
+
+
+def _margin_cls(pfc, cfg):
+    return {"arcface": pfc.ArcFace, "cosface": pfc.CosFace}[cfg["margin"]]
+
+
+def _make_head(pfc, cfg, weights, fused=False, adam=False):
+    conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
+                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused)
+    cls = pfc.PartialFCAdamW if adam else pfc.PartialFC
+    head = cls(conf, cfg["C"], margin_loss=_margin_cls(pfc, cfg))
+    head.load_state_dict({"weight": weights[0].clone()})
+    head = head.train().cuda()
+    return head
+
+
+@pytest.mark.parametrize("name", ["head_w1_full", "head_w1_s30", "head_w1_cosface", "head_w1_sampled",
+                                  "head_w1_manypos", "head_w1_d512"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_steps_match_reference_and_oracle(pfc, name, fused):
+    cfg, z = load_case(name)
+    weights, xs, ls = case_inputs(cfg)
+    head = _make_head(pfc, cfg, weights, fused=fused)
+    dummy = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+    opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
+                          momentum=cfg["momentum"], weight_decay=cfg["wd"])
+    orc = ho.PartialFCOracle(weights, cfg["C"], case_margin(cfg), cfg["sample_rate"], cfg["lr"], cfg["momentum"],
+                             cfg["wd"])
+    for s in range(cfg["steps"]):
+        perms = case_perms(cfg, z, s)
+        res = orc.step([xs[s]], [ls[s]], perms)
+        x = xs[s].clone().cuda().requires_grad_(True)
+        lab = ls[s].clone().cuda()
+        opt.zero_grad()
+        perm = perms[0].cuda() if perms is not None and perms[0].numel() else None
+        loss = head(x, lab, opt, perm=perm)
+        loss.backward()
+        ref_loss = float(z[f"r0_loss_{s}"])
+        assert abs(float(loss) - ref_loss) <= LOSS_RTOL * abs(ref_loss), (s, float(loss), ref_loss)
+        assert abs(float(loss) - float(res.loss)) <= LOSS_RTOL * abs(float(res.loss))
+        assert cosine(x.grad.cpu(), z[f"r0_dx_{s}"]) >= COS_MIN
+        assert cosine(x.grad.cpu(), res.dx_local[0]) >= COS_MIN
+        # magnitude, not only direction
+        assert abs(float(x.grad.norm()) / np.linalg.norm(z[f"r0_dx_{s}"]) - 1) < 2e-2
+        if cfg["sample_rate"] < 1:
+            assert np.array_equal(head.weight_index.cpu().numpy(), z[f"r0_index_{s}"])     # bit-exact index set
+        if not fused:
+            g = head.weight_activated.grad
+            assert cosine(g.cpu(), z[f"r0_dw_{s}"]) >= COS_MIN
+            assert cosine(g.cpu(), res.dw[0]) >= COS_MIN
+            assert abs(float(g.norm()) / np.linalg.norm(z[f"r0_dw_{s}"]) - 1) < 2e-2
+        else:
+            assert head.weight_activated.grad is None
+        opt.step()
+    if cfg["sample_rate"] < 1:
+        head.update()
+        w_final, m_final = head.weight, head.weight_mom
+    else:
+        w_final = head.weight_activated.data
+        m_final = head.weight_activated_mom if fused else opt.state[head.weight_activated]["momentum_buffer"]
+    w0 = weights[0].double()
+    assert cosine(w_final.cpu().double() - w0, torch.from_numpy(z["r0_weight_final"]).double() - w0) >= COS_MIN
+    assert cosine(m_final.cpu(), z["r0_mom_final"]) >= COS_MIN
+    np.testing.assert_allclose(w_final.cpu().numpy(), z["r0_weight_final"], rtol=0, atol=3e-2 * np.abs(z["r0_weight_final"]).max())
+    sd = head.state_dict()
+    assert list(sd.keys()) == ["weight"] and tuple(sd["weight"].shape) == (head.num_local, cfg["d"])
+
+
+def test_adamw_fused_matches_torch_adamw(pfc):
+    cfg, z = load_case("head_w1_full")
+    weights, xs, ls = case_inputs(cfg)
+    heads, opts = [], []
+    for fused in (False, True):
+        h = _make_head(pfc, cfg, weights, fused=fused, adam=True)
+        dummy = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+        o = torch.optim.AdamW([{"params": [dummy]}, {"params": h.parameters()}], lr=1e-3, weight_decay=0.05)
+        heads.append(h); opts.append(o)
+    for s in range(cfg["steps"]):
+        for h, o in zip(heads, opts):
+            x = xs[s].clone().cuda().requires_grad_(True)
+            o.zero_grad()
+            h(x, ls[s].clone().cuda(), o).backward()
+            o.step()
+    a, b = heads[0].weight_activated.data, heads[1].weight_activated.data
+    w0 = weights[0].cuda()
+    assert cosine((a - w0).cpu(), (b - w0).cpu()) >= 0.9999
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=0, atol=2e-5)
+
+
+def test_batch_size_change_asserts(pfc):
+    cfg, z = load_case("head_w1_full")
+    weights, xs, ls = case_inputs(cfg)
+    head = _make_head(pfc, cfg, weights)
+    opt = torch.optim.SGD(head.parameters(), lr=0.1)
+    head(xs[0].cuda(), ls[0].cuda(), opt)
+    with pytest.raises(AssertionError):
+        head(xs[0][:8].cuda(), ls[0][:8].cuda(), opt)
+
+
+def test_scale_out_of_range_fails_loudly(pfc):
+    cfg, z = load_case("head_w1_full")
+    weights, xs, ls = case_inputs(cfg)
+    cfg = dict(cfg, s=128.0)
+    head = _make_head(pfc, cfg, weights)
+    opt = torch.optim.SGD(head.parameters(), lr=0.1)
+    with pytest.raises(RuntimeError):
+        head(xs[0].cuda(), ls[0].cuda(), opt)
+
+
+def test_full_size_properties_cfg2(pfc):
+    """BASELINE configs[1] shape on one GPU: B=1024, C=93431, d=512.  Size-independent checks: the loss against the
+    oracle run in fp32 on the host, gradient rows orthogonal to the (normalised) rows they belong to, and
+    softmax mass conservation sum_c dz_ic = 0 expressed through dX = sum_c dz_ic Wn_c for identical class rows."""
+    C, d, B = 93431, 512, 1024
+    g = torch.Generator().manual_seed(1234)
+    w = torch.normal(0, 0.01, (C, d), generator=g)
+    lab = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(7))
+    x = torch.nn.functional.normalize(torch.nn.functional.normalize(w[lab]) +
+                                      torch.randn(B, d, generator=torch.Generator().manual_seed(42)) / d ** 0.5)
+    cfg = dict(C=C, d=d, sample_rate=1.0, s=64.0, m=0.5, margin="arcface")
+    head = _make_head(pfc, cfg, [w])
+    opt = torch.optim.SGD(head.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    xg = x.clone().cuda().requires_grad_(True)
+    loss = head(xg, lab.clone().cuda(), opt)
+    loss.backward()
+    res = ho.head_step([x], [lab], [w], C, ho.Margin("arcface", 64.0, 0.5), dtype=torch.float32)
+    assert abs(float(loss) - float(res.loss)) <= LOSS_RTOL * abs(float(res.loss))
+    assert cosine(xg.grad.cpu(), res.dx_local[0]) >= COS_MIN
+    gw = head.weight_activated.grad
+    assert cosine(gw.cpu(), res.dw[0]) >= COS_MIN
+    # normalise-backward projects out the row direction
+    xn = torch.nn.functional.normalize(xg.detach())
+    assert float(((xg.grad * xn).sum(1)).abs().max()) <= 1e-4 * float(xg.grad.norm(dim=1).max())
+    wn = torch.nn.functional.normalize(head.weight_activated.data)
+    assert float(((gw * wn).sum(1)).abs().max()) <= 1e-4 * float(gw.norm(dim=1).max())
