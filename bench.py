@@ -1,0 +1,384 @@
+"""Headline benchmark: PartialFC ArcFace fwd + bwd (+ fused SGD update) samples/s at 93,431 classes, d = 512,
+global batch 1024 (BASELINE.json configs[1]) on N B200s of one node, with the roofline of the dominant kernel and the
+reference head's CPU implementation timed on the host cores beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-graph]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" is one pass of the head's hot path over one synthetic global batch:
+normalise -> (all-gather) -> cosine GEMM + margin/softmax epilogue -> (all-reduce) -> loss -> backward GEMMs ->
+(reduce-scatter) -> normalise-backward -> SGD/momentum update of the class shard.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C_CLASSES, EMB, GLOBAL_BATCH = 93431, 512, 1024
+S, M = 64.0, 0.5
+LR, MOMENTUM, WD = 0.1, 0.9, 5e-4
+METRIC = "PartialFC ArcFace fwd+bwd samples/sec @93k cls,d=512"
+UNIT = "samples/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm=j["hbm_gbs"], tf_burst=j["bf16_tflops"], tf_sust=j.get("bf16_tflops_sustained", j["bf16_tflops"]),
+                    kind="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, kind="fallback")
+
+
+def synth(rank, world, steps, device):
+    """Synthetic data of the named shape: N(0, 0.01) class centres (this rank's shard), uniform labels, trained-like
+    unit embeddings (cos to the target ~0.7).  Generated on the host, seeded, identical on every rank."""
+    import torch
+    from face_recognition_pytorch_b200 import shard_range
+    nl, cs = shard_range(C_CLASSES, rank, world)
+    g = torch.Generator().manual_seed(1234)
+    w_full = torch.normal(0, 0.01, (C_CLASSES, EMB), generator=g)
+    b = GLOBAL_BATCH // world
+    xs, ls = [], []
+    for s in range(steps):
+        lab = torch.randint(0, C_CLASSES, (GLOBAL_BATCH,), generator=torch.Generator().manual_seed(7 + s))
+        x = torch.nn.functional.normalize(w_full[lab]) + \
+            torch.randn(GLOBAL_BATCH, EMB, generator=torch.Generator().manual_seed(42 + s)) / EMB ** 0.5
+        x = torch.nn.functional.normalize(x)
+        xs.append(x[rank * b:(rank + 1) * b].contiguous())
+        ls.append(lab[rank * b:(rank + 1) * b].contiguous())
+    return w_full[cs:cs + nl].clone(), xs, ls
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        load = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """The reference head's own CPU implementation of the path (oracle port, fp32, all host threads), one rank,
+    same config / metric / unit.  /root/reference is not on the GPU box, and the reference is pure Python over torch,
+    so the port in oracle/head_oracle.py::cpu_reference_step (op-for-op the reference's sequence) is what is timed."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import head_oracle as ho
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1234)
+    w = torch.nn.Parameter(torch.normal(0, 0.01, (C_CLASSES, EMB), generator=g))
+    opt = torch.optim.SGD([w], lr=LR, momentum=MOMENTUM, weight_decay=WD)
+    margin = ho.Margin("arcface", S, M)
+    steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    data = []
+    for s in range(steps + warm):
+        lab = torch.randint(0, C_CLASSES, (GLOBAL_BATCH,), generator=torch.Generator().manual_seed(7 + s))
+        x = torch.nn.functional.normalize(torch.nn.functional.normalize(w.detach()[lab]) + torch.randn(
+            GLOBAL_BATCH, EMB, generator=torch.Generator().manual_seed(42 + s)) / EMB ** 0.5)
+        data.append((x, lab))
+    for i in range(warm):
+        ho.cpu_reference_step(data[i][0], data[i][1], w, opt, margin)
+    t0 = time.perf_counter()
+    for i in range(warm, warm + steps):
+        ho.cpu_reference_step(data[i][0], data[i][1], w, opt, margin)
+    dt = (time.perf_counter() - t0) / steps
+    v = GLOBAL_BATCH / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: PartialFC C=93431 d=512 global_batch=1024 sample_rate=1.0 s=64 m=0.5 SGD",
+                       "note": "reference head on host CPU, one rank, fp32, each step = one full global batch"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{steps} full steps (B=1024, C=93431, d=512) after {warm} warm-up"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample():
+    import torch
+    from oracle import head_oracle as ho
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(1234)
+    w = torch.nn.Parameter(torch.normal(0, 0.01, (C_CLASSES, EMB), generator=g))
+    opt = torch.optim.SGD([w], lr=LR, momentum=MOMENTUM, weight_decay=WD)
+    margin = ho.Margin("arcface", S, M)
+    lab = torch.randint(0, C_CLASSES, (GLOBAL_BATCH,), generator=torch.Generator().manual_seed(7))
+    x = torch.nn.functional.normalize(torch.randn(GLOBAL_BATCH, EMB, generator=torch.Generator().manual_seed(42)))
+    ho.cpu_reference_step(x, lab, w, opt, margin)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or (time.perf_counter() - t0 < 10 and n < 12):
+        ho.cpu_reference_step(x, lab, w, opt, margin)
+        n += 1
+    dt = (time.perf_counter() - t0) / n
+    return {"value": GLOBAL_BATCH / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} full steps of the same workload (B=1024, C=93431, d=512, fp32) after 1 warm-up, "
+                      f"{dt * 1e3:.0f} ms/step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="hand dW to torch.optim.SGD instead of the fused update")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if not dist.is_initialized():
+        if "MASTER_ADDR" in os.environ and "RANK" in os.environ:
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29541", rank=0, world_size=1, device_id=dev)
+    import face_recognition_pytorch_b200 as pfc
+    from face_recognition_pytorch_b200 import kernels as K
+
+    n_data = 4
+    w_shard, xs, ls = synth(rank, world, n_data, dev)
+    b = GLOBAL_BATCH // world
+    conf = types.SimpleNamespace(emd_size=EMB, sample_rate=1.0, mixed_precision=False, loss_s=S, loss_m=M,
+                                 fused_optimizer=not args.unfused)
+    head = pfc.PartialFC(conf, C_CLASSES)
+    head.load_state_dict({"weight": w_shard})
+    head = head.train().cuda()
+    dummy = torch.nn.Parameter(torch.zeros(1, device=dev))
+    opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=LR, momentum=MOMENTUM,
+                          weight_decay=WD)
+    x_dev = [x.to(dev).requires_grad_(True) for x in xs]
+    l_dev = [l.to(dev) for l in ls]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    static_x = x_dev[0].detach().clone().requires_grad_(True)
+    static_l = l_dev[0].clone()
+
+    def step_eager(x, lab):
+        loss = head(x, lab, opt)
+        loss.backward()
+        if args.unfused:
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+        return loss
+
+    # ---- warm-up (also builds workspaces, NCCL communicators)
+    for i in range(args.warmup):
+        step_eager(x_dev[i % n_data], l_dev[i % n_data])
+    torch.cuda.synchronize()
+
+    graph = None
+    if not args.no_graph and not args.unfused:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    static_x.grad = None
+                    step_eager(static_x, static_l)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            static_x.grad = None
+            with torch.cuda.graph(graph):
+                static_loss = step_eager(static_x, static_l)
+            torch.cuda.synchronize()
+        except Exception as e:   # report, fall back to eager launches (still the CUDA path)
+            if rank == 0:
+                print(f"# CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        if graph is not None:
+            static_x.data.copy_(x_dev[i % n_data].data)
+            static_l.copy_(l_dev[i % n_data])
+            graph.replay()
+        else:
+            x_dev[i % n_data].grad = None
+            step_eager(x_dev[i % n_data], l_dev[i % n_data])
+
+    for i in range(3):
+        run_step(i)
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device time by CUDA events per step (L2 flushed, untimed, between steps)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = K.launch_count()
+    dist.barrier()
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clk:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()
+            ev[i][0].record()
+            run_step(i)
+            ev[i][1].record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = K.launch_count() - launches0
+    ms_steps = [a.elapsed_time(bb) for a, bb in ev]
+    t = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = GLOBAL_BATCH / (ms_per_step * 1e-3)
+
+    # ---- per-kernel durations (separate instrumented eager pass; events around each C-ABI call)
+    K.enable_timing(True)
+    for i in range(6):
+        flush.zero_()
+        x_dev[i % n_data].grad = None
+        step_eager(x_dev[i % n_data], l_dev[i % n_data])
+    torch.cuda.synchronize()
+    kt = K.collect_timing()
+    K.enable_timing(False)
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    hx = [x.pin_memory() for x in xs]
+    hl = [l.pin_memory() for l in ls]
+    e2e_steps = max(5, min(args.steps, 20))
+    dx_host = torch.empty(b, EMB, dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        x = hx[i % n_data].to(dev, non_blocking=True).requires_grad_(True)
+        lab = hl[i % n_data].to(dev, non_blocking=True)
+        loss = head(x, lab, opt)
+        loss.backward()
+        dx_host.copy_(x.grad, non_blocking=True)
+        return float(loss.item())
+
+    for i in range(3):
+        e2e_step(i)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    dist.barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(te, dist.ReduceOp.MAX)
+    e2e_value = GLOBAL_BATCH / float(te.item())
+
+    if rank != 0:
+        dist.barrier()
+        return
+
+    pk = peaks()
+    nl = head.num_local
+    flops_gemm = 2.0 * GLOBAL_BATCH * nl * EMB
+    kern = {k: v for k, v in kt.items()}
+    # algorithmic work per launch of each timed kernel ("Kernels and rooflines")
+    alg = {
+        "pfc_forward": ("tensor", flops_gemm), "pfc_backward_dx": ("tensor", flops_gemm),
+        "pfc_backward_dw": ("tensor", flops_gemm),
+        "pfc_dw_sgd": ("hbm", nl * EMB * (4 * 5 + 2.0)),          # read dwn,w,mom; write w,mom (fp32) + wn (bf16)
+        "pfc_dw_finalize": ("hbm", nl * EMB * 4 * 3.0),
+        "pfc_l2norm_rows": ("hbm", None),
+    }
+    dom = max((k for k in kern if k in alg and alg[k][1]), key=lambda k: kern[k]["ms_total"], default=None)
+    roof = None
+    if dom:
+        bound, work = alg[dom]
+        ms = kern[dom]["ms_avg"]
+        if bound == "tensor":
+            ach, peak, unit = work / (ms * 1e-3) / 1e12, pk["tf_sust"], "TFLOP/s"
+        else:
+            ach, peak, unit = work / (ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+        roof = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                "traffic": None, "peak_source": pk["kind"] + (" sustained bf16" if bound == "tensor" else " copy"),
+                "ms_per_launch": ms}
+    step_tf = 3 * flops_gemm / (ms_per_step * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]: PartialFC C=93431 d=512 global_batch=1024 sample_rate=1.0 s=64 m=0.5, "
+                               "fwd+bwd+" + ("torch SGD step" if args.unfused else "fused SGD update"),
+                   "classes_per_gpu": nl, "local_batch": b, "parallelism": f"class-sharded x{world}",
+                   "launch": "cuda-graph replay" if graph is not None else "eager",
+                   "l2": "256 MB buffer written between timed steps (untimed); per-step CUDA events summed"},
+        "roofline": roof,
+        "step_roofline": {"bound": "tensor", "achieved": step_tf / world, "peak": pk["tf_burst"], "unit": "TFLOP/s/GPU",
+                          "frac": step_tf / world / pk["tf_burst"], "work": "6*B*n*D per step (3 GEMMs, no recompute credited)",
+                          "peak_source": pk["kind"] + " burst bf16"},
+        "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in kern.items()},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * EMB * 4 + b * 8,
+                "d2h_bytes_per_step": 4 + b * EMB * 4, "steps": e2e_steps, "timing": "host wall clock, max over ranks"},
+        "gpu_launches": launches,
+        "clocks": clk.summary(),
+        "wall_ms_per_step": t_wall / args.steps * 1e3,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    dist.barrier()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,50 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- accounting used by bench.py: how many kernels were launched, and (optionally) their device time
+_LAUNCHES_PER_CALL = {"pfc_sample": 11}
+_count = 0
+_timing = None      # name -> list of (start_event, end_event) while enabled
+
+
+def launch_count():
+    return _count
+
+
+def enable_timing(on):
+    global _timing
+    _timing = {} if on else None
+
+
+def collect_timing():
+    """{name: {"calls", "ms_total", "ms_avg"}} for the calls made since enable_timing(True); synchronises."""
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in (_timing or {}).items():
+        ms = [a.elapsed_time(b) for a, b in evs]
+        out[name] = {"calls": len(ms), "ms_total": sum(ms), "ms_avg": sum(ms) / max(1, len(ms))}
+    return out
+
+
+def _timed(name):
+    def deco(fn):
+        def wrapper(*a, **k):
+            global _count
+            _count += _LAUNCHES_PER_CALL.get(name, 1)
+            if _timing is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            _timing.setdefault(name, []).append((e0, e1))
+            return r
+        wrapper.__name__ = fn.__name__
+        wrapper.__doc__ = fn.__doc__
+        return wrapper
+    return deco
+
+
 F32, BF16, I32, I64, U8, F64 = torch.float32, torch.bfloat16, torch.int32, torch.int64, torch.uint8, torch.float64
 
 exp_top = lib.pfc_exp_top
@@ -42,23 +86,27 @@ sample_workspace_bytes = lib.pfc_sample_workspace_bytes
 hist_bins = lib.pfc_eval_hist_bins
 
 
+@_timed("pfc_l2norm_rows")
 def l2norm_rows(x, index, rows, xn, inv_norm):
     d = x.shape[1]
     check(lib.pfc_l2norm_rows(_p(x, F32), _p(index, I64), rows, d, _p(xn, BF16), _p(inv_norm, F32), _stream()),
           "pfc_l2norm_rows")
 
 
+@_timed("pfc_localize_labels")
 def localize_labels(labels, class_start, num_local, out):
     check(lib.pfc_localize_labels(_p(labels, I64), labels.numel(), class_start, num_local, _p(out, I32), _stream()),
           "pfc_localize_labels")
 
 
+@_timed("pfc_sample")
 def sample(perm, labels_local, num_local, num_sample, index_out, n_out, labels_remapped, workspace):
     check(lib.pfc_sample(_p(perm, F32), _p(labels_local, I32), labels_local.numel(), num_local, num_sample,
                          _p(index_out, I64), _p(n_out, I32), _p(labels_remapped, I32), _p(workspace, U8),
                          workspace.numel(), _stream()), "pfc_sample")
 
 
+@_timed("pfc_gather_rows")
 def gather_rows(srcs, dsts, index, rows):
     d = srcs[0].shape[1]
     check(lib.pfc_gather_rows(_lib.ptr_array([_p(s, F32).value for s in srcs]),
@@ -66,6 +114,7 @@ def gather_rows(srcs, dsts, index, rows):
                               _stream()), "pfc_gather_rows")
 
 
+@_timed("pfc_scatter_rows")
 def scatter_rows(srcs, dsts, index, rows):
     d = srcs[0].shape[1]
     check(lib.pfc_scatter_rows(_lib.ptr_array([_p(s, F32).value for s in srcs]),
@@ -73,6 +122,7 @@ def scatter_rows(srcs, dsts, index, rows):
                                _stream()), "pfc_scatter_rows")
 
 
+@_timed("pfc_forward")
 def forward(xn, wn, labels_local, B, n, d, s, margin_kind, m2, m3, filter_thr, E, n_pad, part_sum, tgt_raw, tgt_e,
             tgt_z):
     check(lib.pfc_forward(_p(xn, BF16), _p(wn, BF16), _p(labels_local, I32), B, n, d, s, margin_kind, m2, m3,
@@ -80,21 +130,25 @@ def forward(xn, wn, labels_local, B, n, d, s, margin_kind, m2, m3, filter_thr, E
                           _p(tgt_z, F32), _stream()), "pfc_forward")
 
 
+@_timed("pfc_margin_apply")
 def margin_apply(logits, labels, margin_kind, s, m2, m3, filter_thr, out, gate):
     B, n = logits.shape
     check(lib.pfc_margin_apply(_p(logits, F32), _p(labels, I64), B, n, margin_kind, s, m2, m3, filter_thr,
                                _p(out, F32), _p(gate, F32), _stream()), "pfc_margin_apply")
 
 
+@_timed("pfc_row_stats")
 def row_stats(part_sum, n_tiles, B, labels_local, tgt_e, stats):
     check(lib.pfc_row_stats(_p(part_sum, F32), n_tiles, B, _p(labels_local, I32), _p(tgt_e, F32), _p(stats, F32),
                             _stream()), "pfc_row_stats")
 
 
+@_timed("pfc_loss")
 def loss(stats, B, row_L, out):
     check(lib.pfc_loss(_p(stats, F32), B, _p(row_L, F32), _p(out, F32), _stream()), "pfc_loss")
 
 
+@_timed("pfc_backward_prepare")
 def backward_prepare(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E,
                      n_pad):
     check(lib.pfc_backward_prepare(_p(stats, F32), _p(row_L, F32), _p(grad_loss, F32), s, B, d, _p(labels_local, I32),
@@ -102,32 +156,38 @@ def backward_prepare(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, ma
                                    _p(E, BF16), n_pad, _stream()), "pfc_backward_prepare")
 
 
+@_timed("pfc_backward_dx")
 def backward_dx(E, n_pad, wn, B, n, d, partial, splits):
     check(lib.pfc_backward_dx(_p(E, BF16), n_pad, _p(wn, BF16), B, n, d, _p(partial, F32), splits, _stream()),
           "pfc_backward_dx")
 
 
+@_timed("pfc_dx_finalize")
 def dx_finalize(partial, splits, coef, x, inv_norm, scale, rows, rows_total, d, out):
     check(lib.pfc_dx_finalize(_p(partial, F32), splits, _p(coef, F32), _p(x, F32), _p(inv_norm, F32), scale, rows,
                               rows_total, d, _p(out, F32), _stream()), "pfc_dx_finalize")
 
 
+@_timed("pfc_backward_dw")
 def backward_dw(E, n_pad, xs, B, n, d, dwn):
     check(lib.pfc_backward_dw(_p(E, BF16), n_pad, _p(xs, BF16), B, n, d, _p(dwn, F32), _stream()),
           "pfc_backward_dw")
 
 
+@_timed("pfc_dw_finalize")
 def dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, dw):
     check(lib.pfc_dw_finalize(_p(dwn, F32), _p(w, F32), _p(inv_norm_w, F32), rows, d, inv_grad_scale, _p(dw, F32),
                               _stream()), "pfc_dw_finalize")
 
 
+@_timed("pfc_dw_sgd")
 def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, inv_grad_scale, wn_next, inv_norm_next):
     check(lib.pfc_dw_sgd(_p(dwn, F32), _p(w, F32), _p(mom, F32), _p(inv_norm_w, F32), rows, d, lr, momentum,
                          weight_decay, inv_grad_scale, _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()),
           "pfc_dw_sgd")
 
 
+@_timed("pfc_dw_adam")
 def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, weight_decay, step, decoupled,
             inv_grad_scale, wn_next, inv_norm_next):
     check(lib.pfc_dw_adam(_p(dwn, F32), _p(w, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), _p(inv_norm_w, F32), rows,
@@ -136,21 +196,25 @@ def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, 
 
 
 # ---- verification scorer
+@_timed("fr_pair_score")
 def pair_score(e1, e2, labels_u8, scores, dist, hist_g, hist_i):
     N, d = e1.shape
     check(lib.fr_pair_score(_p(e1, F32), _p(e2, F32), _p(labels_u8, U8), N, d, _p(scores, F64), _p(dist, F64),
                             _p(hist_g, I64), _p(hist_i, I64), _stream()), "fr_pair_score")
 
 
+@_timed("fr_roc")
 def roc(hist_g, hist_i, min_level, max_level, out_bytes):
     check(lib.fr_roc(_p(hist_g, I64), _p(hist_i, I64), min_level, max_level, _p(out_bytes, U8), _stream()), "fr_roc")
 
 
+@_timed("fr_acc_counts")
 def acc_counts(scores, labels_u8, threshold, fr_fa):
     check(lib.fr_acc_counts(_p(scores, F64), _p(labels_u8, U8), scores.numel(), threshold, _p(fr_fa, I64), _stream()),
           "fr_acc_counts")
 
 
+@_timed("fr_kfold_acc")
 def kfold_acc(dist, labels_u8, folds, n_thr, step, correct_ws, acc, best_idx):
     check(lib.fr_kfold_acc(_p(dist, F64), _p(labels_u8, U8), dist.numel(), folds, n_thr, step, _p(correct_ws, I32),
                            _p(acc, F64), _p(best_idx, I32), _stream()), "fr_kfold_acc")
