@@ -222,32 +222,38 @@ class _PartialFCBase(torch.nn.Module):
         if local_embeddings.dtype != torch.float32:
             local_embeddings = local_embeddings.float()
         ws = self._ensure_workspace(batch_size, local_embeddings.device)
-        self._labels_in = local_labels.contiguous()
         self._optimizer = optimizer
-        self._perm = perm
         self._step_id += 1
+        self._prepare(local_embeddings, local_labels.contiguous(), optimizer, perm)
+        # sampling may just have replaced weight_activated (:120): hand autograd the CURRENT parameter
         return _HeadFunction.apply(local_embeddings, self.weight_activated, self)
 
     def _read_optimizer(self, optimizer):
         raise NotImplementedError
 
+    @torch.no_grad()
+    def _prepare(self, local_embeddings, labels_in, optimizer, perm):
+        """Everything that precedes the differentiable part: normalise + gather the batch, localise the labels,
+        sample the active classes (nets/PartialFC.py:175-196)."""
+        ws, W = self._ws, self.world_size
+        x = local_embeddings.detach().contiguous()
+        self._x_local = x
+        K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
+        if W > 1:
+            distributed.all_gather_into_tensor(ws.xn_all, ws.xn_local)            # :182 (bf16: half the bytes)
+            distributed.all_gather_into_tensor(ws.labels_all, labels_in)          # :183
+            labels_all = ws.labels_all
+        else:
+            labels_all = labels_in
+        K.localize_labels(labels_all, self.class_start, self.num_local, ws.labels_local)   # :188-193
+        if self.sample_rate < 1:
+            self.sample(ws.labels_local, None, optimizer, perm)                   # :195-196
+        else:
+            self._n = self.num_local
+
     def _forward_impl(self, local_embeddings):
         ws, W, d = self._ws, self.world_size, self.embedding_size
         b, B = ws.b, ws.B
-        x = local_embeddings.detach().contiguous()
-        self._x_local = x
-        K.l2norm_rows(x, None, b, ws.xn_local, ws.inv_x)
-        if W > 1:
-            distributed.all_gather_into_tensor(ws.xn_all, ws.xn_local)            # :182 (bf16: half the bytes)
-            distributed.all_gather_into_tensor(ws.labels_all, self._labels_in)    # :183
-            labels_all = ws.labels_all
-        else:
-            labels_all = self._labels_in
-        K.localize_labels(labels_all, self.class_start, self.num_local, ws.labels_local)   # :188-193
-        if self.sample_rate < 1:
-            self.sample(ws.labels_local, None, self._optimizer, self._perm)             # :195-196
-        else:
-            self._n = self.num_local
         n = self._n
         w = self.weight_activated.data
         if not self._wn_valid:

@@ -1,0 +1,104 @@
+"""world_size-2 tests of the head's HOST logic on CPU (gloo): class sharding with an uneven split, all-gather
+order, label localisation, the single [B,2] statistics all-reduce, the dX reduce-scatter and its x world_size,
+sampling + optimizer patching + scatter-back.  The CUDA kernels are replaced by tests/fake_kernels.py (the C-ABI
+contract restated on CPU); results are compared with fixtures the unmodified reference produced with 2 gloo ranks."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _rank_main(rank, W, port, name, fused, q):
+    for p in (ROOT, HERE, os.path.join(HERE, "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from helpers import load_case, case_inputs, case_perms
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=W)
+    import face_recognition_pytorch_b200 as pfc
+    from face_recognition_pytorch_b200 import partial_fc, kernels
+    from fake_kernels import FakeKernels
+    partial_fc.K = FakeKernels(kernels)            # test-only substitution of the kernel layer
+    cfg, z = load_case(name)
+    weights, xs, ls = case_inputs(cfg)
+    b = cfg["b"]
+    conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
+                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused)
+    head = pfc.PartialFC(conf, cfg["C"])
+    assert (head.num_local, head.class_start) == pfc.shard_range(cfg["C"], rank, W)
+    head.load_state_dict({"weight": weights[rank].clone()})
+    dummy = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
+                          momentum=cfg["momentum"], weight_decay=cfg["wd"])
+    out = {}
+    for s in range(cfg["steps"]):
+        x = xs[s][rank * b:(rank + 1) * b].clone().requires_grad_(True)
+        lab = ls[s][rank * b:(rank + 1) * b].clone()
+        perms = case_perms(cfg, z, s)
+        opt.zero_grad()
+        loss = head(x, lab, opt, perm=None if perms is None else perms[rank])
+        loss.backward()
+        out[f"loss_{s}"] = float(loss.detach())
+        out[f"dx_{s}"] = x.grad.numpy().copy()
+        if not fused:
+            out[f"dw_{s}"] = head.weight_activated.grad.numpy().copy()
+        if cfg["sample_rate"] < 1:
+            out[f"index_{s}"] = head.weight_index.numpy().copy()
+        opt.step()
+    if cfg["sample_rate"] < 1:
+        head.update()
+        out["weight_final"] = head.weight.numpy().copy()
+    else:
+        out["weight_final"] = head.weight_activated.detach().numpy().copy()
+    out["state_dict_shape"] = tuple(head.state_dict()["weight"].shape)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _cos(a, b):
+    a, b = a.astype(np.float64).ravel(), b.astype(np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+
+
+@pytest.mark.parametrize("name,fused,port", [("head_w2_full", False, 29821), ("head_w2_sampled", False, 29822),
+                                             ("head_w2_full", True, 29823), ("head_w2_sampled", True, 29824)])
+def test_two_rank_host_logic_matches_reference(name, fused, port):
+    sys.path.insert(0, HERE)
+    from helpers import load_case
+    cfg, z = load_case(name)
+    W = cfg["W"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, q)) for r in range(W)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(W))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for s in range(cfg["steps"]):
+        assert res[0][f"loss_{s}"] == res[1][f"loss_{s}"]                    # every rank returns the global loss
+        for r in range(W):
+            ref_loss = float(z[f"r{r}_loss_{s}"])
+            assert abs(res[r][f"loss_{s}"] - ref_loss) <= 6e-3 * abs(ref_loss)   # bf16 operands at d = 64 (see test_gpu_head.py)
+            assert _cos(res[r][f"dx_{s}"], z[f"r{r}_dx_{s}"]) >= 0.999
+            assert abs(np.linalg.norm(res[r][f"dx_{s}"]) / np.linalg.norm(z[f"r{r}_dx_{s}"]) - 1) < 2e-2   # incl. x W
+            if not fused:
+                assert _cos(res[r][f"dw_{s}"], z[f"r{r}_dw_{s}"]) >= 0.999
+            if cfg["sample_rate"] < 1:
+                assert np.array_equal(res[r][f"index_{s}"], z[f"r{r}_index_{s}"])
+    from inputs import synth_inputs, shard
+    w_full, _, _ = synth_inputs(cfg["C"], cfg["d"], cfg["b"] * W, 1)
+    for r in range(W):
+        nl, cs = shard(cfg["C"], r, W)
+        assert res[r]["state_dict_shape"] == (nl, cfg["d"])
+        w0 = w_full[cs:cs + nl].numpy()
+        assert _cos(res[r]["weight_final"] - w0, z[f"r{r}_weight_final"] - w0) >= 0.999

@@ -1,0 +1,102 @@
+"""Two-rank NCCL run of the CUDA head against the reference's 2-rank fixtures (needs >= 2 GPUs: gpurun --gpus 2).
+Same comparison as tests/test_dist_gloo.py, but with the real kernels and NCCL collectives."""
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+pytestmark = pytest.mark.gpu
+
+
+def _rank_main(rank, W, port, name, fused, q):
+    for p in (ROOT, HERE, os.path.join(HERE, "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from helpers import load_case, case_inputs, case_perms
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=W, device_id=dev)
+    import face_recognition_pytorch_b200 as pfc
+    cfg, z = load_case(name)
+    weights, xs, ls = case_inputs(cfg)
+    b = cfg["b"]
+    conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
+                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused)
+    head = pfc.PartialFC(conf, cfg["C"])
+    head.load_state_dict({"weight": weights[rank].clone()})
+    head = head.train().cuda()
+    dummy = torch.nn.Parameter(torch.zeros(1, device=dev))
+    opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
+                          momentum=cfg["momentum"], weight_decay=cfg["wd"])
+    out = {}
+    for s in range(cfg["steps"]):
+        x = xs[s][rank * b:(rank + 1) * b].clone().to(dev).requires_grad_(True)
+        lab = ls[s][rank * b:(rank + 1) * b].clone().to(dev)
+        perms = case_perms(cfg, z, s)
+        opt.zero_grad()
+        loss = head(x, lab, opt, perm=None if perms is None else perms[rank].to(dev))
+        loss.backward()
+        out[f"loss_{s}"] = float(loss.detach())
+        out[f"dx_{s}"] = x.grad.cpu().numpy().copy()
+        if not fused:
+            out[f"dw_{s}"] = head.weight_activated.grad.cpu().numpy().copy()
+        if cfg["sample_rate"] < 1:
+            out[f"index_{s}"] = head.weight_index.cpu().numpy().copy()
+        opt.step()
+    if cfg["sample_rate"] < 1:
+        head.update()
+        out["weight_final"] = head.weight.cpu().numpy().copy()
+    else:
+        out["weight_final"] = head.weight_activated.detach().cpu().numpy().copy()
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _cos(a, b):
+    a, b = a.astype(np.float64).ravel(), b.astype(np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+
+
+@pytest.mark.parametrize("name,fused,port", [("head_w2_full", False, 29841), ("head_w2_sampled", False, 29842),
+                                             ("head_w2_full", True, 29843), ("head_w2_sampled", True, 29844)])
+def test_two_rank_nccl_matches_reference(name, fused, port):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, HERE)
+    from helpers import load_case
+    cfg, z = load_case(name)
+    W = cfg["W"]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, q)) for r in range(W)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(W))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for s in range(cfg["steps"]):
+        assert res[0][f"loss_{s}"] == res[1][f"loss_{s}"]
+        for r in range(W):
+            ref_loss = float(z[f"r{r}_loss_{s}"])
+            assert abs(res[r][f"loss_{s}"] - ref_loss) <= 6e-3 * abs(ref_loss)     # bf16 operands at d = 64
+            assert _cos(res[r][f"dx_{s}"], z[f"r{r}_dx_{s}"]) >= 0.999
+            assert abs(np.linalg.norm(res[r][f"dx_{s}"]) / np.linalg.norm(z[f"r{r}_dx_{s}"]) - 1) < 2e-2
+            if not fused:
+                assert _cos(res[r][f"dw_{s}"], z[f"r{r}_dw_{s}"]) >= 0.999
+            if cfg["sample_rate"] < 1:
+                assert np.array_equal(res[r][f"index_{s}"], z[f"r{r}_index_{s}"])
+    from inputs import synth_inputs, shard
+    w_full, _, _ = synth_inputs(cfg["C"], cfg["d"], cfg["b"] * W, 1)
+    for r in range(W):
+        nl, cs = shard(cfg["C"], r, W)
+        w0 = w_full[cs:cs + nl].numpy()
+        assert _cos(res[r]["weight_final"] - w0, z[f"r{r}_weight_final"] - w0) >= 0.999
