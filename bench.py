@@ -224,7 +224,12 @@ def main():
             opt.zero_grad(set_to_none=True)
         return loss
 
+    clk = ClockSampler(local_rank)
+    clk.__enter__()                     # sampled every 200 ms across warm-up, timed region and e2e (all under load)
     # ---- warm-up (also builds workspaces, NCCL communicators)
+    l0 = K.launch_count()
+    step_eager(x_dev[0], l_dev[0])
+    launches_per_step = K.launch_count() - l0
     for i in range(args.warmup):
         step_eager(x_dev[i % n_data], l_dev[i % n_data])
     torch.cuda.synchronize()
@@ -266,20 +271,18 @@ def main():
 
     # ---- timed region: K steps, device time by CUDA events per step (L2 flushed, untimed, between steps)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = K.launch_count()
     dist.barrier()
     torch.cuda.synchronize()
-    with ClockSampler(local_rank) as clk:
-        t_wall0 = time.perf_counter()
-        for i in range(args.steps):
-            flush.zero_()
-            ev[i][0].record()
-            run_step(i)
-            ev[i][1].record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        t_wall = time.perf_counter() - t_wall0
-    launches = K.launch_count() - launches0
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        run_step(i)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = launches_per_step * args.steps      # kernels of libpfc_b200 per step (replayed from the graph or eager)
     ms_steps = [a.elapsed_time(bb) for a, bb in ev]
     t = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, dist.ReduceOp.MAX)
@@ -323,6 +326,15 @@ def main():
     dist.all_reduce(te, dist.ReduceOp.MAX)
     e2e_value = GLOBAL_BATCH / float(te.item())
 
+    # keep the GPU under the same load until the sampler has a few readings
+    t_hold = time.perf_counter()
+    i = 0
+    while len(clk.rows) < 5 and time.perf_counter() - t_hold < 3.0:
+        run_step(i); i += 1
+        if i % 50 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    clk.__exit__()
     if rank != 0:
         dist.barrier()
         return
