@@ -329,11 +329,14 @@ def main():
     # keep the GPU under the same load until the sampler has a few readings
     t_hold = time.perf_counter()
     i = 0
-    while len(clk.rows) < 5 and time.perf_counter() - t_hold < 3.0:
-        run_step(i); i += 1
-        if i % 50 == 0:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
+    while True:                                   # rank 0 decides, so every rank issues the same collectives
+        for _ in range(100):
+            run_step(i); i += 1
+        torch.cuda.synchronize()
+        more = torch.tensor([1 if (len(clk.rows) < 5 and time.perf_counter() - t_hold < 3.0) else 0], device=dev)
+        dist.broadcast(more, 0)
+        if int(more.item()) == 0:
+            break
     clk.__exit__()
     if rank != 0:
         dist.barrier()

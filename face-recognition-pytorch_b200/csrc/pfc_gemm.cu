@@ -29,7 +29,7 @@ struct FwdPolicy {
         int margin_kind;         // 0 = ArcFace-style (cos(theta+m)), 1 = CosFace-style (t - m3)
         float filter_thr;        // CombinedMarginLoss.interclass_filtering_threshold (0 = off)
         __nv_bfloat16* E;        // [B, n_pad]
-        float* part_sum;         // [n_tiles_n, B_pad] sum of non-target e over this class tile
+        float* part_sum;         // [2 * n_tiles_n, B_pad] sum of non-target e over each 128-class half tile
         float* tgt_raw;          // [B] raw (unclamped) target cosine, written by the owning tile only
         float* tgt_e;            // [B] e of the margin-adjusted target logit
         float* tgt_z;            // [B] margin-adjusted target logit (already * s)
@@ -47,8 +47,9 @@ struct FwdPolicy {
         return tc;
     }
 
-    template <bool kHasTarget, bool kTail, bool kFilter>
-    __device__ static __forceinline__ float chunk(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[16],
+    // 32 accumulator columns -> 16 packed bf16x2 words o[kOff .. kOff+16); returns the sum of the non-target terms
+    template <bool kHasTarget, bool kTail, bool kFilter, int kOff>
+    __device__ static __forceinline__ float chunk(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[32],
                                                   int col_base, int jt) {
         float sum = 0.f;
 #pragma unroll
@@ -72,65 +73,78 @@ struct FwdPolicy {
                 sum += e;
                 e2[u] = keep ? e : 0.f;
             }
-            o[j >> 1] = pack_bf16x2(e2[0], e2[1]);
+            o[kOff + (j >> 1)] = pack_bf16x2(e2[0], e2[1]);
         }
         return sum;
     }
 
-    __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr,
-                                                    int row_in_tile, int lane) {
-        const int row = tc.m0 + row_in_tile;
+    template <int kOff>
+    __device__ static __forceinline__ float chunk32(const Params& p, uint32_t taddr, uint32_t (&o)[32], int col_base,
+                                                    int row, int tgt_off_in_tile, int tile_col) {
+        // tile_col = column of this chunk inside the 256-wide tile; tgt_off_in_tile = target column inside the tile or -1
+        uint32_t v[32];
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        const bool has_t = (tgt_off_in_tile >= tile_col) && (tgt_off_in_tile < tile_col + 32);
+        const bool tail = col_base + 32 > p.n;
+        const bool filt = p.filter_thr > 0.f;
+        const int jt = has_t ? (tgt_off_in_tile - tile_col) : -1;
+        float sum;
+        if (!has_t && !tail && !filt) {
+            sum = chunk<false, false, false, kOff>(p, v, o, col_base, jt);
+        } else if (!filt) {
+            sum = chunk<true, true, false, kOff>(p, v, o, col_base, jt);
+        } else {
+            sum = chunk<true, true, true, kOff>(p, v, o, col_base, jt);
+        }
+        if (has_t) {
+            float raw = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) raw = (j == jt) ? __uint_as_float(v[j]) : raw;
+            const float t = fminf(fmaxf(raw, -1.f), 1.f);
+            float fin;
+            if (p.margin_kind == 0) {
+                const float sin_t = sqrtf(fmaxf(1.f - t * t, 0.f));
+                const float ctm = t * p.cos_m - sin_t * p.sin_m;
+                fin = (t > p.theta) ? ctm : (t - p.sinmm);
+            } else {
+                fin = t - p.m3;
+            }
+            p.tgt_raw[row] = raw;
+            p.tgt_e[row] = fast_exp2(fmaf(fin, p.k1, -p.k2));
+            p.tgt_z[row] = fin * p.s;
+        }
+        return sum;
+    }
+
+    __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr, int quarter,
+                                                    int half, int lane, uint8_t* stage) {
+        const int row0 = tc.m0 + quarter * 32;
+        const int row = row0 + lane;
         const bool row_ok = row < p.B;
         const int lbl = row_ok ? p.labels[row] : -1;
         const int tgt_off = (lbl >= tc.n0 && lbl < tc.n0 + BN) ? (lbl - tc.n0) : -1;
+        const int rows_valid = min(32, max(0, p.B - row0));
         float sum = 0.f;
-        __nv_bfloat16* erow = p.E + static_cast<size_t>(row_ok ? row : 0) * p.n_pad;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            const int col_base = tc.n0 + c * 32;
-            if (col_base >= p.n) break;                  // warp-uniform: nothing valid from here on
-            uint32_t v[32];
-            tmem_ld_32x32(taddr + c * 32, v);
-            tmem_ld_wait();
-            uint32_t o[16];
-            const bool has_t = (tgt_off >= 0) && ((tgt_off >> 5) == c);
-            const bool tail = col_base + 32 > p.n;
-            const bool filt = p.filter_thr > 0.f;
-            const int jt = tgt_off & 31;
-            if (!has_t && !tail && !filt) {
-                sum += chunk<false, false, false>(p, v, o, col_base, jt);
-            } else if (!filt) {
-                sum += chunk<true, true, false>(p, v, o, col_base, has_t ? jt : -1);
+        for (int cc = 0; cc < EPI_COLS / 64; ++cc) {
+            const int tile_col = half * EPI_COLS + cc * 64;
+            const int col64 = tc.n0 + tile_col;
+            if (col64 >= p.n) break;                     // warp-uniform: nothing valid from here on
+            uint32_t o[32];
+            sum += chunk32<0>(p, taddr + cc * 64, o, col64, row, tgt_off, tile_col);
+            if (col64 + 32 < p.n) {
+                sum += chunk32<16>(p, taddr + cc * 64 + 32, o, col64 + 32, row, tgt_off, tile_col + 32);
             } else {
-                sum += chunk<true, true, true>(p, v, o, col_base, has_t ? jt : -1);
-            }
-            if (has_t) {
-                float raw = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) raw = (j == jt) ? __uint_as_float(v[j]) : raw;
-                const float t = fminf(fmaxf(raw, -1.f), 1.f);
-                float fin;
-                if (p.margin_kind == 0) {
-                    const float sin_t = sqrtf(fmaxf(1.f - t * t, 0.f));
-                    const float ctm = t * p.cos_m - sin_t * p.sin_m;
-                    fin = (t > p.theta) ? ctm : (t - p.sinmm);
-                } else {
-                    fin = t - p.m3;
-                }
-                p.tgt_raw[row] = raw;
-                p.tgt_e[row] = fast_exp2(fmaf(fin, p.k1, -p.k2));
-                p.tgt_z[row] = fin * p.s;
+                for (int j = 16; j < 32; ++j) o[j] = 0u;
             }
-            if (row_ok) {
-                uint4* dst = reinterpret_cast<uint4*>(erow + col_base);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (col_base + q * 8 + 8 <= p.n_pad)
-                        dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-                }
-            }
+            const int bytes_valid = min(128, (p.n_pad - col64) * 2);
+            warp_store_rows_128B(stage, lane, o,
+                                 reinterpret_cast<uint8_t*>(p.E + static_cast<size_t>(row0) * p.n_pad + col64),
+                                 static_cast<size_t>(p.n_pad) * 2, rows_valid, bytes_valid);
         }
-        if (row_ok) p.part_sum[static_cast<size_t>(tc.aux) * p.B_pad + row] = sum;
+        if (row_ok) p.part_sum[static_cast<size_t>(tc.aux * 2 + half) * p.B_pad + row] = sum;
     }
 };
 
@@ -170,28 +184,20 @@ struct StorePolicy {
         tc.aux = z;
         return tc;
     }
-    __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr,
-                                                    int row_in_tile, int lane) {
-        const int row = tc.m0 + row_in_tile;
-        const bool row_ok = row < p.rows_valid;
-        float* orow = p.out + static_cast<size_t>(tc.aux) * p.split_stride +
-                      static_cast<size_t>(row_ok ? row : 0) * p.ld;
+    __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr, int quarter,
+                                                    int half, int lane, uint8_t* stage) {
+        const int row0 = tc.m0 + quarter * 32;
+        const int rows_valid = min(32, max(0, p.rows_valid - row0));
+        float* obase = p.out + static_cast<size_t>(tc.aux) * p.split_stride + static_cast<size_t>(row0) * p.ld;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            const int col_base = tc.n0 + c * 32;
-            if (col_base >= p.cols_valid) break;
+        for (int c = 0; c < EPI_COLS / 32; ++c) {
+            const int col_base = tc.n0 + half * EPI_COLS + c * 32;
+            if (col_base >= p.cols_valid) break;         // warp-uniform
             uint32_t v[32];
             tmem_ld_32x32(taddr + c * 32, v);
             tmem_ld_wait();
-            if (row_ok) {
-                float4* dst = reinterpret_cast<float4*>(orow + col_base);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (col_base + q * 4 + 4 <= p.cols_valid)
-                        dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                             __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                }
-            }
+            warp_store_rows_128B(stage, lane, v, reinterpret_cast<uint8_t*>(obase + col_base),
+                                 static_cast<size_t>(p.ld) * 4, rows_valid, min(128, (p.cols_valid - col_base) * 4));
         }
     }
 };
@@ -281,7 +287,7 @@ void pfc_debug_mn_desc(unsigned lbo, unsigned sbo, unsigned kstep) {
 }
 
 int pfc_padded_classes(int n) { return (n + 63) / 64 * 64; }
-int pfc_num_class_tiles(int n) { return (n + BN - 1) / BN; }
+int pfc_num_class_tiles(int n) { return 2 * ((n + BN - 1) / BN); }   // one part_sum slab per 128-column half tile
 int pfc_padded_batch(int B) { return (B + BM - 1) / BM * BM; }
 
 int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int B, int n, int d, float s,
@@ -300,7 +306,7 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     p.B = B; p.n = n; p.n_pad = n_pad; p.B_pad = pfc_padded_batch(B);
     p.m_tiles = (B + BM - 1) / BM;
     p.k_stages = (d + BK - 1) / BK;
-    p.num_tiles = p.m_tiles * pfc_num_class_tiles(n);
+    p.num_tiles = p.m_tiles * ((n + BN - 1) / BN);
     p.labels = labels_local;
     p.k1 = s * log2e;
     p.k2 = s * log2e - (float)PFC_EXP_TOP;

@@ -323,6 +323,69 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
     if (lane == 0) inv_norm_next[row] = 1.f / denom;
 }
 
+// Specialised fused SGD row kernel for d = 128 * NV: all three input streams (dwn, w, momentum) are requested
+// up front (12 x 16-byte loads per lane in flight at d = 512) so a warp is never waiting on a dependent phase,
+// arrays are sized exactly (no predicated dead registers), 4 rows per CTA for occupancy.
+template <int NV>
+__global__ void __launch_bounds__(128)
+dw_sgd_rows_kernel(const float* __restrict__ dwn, float* __restrict__ w, float* __restrict__ mom,
+                   const float* inv_norm_w, int rows, float lr, float momentum, float wd, float inv_grad_scale,
+                   __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
+    constexpr int d = 128 * NV;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const size_t base = static_cast<size_t>(row) * d;
+    float4 g[NV], wv[NV], mv[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) g[j] = ld4_stream(dwn + base + 4 * (lane + 32 * j));
+#pragma unroll
+    for (int j = 0; j < NV; ++j) wv[j] = ld4(w + base + 4 * (lane + 32 * j));
+#pragma unroll
+    for (int j = 0; j < NV; ++j) mv[j] = ld4(mom + base + 4 * (lane + 32 * j));
+    const float inv = inv_norm_w[row];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+        dot += wv[j].x * g[j].x + wv[j].y * g[j].y + wv[j].z * g[j].z + wv[j].w * g[j].w;
+    dot = warp_sum(dot) * inv;
+    const float wscale = dot * inv;
+    const float gs = inv * inv_grad_scale;
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        float4 a, b = mv[j], q = wv[j];
+        a.x = (g[j].x - q.x * wscale) * gs + wd * q.x;
+        a.y = (g[j].y - q.y * wscale) * gs + wd * q.y;
+        a.z = (g[j].z - q.z * wscale) * gs + wd * q.z;
+        a.w = (g[j].w - q.w * wscale) * gs + wd * q.w;
+        b.x = momentum * b.x + a.x; b.y = momentum * b.y + a.y;
+        b.z = momentum * b.z + a.z; b.w = momentum * b.w + a.w;
+        q.x -= lr * b.x; q.y -= lr * b.y; q.z -= lr * b.z; q.w -= lr * b.w;
+        st4(mom + base + 4 * (lane + 32 * j), b);
+        st4(w + base + 4 * (lane + 32 * j), q);
+        wv[j] = q;
+        ss += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    }
+    if (wn_next == nullptr) return;
+    ss = warp_sum(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const float4 q = make_float4(wv[j].x / denom, wv[j].y / denom, wv[j].z / denom, wv[j].w / denom);
+        *reinterpret_cast<uint2*>(wn_next + base + 4 * (lane + 32 * j)) = pack4_bf16(q);
+    }
+    if (lane == 0) inv_norm_next[row] = 1.f / denom;
+}
+
+template <int NV>
+static void launch_dw_sgd_rows(const float* dwn, float* w, float* mom, const float* inv_norm_w, int rows, float lr,
+                               float momentum, float wd, float igs, __nv_bfloat16* wn_next, float* inv_next,
+                               cudaStream_t st) {
+    dw_sgd_rows_kernel<NV><<<(rows + 3) / 4, 128, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd, igs,
+                                                            wn_next, inv_next);
+}
+
 // dst[r] = src[index[r]]  /  dst[index[r]] = src[r]   (nets/PartialFC.py:120-121, :142-143), up to 3 tensors at once
 struct RowSet { const float* src[3]; float* dst[3]; int count; };
 
@@ -446,6 +509,21 @@ int pfc_dw_sgd(const float* dwn, float* w, float* mom, const float* inv_norm_w, 
                float momentum, float weight_decay, float inv_grad_scale, void* wn_next, float* inv_norm_next,
                void* stream) {
     if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
+    if (d % 128 == 0 && mom != nullptr) {
+        cudaStream_t st = (cudaStream_t)stream;
+        __nv_bfloat16* wnn = reinterpret_cast<__nv_bfloat16*>(wn_next);
+        switch (d / 128) {
+            case 1: launch_dw_sgd_rows<1>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+            case 2: launch_dw_sgd_rows<2>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+            case 3: launch_dw_sgd_rows<3>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+            case 4: launch_dw_sgd_rows<4>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+            case 5: launch_dw_sgd_rows<5>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+            case 6: launch_dw_sgd_rows<6>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+            case 7: launch_dw_sgd_rows<7>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+            default: launch_dw_sgd_rows<8>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+        }
+        return check_launch();
+    }
     OptArgs o = {};
     o.kind = OPT_SGD;
     o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.inv_grad_scale = inv_grad_scale;

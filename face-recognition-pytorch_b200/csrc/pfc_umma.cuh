@@ -2,12 +2,14 @@
 //   G1  logits tile  S  = Xn  . Wn^T      (A K-major,  B K-major,  epilogue = margin/exp/row-sum/bf16 spill)
 //   G2  dXn          += E' . Wn           (A K-major,  B MN-major, split over classes, epilogue = fp32 partial)
 //   G3  dWn           = E'^T . Xs         (A MN-major, B MN-major, epilogue = fp32 tile store)
-// One CTA per SM: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
-// warps 2..5 = epilogue (one per TMEM lane quarter).  Three pipelines: smem full/empty (TMA<->MMA),
-// TMEM full/empty (MMA<->epilogue, two 256-column accumulators), and the static persistent tile loop.
+// One CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane) + TMEM owner,
+// warps 2..9 = epilogue: two warps per TMEM lane quarter, each owning one 128-column half of the accumulator.
+// Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue, two 256-column accumulators),
+// and the static persistent tile loop.
 //
 // Tile = 128 (TMEM lanes) x 256 (TMEM columns) fp32, K consumed in 64-element (128-byte, SWIZZLE_128B)
-// stages, 4 stages x (16 KB A + 32 KB B) = 192 KB of shared memory.
+// stages, 4 stages x (16 KB A + 32 KB B) = 192 KB of shared memory, plus 4 KB per epilogue warp used to
+// transpose "one thread = one row" register fragments into full 128-byte-line global stores.
 #pragma once
 #include "pfc_ptx.cuh"
 
@@ -21,8 +23,11 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = BN * BK * 2;
 constexpr int MN_BOX_BYTES = 64 * BK * 2;   // one 64(MN) x 64(K) box of an MN-major operand
-constexpr int GEMM_THREADS = 192;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024;   // +1024: manual alignment
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_COLS = BN / (EPI_WARPS / 4);   // columns owned by one epilogue warp (128)
+constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int EPI_STAGE_BYTES = 32 * 128;   // per epilogue warp: 32 rows x 128 B
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_WARPS * EPI_STAGE_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
 
 struct TileCoord {
@@ -43,13 +48,37 @@ __host__ __device__ constexpr DescCfg default_desc_cfg(bool a_mn, bool b_mn) {
                    b_mn ? (uint32_t)MN_BOX_BYTES : 16u, 1024u, b_mn ? 2048u : 32u};
 }
 
+// Each lane holds 128 bytes of ITS row (v[0..31]); the warp writes 32 rows x 128 B to global memory as full
+// 128-byte lines (8 lanes per row) after an XOR-swizzled (bank-conflict-free) transpose through `stage`.
+// gbase points at (row 0 of this warp, first byte of the 128-byte column block); rows >= rows_valid and 16-byte
+// pieces beyond bytes_valid are not written.
+__device__ __forceinline__ void warp_store_rows_128B(uint8_t* stage, int lane, const uint32_t (&v)[32], uint8_t* gbase,
+                                                     size_t row_stride_bytes, int rows_valid, int bytes_valid) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int c = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const uint4 q = *reinterpret_cast<const uint4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
+        if (r < rows_valid && c * 16 + 16 <= bytes_valid)
+            *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(r) * row_stride_bytes + c * 16) = q;
+    }
+    __syncwarp();
+}
+
 // Policy contract:
 //   static constexpr bool A_MN, B_MN;           operand major-ness in shared memory
 //   struct Params { int num_tiles; ... };
 //   static DescCfg desc(const Params&);         smem descriptor geometry (default_desc_cfg(A_MN, B_MN))
 //   static TileCoord tile(const Params&, int t);
-//   static void epilogue(const Params&, const TileCoord&, uint32_t taddr, int row_in_tile, int lane);
-//        taddr = TMEM address of this warp's lane quarter, column 0 of the tile's accumulator.
+//   static void epilogue(const Params&, const TileCoord&, uint32_t taddr, int quarter, int half, int lane,
+//                        uint8_t* stage);
+//        taddr = TMEM address of this warp's lane quarter at column (half * EPI_COLS) of the tile's accumulator;
+//        the warp owns rows [32*quarter, 32*quarter+32) x columns [half*EPI_COLS, (half+1)*EPI_COLS) of the tile.
 template <class P>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -58,6 +87,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+    uint8_t* sEpi = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
 
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
@@ -79,7 +109,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 4);   // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[a], EPI_WARPS);   // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -154,9 +184,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (4 warps)
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        const int ew = warp - 2;
         const int quarter = warp & 3;                  // TMEM lanes [32q, 32q+32) are the only ones this warp may read
-        const int row_in_tile = quarter * 32 + lane;
+        const int half = ew >> 2;                      // which 128-column half of the accumulator
+        uint8_t* stage_buf = sEpi + ew * EPI_STAGE_BYTES;
         int tl = 0;
         for (int t = blockIdx.x; t < prm.num_tiles; t += gridDim.x, ++tl) {
             const TileCoord tc = P::tile(prm, t);
@@ -164,8 +196,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const uint32_t acc_phase = (tl >> 1) & 1;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-            P::epilogue(prm, tc, taddr, row_in_tile, lane);
+            const uint32_t taddr =
+                tmem_base + acc * BN + half * EPI_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
+            P::epilogue(prm, tc, taddr, quarter, half, lane, stage_buf);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);

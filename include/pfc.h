@@ -39,7 +39,7 @@ const char* pfc_error_string(int code);           /* host string */
 int pfc_exp_top(void);                            /* exponent offset of the spilled e terms (see pfc_forward) */
 int pfc_padded_classes(int n);                    /* row stride (elements) of the E' spill for n active classes */
 int pfc_padded_batch(int B);                      /* row count the part_sum slabs are padded to */
-int pfc_num_class_tiles(int n);                   /* number of 256-class tiles = leading dim of part_sum */
+int pfc_num_class_tiles(int n);                   /* number of 128-class half tiles = leading dim of part_sum */
 int pfc_dx_splits(int B, int n, int d);           /* class splits pfc_backward_dx will use for this shape */
 int pfc_dx_max_splits(int B, int d);              /* upper bound of pfc_dx_splits over all n (sizes `partial`) */
 
@@ -75,7 +75,7 @@ int pfc_scatter_rows(const float* const* src, float* const* dst, int count, cons
  * nets/ArcFace.py:76-91 (or :100-105), nets/PartialFC.py:446-458.  tcgen05 GEMM Xn[B,d] . Wn[n,d]^T whose epilogue
  * never writes logits: for every (sample i, class c) it forms e_ic = 2^(log2e*(z_ic - s) + pfc_exp_top()) with
  * z = s*clamp(cos,-1,1) (margin applied on the target column), accumulates the per-row sum of the NON-target terms
- * per 256-class tile into part_sum[tile][i] and spills e (zeroed where the clamp blocks the gradient) as bf16
+ * per 128-class half tile into part_sum[slab][i] and spills e (zeroed where the clamp blocks the gradient) as bf16
  * into E[i*n_pad + c].  For rows whose target class is local it also writes the raw target cosine, the target's
  * e term and the target logit.  labels_local: -1 = target on another rank. */
 int pfc_forward(const void* xn_bf16, const void* wn_bf16, const int32_t* labels_local, int B, int n, int d, float s,

@@ -85,7 +85,7 @@ class FakeKernels:
         nt, Bp = self.num_class_tiles(n), self.padded_batch(B)
         ps = part_sum[: nt * Bp].view(nt, Bp)
         for tix in range(nt):
-            ps[tix, :B] = e[:, tix * 256:(tix + 1) * 256].sum(1)
+            ps[tix, :B] = e[:, tix * 128:(tix + 1) * 128].sum(1)      # one slab per 128-class half tile
 
     def row_stats(self, part_sum, n_tiles, B, labels, tgt_e, stats):
         Bp = self.padded_batch(B)

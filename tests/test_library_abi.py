@@ -36,7 +36,7 @@ def test_version_and_error_strings():
 def test_shape_helpers():
     from face_recognition_pytorch_b200 import kernels as K
     assert K.padded_classes(93431) == 93440 and K.padded_classes(64) == 64
-    assert K.num_class_tiles(93431) == 365 and K.num_class_tiles(256) == 1 and K.num_class_tiles(257) == 2
+    assert K.num_class_tiles(93431) == 730 and K.num_class_tiles(256) == 2 and K.num_class_tiles(257) == 4
     assert K.padded_batch(1000) == 1024
     assert K.exp_top() == 64
     for B, n, d in [(1024, 93431, 512), (128, 10000, 512), (4096, 51497, 512), (32, 100, 64)]:
