@@ -19,12 +19,14 @@ namespace pfc {
 struct FwdPolicy {
     static constexpr bool A_MN = false;
     static constexpr bool B_MN = false;
+    static constexpr bool SHARE_B = true;    // a CTA pair = two sample tiles sharing one class (W) stage
     struct Params {
         int num_tiles;
         int B, n, n_pad, B_pad;
         int m_tiles, k_stages;
         const int32_t* labels;   // [B] shard-local class id (after sampling remap) or -1
         float k1, k2;            // e = exp2(clamp(cos) * k1 - k2)
+        float k1x2, k12;         // same through h = (clamp+1)/2: e = exp2(h * k1x2 - k12)
         float cos_m, sin_m, theta, sinmm, m3;
         int margin_kind;         // 0 = ArcFace-style (cos(theta+m)), 1 = CosFace-style (t - m3)
         float filter_thr;        // CombinedMarginLoss.interclass_filtering_threshold (0 = off)
@@ -58,12 +60,16 @@ struct FwdPolicy {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const float raw = __uint_as_float(v[j + u]);
-                float cl = fminf(fmaxf(raw, -1.f), 1.f);
-                bool keep = fabsf(raw) <= 1.f;           // clamp backward passes gradient only inside [-1, 1]
+                // clamp(raw,-1,1) on the FMA pipe: h = sat(raw/2 + 1/2) = (clamp+1)/2, e = 2^(2 k1 h - (k1 + k2)).
+                // The clamp's gradient gate (|raw| <= 1) is applied on the target column only (backward_prepare):
+                // for a non-target class it could only fire if a foreign class centre coincided with the sample,
+                // where the reference's own fp32 rounding decides the gate at random.
+                float h = __saturatef(fmaf(raw, 0.5f, 0.5f));
+                bool keep = true;
                 if (kFilter) {
-                    if (cl > p.filter_thr) { cl = 0.f; keep = false; }
+                    if (fmaf(h, 2.f, -1.f) > p.filter_thr) { h = 0.5f; keep = false; }
                 }
-                float e = fast_exp2(fmaf(cl, p.k1, -p.k2));
+                float e = fast_exp2(fmaf(h, p.k1x2, -p.k12));
                 if (kTail) {
                     if (col_base + j + u >= p.n) e = 0.f;
                 }
@@ -166,6 +172,9 @@ template <bool kAMN>
 struct StorePolicy {
     static constexpr bool A_MN = kAMN;
     static constexpr bool B_MN = true;
+    // dX (A K-major): a CTA pair = two sample tiles sharing the Wn stage.
+    // dW (A MN-major): a CTA pair = the two D halves of one class tile sharing the E'^T stage.
+    static constexpr bool SHARE_B = !kAMN;
     using Params = StoreParams;
     __device__ static __forceinline__ DescCfg desc(const Params& p) { return p.dc; }
     __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
@@ -255,23 +264,41 @@ static DescCfg store_desc_cfg(bool a_mn) {
     return dc;
 }
 
-template <class P>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const typename P::Params& prm,
-                       cudaStream_t stream) {
+static int g_dbg_cluster = -1;   // debug / A-B switch: -1 auto, 1 = never cluster, 2 = cluster when possible
+
+template <class P, int CL>
+static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const typename P::Params& prm,
+                          cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<P, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              GEMM_SMEM_BYTES);
         if (e != cudaSuccess) return PFC_ERR_CUDA;
         attr_set = true;
     }
     const int sms = num_sms();
     if (sms <= 0) return PFC_ERR_CUDA;
-    const int grid = prm.num_tiles < sms ? prm.num_tiles : sms;
-    if (grid <= 0) return PFC_OK;
-    umma_gemm_kernel<P><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta, tb, prm);
-    return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
+    if (prm.num_tiles <= 0) return PFC_OK;
+    if (prm.num_tiles % CL) return PFC_ERR_SHAPE;
+    int grid = prm.num_tiles < sms ? prm.num_tiles : sms;
+    grid = grid / CL * CL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<P, CL>, ta, tb, prm);
+    return e == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
+
+static bool want_cluster(int pair_dim_tiles) { return g_dbg_cluster != 1 && pair_dim_tiles % 2 == 0; }
 
 }  // namespace pfc
 
@@ -285,6 +312,8 @@ int pfc_exp_top(void) { return PFC_EXP_TOP; }
 void pfc_debug_mn_desc(unsigned lbo, unsigned sbo, unsigned kstep) {
     g_dbg_mn_lbo = lbo; g_dbg_mn_sbo = sbo; g_dbg_mn_kstep = kstep;
 }
+// not part of the public header: 1 = never use CTA-pair clusters, 2 / -1 = use them whenever the paired dimension is even
+void pfc_debug_cluster(int mode) { g_dbg_cluster = mode; }
 
 int pfc_padded_classes(int n) { return (n + 63) / 64 * 64; }
 int pfc_num_class_tiles(int n) { return 2 * ((n + BN - 1) / BN); }   // one part_sum slab per 128-column half tile
@@ -297,10 +326,11 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     const float log2e = 1.4426950408889634f;
     // every representable term must stay a normal bf16/fp32 number: 2*s*log2e <= TOP + 126
     if (!(s > 0.f) || 2.f * s * log2e > PFC_EXP_TOP + 126.f) return PFC_ERR_SCALE_RANGE;
+    const bool cl2 = want_cluster((B + BM - 1) / BM);   // pairs of sample tiles share the class stage
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, xn, d, B, d, BK, BM);
     if (rc) return rc;
-    rc = make_tmap(&tb, wn, d, n, d, BK, BN);
+    rc = make_tmap(&tb, wn, d, n, d, BK, cl2 ? BN / 2 : BN);   // each CTA of a pair fetches half of the 256 class rows
     if (rc) return rc;
     FwdPolicy::Params p;
     p.B = B; p.n = n; p.n_pad = n_pad; p.B_pad = pfc_padded_batch(B);
@@ -310,6 +340,8 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     p.labels = labels_local;
     p.k1 = s * log2e;
     p.k2 = s * log2e - (float)PFC_EXP_TOP;
+    p.k1x2 = 2.f * p.k1;
+    p.k12 = p.k1 + p.k2;
     {   // same double-precision constants the reference computes with math.cos/sin (nets/ArcFace.py:69-72)
         const double pi = 3.14159265358979323846;
         p.cos_m = (float)cos((double)m2); p.sin_m = (float)sin((double)m2);
@@ -319,7 +351,8 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     p.m3 = m3; p.margin_kind = margin_kind; p.filter_thr = filter_thr;
     p.E = reinterpret_cast<__nv_bfloat16*>(E);
     p.part_sum = part_sum; p.tgt_raw = tgt_raw; p.tgt_e = tgt_e; p.tgt_z = tgt_z; p.s = s;
-    return launch_gemm<FwdPolicy>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    return cl2 ? launch_gemm_cl<FwdPolicy, 2>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream))
+               : launch_gemm_cl<FwdPolicy, 1>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Number of class splits the dX contraction uses for a given shape (callers size `partial` with it).
@@ -363,7 +396,8 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     p.split_stride = static_cast<size_t>(B) * d;
     p.out = partial;
     p.dc = store_desc_cfg(false);
-    return launch_gemm<StorePolicy<false>>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    return want_cluster(p.m_tiles) ? launch_gemm_cl<StorePolicy<false>, 2>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream))
+                                   : launch_gemm_cl<StorePolicy<false>, 1>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // dwn[n][d] (fp32) = E'^T . Xs,   Xs = c_i * Xn_i (bf16, [B, d])
@@ -386,7 +420,8 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.split_stride = 0;
     p.out = dwn;
     p.dc = store_desc_cfg(true);
-    return launch_gemm<StorePolicy<true>>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    return want_cluster(p.n_tiles) ? launch_gemm_cl<StorePolicy<true>, 2>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream))
+                                   : launch_gemm_cl<StorePolicy<true>, 1>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -79,7 +79,12 @@ __device__ __forceinline__ void warp_store_rows_128B(uint8_t* stage, int lane, c
 //                        uint8_t* stage);
 //        taddr = TMEM address of this warp's lane quarter at column (half * EPI_COLS) of the tile's accumulator;
 //        the warp owns rows [32*quarter, 32*quarter+32) x columns [half*EPI_COLS, (half+1)*EPI_COLS) of the tile.
-template <class P>
+//
+// CL = 2 runs CTA pairs as a thread-block cluster working on two adjacent tiles that share one operand stage
+// (P::SHARE_B: the pair differs in m0 and shares B; otherwise it differs in n0 and shares A).  Each CTA fetches
+// half of the shared stage and TMA-multicasts it into both CTAs' shared memory, halving that operand's L2 traffic;
+// a stage is recycled only after BOTH CTAs' MMAs have retired (multicast tcgen05.commit on the empty barrier).
+template <class P, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const typename P::Params prm) {
@@ -104,7 +109,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], 1);
+            mbar_init(&empty_bar[s], CL);       // one multicast commit from every CTA of the cluster
         }
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -115,15 +120,20 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
     if (warp == 1) tmem_alloc(&tmem_base_slot, TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // peer barriers must be initialised before any remote arrive
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    const int crank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
+    const int first_tile = (blockIdx.x / CL) * CL + crank;   // cluster c works on tiles CL*c .. CL*c+CL-1, then strides
+    const int tile_stride = gridDim.x;                        // gridDim.x is a multiple of CL
+    constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1);
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < prm.num_tiles; t += gridDim.x) {
+            for (int t = first_tile; t < prm.num_tiles; t += tile_stride) {
                 const TileCoord tc = P::tile(prm, t);
                 for (int kc = tc.k0; kc < tc.k1; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -131,19 +141,41 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
                     uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
                     const int kel = kc * BK;
+                    constexpr bool kShareA = (CL > 1) && !P::SHARE_B;
+                    constexpr bool kShareB = (CL > 1) && P::SHARE_B;
                     if constexpr (P::A_MN) {
+                        constexpr int nb = BM / 64 / (kShareA ? CL : 1);      // boxes this CTA fetches
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)
-                            tma_load_2d(a_dst + j * MN_BOX_BYTES, &tma_a, &full_bar[stage], tc.m0 + j * 64, kel);
+                        for (int jj = 0; jj < nb; ++jj) {
+                            const int j = kShareA ? crank * nb + jj : jj;
+                            if constexpr (kShareA)
+                                tma_load_2d_mcast(a_dst + j * MN_BOX_BYTES, &tma_a, &full_bar[stage], tc.m0 + j * 64, kel, kMask);
+                            else
+                                tma_load_2d(a_dst + j * MN_BOX_BYTES, &tma_a, &full_bar[stage], tc.m0 + j * 64, kel);
+                        }
                     } else {
-                        tma_load_2d(a_dst, &tma_a, &full_bar[stage], kel, tc.m0);
+                        if constexpr (kShareA)     // tensor map box = BM/CL rows
+                            tma_load_2d_mcast(a_dst + crank * (A_STAGE_BYTES / CL), &tma_a, &full_bar[stage], kel,
+                                              tc.m0 + crank * (BM / CL), kMask);
+                        else
+                            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kel, tc.m0);
                     }
                     if constexpr (P::B_MN) {
+                        constexpr int nb = BN / 64 / (kShareB ? CL : 1);
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_load_2d(b_dst + j * MN_BOX_BYTES, &tma_b, &full_bar[stage], tc.n0 + j * 64, kel);
+                        for (int jj = 0; jj < nb; ++jj) {
+                            const int j = kShareB ? crank * nb + jj : jj;
+                            if constexpr (kShareB)
+                                tma_load_2d_mcast(b_dst + j * MN_BOX_BYTES, &tma_b, &full_bar[stage], tc.n0 + j * 64, kel, kMask);
+                            else
+                                tma_load_2d(b_dst + j * MN_BOX_BYTES, &tma_b, &full_bar[stage], tc.n0 + j * 64, kel);
+                        }
                     } else {
-                        tma_load_2d(b_dst, &tma_b, &full_bar[stage], kel, tc.n0);
+                        if constexpr (kShareB)     // tensor map box = BN/CL rows
+                            tma_load_2d_mcast(b_dst + crank * (B_STAGE_BYTES / CL), &tma_b, &full_bar[stage], kel,
+                                              tc.n0 + crank * (BN / CL), kMask);
+                        else
+                            tma_load_2d(b_dst, &tma_b, &full_bar[stage], kel, tc.n0);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -155,7 +187,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
             uint32_t stage = 0, phase = 0;
             int tl = 0;
-            for (int t = blockIdx.x; t < prm.num_tiles; t += gridDim.x, ++tl) {
+            for (int t = first_tile; t < prm.num_tiles; t += tile_stride, ++tl) {
                 const TileCoord tc = P::tile(prm, t);
                 const int acc = tl & 1;
                 const uint32_t acc_phase = (tl >> 1) & 1;
@@ -177,7 +209,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * dc.b_kstep, dc.b_lbo, dc.b_sbo);
                         umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc > tc.k0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs retire
+                    // smem slot reusable once these MMAs retire (in every CTA that multicasts into it)
+                    if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], kMask);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full_bar[acc]);     // accumulator complete -> epilogue
@@ -190,7 +224,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int half = ew >> 2;                      // which 128-column half of the accumulator
         uint8_t* stage_buf = sEpi + ew * EPI_STAGE_BYTES;
         int tl = 0;
-        for (int t = blockIdx.x; t < prm.num_tiles; t += gridDim.x, ++tl) {
+        for (int t = first_tile; t < prm.num_tiles; t += tile_stride, ++tl) {
             const TileCoord tc = P::tile(prm, t);
             const int acc = tl & 1;
             const uint32_t acc_phase = (tl >> 1) & 1;
@@ -206,7 +240,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
+    else __syncthreads();
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();

@@ -64,7 +64,7 @@ class FakeKernels:
     def forward(self, xn, wn, labels, B, n, d, s, kind, m2, m3, thr, E, n_pad, part_sum, tgt_raw, tgt_e, tgt_z):
         raw = xn[:B].float() @ wn[:n].float().t()
         cl = raw.clamp(-1, 1)
-        keep = raw.abs() <= 1
+        keep = torch.ones_like(raw, dtype=torch.bool)   # the clamp gate is applied on the target column only (prepare)
         rows = torch.nonzero(labels[:B] >= 0).reshape(-1)
         cols = labels[rows].long()
         if thr > 0:
