@@ -7,8 +7,8 @@ Importing the package loads (building it first if needed) the CUDA library; ther
 from . import _lib                                    # noqa: F401  (fails loudly if the extension is unavailable)
 from .arcface import ArcFace, CosFace, CombinedMarginLoss
 from .partial_fc import PartialFC, PartialFCAdamW, shard_range
-from .eval import pair_score, performance_roc, performance_acc, kfold_accuracy
+from .eval import pair_score, cross_score, performance_roc, performance_acc, kfold_accuracy
 
 __all__ = ["ArcFace", "CosFace", "CombinedMarginLoss", "PartialFC", "PartialFCAdamW", "shard_range", "pair_score",
-           "performance_roc", "performance_acc", "kfold_accuracy"]
+           "cross_score", "performance_roc", "performance_acc", "kfold_accuracy"]
 __version__ = "0.1.0"

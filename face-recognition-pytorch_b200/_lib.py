@@ -62,6 +62,7 @@ _SIGS = {
                             c_float, p, p, p]),
     "pfc_eval_hist_bins": (c_int, []),
     "fr_pair_score": (c_int, [p, p, p, c_int, c_int, p, p, p, p, p]),
+    "fr_cross_score": (c_int, [p, p, c_int, c_int, p, p, p, p, p]),
     "fr_roc": (c_int, [p, p, c_int, c_int, p, p]),
     "fr_acc_counts": (c_int, [p, p, c_int, c_double, p, p]),
     "fr_kfold_acc": (c_int, [p, p, c_int, c_int, c_int, c_double, p, p, p, p]),

@@ -59,6 +59,44 @@ pair_score_kernel(const float* __restrict__ e1, const float* __restrict__ e2, co
     }
 }
 
+// cross_score (utils/eval.py:102-137): every pair j < i of one embedding set, pair index l = i(i-1)/2 + j.
+// One thread per pair inside a 32x32 tile; rows are staged through shared memory in 32-float chunks and each
+// thread accumulates its pair in fp64 in k order, i.e. the reference's sequential loop, bit for bit.
+__global__ void __launch_bounds__(1024)
+cross_score_kernel(const float* __restrict__ e, const long long* __restrict__ labels, int N, int d,
+                   double* __restrict__ scores, double* __restrict__ label_list, unsigned long long* __restrict__ hist_g,
+                   unsigned long long* __restrict__ hist_i) {
+    const int ti0 = blockIdx.y * 32, tj0 = blockIdx.x * 32;
+    if (tj0 > ti0) return;                       // only tiles touching the lower triangle
+    __shared__ float sa[32][33], sb[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // tx -> j, ty -> i
+    const int i = ti0 + ty, j = tj0 + tx;
+    double acc = 0.0;
+    for (int k0 = 0; k0 < d; k0 += 32) {
+        // row (ty) of each tile, column k0 + tx
+        const int k = k0 + tx;
+        sa[ty][tx] = (ti0 + ty < N && k < d) ? e[static_cast<size_t>(ti0 + ty) * d + k] : 0.f;
+        sb[ty][tx] = (tj0 + ty < N && k < d) ? e[static_cast<size_t>(tj0 + ty) * d + k] : 0.f;
+        __syncthreads();
+        const int kn = min(32, d - k0);
+        for (int kk = 0; kk < kn; ++kk) {
+            const double dd = (double)(sb[tx][kk] - sa[ty][kk]);   // embeddings[j,k] - embeddings[i,k], fp32
+            acc += dd * dd;
+        }
+        __syncthreads();
+    }
+    if (i < N && j < i) {
+        const double score = 1.0 - acc / 4.0;
+        const size_t l = static_cast<size_t>(i) * (i - 1) / 2 + j;
+        scores[l] = score;
+        const bool same = labels[j] == labels[i];
+        label_list[l] = same ? 1.0 : 0.0;
+        long long idx = (long long)((1e5 - 1.0) * score);
+        if (idx < 0) idx += HIST_BINS;
+        if (idx >= 0 && idx < HIST_BINS) atomicAdd((same ? hist_g : hist_i) + idx, 1ull);
+    }
+}
+
 struct RocOut {
     int eer_threshold;
     int pad;
@@ -293,6 +331,18 @@ int fr_kfold_acc(const double* dist, const uint8_t* labels, int N, int folds, in
     cudaStream_t stream = (cudaStream_t)stream_;
     kfold_count_kernel<<<n_thr, 256, 0, stream>>>(dist, labels, N, folds, n_thr, step, correct_ws);
     kfold_pick_kernel<<<1, 64, 0, stream>>>(correct_ws, N, folds, n_thr, acc, best_idx);
+    return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
+}
+
+int fr_cross_score(const float* e, const long long* labels, int N, int d, double* scores, double* label_list,
+                   unsigned long long* hist_g, unsigned long long* hist_i, void* stream_) {
+    if (N < 0 || d <= 0) return PFC_ERR_SHAPE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (cudaMemsetAsync(hist_g, 0, sizeof(unsigned long long) * HIST_BINS, stream) != cudaSuccess) return PFC_ERR_CUDA;
+    if (cudaMemsetAsync(hist_i, 0, sizeof(unsigned long long) * HIST_BINS, stream) != cudaSuccess) return PFC_ERR_CUDA;
+    if (N < 2) return PFC_OK;
+    const int t = (N + 31) / 32;
+    cross_score_kernel<<<dim3(t, t), 1024, 0, stream>>>(e, labels, N, d, scores, label_list, hist_g, hist_i);
     return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 

@@ -1,2 +1,2 @@
 # replaces utils/eval.py of the reference
-from face_recognition_pytorch_b200.eval import pair_score, performance_roc, performance_acc, kfold_accuracy  # noqa: F401
+from face_recognition_pytorch_b200.eval import pair_score, cross_score, performance_roc, performance_acc, kfold_accuracy  # noqa: F401

@@ -45,6 +45,26 @@ def pair_score(embedding_1, embedding_2, labels, metric="euclidean", min_level=3
     return out
 
 
+def cross_score(embeddings, labels, metric="euclidean"):
+    """utils/eval.py:102-137 -> (hist_genuine, hist_imposter, score_list, label_list) over all pairs j < i."""
+    assert metric in ["euclidean", "cosine"], "Invalid metric !!!"
+    e = _to_dev(embeddings, torch.float32)
+    lab = _to_dev(np.asarray(labels).astype(np.int64), torch.int64)
+    N = e.shape[0]
+    npairs = int((N - 1) * N / 2)
+    bins = K.hist_bins()
+    scores = torch.zeros(npairs, dtype=torch.float64, device=e.device)
+    label_list = torch.zeros(npairs, dtype=torch.float64, device=e.device)
+    hg = torch.empty(bins, dtype=torch.int64, device=e.device)
+    hi = torch.empty(bins, dtype=torch.int64, device=e.device)
+    if metric == "euclidean":
+        K.cross_score(e, lab, scores, label_list, hg, hi)
+    else:
+        hg.zero_(); hi.zero_()
+    return (hg.cpu().numpy().astype(np.float64), hi.cpu().numpy().astype(np.float64), scores.cpu().numpy(),
+            label_list.cpu().numpy())
+
+
 def roc_sweep(hist_genuine, hist_imposter, min_level=3, max_level=9):
     """The numbers behind performance_roc: EER threshold / value and FRR @ FAR=1e-k."""
     hg = _to_dev(np.asarray(hist_genuine).astype(np.int64), torch.int64)

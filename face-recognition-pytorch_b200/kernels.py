@@ -203,6 +203,13 @@ def pair_score(e1, e2, labels_u8, scores, dist, hist_g, hist_i):
                             _p(hist_g, I64), _p(hist_i, I64), _stream()), "fr_pair_score")
 
 
+@_timed("fr_cross_score")
+def cross_score(e, labels_i64, scores, label_list, hist_g, hist_i):
+    N, d = e.shape
+    check(lib.fr_cross_score(_p(e, F32), _p(labels_i64, I64), N, d, _p(scores, F64), _p(label_list, F64),
+                             _p(hist_g, I64), _p(hist_i, I64), _stream()), "fr_cross_score")
+
+
 @_timed("fr_roc")
 def roc(hist_g, hist_i, min_level, max_level, out_bytes):
     check(lib.fr_roc(_p(hist_g, I64), _p(hist_i, I64), min_level, max_level, _p(out_bytes, U8), _stream()), "fr_roc")

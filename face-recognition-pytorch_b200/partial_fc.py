@@ -240,8 +240,14 @@ class _PartialFCBase(torch.nn.Module):
         self._x_local = x
         K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
         if W > 1:
-            distributed.all_gather_into_tensor(ws.xn_all, ws.xn_local)            # :182 (bf16: half the bytes)
-            distributed.all_gather_into_tensor(ws.labels_all, labels_in)          # :183
+            if distributed.get_backend() == "nccl":
+                # one NCCL launch for both gathers (ncclGroupStart/End); every collective of the step is latency-bound
+                with distributed._coalescing_manager(device=x.device):
+                    distributed.all_gather_into_tensor(ws.xn_all, ws.xn_local)    # :182 (bf16: half the bytes)
+                    distributed.all_gather_into_tensor(ws.labels_all, labels_in)  # :183
+            else:
+                distributed.all_gather_into_tensor(ws.xn_all, ws.xn_local)
+                distributed.all_gather_into_tensor(ws.labels_all, labels_in)
             labels_all = ws.labels_all
         else:
             labels_all = labels_in
@@ -278,7 +284,7 @@ class _PartialFCBase(torch.nn.Module):
         g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
                            ws.coef, ws.E, n_pad)
-        dx = None
+        dx, rs_work = None, None
         if x_in.requires_grad:
             splits = K.dx_splits(B, n, d)
             K.backward_dx(ws.E, n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
@@ -287,16 +293,21 @@ class _PartialFCBase(torch.nn.Module):
                 K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
             else:
                 K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
-                distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM)   # :505-519
-                K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)    # :521
+                # :505-519 -- issued asynchronously so that it overlaps the rank-local dW GEMM + update below
+                rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
+                                                            async_op=True)
         K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, ws.dwn)
         w = self.weight_activated.data
+        dw = None
         if self.fused_optimizer:
             self._fused_step(w, n, d)
-            return dx, None
-        dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
-        K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
-        self._wn_valid = False            # an external optimizer is about to change the weights
+        else:
+            dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
+            K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
+            self._wn_valid = False        # an external optimizer is about to change the weights
+        if rs_work is not None:
+            rs_work.wait()
+            K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)        # :521
         return dx, dw
 
     def _fused_step(self, w, n, d):

@@ -144,6 +144,10 @@ typedef struct {
 int pfc_eval_hist_bins(void);
 int fr_pair_score(const float* e1, const float* e2, const uint8_t* labels, int N, int d, double* scores, double* dist,
                   unsigned long long* hist_genuine, unsigned long long* hist_imposter, void* stream);
+/* fr_cross_score (utils/eval.py:102-137): all pairs j < i of ONE embedding set; scores / label_list have
+ * N(N-1)/2 entries in the reference's order l = i(i-1)/2 + j; genuine when labels[j] == labels[i] (int64 ids). */
+int fr_cross_score(const float* e, const long long* labels, int N, int d, double* scores, double* label_list,
+                   unsigned long long* hist_genuine, unsigned long long* hist_imposter, void* stream);
 int fr_roc(const unsigned long long* hist_genuine, const unsigned long long* hist_imposter, int min_level,
            int max_level, void* roc_out /* fr_roc_out_t, device */, void* stream);
 int fr_acc_counts(const double* scores, const uint8_t* labels, int N, double threshold, unsigned long long* fr_fa,

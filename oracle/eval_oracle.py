@@ -24,6 +24,24 @@ def pair_score(e1: np.ndarray, e2: np.ndarray, labels: np.ndarray):
     return hist_g, hist_i, score
 
 
+def cross_score(embeddings: np.ndarray, labels: np.ndarray):
+    """utils/eval.py:102-137: all pairs j < i, pair index l = i(i-1)/2 + j, sequential fp64 accumulation over k."""
+    e = embeddings.astype(np.float32)
+    N = e.shape[0]
+    ii, jj = np.tril_indices(N, -1)                      # rows i > j, ordered by i then j == the reference's l
+    diff = (e[jj] - e[ii]).astype(np.float64)
+    acc = np.zeros(len(ii))
+    for k in range(e.shape[1]):                          # same summation order as the reference loop
+        acc += diff[:, k] * diff[:, k]
+    score = 1.0 - acc / 4.0
+    same = np.asarray(labels)[jj] == np.asarray(labels)[ii]
+    idx = np.trunc((1e5 - 1.0) * score).astype(np.int64)
+    idx = np.where(idx < 0, idx + HIST_BINS, idx)
+    hist_g = np.bincount(idx[same], minlength=HIST_BINS).astype(np.float64)
+    hist_i = np.bincount(idx[~same], minlength=HIST_BINS).astype(np.float64)
+    return hist_g, hist_i, score, same.astype(np.float64)
+
+
 def roc_sweep(hist_g: np.ndarray, hist_i: np.ndarray, min_level: int = 3, max_level: int = 9):
     """The numbers behind performance_roc (utils/eval.py:7-51, :140-144).
 

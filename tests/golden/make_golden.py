@@ -136,7 +136,7 @@ def make_margin_case():
 
 def make_eval_case():
     sys.path.insert(0, REF)
-    from utils.eval import pair_score, performance_roc, performance_acc
+    from utils.eval import pair_score, performance_roc, performance_acc, cross_score
     out = {}
     # small case with full inputs
     rng = np.random.default_rng(11)
@@ -154,6 +154,14 @@ def make_eval_case():
     out.update(small_e1=e1, small_e2=e2, small_lab=lab, small_scores=sc, small_hg_nz=np.nonzero(hg)[0],
                small_hg_val=hg[np.nonzero(hg)[0]], small_hi_nz=np.nonzero(hi)[0], small_hi_val=hi[np.nonzero(hi)[0]],
                small_th=np.array(th), small_acc=np.array(acc), small_report=np.array(rep))
+    # cross_score: all pairs of a small labelled set
+    rngc = np.random.default_rng(21)
+    ce = rngc.standard_normal((70, 64)).astype(np.float32)
+    ce /= np.linalg.norm(ce, axis=1, keepdims=True)
+    clab = rngc.integers(0, 9, 70)
+    chg, chi, csc, clb = cross_score(ce, clab)
+    out.update(cross_e=ce, cross_lab=clab, cross_scores=csc, cross_labels=clb, cross_hg_nz=np.nonzero(chg)[0],
+               cross_hg_val=chg[np.nonzero(chg)[0]], cross_hi_nz=np.nonzero(chi)[0], cross_hi_val=chi[np.nonzero(chi)[0]])
     # cfg-5: inputs are regenerated from the seed, only results are stored
     a, b, lab5 = eval_inputs_cfg5()
     hg, hi, sc = pair_score(a, b, lab5)

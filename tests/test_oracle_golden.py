@@ -111,3 +111,11 @@ def test_kfold_protocol_properties():
     d2 = np.where(lab, 0.5, 2.5)
     acc2, _ = eo.kfold_accuracy(d2, lab)
     assert np.all(acc2 == 1.0)
+
+
+def test_cross_score_matches_reference():
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "eval.npz"))
+    hg, hi, sc, lb = eo.cross_score(z["cross_e"], z["cross_lab"])
+    assert np.array_equal(sc, z["cross_scores"])            # same sequential fp64 accumulation: bit-identical
+    assert np.array_equal(lb, z["cross_labels"])
+    assert np.array_equal(hg, _hist(z, "cross", "hg")) and np.array_equal(hi, _hist(z, "cross", "hi"))
