@@ -71,3 +71,25 @@ def test_eval_small_golden_bit_exact():
     # empty input
     hg0, hi0, sc0 = pfc.pair_score(np.zeros((0, 64), np.float32), np.zeros((0, 64), np.float32), np.zeros(0, bool))
     assert hg0.sum() == 0 and sc0.shape == (0,)
+
+
+def test_cross_score_golden_bit_exact():
+    import os
+    import numpy as np
+    import face_recognition_pytorch_b200 as pfc
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "eval.npz"))
+    hg, hi, sc, lb = pfc.cross_score(z["cross_e"], z["cross_lab"])
+    assert np.array_equal(sc, z["cross_scores"]) and np.array_equal(lb, z["cross_labels"])
+    ref_hg = np.zeros(100001); ref_hg[z["cross_hg_nz"]] = z["cross_hg_val"]
+    ref_hi = np.zeros(100001); ref_hi[z["cross_hi_nz"]] = z["cross_hi_val"]
+    assert np.array_equal(hg, ref_hg) and np.array_equal(hi, ref_hi)
+    # odd sizes / d not a multiple of 32
+    rng = np.random.default_rng(3)
+    e = rng.standard_normal((45, 50)).astype(np.float32)
+    lab = rng.integers(0, 4, 45)
+    from oracle import eval_oracle as eo
+    a = pfc.cross_score(e, lab)
+    b = eo.cross_score(e, lab)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
