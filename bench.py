@@ -176,6 +176,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="run the fused update after the dX GEMM, not under it")
     ap.add_argument("--unfused", action="store_true", help="hand dW to torch.optim.SGD instead of the fused update")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -202,7 +203,7 @@ def main():
     w_shard, xs, ls = synth(rank, world, n_data, dev)
     b = GLOBAL_BATCH // world
     conf = types.SimpleNamespace(emd_size=EMB, sample_rate=1.0, mixed_precision=False, loss_s=S, loss_m=M,
-                                 fused_optimizer=not args.unfused)
+                                 fused_optimizer=not args.unfused, overlap_update=not (args.unfused or args.no_overlap))
     head = pfc.PartialFC(conf, C_CLASSES)
     head.load_state_dict({"weight": w_shard})
     head = head.train().cuda()
@@ -213,8 +214,10 @@ def main():
     l_dev = [l.to(dev) for l in ls]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    static_x = x_dev[0].detach().clone().requires_grad_(True)
-    static_l = l_dev[0].clone()
+    # two static input slots / two graphs: with overlap_update the normalised shard ping-pongs between two buffers,
+    # so consecutive steps are two different graphs that are replayed alternately
+    static_x = [x_dev[0].detach().clone().requires_grad_(True) for _ in range(2)]
+    static_l = [l_dev[0].clone() for _ in range(2)]
 
     def step_eager(x, lab):
         loss = head(x, lab, opt)
@@ -234,33 +237,49 @@ def main():
         step_eager(x_dev[i % n_data], l_dev[i % n_data])
     torch.cuda.synchronize()
 
-    graph = None
+    graphs = None
+    ws = head._ws
+    wn_ptr0 = ws.wn.data_ptr()
+
+    def parity():
+        return 0 if ws.wn.data_ptr() == wn_ptr0 else 1
+
     if not args.no_graph and not args.unfused:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):
-                    static_x.grad = None
-                    step_eager(static_x, static_l)
+                for k in range(2):
+                    static_x[k].grad = None
+                    step_eager(static_x[k], static_l[k])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            static_x.grad = None
-            with torch.cuda.graph(graph):
-                static_loss = step_eager(static_x, static_l)
+            graphs = {}
+            for _ in range(2):
+                k = parity()
+                g = torch.cuda.CUDAGraph()
+                static_x[k].grad = None
+                with torch.cuda.graph(g):
+                    step_eager(static_x[k], static_l[k])    # capturing flips the ping-pong on the host side only
+                graphs[k] = g
+                if ws.wn_alt is None:                       # no ping-pong: one graph serves every step
+                    graphs[1 - k] = g
+                    break
             torch.cuda.synchronize()
         except Exception as e:   # report, fall back to eager launches (still the CUDA path)
             if rank == 0:
                 print(f"# CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
-            graph = None
+            graphs = None
             torch.cuda.synchronize()
 
     def run_step(i):
-        if graph is not None:
-            static_x.data.copy_(x_dev[i % n_data].data)
-            static_l.copy_(l_dev[i % n_data])
-            graph.replay()
+        if graphs is not None:
+            k = parity()
+            static_x[k].data.copy_(x_dev[i % n_data].data)
+            static_l[k].copy_(l_dev[i % n_data])
+            graphs[k].replay()
+            if ws.wn_alt is not None:
+                ws.wn, ws.wn_alt = ws.wn_alt, ws.wn         # what the replayed step did on the device
         else:
             x_dev[i % n_data].grad = None
             step_eager(x_dev[i % n_data], l_dev[i % n_data])
@@ -374,7 +393,8 @@ def main():
         "config": {"workload": "configs[1]: PartialFC C=93431 d=512 global_batch=1024 sample_rate=1.0 s=64 m=0.5, "
                                "fwd+bwd+" + ("torch SGD step" if args.unfused else "fused SGD update"),
                    "classes_per_gpu": nl, "local_batch": b, "parallelism": f"class-sharded x{world}",
-                   "launch": "cuda-graph replay" if graph is not None else "eager",
+                   "launch": "cuda-graph replay" if graphs is not None else "eager",
+                   "overlap_update": bool(conf.overlap_update),
                    "l2": "256 MB buffer written between timed steps (untimed); per-step CUDA events summed"},
         "roofline": roof,
         "step_roofline": {"bound": "tensor", "achieved": step_tf / world, "peak": pk["tf_burst"], "unit": "TFLOP/s/GPU",

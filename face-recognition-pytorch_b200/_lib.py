@@ -55,9 +55,9 @@ _SIGS = {
     "pfc_backward_prepare": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, c_int, p]),
     "pfc_backward_dx": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dx_finalize": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p]),
-    "pfc_backward_dw": (c_int, [p, c_int, p, c_int, c_int, c_int, p, p]),
+    "pfc_backward_dw": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dw_finalize": (c_int, [p, p, p, c_int, c_int, c_float, p, p]),
-    "pfc_dw_sgd": (c_int, [p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, p, p, p]),
+    "pfc_dw_sgd": (c_int, [p, c_int, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, p, p, p]),
     "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int,
                             c_float, p, p, p]),
     "pfc_eval_hist_bins": (c_int, []),

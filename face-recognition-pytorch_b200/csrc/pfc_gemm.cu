@@ -165,6 +165,7 @@ struct StoreParams {
     int ld;                 // row stride of out (elements)
     size_t split_stride;    // elements between split slabs
     float* out;
+    int out_bf16;           // 1: `out` is a bf16 matrix (same ld in elements); used for the dWn spill in fused mode
     DescCfg dc;             // descriptor geometry (runtime so that tools/gpu_probe.py can try alternatives)
 };
 
@@ -197,6 +198,28 @@ struct StorePolicy {
                                                     int half, int lane, uint8_t* stage) {
         const int row0 = tc.m0 + quarter * 32;
         const int rows_valid = min(32, max(0, p.rows_valid - row0));
+        if (p.out_bf16) {
+            // bf16 spill: two 32-column chunks make one 128-byte line per row
+            __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row0) * p.ld;
+#pragma unroll 1
+            for (int cc = 0; cc < EPI_COLS / 64; ++cc) {
+                const int col64 = tc.n0 + half * EPI_COLS + cc * 64;
+                if (col64 >= p.cols_valid) break;        // warp-uniform
+                uint32_t o[32];
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + cc * 64 + h2 * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        o[h2 * 16 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                }
+                warp_store_rows_128B(stage, lane, o, reinterpret_cast<uint8_t*>(ob + col64),
+                                     static_cast<size_t>(p.ld) * 2, rows_valid, min(128, (p.cols_valid - col64) * 2));
+            }
+            return;
+        }
         float* obase = p.out + static_cast<size_t>(tc.aux) * p.split_stride + static_cast<size_t>(row0) * p.ld;
 #pragma unroll 1
         for (int c = 0; c < EPI_COLS / 32; ++c) {
@@ -395,13 +418,15 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     p.rows_valid = B; p.cols_valid = d; p.ld = d;
     p.split_stride = static_cast<size_t>(B) * d;
     p.out = partial;
+    p.out_bf16 = 0;
     p.dc = store_desc_cfg(false);
     return want_cluster(p.m_tiles) ? launch_gemm_cl<StorePolicy<false>, 2>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream))
                                    : launch_gemm_cl<StorePolicy<false>, 1>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // dwn[n][d] (fp32) = E'^T . Xs,   Xs = c_i * Xn_i (bf16, [B, d])
-int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int d, float* dwn, void* stream) {
+int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int d, void* dwn, int dwn_bf16,
+                    void* stream) {
     if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 8) return PFC_ERR_SHAPE;
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, E, n, B, n_pad, 64, BK);       // A: E' [B(K), n(M)] MN-major boxes 64(M) x 64(K)
@@ -418,7 +443,8 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.n_fastest = 1;
     p.rows_valid = n; p.cols_valid = d; p.ld = d;
     p.split_stride = 0;
-    p.out = dwn;
+    p.out = reinterpret_cast<float*>(dwn);
+    p.out_bf16 = dwn_bf16 ? 1 : 0;
     p.dc = store_desc_cfg(true);
     return want_cluster(p.n_tiles) ? launch_gemm_cl<StorePolicy<true>, 2>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream))
                                    : launch_gemm_cl<StorePolicy<true>, 1>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));

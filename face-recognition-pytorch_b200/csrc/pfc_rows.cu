@@ -326,9 +326,9 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
 // Specialised fused SGD row kernel for d = 128 * NV: all three input streams (dwn, w, momentum) are requested
 // up front (12 x 16-byte loads per lane in flight at d = 512) so a warp is never waiting on a dependent phase,
 // arrays are sized exactly (no predicated dead registers), 4 rows per CTA for occupancy.
-template <int NV>
+template <int NV, bool kGradBf16>
 __global__ void __launch_bounds__(128)
-dw_sgd_rows_kernel(const float* __restrict__ dwn, float* __restrict__ w, float* __restrict__ mom,
+dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* __restrict__ mom,
                    const float* inv_norm_w, int rows, float lr, float momentum, float wd, float inv_grad_scale,
                    __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
     constexpr int d = 128 * NV;
@@ -338,7 +338,16 @@ dw_sgd_rows_kernel(const float* __restrict__ dwn, float* __restrict__ w, float* 
     const size_t base = static_cast<size_t>(row) * d;
     float4 g[NV], wv[NV], mv[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) g[j] = ld4_stream(dwn + base + 4 * (lane + 32 * j));
+    for (int j = 0; j < NV; ++j) {
+        if constexpr (kGradBf16) {
+            uint2 r;
+            const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(dwn_) + base + 4 * (lane + 32 * j);
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(gp));
+            g[j] = unpack4_bf16(r);
+        } else {
+            g[j] = ld4_stream(static_cast<const float*>(dwn_) + base + 4 * (lane + 32 * j));
+        }
+    }
 #pragma unroll
     for (int j = 0; j < NV; ++j) wv[j] = ld4(w + base + 4 * (lane + 32 * j));
 #pragma unroll
@@ -379,11 +388,15 @@ dw_sgd_rows_kernel(const float* __restrict__ dwn, float* __restrict__ w, float* 
 }
 
 template <int NV>
-static void launch_dw_sgd_rows(const float* dwn, float* w, float* mom, const float* inv_norm_w, int rows, float lr,
-                               float momentum, float wd, float igs, __nv_bfloat16* wn_next, float* inv_next,
+static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom, const float* inv_norm_w, int rows,
+                               float lr, float momentum, float wd, float igs, __nv_bfloat16* wn_next, float* inv_next,
                                cudaStream_t st) {
-    dw_sgd_rows_kernel<NV><<<(rows + 3) / 4, 128, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd, igs,
-                                                            wn_next, inv_next);
+    if (bf16)
+        dw_sgd_rows_kernel<NV, true><<<(rows + 3) / 4, 128, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd,
+                                                                      igs, wn_next, inv_next);
+    else
+        dw_sgd_rows_kernel<NV, false><<<(rows + 3) / 4, 128, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd,
+                                                                       igs, wn_next, inv_next);
 }
 
 // dst[r] = src[index[r]]  /  dst[index[r]] = src[r]   (nets/PartialFC.py:120-121, :142-143), up to 3 tensors at once
@@ -505,31 +518,37 @@ int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, i
     return check_launch();
 }
 
-int pfc_dw_sgd(const float* dwn, float* w, float* mom, const float* inv_norm_w, int rows, int d, float lr,
+int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float* inv_norm_w, int rows, int d, float lr,
                float momentum, float weight_decay, float inv_grad_scale, void* wn_next, float* inv_norm_next,
                void* stream) {
     if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
     if (d % 128 == 0 && mom != nullptr) {
         cudaStream_t st = (cudaStream_t)stream;
         __nv_bfloat16* wnn = reinterpret_cast<__nv_bfloat16*>(wn_next);
+        const bool bf = dwn_bf16 != 0;
+#define PFC_SGD_CASE(NV) \
+    launch_dw_sgd_rows<NV>(dwn, bf, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, \
+                           inv_norm_next, st)
         switch (d / 128) {
-            case 1: launch_dw_sgd_rows<1>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
-            case 2: launch_dw_sgd_rows<2>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
-            case 3: launch_dw_sgd_rows<3>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
-            case 4: launch_dw_sgd_rows<4>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
-            case 5: launch_dw_sgd_rows<5>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
-            case 6: launch_dw_sgd_rows<6>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
-            case 7: launch_dw_sgd_rows<7>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
-            default: launch_dw_sgd_rows<8>(dwn, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, inv_norm_next, st); break;
+            case 1: PFC_SGD_CASE(1); break;
+            case 2: PFC_SGD_CASE(2); break;
+            case 3: PFC_SGD_CASE(3); break;
+            case 4: PFC_SGD_CASE(4); break;
+            case 5: PFC_SGD_CASE(5); break;
+            case 6: PFC_SGD_CASE(6); break;
+            case 7: PFC_SGD_CASE(7); break;
+            default: PFC_SGD_CASE(8); break;
         }
+#undef PFC_SGD_CASE
         return check_launch();
     }
+    if (dwn_bf16) return PFC_ERR_SHAPE;   // the generic row kernel reads an fp32 gradient
     OptArgs o = {};
     o.kind = OPT_SGD;
     o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.inv_grad_scale = inv_grad_scale;
     dw_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        dwn, w, inv_norm_w, rows, d, o, nullptr, mom, nullptr, reinterpret_cast<__nv_bfloat16*>(wn_next),
-        inv_norm_next);
+        static_cast<const float*>(dwn), w, inv_norm_w, rows, d, o, nullptr, mom, nullptr,
+        reinterpret_cast<__nv_bfloat16*>(wn_next), inv_norm_next);
     return check_launch();
 }
 

@@ -170,8 +170,10 @@ def dx_finalize(partial, splits, coef, x, inv_norm, scale, rows, rows_total, d, 
 
 @_timed("pfc_backward_dw")
 def backward_dw(E, n_pad, xs, B, n, d, dwn):
-    check(lib.pfc_backward_dw(_p(E, BF16), n_pad, _p(xs, BF16), B, n, d, _p(dwn, F32), _stream()),
-          "pfc_backward_dw")
+    """dwn: fp32 [n,d], or bf16 [n,d] (fused-SGD spill)."""
+    is_bf16 = dwn.dtype == BF16
+    check(lib.pfc_backward_dw(_p(E, BF16), n_pad, _p(xs, BF16), B, n, d, _p(dwn, BF16 if is_bf16 else F32),
+                              int(is_bf16), _stream()), "pfc_backward_dw")
 
 
 @_timed("pfc_dw_finalize")
@@ -182,9 +184,10 @@ def dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, dw):
 
 @_timed("pfc_dw_sgd")
 def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, inv_grad_scale, wn_next, inv_norm_next):
-    check(lib.pfc_dw_sgd(_p(dwn, F32), _p(w, F32), _p(mom, F32), _p(inv_norm_w, F32), rows, d, lr, momentum,
-                         weight_decay, inv_grad_scale, _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()),
-          "pfc_dw_sgd")
+    is_bf16 = dwn.dtype == BF16
+    check(lib.pfc_dw_sgd(_p(dwn, BF16 if is_bf16 else F32), int(is_bf16), _p(w, F32), _p(mom, F32),
+                         _p(inv_norm_w, F32), rows, d, lr, momentum, weight_decay, inv_grad_scale, _p(wn_next, BF16),
+                         _p(inv_norm_next, F32), _stream()), "pfc_dw_sgd")
 
 
 @_timed("pfc_dw_adam")

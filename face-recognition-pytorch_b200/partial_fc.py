@@ -19,6 +19,9 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       weight_activated.grad = None so optimizer.step() skips it.  Hyper-parameters are re-read from
       optimizer.param_groups[-1] every step (the scheduler mutates lr, utils/scheduler.py:87-88).  Not valid together
       with a GradScaler (inf-skipping cannot be honoured); the un-fused default is.
+  conf.overlap_update (bool, default False; needs fused_optimizer): run the fused update on a side stream underneath
+      the dX GEMM.  The normalised shard is then double-buffered and the two buffers swap roles every step, so a
+      CUDA graph of the step must capture an EVEN number of steps (bench.py captures two).
 """
 import collections
 from typing import Callable
@@ -55,6 +58,7 @@ class _Workspace:
         self.labels_local = z(B, dt=i32)
         self.labels_act = z(B, dt=i32) if sampled else self.labels_local
         self.wn = z(n_max, d, dt=bf16)
+        self.wn_alt = None                        # second buffer, allocated when conf.overlap_update is set
         self.inv_w = z(n_max)
         self.E = z(B * self.n_pad_max, dt=bf16)
         self.part_sum = z(K.num_class_tiles(n_max) * self.B_pad)
@@ -69,6 +73,7 @@ class _Workspace:
         self.dxn_all = z(B, d) if W > 1 else None
         self.dxn_local = z(b, d) if W > 1 else None
         self.dwn = z(n_max, d)
+        self.dwn_bf16 = z(n_max, d, dt=bf16)      # fused-SGD mode spills the un-normalised dW in bf16
         if sampled:
             self.perm = z(nl)
             self.index = z(n_max, dt=i64)
@@ -110,6 +115,7 @@ class _PartialFCBase(torch.nn.Module):
         self.sample_rate: float = conf.sample_rate
         self.fp16 = conf.mixed_precision           # kept for interface parity; the kernels always run bf16-in / fp32-acc
         self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
+        self.overlap_update = bool(getattr(conf, "overlap_update", False))
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
         self.last_batch_size: int = 0
@@ -143,6 +149,7 @@ class _PartialFCBase(torch.nn.Module):
         self._fused_state = None        # optimizer state for the fused step when sample_rate == 1
         self._n = self.num_local        # active classes this step
         self._opt_args = None
+        self._side_stream = None
 
     # ------------------------------------------------------------------ reference-visible helpers
     def _optimizer_state_names(self):
@@ -202,6 +209,8 @@ class _PartialFCBase(torch.nn.Module):
         n_max = self.num_local if not sampled else max(self.num_sample, min(B, self.num_local))
         if self._ws is None or self._ws.b != b or self._ws.xn_local.device != dev:
             self._ws = _Workspace(dev, b, self.world_size, n_max, self.num_local, d, sampled)
+            if self.fused_optimizer and self.overlap_update:
+                self._ws.wn_alt = torch.zeros_like(self._ws.wn)
             self._wn_valid = False
             if sampled:
                 k = 1 + len(self._state_names)
@@ -284,33 +293,51 @@ class _PartialFCBase(torch.nn.Module):
         g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
                            ws.coef, ws.E, n_pad)
+        # Rank-local dW first.  With conf.overlap_update its HBM-bound optimizer kernel then runs on a side stream
+        # underneath the tensor-bound dX GEMM (the row kernel needs no shared memory, so its CTAs co-reside with the
+        # GEMM's); it writes next step's normalised rows into the OTHER wn buffer because dX still reads this one.
+        w = self.weight_activated.data
+        spill_bf16 = self.fused_optimizer and self._optimizer_kind == "sgd" and d % 128 == 0
+        dwn = ws.dwn_bf16 if spill_bf16 else ws.dwn
+        K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
+        overlap = self.fused_optimizer and self.overlap_update and w.is_cuda
+        dw, side = None, None
+        wn_now = ws.wn
+        if overlap:
+            cur = torch.cuda.current_stream()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=w.device)
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._fused_step(w, n, d, dwn, ws.wn_alt)
+            ws.wn, ws.wn_alt = ws.wn_alt, ws.wn       # ping-pong: the next forward reads what the update wrote
+        elif not self.fused_optimizer:
+            dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
+            K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
+            self._wn_valid = False        # an external optimizer is about to change the weights
         dx, rs_work = None, None
         if x_in.requires_grad:
             splits = K.dx_splits(B, n, d)
-            K.backward_dx(ws.E, n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
+            K.backward_dx(ws.E, n_pad, wn_now, B, n, d, ws.dx_partial, splits)
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
             if W == 1:
                 K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
             else:
                 K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
-                # :505-519 -- issued asynchronously so that it overlaps the rank-local dW GEMM + update below
+                # :505-519 -- asynchronous: it overlaps the rank-local update below / on the side stream
                 rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
                                                             async_op=True)
-        K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, ws.dwn)
-        w = self.weight_activated.data
-        dw = None
-        if self.fused_optimizer:
-            self._fused_step(w, n, d)
-        else:
-            dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
-            K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
-            self._wn_valid = False        # an external optimizer is about to change the weights
+        if self.fused_optimizer and not overlap:
+            self._fused_step(w, n, d, dwn, ws.wn)     # in place, after the dX GEMM has consumed wn
         if rs_work is not None:
             rs_work.wait()
             K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)        # :521
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         return dx, dw
 
-    def _fused_step(self, w, n, d):
+    def _fused_step(self, w, n, d, dwn, wn_out):
         raise NotImplementedError
 
     # ------------------------------------------------------------------ checkpoint layout (nets/PartialFC.py:210-232)
@@ -366,7 +393,7 @@ class PartialFC(_PartialFCBase):
             raise RuntimeError("fused SGD supports dampening=0, nesterov=False, maximize=False")
         return dict(lr=float(g["lr"]), momentum=float(g["momentum"]), wd=float(g["weight_decay"]))
 
-    def _fused_step(self, w, n, d):
+    def _fused_step(self, w, n, d, dwn, wn_out):
         ws, o = self._ws, self._opt_args
         if self.sample_rate < 1:
             mom = self.weight_activated_mom
@@ -375,7 +402,7 @@ class PartialFC(_PartialFCBase):
                 self._fused_state = torch.zeros_like(w)
                 self.weight_activated_mom = self._fused_state
             mom = self._fused_state
-        K.dw_sgd(ws.dwn, w, mom, ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], 1.0, ws.wn, ws.inv_w)
+        K.dw_sgd(dwn, w, mom, ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], 1.0, wn_out, ws.inv_w)
         self._wn_valid = True             # the update wrote next step's normalised bf16 rows and 1/norm in place
 
 
@@ -413,7 +440,7 @@ class PartialFCAdamW(_PartialFCBase):
         return dict(lr=float(g["lr"]), beta1=float(g["betas"][0]), beta2=float(g["betas"][1]), eps=float(g["eps"]),
                     wd=float(g["weight_decay"]), decoupled=decoupled)
 
-    def _fused_step(self, w, n, d):
+    def _fused_step(self, w, n, d, dwn, wn_out):
         ws, o = self._ws, self._opt_args
         if self.sample_rate < 1:
             m, v = self.weight_activated_exp_avg, self.weight_activated_exp_avg_sq
@@ -424,6 +451,6 @@ class PartialFCAdamW(_PartialFCBase):
             m, v = self._fused_state
             self.step += 1
             step = self.step
-        K.dw_adam(ws.dwn, w, m, v, ws.inv_w, n, d, o["lr"], o["beta1"], o["beta2"], o["eps"], o["wd"], step,
-                  o["decoupled"], 1.0, ws.wn, ws.inv_w)
+        K.dw_adam(dwn, w, m, v, ws.inv_w, n, d, o["lr"], o["beta1"], o["beta2"], o["eps"], o["wd"], step,
+                  o["decoupled"], 1.0, wn_out, ws.inv_w)
         self._wn_valid = True

@@ -114,13 +114,14 @@ int pfc_backward_dx(const void* E_bf16, int n_pad, const void* wn_bf16, int B, i
                     int splits, void* stream);
 int pfc_dx_finalize(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
                     float scale, int rows, int rows_total, int d, float* out, void* stream);
-int pfc_backward_dw(const void* E_bf16, int n_pad, const void* xs_bf16, int B, int n, int d, float* dwn,
+/* dwn_bf16 != 0: dwn is a bf16 [n,d] matrix (halves the spill that pfc_dw_sgd re-reads; fused-SGD mode only). */
+int pfc_backward_dw(const void* E_bf16, int n_pad, const void* xs_bf16, int B, int n, int d, void* dwn, int dwn_bf16,
                     void* stream);
 int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, int rows, int d, float inv_grad_scale,
                     float* dw, void* stream);
-int pfc_dw_sgd(const float* dwn, float* w, float* momentum_buf, const float* inv_norm_w, int rows, int d, float lr,
-               float momentum, float weight_decay, float inv_grad_scale, void* wn_next_bf16, float* inv_norm_next,
-               void* stream);
+int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* momentum_buf, const float* inv_norm_w, int rows, int d,
+               float lr, float momentum, float weight_decay, float inv_grad_scale, void* wn_next_bf16,
+               float* inv_norm_next, void* stream);
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                 float inv_grad_scale, void* wn_next_bf16, float* inv_norm_next, void* stream);

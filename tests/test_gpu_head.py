@@ -119,6 +119,34 @@ def test_adamw_fused_matches_torch_adamw(pfc):
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=0, atol=2e-5)
 
 
+def test_overlap_update_is_bit_identical_to_serial(pfc):
+    """conf.overlap_update only changes scheduling (side stream + ping-pong wn buffers): same bits as the serial path."""
+    cfg, z = load_case("head_w1_d512")
+    weights, xs, ls = case_inputs(cfg)
+    outs = []
+    for overlap in (False, True):
+        conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
+                                     loss_m=cfg["m"], fused_optimizer=True, overlap_update=overlap)
+        head = pfc.PartialFC(conf, cfg["C"])
+        head.load_state_dict({"weight": weights[0].clone()})
+        head = head.train().cuda()
+        opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
+        losses, grads = [], []
+        for s in range(5):
+            x = xs[0].clone().cuda().requires_grad_(True)
+            loss = head(x, ls[0].clone().cuda(), opt)
+            loss.backward()
+            losses.append(float(loss.detach()))
+            grads.append(x.grad.clone())
+        torch.cuda.synchronize()
+        outs.append((losses, grads, head.weight_activated.data.clone(), head.weight_activated_mom.clone()))
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
+    assert outs[0][0][4] < outs[0][0][0]            # and the fused SGD actually trains
+
+
 def test_batch_size_change_asserts(pfc):
     cfg, z = load_case("head_w1_full")
     weights, xs, ls = case_inputs(cfg)

@@ -87,6 +87,7 @@ def test_cross_score_golden_bit_exact():
     # odd sizes / d not a multiple of 32
     rng = np.random.default_rng(3)
     e = rng.standard_normal((45, 50)).astype(np.float32)
+    e /= np.linalg.norm(e, axis=1, keepdims=True)          # the scorer is defined on unit vectors (score in [0, 1])
     lab = rng.integers(0, 4, 45)
     from oracle import eval_oracle as eo
     a = pfc.cross_score(e, lab)
