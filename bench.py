@@ -143,7 +143,7 @@ def run_reference(args, rank, world):
                              "sample": f"{steps} full steps (B=1024, C=93431, d=512) after {warm} warm-up"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_sample():
@@ -168,7 +168,26 @@ def cpu_baseline_sample():
                       f"{dt * 1e3:.0f} ms/step"}
 
 
+_REAL_STDOUT = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -411,7 +430,7 @@ def main():
         line["cpu_baseline"] = cpu_baseline_sample()
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    emit(line)
     dist.barrier()
 
 
