@@ -11,6 +11,7 @@
 // where L_i is the global row sum and the target column of E' is patched to -dm_i*mask_i*Lothers_i
 // (pfc_backward_prepare) so that the one-hot term needs no separate pass.
 #include "pfc_umma.cuh"
+#include "pfc_umma2.cuh"
 #include "pfc_internal.h"
 
 namespace pfc {
@@ -287,41 +288,61 @@ static DescCfg store_desc_cfg(bool a_mn) {
     return dc;
 }
 
-static int g_dbg_cluster = -1;   // debug / A-B switch: -1 auto, 1 = never cluster, 2 = cluster when possible
+// GEMM launch mode (pfc_debug_cluster): 0 = auto (CTA-pair cta_group::2 kernel whenever the M dimension has >= 2
+// tiles, single-CTA kernel otherwise), 1 = single-CTA kernel, 2 = CTA pair sharing one operand by TMA multicast,
+// 3 = cta_group::2 pair kernel.
+static int g_gemm_mode = 0;
+enum { MODE_SINGLE = 1, MODE_MCAST = 2, MODE_PAIR = 3 };
 
-template <class P, int CL>
-static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const typename P::Params& prm,
-                          cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel<P, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             GEMM_SMEM_BYTES);
-        if (e != cudaSuccess) return PFC_ERR_CUDA;
-        attr_set = true;
-    }
+static int pick_mode(int m_tiles, int mcast_dim_tiles) {
+    int mode = g_gemm_mode == 0 ? MODE_PAIR : g_gemm_mode;
+    if (mode == MODE_PAIR && m_tiles < 2) mode = MODE_SINGLE;
+    if (mode == MODE_MCAST && (mcast_dim_tiles % 2)) mode = MODE_SINGLE;
+    return mode;
+}
+
+template <class Kern, class Params>
+static int launch_cluster(Kern kern, int cluster, int smem_bytes, const CUtensorMap& ta, const CUtensorMap& tb,
+                          const Params& prm, cudaStream_t stream) {
     const int sms = num_sms();
     if (sms <= 0) return PFC_ERR_CUDA;
     if (prm.num_tiles <= 0) return PFC_OK;
-    if (prm.num_tiles % CL) return PFC_ERR_SHAPE;
+    if (prm.num_tiles % cluster) return PFC_ERR_SHAPE;
     int grid = prm.num_tiles < sms ? prm.num_tiles : sms;
-    grid = grid / CL * CL;
+    grid = grid / cluster * cluster;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GEMM_SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CL;
+    at[0].val.clusterDim.x = cluster;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, umma_gemm_kernel<P, CL>, ta, tb, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, prm);
     return e == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 
-static bool want_cluster(int pair_dim_tiles) { return g_dbg_cluster != 1 && pair_dim_tiles % 2 == 0; }
+template <class P>
+static int launch_gemm(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const typename P::Params& prm,
+                       cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(umma_gemm_kernel<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(umma_gemm_kernel<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(umma_gemm_pair_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess)
+            return PFC_ERR_CUDA;
+        attr_set = true;
+    }
+    if (mode == MODE_PAIR) return launch_cluster(umma_gemm_pair_kernel<P>, 2, PAIR_SMEM_BYTES, ta, tb, prm, stream);
+    if (mode == MODE_MCAST) return launch_cluster(umma_gemm_kernel<P, 2>, 2, GEMM_SMEM_BYTES, ta, tb, prm, stream);
+    return launch_cluster(umma_gemm_kernel<P, 1>, 1, GEMM_SMEM_BYTES, ta, tb, prm, stream);
+}
+
+static int even_up(int v) { return (v + 1) / 2 * 2; }
 
 }  // namespace pfc
 
@@ -335,8 +356,8 @@ int pfc_exp_top(void) { return PFC_EXP_TOP; }
 void pfc_debug_mn_desc(unsigned lbo, unsigned sbo, unsigned kstep) {
     g_dbg_mn_lbo = lbo; g_dbg_mn_sbo = sbo; g_dbg_mn_kstep = kstep;
 }
-// not part of the public header: 1 = never use CTA-pair clusters, 2 / -1 = use them whenever the paired dimension is even
-void pfc_debug_cluster(int mode) { g_dbg_cluster = mode; }
+// not part of the public header: GEMM launch mode, see g_gemm_mode
+void pfc_debug_cluster(int mode) { g_gemm_mode = mode; }
 
 int pfc_padded_classes(int n) { return (n + 63) / 64 * 64; }
 int pfc_num_class_tiles(int n) { return 2 * ((n + BN - 1) / BN); }   // one part_sum slab per 128-column half tile
@@ -349,15 +370,17 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     const float log2e = 1.4426950408889634f;
     // every representable term must stay a normal bf16/fp32 number: 2*s*log2e <= TOP + 126
     if (!(s > 0.f) || 2.f * s * log2e > PFC_EXP_TOP + 126.f) return PFC_ERR_SCALE_RANGE;
-    const bool cl2 = want_cluster((B + BM - 1) / BM);   // pairs of sample tiles share the class stage
+    const int m_tiles = (B + BM - 1) / BM;
+    const int mode = pick_mode(m_tiles, m_tiles);   // pairs of sample tiles share the class (W) stage
     CUtensorMap ta, tb;
     int rc = make_tmap(&ta, xn, d, B, d, BK, BM);
     if (rc) return rc;
-    rc = make_tmap(&tb, wn, d, n, d, BK, cl2 ? BN / 2 : BN);   // each CTA of a pair fetches half of the 256 class rows
+    // in both pair modes each CTA fetches half of the 256 class rows of a stage
+    rc = make_tmap(&tb, wn, d, n, d, BK, mode == MODE_SINGLE ? BN : BN / 2);
     if (rc) return rc;
     FwdPolicy::Params p;
     p.B = B; p.n = n; p.n_pad = n_pad; p.B_pad = pfc_padded_batch(B);
-    p.m_tiles = (B + BM - 1) / BM;
+    p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;   // an odd count gets one all-padding tile
     p.k_stages = (d + BK - 1) / BK;
     p.num_tiles = p.m_tiles * ((n + BN - 1) / BN);
     p.labels = labels_local;
@@ -374,14 +397,13 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     p.m3 = m3; p.margin_kind = margin_kind; p.filter_thr = filter_thr;
     p.E = reinterpret_cast<__nv_bfloat16*>(E);
     p.part_sum = part_sum; p.tgt_raw = tgt_raw; p.tgt_e = tgt_e; p.tgt_z = tgt_z; p.s = s;
-    return cl2 ? launch_gemm_cl<FwdPolicy, 2>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream))
-               : launch_gemm_cl<FwdPolicy, 1>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    return launch_gemm<FwdPolicy>(mode, ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Number of class splits the dX contraction uses for a given shape (callers size `partial` with it).
 int pfc_dx_splits(int B, int n, int d) {
     const int sms = num_sms() > 0 ? num_sms() : 148;
-    const int base = ((B + BM - 1) / BM) * ((d + BN - 1) / BN);
+    const int base = even_up((B + BM - 1) / BM) * ((d + BN - 1) / BN);
     const int k_total = (n + BK - 1) / BK;
     int splits = sms / base;
     if (splits < 1) splits = 1;
@@ -393,7 +415,7 @@ int pfc_dx_splits(int B, int n, int d) {
 // Upper bound of pfc_dx_splits over every n (callers size the partial buffer with it).
 int pfc_dx_max_splits(int B, int d) {
     const int sms = num_sms() > 0 ? num_sms() : 148;
-    const int base = ((B + BM - 1) / BM) * ((d + BN - 1) / BN);
+    const int base = even_up((B + BM - 1) / BM) * ((d + BN - 1) / BN);
     return sms / base > 1 ? sms / base : 1;
 }
 
@@ -407,7 +429,9 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     rc = make_tmap(&tb, wn, d, n, d, 64, BK);              // B: Wn [n(K), d(N)] MN-major boxes 64(N) x 64(K)
     if (rc) return rc;
     StoreParams p;
-    p.m_tiles = (B + BM - 1) / BM;
+    const int m_tiles = (B + BM - 1) / BM;
+    const int mode = pick_mode(m_tiles, m_tiles);          // pairs of sample tiles share the Wn stage
+    p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;
     p.n_tiles = (d + BN - 1) / BN;
     p.k_stages_total = (n + BK - 1) / BK;
     p.k_stages_per_split = (p.k_stages_total + splits - 1) / splits;
@@ -420,11 +444,10 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     p.out = partial;
     p.out_bf16 = 0;
     p.dc = store_desc_cfg(false);
-    return want_cluster(p.m_tiles) ? launch_gemm_cl<StorePolicy<false>, 2>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream))
-                                   : launch_gemm_cl<StorePolicy<false>, 1>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    return launch_gemm<StorePolicy<false>>(mode, ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
-// dwn[n][d] (fp32) = E'^T . Xs,   Xs = c_i * Xn_i (bf16, [B, d])
+// dwn[n][d] = E'^T . Xs,   Xs = c_i * Xn_i (bf16, [B, d]);  dwn fp32 or (dwn_bf16) bf16
 int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int d, void* dwn, int dwn_bf16,
                     void* stream) {
     if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 8) return PFC_ERR_SHAPE;
@@ -434,20 +457,23 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     rc = make_tmap(&tb, xs, d, B, d, 64, BK);              // B: Xs [B(K), d(N)] MN-major
     if (rc) return rc;
     StoreParams p;
-    p.m_tiles = (n + BM - 1) / BM;
+    const int m_tiles = (n + BM - 1) / BM;
     p.n_tiles = (d + BN - 1) / BN;
+    // cta_group::2: pairs of CLASS tiles share the Xs stage (m fastest); multicast mode: the two D halves of one
+    // class tile share the E'^T stage (n fastest)
+    const int mode = pick_mode(m_tiles, p.n_tiles);
+    p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;
     p.splits = 1;
     p.k_stages_total = (B + BK - 1) / BK;
     p.k_stages_per_split = p.k_stages_total;
     p.num_tiles = p.m_tiles * p.n_tiles;
-    p.n_fastest = 1;
+    p.n_fastest = mode == MODE_PAIR ? 0 : 1;
     p.rows_valid = n; p.cols_valid = d; p.ld = d;
     p.split_stride = 0;
     p.out = reinterpret_cast<float*>(dwn);
     p.out_bf16 = dwn_bf16 ? 1 : 0;
     p.dc = store_desc_cfg(true);
-    return want_cluster(p.n_tiles) ? launch_gemm_cl<StorePolicy<true>, 2>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream))
-                                   : launch_gemm_cl<StorePolicy<true>, 1>(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    return launch_gemm<StorePolicy<true>>(mode, ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

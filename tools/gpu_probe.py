@@ -236,6 +236,11 @@ def main():
         import torch
         print(f"[{args.case}] device={torch.cuda.get_device_name(0)} sms={torch.cuda.get_device_properties(0).multi_processor_count}",
               flush=True)
+        mode = int(os.environ.get("PFC_GEMM_MODE", "0"))   # 0 auto, 1 single CTA, 2 multicast pair, 3 cta_group::2 pair
+        if mode:
+            from face_recognition_pytorch_b200 import _lib
+            _lib.lib.pfc_debug_cluster(mode)
+            print(f"  (GEMM mode {mode})", flush=True)
         ok = globals()["case_" + args.case]()
         sys.exit(0 if ok or ok is None else 3)
     results = {}
