@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="run the fused update after the dX GEMM, not under it")
+    ap.add_argument("--overlap", action="store_true", help="run the fused update on a side stream under the dX GEMM")
     ap.add_argument("--unfused", action="store_true", help="hand dW to torch.optim.SGD instead of the fused update")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -222,7 +222,7 @@ def main():
     w_shard, xs, ls = synth(rank, world, n_data, dev)
     b = GLOBAL_BATCH // world
     conf = types.SimpleNamespace(emd_size=EMB, sample_rate=1.0, mixed_precision=False, loss_s=S, loss_m=M,
-                                 fused_optimizer=not args.unfused, overlap_update=not (args.unfused or args.no_overlap))
+                                 fused_optimizer=not args.unfused, overlap_update=bool(args.overlap) and not args.unfused)
     head = pfc.PartialFC(conf, C_CLASSES)
     head.load_state_dict({"weight": w_shard})
     head = head.train().cuda()
