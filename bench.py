@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap", action="store_true", help="run the fused update on a side stream under the dX GEMM")
+    ap.add_argument("--sgd-warps", type=int, default=0, help="with --overlap: persistent SGD grid, warps per SM")
+    ap.add_argument("--gemm-mode", type=int, default=0, help="0 auto, 1 single CTA, 2 multicast pair, 3 cta_group::2")
     ap.add_argument("--unfused", action="store_true", help="hand dW to torch.optim.SGD instead of the fused update")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -218,6 +220,10 @@ def main():
     import face_recognition_pytorch_b200 as pfc
     from face_recognition_pytorch_b200 import kernels as K
 
+    if args.sgd_warps:
+        pfc._lib.lib.pfc_debug_sgd_persistent(int(args.sgd_warps))
+    if args.gemm_mode:
+        pfc._lib.lib.pfc_debug_cluster(int(args.gemm_mode))
     n_data = 4
     w_shard, xs, ls = synth(rank, world, n_data, dev)
     b = GLOBAL_BATCH // world

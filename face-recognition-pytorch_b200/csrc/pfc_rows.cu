@@ -332,9 +332,11 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
                    const float* inv_norm_w, int rows, float lr, float momentum, float wd, float inv_grad_scale,
                    __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
     constexpr int d = 128 * NV;
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    const int warps = blockDim.x >> 5;
+    // grid-stride over rows: with one row per warp and a full grid this is a single trip; the persistent launch
+    // (a few CTAs per SM, see pfc_debug_sgd_persistent) loops so that the kernel can share SMs with a GEMM
+    for (int row = blockIdx.x * warps + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps) {
     const size_t base = static_cast<size_t>(row) * d;
     float4 g[NV], wv[NV], mv[NV];
 #pragma unroll
@@ -376,7 +378,7 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
         wv[j] = q;
         ss += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
     }
-    if (wn_next == nullptr) return;
+    if (wn_next == nullptr) continue;
     ss = warp_sum(ss);
     const float denom = fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
@@ -385,18 +387,33 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
         *reinterpret_cast<uint2*>(wn_next + base + 4 * (lane + 32 * j)) = pack4_bf16(q);
     }
     if (lane == 0) inv_norm_next[row] = 1.f / denom;
+    }
 }
+
+static int g_sgd_persistent_warps = 0;   // 0: one row per warp, full grid; > 0: that many warps per SM, grid-stride
 
 template <int NV>
 static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom, const float* inv_norm_w, int rows,
                                float lr, float momentum, float wd, float igs, __nv_bfloat16* wn_next, float* inv_next,
                                cudaStream_t st) {
+    int grid = (rows + 3) / 4, block = 128;
+    if (g_sgd_persistent_warps > 0) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        block = 32 * g_sgd_persistent_warps;
+        if (block > 128) block = 128;                 // __launch_bounds__(128): several CTAs per SM instead
+        const int ctas_per_sm = (32 * g_sgd_persistent_warps + block - 1) / block;
+        grid = sms * ctas_per_sm;
+        const int need = (rows + block / 32 - 1) / (block / 32);
+        if (grid > need) grid = need;
+    }
     if (bf16)
-        dw_sgd_rows_kernel<NV, true><<<(rows + 3) / 4, 128, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd,
-                                                                      igs, wn_next, inv_next);
+        dw_sgd_rows_kernel<NV, true><<<grid, block, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd, igs,
+                                                              wn_next, inv_next);
     else
-        dw_sgd_rows_kernel<NV, false><<<(rows + 3) / 4, 128, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd,
-                                                                       igs, wn_next, inv_next);
+        dw_sgd_rows_kernel<NV, false><<<grid, block, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd, igs,
+                                                               wn_next, inv_next);
 }
 
 // dst[r] = src[index[r]]  /  dst[index[r]] = src[r]   (nets/PartialFC.py:120-121, :142-143), up to 3 tensors at once
@@ -455,6 +472,10 @@ static inline bool bad_d(int d) { return d <= 0 || (d & 7) || d > 128 * MAXV; }
 using namespace pfc;
 
 extern "C" {
+
+// not part of the public header: > 0 runs the fused SGD row kernel as a persistent grid with that many warps per SM
+// (used when it is overlapped with a GEMM on another stream), 0 restores the full grid
+void pfc_debug_sgd_persistent(int warps_per_sm) { g_sgd_persistent_warps = warps_per_sm; }
 
 int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void* xn, float* inv_norm, void* stream) {
     if (rows < 0 || bad_d(d)) return PFC_ERR_SHAPE;
