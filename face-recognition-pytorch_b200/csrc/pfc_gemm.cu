@@ -51,10 +51,11 @@ struct FwdPolicy {
     }
 
     // 32 accumulator columns -> 16 packed bf16x2 words o[kOff .. kOff+16); returns the sum of the non-target terms
+    // (four independent partial sums: no 32-long dependent FADD chain)
     template <bool kHasTarget, bool kTail, bool kFilter, int kOff>
     __device__ static __forceinline__ float chunk(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[32],
                                                   int col_base, int jt) {
-        float sum = 0.f;
+        float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
             float e2[2];
@@ -77,21 +78,19 @@ struct FwdPolicy {
                 if (kHasTarget) {
                     if (j + u == jt) e = 0.f;            // the target column is accounted separately
                 }
-                sum += e;
+                sum[((j >> 1) & 1) * 2 + u] += e;
                 e2[u] = keep ? e : 0.f;
             }
             o[kOff + (j >> 1)] = pack_bf16x2(e2[0], e2[1]);
         }
-        return sum;
+        return (sum[0] + sum[1]) + (sum[2] + sum[3]);
     }
 
+    // v = 32 accumulator columns already in registers
     template <int kOff>
-    __device__ static __forceinline__ float chunk32(const Params& p, uint32_t taddr, uint32_t (&o)[32], int col_base,
-                                                    int row, int tgt_off_in_tile, int tile_col) {
+    __device__ static __forceinline__ float chunk32(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[32],
+                                                    int col_base, int row, int tgt_off_in_tile, int tile_col) {
         // tile_col = column of this chunk inside the 256-wide tile; tgt_off_in_tile = target column inside the tile or -1
-        uint32_t v[32];
-        tmem_ld_32x32(taddr, v);
-        tmem_ld_wait();
         const bool has_t = (tgt_off_in_tile >= tile_col) && (tgt_off_in_tile < tile_col + 32);
         const bool tail = col_base + 32 > p.n;
         const bool filt = p.filter_thr > 0.f;
@@ -124,6 +123,8 @@ struct FwdPolicy {
         return sum;
     }
 
+    // The warp owns 32 rows x 128 columns: four 32-column TMEM loads, software-pipelined so that the next chunk is in
+    // flight while the current one goes through the FMA / MUFU pipes.
     __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr, int quarter,
                                                     int half, int lane, uint8_t* stage) {
         const int row0 = tc.m0 + quarter * 32;
@@ -133,15 +134,21 @@ struct FwdPolicy {
         const int tgt_off = (lbl >= tc.n0 && lbl < tc.n0 + BN) ? (lbl - tc.n0) : -1;
         const int rows_valid = min(32, max(0, p.B - row0));
         float sum = 0.f;
-#pragma unroll 1
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(taddr, va);
+#pragma unroll
         for (int cc = 0; cc < EPI_COLS / 64; ++cc) {
             const int tile_col = half * EPI_COLS + cc * 64;
             const int col64 = tc.n0 + tile_col;
             if (col64 >= p.n) break;                     // warp-uniform: nothing valid from here on
             uint32_t o[32];
-            sum += chunk32<0>(p, taddr + cc * 64, o, col64, row, tgt_off, tile_col);
+            tmem_ld_wait();                              // va = columns [cc*64, cc*64+32)
+            tmem_ld_32x32(taddr + cc * 64 + 32, vb);     // next chunk in flight during the math below
+            sum += chunk32<0>(p, va, o, col64, row, tgt_off, tile_col);
+            tmem_ld_wait();                              // vb ready
+            if (cc + 1 < EPI_COLS / 64) tmem_ld_32x32(taddr + (cc + 1) * 64, va);
             if (col64 + 32 < p.n) {
-                sum += chunk32<16>(p, taddr + cc * 64 + 32, o, col64 + 32, row, tgt_off, tile_col + 32);
+                sum += chunk32<16>(p, vb, o, col64 + 32, row, tgt_off, tile_col + 32);
             } else {
 #pragma unroll
                 for (int j = 16; j < 32; ++j) o[j] = 0u;
@@ -151,6 +158,7 @@ struct FwdPolicy {
                                  reinterpret_cast<uint8_t*>(p.E + static_cast<size_t>(row0) * p.n_pad + col64),
                                  static_cast<size_t>(p.n_pad) * 2, rows_valid, bytes_valid);
         }
+        tmem_ld_wait();                                  // nothing may be outstanding when the accumulator is released
         if (row_ok) p.part_sum[static_cast<size_t>(tc.aux * 2 + half) * p.B_pad + row] = sum;
     }
 };
@@ -288,14 +296,16 @@ static DescCfg store_desc_cfg(bool a_mn) {
     return dc;
 }
 
-// GEMM launch mode (pfc_debug_cluster): 0 = auto (CTA-pair cta_group::2 kernel whenever the M dimension has >= 2
-// tiles, single-CTA kernel otherwise), 1 = single-CTA kernel, 2 = CTA pair sharing one operand by TMA multicast,
-// 3 = cta_group::2 pair kernel.
+// GEMM launch mode (pfc_debug_cluster): 0 = auto, 1 = single-CTA kernel, 2 = CTA pair sharing one operand stage by
+// TMA multicast, 3 = cta_group::2 pair kernel (pfc_umma2.cuh).  Measured on B200 at cfg-2 (profiles/README.md): all
+// three run within a few percent of each other because under sustained load the GEMMs are power-capped (~1.6 GHz),
+// not shared-memory- or L2-bound; the single-CTA kernel is the fastest for the forward (heavier epilogue) and is
+// what auto selects.  The pair kernels stay selectable and are covered by the GPU tests.
 static int g_gemm_mode = 0;
 enum { MODE_SINGLE = 1, MODE_MCAST = 2, MODE_PAIR = 3 };
 
 static int pick_mode(int m_tiles, int mcast_dim_tiles) {
-    int mode = g_gemm_mode == 0 ? MODE_PAIR : g_gemm_mode;
+    int mode = g_gemm_mode == 0 ? MODE_SINGLE : g_gemm_mode;
     if (mode == MODE_PAIR && m_tiles < 2) mode = MODE_SINGLE;
     if (mode == MODE_MCAST && (mcast_dim_tiles % 2)) mode = MODE_SINGLE;
     return mode;
