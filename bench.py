@@ -394,7 +394,8 @@ def main():
     alg = {
         "pfc_forward": ("tensor", flops_gemm), "pfc_backward_dx": ("tensor", flops_gemm),
         "pfc_backward_dw": ("tensor", flops_gemm),
-        "pfc_dw_sgd": ("hbm", nl * EMB * (4 * 5 + 2.0)),          # read dwn,w,mom; write w,mom (fp32) + wn (bf16)
+        # read dWn (bf16 spill) + w, momentum (fp32); write w, momentum (fp32) + next wn (bf16) = 20 B per element
+        "pfc_dw_sgd": ("hbm", nl * EMB * (2 + 4 * 4 + 2.0)),
         "pfc_dw_finalize": ("hbm", nl * EMB * 4 * 3.0),
         "pfc_l2norm_rows": ("hbm", None),
     }
@@ -407,8 +408,12 @@ def main():
             ach, peak, unit = work / (ms * 1e-3) / 1e12, pk["tf_sust"], "TFLOP/s"
         else:
             ach, peak, unit = work / (ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+        # (profiles/r01_final_ncu_full_summary.txt), valid for the single-GPU shape only
+        ncu_traffic = {"pfc_dw_sgd": 478.76e6 + 421.98e6, "pfc_forward": 96.85e6 + 144.27e6,
+                       "pfc_backward_dw": 192.51e6 + 69.82e6, "pfc_backward_dx": 287.64e6 + 5.10e6}
         roof = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                "traffic": None, "peak_source": pk["kind"] + (" sustained bf16" if bound == "tensor" else " copy"),
+                "traffic": ncu_traffic.get(dom) if world == 1 else None, "algorithmic_work": work, "peak_source": pk["kind"] + (" sustained bf16" if bound == "tensor" else " copy"),
                 "ms_per_launch": ms}
     step_tf = 3 * flops_gemm / (ms_per_step * 1e-3) / 1e12
     line = {
