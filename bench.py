@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--sgd-warps", type=int, default=0, help="with --overlap: persistent SGD grid, warps per SM")
     ap.add_argument("--gemm-mode", type=int, default=0, help="0 auto, 1 single CTA, 2 multicast pair, 3 cta_group::2")
     ap.add_argument("--unfused", action="store_true", help="hand dW to torch.optim.SGD instead of the fused update")
+    ap.add_argument("--no-peer", action="store_true",
+                    help="N>1: NCCL collectives instead of the peer-memory (NVLink) exchanges fused into the kernels")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -228,7 +230,8 @@ def main():
     w_shard, xs, ls = synth(rank, world, n_data, dev)
     b = GLOBAL_BATCH // world
     conf = types.SimpleNamespace(emd_size=EMB, sample_rate=1.0, mixed_precision=False, loss_s=S, loss_m=M,
-                                 fused_optimizer=not args.unfused, overlap_update=bool(args.overlap) and not args.unfused)
+                                 fused_optimizer=not args.unfused, overlap_update=bool(args.overlap) and not args.unfused,
+                                 peer_collectives=False if args.no_peer else "auto")
     head = pfc.PartialFC(conf, C_CLASSES)
     head.load_state_dict({"weight": w_shard})
     head = head.train().cuda()
@@ -425,6 +428,9 @@ def main():
                    "classes_per_gpu": nl, "local_batch": b, "parallelism": f"class-sharded x{world}",
                    "launch": "cuda-graph replay" if graphs is not None else "eager",
                    "overlap_update": bool(conf.overlap_update),
+                   "exchange": ("none (1 GPU)" if world == 1 else
+                                "peer-memory stores + flag barriers (NVLink)" if head._peer is not None else
+                                "NCCL all-gather / all-reduce / reduce-scatter"),
                    "l2": "256 MB buffer written between timed steps (untimed); per-step CUDA events summed"},
         "roofline": roof,
         "step_roofline": {"bound": "tensor", "achieved": step_tf / world, "peak": pk["tf_burst"], "unit": "TFLOP/s/GPU",

@@ -1,0 +1,243 @@
+// Peer-memory (NVLink / NVSwitch) versions of the head's three exchanges, fused into the kernels that produce the
+// data: every rank stores its contribution straight into every peer's symmetric buffer, a flag barrier publishes
+// the stores, and the consumer is a plain local kernel.  They replace the NCCL all-gather / all-reduce /
+// reduce-scatter of the step (reference: nets/PartialFC.py:182-186, :448/:453/:459, :505-522), each of which costs
+// ~30 us inside a CUDA graph at 8 ranks for a payload of a few KB to 2 MB.
+//
+//   pfc_peer_l2norm_gather : xn = normalise(x) as bf16 -> rows [rank*b, rank*b+b) of EVERY rank's xn_all (+ labels)
+//   pfc_peer_row_stats     : this rank's [B,2] softmax statistics -> slot `rank` of EVERY rank's slots[W][B][2]
+//   pfc_peer_loss          : sum of the W slots in rank order (bit-identical on all ranks) -> stats, row_L, loss
+//   pfc_peer_dx_scatter    : c_i * sum_z partial[z][i,:] for the rows owned by rank r -> slot `rank` of rank r's
+//                            dx_slots[W][b][d]   (the consumer is pfc_dx_finalize with splits = W)
+//   pfc_peer_barrier       : all ranks' previous stores are visible everywhere after it (one tiny kernel per rank)
+//
+// Peer buffers come from torch's symmetric-memory allocator (host code passes the mapped device pointers); the
+// barrier uses one uint32 flag per (receiver, sender) pair and a per-rank epoch counter kept in device memory, so the
+// same launch sequence can be replayed from a CUDA graph.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "pfc_internal.h"
+
+namespace pfc {
+
+constexpr int MAX_PEERS = 16;
+struct PeerPtrs {
+    void* p[MAX_PEERS];
+};
+
+__device__ __forceinline__ float warp_sum_p(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One CTA, W threads.  flags.p[q] -> rank q's flag array uint32[W]; counter -> this rank's epoch (device memory).
+__global__ void peer_barrier_kernel(PeerPtrs flags, uint32_t* counter, int rank, int W) {
+    __shared__ uint32_t ep_s;
+    if (threadIdx.x == 0) {
+        ep_s = *counter + 1;
+        *counter = ep_s;
+    }
+    __syncthreads();
+    const uint32_t ep = ep_s;
+    __threadfence_system();
+    if (threadIdx.x < W) {
+        uint32_t* remote = static_cast<uint32_t*>(flags.p[threadIdx.x]) + rank;    // my slot in peer's array
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(ep) : "memory");
+        const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + threadIdx.x;
+        uint32_t v;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (static_cast<int32_t>(v - ep) >= 0) break;
+            if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; trap instead of hanging the GPU
+                printf("pfc: peer barrier timed out (rank %d waiting for %d, epoch %u, saw %u)\n", rank,
+                       (int)threadIdx.x, ep, v);
+                __trap();
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+// warp per row; lane l handles float4 #l, #l+32, ... (d <= 1024)
+__global__ void __launch_bounds__(256)
+peer_l2norm_gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, int b, int d, int rank, int W,
+                          PeerPtrs xn_all, PeerPtrs labels_all, float* __restrict__ inv_norm) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= b) return;
+    const float* xr = x + static_cast<size_t>(row) * d;
+    const int nv = d >> 2;
+    float4 v[8];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nv) {
+            v[j] = *reinterpret_cast<const float4*>(xr + 4 * c);
+            ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+        }
+    }
+    ss = warp_sum_p(ss);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    const size_t grow = static_cast<size_t>(rank) * b + row;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        if (c < nv) {
+            __nv_bfloat162 a = __floats2bfloat162_rn(v[j].x / denom, v[j].y / denom);
+            __nv_bfloat162 bb = __floats2bfloat162_rn(v[j].z / denom, v[j].w / denom);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&a);
+            pk.y = *reinterpret_cast<uint32_t*>(&bb);
+            for (int q = 0; q < W; ++q)
+                *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(xn_all.p[q]) + grow * d + 4 * c) = pk;
+        }
+    }
+    if (lane == 0) {
+        inv_norm[row] = 1.f / denom;
+        const int64_t l = labels[row];
+        for (int q = 0; q < W; ++q) static_cast<int64_t*>(labels_all.p[q])[grow] = l;
+    }
+}
+
+// same reduction as row_stats_kernel (pfc_rows.cu), result stored into slot `rank` of every peer
+__global__ void __launch_bounds__(256)
+peer_row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
+                      const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, int rank, int W,
+                      PeerPtrs slots) {
+    __shared__ float red[8][33];
+    const int r = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int row = blockIdx.x * 32 + r;
+    float s = 0.f;
+    if (row < B)
+        for (int t = g; t < n_tiles; t += 8) s += part_sum[static_cast<size_t>(t) * B_pad + row];
+    red[g][r] = s;
+    __syncthreads();
+    if (g == 0 && row < B) {
+        float tot = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += red[k][r];
+        const float2 v = make_float2(tot, (labels[row] >= 0) ? tgt_e[row] : 0.f);
+        for (int q = 0; q < W; ++q)
+            reinterpret_cast<float2*>(static_cast<float*>(slots.p[q]) + static_cast<size_t>(rank) * B * 2)[row] = v;
+    }
+}
+
+// stats[i] = sum_r slots[r][i] (rank order), row_L, loss -- the local half of the exchange + pfc_loss
+__global__ void __launch_bounds__(1024)
+peer_loss_kernel(const float* __restrict__ slots, int W, int B, float* __restrict__ stats, float* __restrict__ row_L,
+                 float* __restrict__ loss) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < B; i += 1024) {
+        float others = 0.f, te = 0.f;
+        for (int r = 0; r < W; ++r) {
+            const float2 v = reinterpret_cast<const float2*>(slots + static_cast<size_t>(r) * B * 2)[i];
+            others += v.x;
+            te += v.y;
+        }
+        stats[2 * i] = others;
+        stats[2 * i + 1] = te;
+        const float L = others + te;
+        row_L[i] = L;
+        acc -= logf(fmaxf(te / L, 1e-30f));
+    }
+    acc = warp_sum_p(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = warp_sum_p(red[threadIdx.x]);
+        if (threadIdx.x == 0) loss[0] = v / static_cast<float>(B);
+    }
+}
+
+// row i of the global batch belongs to rank i / b; its scaled dXn partial goes to that rank's slot `rank`
+__global__ void __launch_bounds__(256)
+peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t split_stride,
+                       const float* __restrict__ coef, int B, int b, int d, int rank, PeerPtrs dx_slots) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const int dst = row / b, lr = row - dst * b;
+    float* out = static_cast<float*>(dx_slots.p[dst]) + (static_cast<size_t>(rank) * b + lr) * d;
+    const float c = coef[row];
+    for (int k = lane; k < (d >> 2); k += 32) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int z = 0; z < splits; ++z) {
+            const float4 p = *reinterpret_cast<const float4*>(partial + z * split_stride + static_cast<size_t>(row) * d + 4 * k);
+            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        }
+        a.x *= c; a.y *= c; a.z *= c; a.w *= c;
+        *reinterpret_cast<float4*>(out + 4 * k) = a;
+    }
+}
+
+static int fill_peers(PeerPtrs* pp, void* const* ptrs, int W) {
+    if (W < 1 || W > MAX_PEERS || ptrs == nullptr) return PFC_ERR_SHAPE;
+    for (int i = 0; i < MAX_PEERS; ++i) pp->p[i] = i < W ? ptrs[i] : nullptr;
+    return PFC_OK;
+}
+static inline int launched() { return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH; }
+
+}  // namespace pfc
+
+using namespace pfc;
+
+extern "C" {
+
+int pfc_peer_max_ranks(void) { return MAX_PEERS; }
+
+int pfc_peer_barrier(void* const* peer_flags, uint32_t* epoch_counter, int rank, int W, void* stream) {
+    PeerPtrs f;
+    int rc = fill_peers(&f, peer_flags, W);
+    if (rc) return rc;
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, epoch_counter, rank, W);
+    return launched();
+}
+
+int pfc_peer_l2norm_gather(const float* x, const int64_t* labels, int b, int d, int rank, int W,
+                           void* const* peer_xn_all, void* const* peer_labels_all, float* inv_norm, void* stream) {
+    if (b <= 0 || d <= 0 || (d & 7) || d > 1024) return PFC_ERR_SHAPE;
+    PeerPtrs xa, la;
+    int rc = fill_peers(&xa, peer_xn_all, W);
+    if (rc) return rc;
+    rc = fill_peers(&la, peer_labels_all, W);
+    if (rc) return rc;
+    peer_l2norm_gather_kernel<<<(b + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, labels, b, d, rank, W, xa, la, inv_norm);
+    return launched();
+}
+
+int pfc_peer_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
+                       int rank, int W, void* const* peer_slots, void* stream) {
+    if (B <= 0 || n_tiles <= 0) return PFC_ERR_SHAPE;
+    PeerPtrs s;
+    int rc = fill_peers(&s, peer_slots, W);
+    if (rc) return rc;
+    const int B_pad = (B + 127) / 128 * 128;
+    peer_row_stats_kernel<<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(part_sum, n_tiles, B, B_pad, labels_local,
+                                                                          tgt_e, rank, W, s);
+    return launched();
+}
+
+int pfc_peer_loss(const float* slots, int W, int B, float* stats, float* row_L, float* loss, void* stream) {
+    if (B <= 0 || W < 1) return PFC_ERR_SHAPE;
+    peer_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(slots, W, B, stats, row_L, loss);
+    return launched();
+}
+
+int pfc_peer_dx_scatter(const float* partial, int splits, const float* coef, int B, int b, int d, int rank, int W,
+                        void* const* peer_dx_slots, void* stream) {
+    if (B <= 0 || b <= 0 || B != b * W || d <= 0 || (d & 7) || splits <= 0) return PFC_ERR_SHAPE;
+    PeerPtrs s;
+    int rc = fill_peers(&s, peer_dx_slots, W);
+    if (rc) return rc;
+    peer_dx_scatter_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, splits, static_cast<size_t>(B) * d,
+                                                                         coef, B, b, d, rank, s);
+    return launched();
+}
+
+}  // extern "C"

@@ -198,6 +198,37 @@ def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, 
                           _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()), "pfc_dw_adam")
 
 
+# ---- peer-memory exchanges (peer_* are ctypes arrays of W mapped device pointers, see partial_fc._PeerExchange)
+@_timed("pfc_peer_barrier")
+def peer_barrier(peer_flags, counter, rank, W):
+    check(lib.pfc_peer_barrier(peer_flags, _p(counter, I32), rank, W, _stream()), "pfc_peer_barrier")
+
+
+@_timed("pfc_peer_l2norm_gather")
+def peer_l2norm_gather(x, labels, rank, W, peer_xn_all, peer_labels_all, inv_norm):
+    b, d = x.shape
+    check(lib.pfc_peer_l2norm_gather(_p(x, F32), _p(labels, I64), b, d, rank, W, peer_xn_all, peer_labels_all,
+                                     _p(inv_norm, F32), _stream()), "pfc_peer_l2norm_gather")
+
+
+@_timed("pfc_peer_row_stats")
+def peer_row_stats(part_sum, n_tiles, B, labels_local, tgt_e, rank, W, peer_slots):
+    check(lib.pfc_peer_row_stats(_p(part_sum, F32), n_tiles, B, _p(labels_local, I32), _p(tgt_e, F32), rank, W,
+                                 peer_slots, _stream()), "pfc_peer_row_stats")
+
+
+@_timed("pfc_peer_loss")
+def peer_loss(slots, W, B, stats, row_L, out):
+    check(lib.pfc_peer_loss(_p(slots, F32), W, B, _p(stats, F32), _p(row_L, F32), _p(out, F32), _stream()),
+          "pfc_peer_loss")
+
+
+@_timed("pfc_peer_dx_scatter")
+def peer_dx_scatter(partial, splits, coef, B, b, d, rank, W, peer_dx_slots):
+    check(lib.pfc_peer_dx_scatter(_p(partial, F32), splits, _p(coef, F32), B, b, d, rank, W, peer_dx_slots,
+                                  _stream()), "pfc_peer_dx_scatter")
+
+
 # ---- verification scorer
 @_timed("fr_pair_score")
 def pair_score(e1, e2, labels_u8, scores, dist, hist_g, hist_i):

@@ -150,6 +150,10 @@ class _PartialFCBase(torch.nn.Module):
         self._n = self.num_local        # active classes this step
         self._opt_args = None
         self._side_stream = None
+        # True / False / "auto": exchange the batch, the softmax statistics and dX through peer (NVLink) memory with
+        # the stores fused into the producing kernels (csrc/pfc_peer.cu) instead of three NCCL collectives
+        self.peer_collectives = getattr(conf, "peer_collectives", "auto")
+        self._peer = None
 
     # ------------------------------------------------------------------ reference-visible helpers
     def _optimizer_state_names(self):
@@ -215,6 +219,19 @@ class _PartialFCBase(torch.nn.Module):
             if sampled:
                 k = 1 + len(self._state_names)
                 self._act_store = [torch.zeros(n_max, d, device=dev) for _ in range(k)]
+            self._peer = None
+            if self.world_size > 1 and dev.type == "cuda" and self.peer_collectives in (True, "auto"):
+                try:
+                    from .peer import PeerExchange
+                    self._peer = PeerExchange(dev, self.rank, self.world_size, b, d)
+                    self._ws.xn_all = self._peer.xn_all          # peers store straight into these
+                    self._ws.labels_all = self._peer.labels_all
+                except Exception as e:                            # no P2P / symmetric memory: keep the NCCL collectives
+                    if self.peer_collectives is True:
+                        raise
+                    import warnings
+                    warnings.warn(f"peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL collectives")
+                    self._peer = None
         return self._ws
 
     def forward(self, local_embeddings: torch.Tensor, local_labels: torch.Tensor, optimizer: torch.optim.Optimizer,
@@ -247,8 +264,14 @@ class _PartialFCBase(torch.nn.Module):
         ws, W = self._ws, self.world_size
         x = local_embeddings.detach().contiguous()
         self._x_local = x
-        K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
-        if W > 1:
+        peer = self._peer
+        if peer is not None:
+            # normalise + all-gather in one kernel: every rank stores its bf16 rows and labels into every peer
+            K.peer_l2norm_gather(x, labels_in, self.rank, W, peer.ptrs("xn_all"), peer.ptrs("labels_all"), ws.inv_x)
+            K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
+            labels_all = peer.labels_all
+        elif W > 1:
+            K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
             if distributed.get_backend() == "nccl":
                 # one NCCL launch for both gathers (ncclGroupStart/End); every collective of the step is latency-bound
                 with distributed._coalescing_manager(device=x.device):
@@ -259,6 +282,7 @@ class _PartialFCBase(torch.nn.Module):
                 distributed.all_gather_into_tensor(ws.labels_all, labels_in)
             labels_all = ws.labels_all
         else:
+            K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
             labels_all = labels_in
         K.localize_labels(labels_all, self.class_start, self.num_local, ws.labels_local)   # :188-193
         if self.sample_rate < 1:
@@ -278,10 +302,18 @@ class _PartialFCBase(torch.nn.Module):
         self._n_pad = K.padded_classes(n)
         K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
                   ws.tgt_raw, ws.tgt_e, ws.tgt_z)                                 # :201-207
-        K.row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats)
-        if W > 1:
-            distributed.all_reduce(ws.stats, distributed.ReduceOp.SUM)            # replaces :448, :453, :459
-        K.loss(ws.stats, B, ws.row_L, ws.loss)                                    # :461
+        peer = self._peer
+        if peer is not None:
+            # statistics straight into every peer's slot, then a rank-ordered local sum (identical bits on all ranks)
+            K.peer_row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, self.rank, W,
+                             peer.ptrs("slots"))
+            K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
+            K.peer_loss(peer.slots, W, B, ws.stats, ws.row_L, ws.loss)            # replaces :448, :453, :459, :461
+        else:
+            K.row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats)
+            if W > 1:
+                distributed.all_reduce(ws.stats, distributed.ReduceOp.SUM)        # replaces :448, :453, :459
+            K.loss(ws.stats, B, ws.row_L, ws.loss)                                # :461
         if self.fused_optimizer:
             self._opt_args = self._read_optimizer(self._optimizer)
         return ws.loss[0].clone()
@@ -317,12 +349,17 @@ class _PartialFCBase(torch.nn.Module):
             K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
             self._wn_valid = False        # an external optimizer is about to change the weights
         dx, rs_work = None, None
+        peer = self._peer
         if x_in.requires_grad:
             splits = K.dx_splits(B, n, d)
             K.backward_dx(ws.E, n_pad, wn_now, B, n, d, ws.dx_partial, splits)
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
             if W == 1:
                 K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
+            elif peer is not None:
+                # :505-522 -- every rank stores its scaled partial of row i into the owner's slot; the owner sums
+                # the W slots in rank order inside the normalise-backward kernel (x W, :521)
+                K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
             else:
                 K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
                 # :505-519 -- asynchronous: it overlaps the rank-local update below / on the side stream
@@ -333,6 +370,11 @@ class _PartialFCBase(torch.nn.Module):
         if rs_work is not None:
             rs_work.wait()
             K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)        # :521
+        if peer is not None:
+            # also the fence that keeps a fast rank's NEXT gather out of xn_all while a slow rank still reads it
+            K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
+            if dx is not None:
+                K.dx_finalize(peer.dx_slots, W, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)    # :521
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         return dx, dw

@@ -126,6 +126,28 @@ int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, c
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                 float inv_grad_scale, void* wn_next_bf16, float* inv_norm_next, void* stream);
 
+/* ---- (5b) the three exchanges of the step over peer memory (NVLink / NVSwitch), fused into the producing kernels.
+ * They replace all_gather (nets/PartialFC.py:182-186), the softmax all_reduces (:448, :453, :459) and the dX
+ * reduce (:505-522).  peer_* arguments are HOST arrays of W device pointers: entry q is rank q's symmetric buffer as
+ * mapped into this process (torch.distributed._symmetric_memory); W <= pfc_peer_max_ranks().
+ * pfc_peer_barrier: every store issued by any rank before it is visible to every rank after it.  peer_flags[q] ->
+ *   rank q's uint32[W] flag array (zeroed once), epoch_counter -> this rank's private uint32 (zeroed once).
+ * pfc_peer_l2norm_gather: pfc_l2norm_rows of the local batch, written as rows [rank*b, rank*b+b) of every rank's
+ *   xn_all [W*b, d] bf16, plus the local labels into every rank's labels_all [W*b] int64.
+ * pfc_peer_row_stats: pfc_row_stats, written into slot `rank` of every rank's slots [W][B][2] fp32.
+ * pfc_peer_loss: stats = sum over the W slots (rank order, so every rank gets identical bits) + pfc_loss.
+ * pfc_peer_dx_scatter: coef[i] * sum_z partial[z][i,:] of global row i -> slot `rank` of rank i/b's dx_slots
+ *   [W][b][d] fp32; the owner then runs pfc_dx_finalize(dx_slots, splits = W, coef = NULL, ...). */
+int pfc_peer_max_ranks(void);
+int pfc_peer_barrier(void* const* peer_flags, uint32_t* epoch_counter, int rank, int W, void* stream);
+int pfc_peer_l2norm_gather(const float* x, const int64_t* labels, int b, int d, int rank, int W,
+                           void* const* peer_xn_all, void* const* peer_labels_all, float* inv_norm, void* stream);
+int pfc_peer_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
+                       int rank, int W, void* const* peer_slots, void* stream);
+int pfc_peer_loss(const float* slots, int W, int B, float* stats, float* row_L, float* loss, void* stream);
+int pfc_peer_dx_scatter(const float* partial, int splits, const float* coef, int B, int b, int d, int rank, int W,
+                        void* const* peer_dx_slots, void* stream);
+
 /* ---- (6) pair verification, utils/eval.py.
  * fr_pair_score  (:68-99): scores[i] = 1 - ||e1_i - e2_i||^2/4 (fp32 difference, fp64 accumulation), optional
  *   dist[i] = ||.||^2, and the 100001-bin genuine / imposter histograms (uint64 counts; zeroed by the call).

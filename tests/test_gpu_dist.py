@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 pytestmark = pytest.mark.gpu
 
 
-def _rank_main(rank, W, port, name, fused, q):
+def _rank_main(rank, W, port, name, fused, peer, q):
     for p in (ROOT, HERE, os.path.join(HERE, "golden")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -28,7 +28,8 @@ def _rank_main(rank, W, port, name, fused, q):
     weights, xs, ls = case_inputs(cfg)
     b = cfg["b"]
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
-                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused)
+                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused,
+                                 peer_collectives=peer)
     head = pfc.PartialFC(conf, cfg["C"])
     head.load_state_dict({"weight": weights[rank].clone()})
     head = head.train().cuda()
@@ -50,6 +51,7 @@ def _rank_main(rank, W, port, name, fused, q):
         if cfg["sample_rate"] < 1:
             out[f"index_{s}"] = head.weight_index.cpu().numpy().copy()
         opt.step()
+    out["peer_active"] = head._peer is not None
     if cfg["sample_rate"] < 1:
         head.update()
         out["weight_final"] = head.weight.cpu().numpy().copy()
@@ -65,9 +67,14 @@ def _cos(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
 
 
-@pytest.mark.parametrize("name,fused,port", [("head_w2_full", False, 29841), ("head_w2_sampled", False, 29842),
-                                             ("head_w2_full", True, 29843), ("head_w2_sampled", True, 29844)])
-def test_two_rank_nccl_matches_reference(name, fused, port):
+# peer = False: the three NCCL collectives; peer = True: the same exchanges through NVLink peer memory, fused into the
+# producing kernels (csrc/pfc_peer.cu) -- must raise rather than fall back if symmetric memory is unavailable
+@pytest.mark.parametrize("name,fused,port,peer", [
+    ("head_w2_full", False, 29841, False), ("head_w2_sampled", False, 29842, False),
+    ("head_w2_full", True, 29843, False), ("head_w2_sampled", True, 29844, False),
+    ("head_w2_full", False, 29845, True), ("head_w2_sampled", True, 29846, True),
+    ("head_w2_full", True, 29847, True)])
+def test_two_rank_nccl_matches_reference(name, fused, port, peer):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     sys.path.insert(0, HERE)
@@ -76,13 +83,14 @@ def test_two_rank_nccl_matches_reference(name, fused, port):
     W = cfg["W"]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, q)) for r in range(W)]
+    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, peer, q)) for r in range(W)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in range(W))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    assert all(res[r]["peer_active"] == peer for r in range(W))
     for s in range(cfg["steps"]):
         assert res[0][f"loss_{s}"] == res[1][f"loss_{s}"]
         for r in range(W):
