@@ -60,6 +60,8 @@ _SIGS = {
     "pfc_dw_sgd": (c_int, [p, c_int, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, p, p, p]),
     "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int,
                             c_float, p, p, p]),
+    "pfc_backward_dw_sgd": (c_int, [p, c_int, p, c_int, c_int, c_int, p, p, p, c_float, c_float, c_float, c_float, p, p,
+                                    p]),
     "pfc_peer_max_ranks": (c_int, []),
     "pfc_peer_barrier": (c_int, [POINTER(c_void_p), p, c_int, c_int, p]),
     "pfc_peer_l2norm_gather": (c_int, [p, p, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), p, p]),

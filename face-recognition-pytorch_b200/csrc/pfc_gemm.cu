@@ -10,8 +10,10 @@
 //   dXn_i = c_i * sum_c E'_ic Wn_c,    dWn_c = sum_i E'_ic (c_i Xn_i),    c_i = g*s / (B * L_i)
 // where L_i is the global row sum and the target column of E' is patched to -dm_i*mask_i*Lothers_i
 // (pfc_backward_prepare) so that the one-hot term needs no separate pass.
+#include <stdlib.h>
 #include "pfc_umma.cuh"
 #include "pfc_umma2.cuh"
+#include "pfc_dwsgd.cuh"
 #include "pfc_internal.h"
 
 namespace pfc {
@@ -126,13 +128,12 @@ struct FwdPolicy {
     // The warp owns 32 rows x 128 columns: four 32-column TMEM loads, software-pipelined so that the next chunk is in
     // flight while the current one goes through the FMA / MUFU pipes.
     __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr, int quarter,
-                                                    int half, int lane, uint8_t* stage) {
+                                                    int half, int lane, uint32_t stage, const CUtensorMap* tmc) {
         const int row0 = tc.m0 + quarter * 32;
         const int row = row0 + lane;
         const bool row_ok = row < p.B;
         const int lbl = row_ok ? p.labels[row] : -1;
         const int tgt_off = (lbl >= tc.n0 && lbl < tc.n0 + BN) ? (lbl - tc.n0) : -1;
-        const int rows_valid = min(32, max(0, p.B - row0));
         float sum = 0.f;
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
@@ -153,10 +154,8 @@ struct FwdPolicy {
 #pragma unroll
                 for (int j = 16; j < 32; ++j) o[j] = 0u;
             }
-            const int bytes_valid = min(128, (p.n_pad - col64) * 2);
-            warp_store_rows_128B(stage, lane, o,
-                                 reinterpret_cast<uint8_t*>(p.E + static_cast<size_t>(row0) * p.n_pad + col64),
-                                 static_cast<size_t>(p.n_pad) * 2, rows_valid, bytes_valid);
+            // E'[row0 .. row0+32) x [col64, col64+64): the store map clips rows >= B (n_pad is a multiple of 64)
+            warp_tma_store_rows(stage, lane, o, tmc, col64, row0, 0);
         }
         tmem_ld_wait();                                  // nothing may be outstanding when the accumulator is released
         if (row_ok) p.part_sum[static_cast<size_t>(tc.aux * 2 + half) * p.B_pad + row] = sum;
@@ -203,13 +202,14 @@ struct StorePolicy {
         tc.aux = z;
         return tc;
     }
+    // Output goes through the store tensor map tmc = {cols_valid, rows_valid, splits} (fp32, boxes of 32 columns) or
+    // {cols_valid, rows_valid, 1} (bf16, boxes of 64 columns); rows / columns beyond the tensor are clipped by TMA.
     __device__ static __forceinline__ void epilogue(const Params& p, const TileCoord& tc, uint32_t taddr, int quarter,
-                                                    int half, int lane, uint8_t* stage) {
+                                                    int half, int lane, uint32_t stage, const CUtensorMap* tmc) {
         const int row0 = tc.m0 + quarter * 32;
-        const int rows_valid = min(32, max(0, p.rows_valid - row0));
+        if (row0 >= p.rows_valid) return;                // warp-uniform: an all-padding row block
         if (p.out_bf16) {
             // bf16 spill: two 32-column chunks make one 128-byte line per row
-            __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row0) * p.ld;
 #pragma unroll 1
             for (int cc = 0; cc < EPI_COLS / 64; ++cc) {
                 const int col64 = tc.n0 + half * EPI_COLS + cc * 64;
@@ -224,12 +224,10 @@ struct StorePolicy {
                     for (int j = 0; j < 16; ++j)
                         o[h2 * 16 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                 }
-                warp_store_rows_128B(stage, lane, o, reinterpret_cast<uint8_t*>(ob + col64),
-                                     static_cast<size_t>(p.ld) * 2, rows_valid, min(128, (p.cols_valid - col64) * 2));
+                warp_tma_store_rows(stage, lane, o, tmc, col64, row0, 0);
             }
             return;
         }
-        float* obase = p.out + static_cast<size_t>(tc.aux) * p.split_stride + static_cast<size_t>(row0) * p.ld;
 #pragma unroll 1
         for (int c = 0; c < EPI_COLS / 32; ++c) {
             const int col_base = tc.n0 + half * EPI_COLS + c * 32;
@@ -237,8 +235,7 @@ struct StorePolicy {
             uint32_t v[32];
             tmem_ld_32x32(taddr + c * 32, v);
             tmem_ld_wait();
-            warp_store_rows_128B(stage, lane, v, reinterpret_cast<uint8_t*>(obase + col_base),
-                                 static_cast<size_t>(p.ld) * 4, rows_valid, min(128, (p.cols_valid - col_base) * 4));
+            warp_tma_store_rows(stage, lane, v, tmc, col_base, row0, tc.aux);
         }
     }
 };
@@ -273,6 +270,43 @@ static int make_tmap(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PFC_OK : PFC_ERR_TENSORMAP;
+}
+
+// Store target: row-major [slabs][outer][inner] tensor of bf16 or fp32, boxes of 128 bytes x 32 rows x 1 slab in the
+// SWIZZLE_128B layout warp_tma_store_rows() stages.
+static int make_store_tmap(CUtensorMap* map, void* ptr, bool is_bf16, uint64_t inner, uint64_t outer, uint64_t slabs,
+                           uint64_t row_stride_elems, uint64_t slab_stride_elems) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return PFC_ERR_DRIVER;
+    const uint64_t es = is_bf16 ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_elems * es) % 16 || (slab_stride_elems * es) % 16)
+        return PFC_ERR_ALIGNMENT;
+    cuuint64_t gdim[3] = {inner, outer, slabs};
+    cuuint64_t gstr[2] = {row_stride_elems * es, (slabs > 1 ? slab_stride_elems : row_stride_elems * outer) * es};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / es), 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, gdim, gstr,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PFC_OK : PFC_ERR_TENSORMAP;
+}
+
+// Generic 2-D row-major tensor map (loads and stores), bf16 or fp32, explicit box and swizzle mode.
+static int make_tmap_2d(CUtensorMap* map, void* ptr, bool is_bf16, uint64_t inner, uint64_t outer,
+                        uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return PFC_ERR_DRIVER;
+    const uint64_t es = is_bf16 ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_elems * es) % 16) return PFC_ERR_ALIGNMENT;
+    cuuint64_t gdim[2] = {inner, outer};
+    cuuint64_t gstr[1] = {row_stride_elems * es};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, gdim, gstr,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? PFC_OK : PFC_ERR_TENSORMAP;
 }
 
@@ -313,7 +347,7 @@ static int pick_mode(int m_tiles, int mcast_dim_tiles) {
 
 template <class Kern, class Params>
 static int launch_cluster(Kern kern, int cluster, int smem_bytes, const CUtensorMap& ta, const CUtensorMap& tb,
-                          const Params& prm, cudaStream_t stream) {
+                          const CUtensorMap& tc, const Params& prm, cudaStream_t stream) {
     const int sms = num_sms();
     if (sms <= 0) return PFC_ERR_CUDA;
     if (prm.num_tiles <= 0) return PFC_OK;
@@ -332,13 +366,13 @@ static int launch_cluster(Kern kern, int cluster, int smem_bytes, const CUtensor
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, prm);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, prm);
     return e == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 
 template <class P>
-static int launch_gemm(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const typename P::Params& prm,
-                       cudaStream_t stream) {
+static int launch_gemm(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                       const typename P::Params& prm, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(umma_gemm_kernel<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
@@ -347,9 +381,9 @@ static int launch_gemm(int mode, const CUtensorMap& ta, const CUtensorMap& tb, c
             return PFC_ERR_CUDA;
         attr_set = true;
     }
-    if (mode == MODE_PAIR) return launch_cluster(umma_gemm_pair_kernel<P>, 2, PAIR_SMEM_BYTES, ta, tb, prm, stream);
-    if (mode == MODE_MCAST) return launch_cluster(umma_gemm_kernel<P, 2>, 2, GEMM_SMEM_BYTES, ta, tb, prm, stream);
-    return launch_cluster(umma_gemm_kernel<P, 1>, 1, GEMM_SMEM_BYTES, ta, tb, prm, stream);
+    if (mode == MODE_PAIR) return launch_cluster(umma_gemm_pair_kernel<P>, 2, PAIR_SMEM_BYTES, ta, tb, tc, prm, stream);
+    if (mode == MODE_MCAST) return launch_cluster(umma_gemm_kernel<P, 2>, 2, GEMM_SMEM_BYTES, ta, tb, tc, prm, stream);
+    return launch_cluster(umma_gemm_kernel<P, 1>, 1, GEMM_SMEM_BYTES, ta, tb, tc, prm, stream);
 }
 
 static int even_up(int v) { return (v + 1) / 2 * 2; }
@@ -382,11 +416,14 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     if (!(s > 0.f) || 2.f * s * log2e > PFC_EXP_TOP + 126.f) return PFC_ERR_SCALE_RANGE;
     const int m_tiles = (B + BM - 1) / BM;
     const int mode = pick_mode(m_tiles, m_tiles);   // pairs of sample tiles share the class (W) stage
-    CUtensorMap ta, tb;
+    if (n_pad % 64) return PFC_ERR_SHAPE;              // the spill is stored in 64-column (128-byte) boxes
+    CUtensorMap ta, tb, tc;
     int rc = make_tmap(&ta, xn, d, B, d, BK, BM);
     if (rc) return rc;
     // in both pair modes each CTA fetches half of the 256 class rows of a stage
     rc = make_tmap(&tb, wn, d, n, d, BK, mode == MODE_SINGLE ? BN : BN / 2);
+    if (rc) return rc;
+    rc = make_store_tmap(&tc, E, true, n_pad, B, 1, n_pad, 0);
     if (rc) return rc;
     FwdPolicy::Params p;
     p.B = B; p.n = n; p.n_pad = n_pad; p.B_pad = pfc_padded_batch(B);
@@ -407,7 +444,7 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     p.m3 = m3; p.margin_kind = margin_kind; p.filter_thr = filter_thr;
     p.E = reinterpret_cast<__nv_bfloat16*>(E);
     p.part_sum = part_sum; p.tgt_raw = tgt_raw; p.tgt_e = tgt_e; p.tgt_z = tgt_z; p.s = s;
-    return launch_gemm<FwdPolicy>(mode, ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    return launch_gemm<FwdPolicy>(mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Number of class splits the dX contraction uses for a given shape (callers size `partial` with it).
@@ -454,7 +491,10 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     p.out = partial;
     p.out_bf16 = 0;
     p.dc = store_desc_cfg(false);
-    return launch_gemm<StorePolicy<false>>(mode, ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    CUtensorMap tc;
+    rc = make_store_tmap(&tc, partial, false, d, B, p.splits, d, static_cast<uint64_t>(B) * d);
+    if (rc) return rc;
+    return launch_gemm<StorePolicy<false>>(mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // dwn[n][d] = E'^T . Xs,   Xs = c_i * Xn_i (bf16, [B, d]);  dwn fp32 or (dwn_bf16) bf16
@@ -483,7 +523,60 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.out = reinterpret_cast<float*>(dwn);
     p.out_bf16 = dwn_bf16 ? 1 : 0;
     p.dc = store_desc_cfg(true);
-    return launch_gemm<StorePolicy<true>>(mode, ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+    CUtensorMap tc;
+    rc = make_store_tmap(&tc, dwn, dwn_bf16 != 0, d, n, 1, d, 0);
+    if (rc) return rc;
+    return launch_gemm<StorePolicy<true>>(mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// dW GEMM + normalise-backward + SGD/momentum step + next step's bf16 shard in ONE kernel (pfc_dwsgd.cuh).
+// Specialised for d = 512 (the two 256-column halves of a class tile run on a CTA pair); other d: PFC_ERR_SHAPE,
+// callers then use pfc_backward_dw + pfc_dw_sgd.
+int pfc_backward_dw_sgd(const void* E, int n_pad, const void* xs, int B, int n, int d, float* w, float* mom,
+                        const float* inv_norm_w, float lr, float momentum, float weight_decay, float inv_grad_scale,
+                        void* wn_next, float* inv_norm_next, void* stream) {
+    if (B <= 0 || n <= 0 || d != DWS_D || n_pad % 8) return PFC_ERR_SHAPE;
+    if (!w || !mom || !inv_norm_w || !wn_next || !inv_norm_next) return PFC_ERR_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(mom) | reinterpret_cast<uintptr_t>(wn_next)) & 31)
+        return PFC_ERR_ALIGNMENT;
+    CUtensorMap ta, tb, tw, tm, twn;
+    int rc = make_tmap(&ta, E, n, B, n_pad, 64, DWS_BK);   // A: E' [B(K), n(M)] MN-major boxes 64(M) x 32(K)
+    if (rc) return rc;
+    rc = make_tmap(&tb, xs, d, B, d, 64, DWS_BK);          // B: Xs [B(K), d(N)] MN-major boxes 64(N) x 32(K)
+    if (rc) return rc;
+    // state streams: boxes of 32 rows x 32 columns, loaded AND stored through the same maps
+    rc = make_tmap_2d(&tw, w, false, d, n, d, 32, 32, true);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tm, mom, false, d, n, d, 32, 32, true);
+    if (rc) return rc;
+    rc = make_tmap_2d(&twn, wn_next, true, d, n, d, 32, 32, false);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(dw_sgd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWS_SMEM_BYTES) != cudaSuccess)
+            return PFC_ERR_CUDA;
+        attr_set = true;
+    }
+    DwSgdParams p;
+    p.num_class_tiles = (n + BM - 1) / BM;
+    p.n = n;
+    p.k_stages = (B + DWS_BK - 1) / DWS_BK;
+    p.inv_w = inv_norm_w;
+    p.inv_next = inv_norm_next;
+    p.lr = lr; p.momentum = momentum; p.wd = weight_decay; p.inv_grad_scale = inv_grad_scale;
+    {
+        const char* e = getenv("PFC_DWS_PREFETCH");   // tuning knob, see pfc_dwsgd.cuh
+        p.prefetch = e ? atoi(e) : 0;
+    }
+    p.dc = store_desc_cfg(true);
+    p.dc.a_lbo = p.dc.b_lbo = DWS_MN_BOX;                  // 64-wide MN blocks are one 32-row box (4 KB) apart
+    const int sms = num_sms();
+    if (sms < 2) return PFC_ERR_CUDA;
+    int pairs = sms / 2;
+    if (pairs > p.num_class_tiles) pairs = p.num_class_tiles;
+    dw_sgd_gemm_kernel<<<2 * pairs, GEMM_THREADS, DWS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
+        ta, tb, tw, tm, twn, p);
+    return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 
 }  // extern "C"

@@ -48,26 +48,26 @@ __host__ __device__ constexpr DescCfg default_desc_cfg(bool a_mn, bool b_mn) {
                    b_mn ? (uint32_t)MN_BOX_BYTES : 16u, 1024u, b_mn ? 2048u : 32u};
 }
 
-// Each lane holds 128 bytes of ITS row (v[0..31]); the warp writes 32 rows x 128 B to global memory as full
-// 128-byte lines (8 lanes per row) after an XOR-swizzled (bank-conflict-free) transpose through `stage`.
-// gbase points at (row 0 of this warp, first byte of the 128-byte column block); rows >= rows_valid and 16-byte
-// pieces beyond bytes_valid are not written.
-__device__ __forceinline__ void warp_store_rows_128B(uint8_t* stage, int lane, const uint32_t (&v)[32], uint8_t* gbase,
-                                                     size_t row_stride_bytes, int rows_valid, int bytes_valid) {
+// Each lane holds 128 bytes of ITS row (v[0..31]).  The warp stages its 32 rows x 128 B in the SWIZZLE_128B layout
+// of the store tensor map (16-byte piece j of row r at r*128 + ((j ^ (r & 7)) << 4); `stage` is 1024-byte aligned)
+// and one lane hands the box to the TMA unit, which writes full lines and clips rows / columns beyond the tensor.
+// Compared with per-thread LDS + STG this removes 16 memory instructions, their 64-bit address arithmetic and the
+// bounds predicates per box from the epilogue warps, which pace the kernel when only two of them share a scheduler.
+// (c0, c1, c2) = element coordinates of the box in the map's (inner, row, slab) dimensions.
+__device__ __forceinline__ void warp_tma_store_rows(uint32_t stage, int lane, const uint32_t (&v)[32],
+                                                    const CUtensorMap* map, int c0, int c1, int c2) {
+    if (lane == 0) tma_store_wait_read<0>();   // the previous box of this warp has left the staging buffer
+    __syncwarp();
+    const uint32_t row = stage + lane * 128;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        sts128(row + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    fence_proxy_async_smem();
     __syncwarp();
-    const int c = lane & 7;
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        const int r = it * 4 + (lane >> 3);
-        const uint4 q = *reinterpret_cast<const uint4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
-        if (r < rows_valid && c * 16 + 16 <= bytes_valid)
-            *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(r) * row_stride_bytes + c * 16) = q;
+    if (lane == 0) {
+        tma_store_3d(map, stage, c0, c1, c2);
+        tma_store_commit();
     }
-    __syncwarp();
 }
 
 // Policy contract:
@@ -76,7 +76,8 @@ __device__ __forceinline__ void warp_store_rows_128B(uint8_t* stage, int lane, c
 //   static DescCfg desc(const Params&);         smem descriptor geometry (default_desc_cfg(A_MN, B_MN))
 //   static TileCoord tile(const Params&, int t);
 //   static void epilogue(const Params&, const TileCoord&, uint32_t taddr, int quarter, int half, int lane,
-//                        uint8_t* stage);
+//                        uint32_t stage, const CUtensorMap* tma_c);
+//        stage = shared-memory address of this warp's 4 KB staging buffer, tma_c = the output's store tensor map;
 //        taddr = TMEM address of this warp's lane quarter at column (half * EPI_COLS) of the tile's accumulator;
 //        the warp owns rows [32*quarter, 32*quarter+32) x columns [half*EPI_COLS, (half+1)*EPI_COLS) of the tile.
 //
@@ -87,7 +88,7 @@ __device__ __forceinline__ void warp_store_rows_128B(uint8_t* stage, int lane, c
 template <class P, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const typename P::Params prm) {
+                 const __grid_constant__ CUtensorMap tma_c, const typename P::Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -106,6 +107,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        tma_prefetch_desc(&tma_c);
 #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -222,7 +224,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int ew = warp - 2;
         const int quarter = warp & 3;                  // TMEM lanes [32q, 32q+32) are the only ones this warp may read
         const int half = ew >> 2;                      // which 128-column half of the accumulator
-        uint8_t* stage_buf = sEpi + ew * EPI_STAGE_BYTES;
+        const uint32_t stage_buf = smem_u32(sEpi + ew * EPI_STAGE_BYTES);
         int tl = 0;
         for (int t = first_tile; t < prm.num_tiles; t += tile_stride, ++tl) {
             const TileCoord tc = P::tile(prm, t);
@@ -232,11 +234,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             tc_fence_after();
             const uint32_t taddr =
                 tmem_base + acc * BN + half * EPI_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
-            P::epilogue(prm, tc, taddr, quarter, half, lane, stage_buf);
+            P::epilogue(prm, tc, taddr, quarter, half, lane, stage_buf, &tma_c);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (lane == 0) tma_store_wait_all();     // this warp's last boxes are in global memory before the CTA exits
     }
 
     tc_fence_before();

@@ -27,7 +27,7 @@ constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + EPI_WARPS * EPI
 template <class P>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                      const typename P::Params prm) {
+                      const __grid_constant__ CUtensorMap tma_c, const typename P::Params prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
@@ -48,6 +48,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
+        tma_prefetch_desc(&tma_c);
 #pragma unroll
         for (int s = 0; s < PAIR_STAGES; ++s) {
             mbar_init(&full_bar[s], 1);
@@ -137,7 +138,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         const int ew = warp - 2;
         const int quarter = warp & 3;
         const int half = ew >> 2;
-        uint8_t* stage_buf = sEpi + ew * EPI_STAGE_BYTES;
+        const uint32_t stage_buf = smem_u32(sEpi + ew * EPI_STAGE_BYTES);
         int tl = 0;
         for (int t = first_tile; t < prm.num_tiles; t += tile_stride, ++tl) {
             const TileCoord tc = P::tile(prm, t);
@@ -147,11 +148,12 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             tc_fence_after();
             const uint32_t taddr =
                 tmem_base + acc * BN + half * EPI_COLS + (static_cast<uint32_t>(quarter * 32) << 16);
-            P::epilogue(prm, tc, taddr, quarter, half, lane, stage_buf);
+            P::epilogue(prm, tc, taddr, quarter, half, lane, stage_buf, &tma_c);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
         }
+        if (lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();

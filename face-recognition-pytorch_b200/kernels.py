@@ -190,6 +190,15 @@ def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, inv_gra
                          _p(inv_norm_next, F32), _stream()), "pfc_dw_sgd")
 
 
+@_timed("pfc_backward_dw_sgd")
+def backward_dw_sgd(E, n_pad, xs, B, n, d, w, mom, inv_norm_w, lr, momentum, weight_decay, inv_grad_scale, wn_next,
+                    inv_norm_next):
+    """dW GEMM with normalise-backward + SGD/momentum + next bf16 shard as its epilogue (d == 512 only)."""
+    check(lib.pfc_backward_dw_sgd(_p(E, BF16), n_pad, _p(xs, BF16), B, n, d, _p(w, F32), _p(mom, F32),
+                                  _p(inv_norm_w, F32), lr, momentum, weight_decay, inv_grad_scale, _p(wn_next, BF16),
+                                  _p(inv_norm_next, F32), _stream()), "pfc_backward_dw_sgd")
+
+
 @_timed("pfc_dw_adam")
 def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, weight_decay, step, decoupled,
             inv_grad_scale, wn_next, inv_norm_next):

@@ -19,6 +19,8 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       weight_activated.grad = None so optimizer.step() skips it.  Hyper-parameters are re-read from
       optimizer.param_groups[-1] every step (the scheduler mutates lr, utils/scheduler.py:87-88).  Not valid together
       with a GradScaler (inf-skipping cannot be honoured); the un-fused default is.
+  conf.fused_dw_update (bool, default True; needs fused_optimizer, SGD, emd_size == 512): run the update as the EPILOGUE
+      of the dW GEMM (pfc_backward_dw_sgd): the un-normalised gradient never leaves tensor memory.
   conf.overlap_update (bool, default False; needs fused_optimizer): run the fused update on a side stream underneath
       the dX GEMM.  The normalised shard is then double-buffered and the two buffers swap roles every step, so a
       CUDA graph of the step must capture an EVEN number of steps (bench.py captures two).
@@ -116,6 +118,7 @@ class _PartialFCBase(torch.nn.Module):
         self.fp16 = conf.mixed_precision           # kept for interface parity; the kernels always run bf16-in / fp32-acc
         self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
         self.overlap_update = bool(getattr(conf, "overlap_update", False))
+        self.fused_dw_update = bool(getattr(conf, "fused_dw_update", True))
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
         self.last_batch_size: int = 0
@@ -329,10 +332,14 @@ class _PartialFCBase(torch.nn.Module):
         # underneath the tensor-bound dX GEMM (the row kernel needs no shared memory, so its CTAs co-reside with the
         # GEMM's); it writes next step's normalised rows into the OTHER wn buffer because dX still reads this one.
         w = self.weight_activated.data
+        overlap = self.fused_optimizer and self.overlap_update and w.is_cuda
+        # one kernel for dW GEMM + update (after the dX GEMM, which still reads this step's normalised shard)
+        fuse_dw = (self.fused_optimizer and self.fused_dw_update and self._optimizer_kind == "sgd" and d == 512
+                   and not overlap)
         spill_bf16 = self.fused_optimizer and self._optimizer_kind == "sgd" and d % 128 == 0
         dwn = ws.dwn_bf16 if spill_bf16 else ws.dwn
-        K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
-        overlap = self.fused_optimizer and self.overlap_update and w.is_cuda
+        if not fuse_dw:
+            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         dw, side = None, None
         wn_now = ws.wn
         if overlap:
@@ -365,7 +372,9 @@ class _PartialFCBase(torch.nn.Module):
                 # :505-519 -- asynchronous: it overlaps the rank-local update below / on the side stream
                 rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
                                                             async_op=True)
-        if self.fused_optimizer and not overlap:
+        if fuse_dw:
+            self._fused_dw_step(w, n, n_pad, d)       # dW GEMM + update in place, after the dX GEMM has consumed wn
+        elif self.fused_optimizer and not overlap:
             self._fused_step(w, n, d, dwn, ws.wn)     # in place, after the dX GEMM has consumed wn
         if rs_work is not None:
             rs_work.wait()
@@ -435,17 +444,24 @@ class PartialFC(_PartialFCBase):
             raise RuntimeError("fused SGD supports dampening=0, nesterov=False, maximize=False")
         return dict(lr=float(g["lr"]), momentum=float(g["momentum"]), wd=float(g["weight_decay"]))
 
+    def _momentum(self, w):
+        if self.sample_rate < 1:
+            return self.weight_activated_mom
+        if self._fused_state is None:
+            self._fused_state = torch.zeros_like(w)
+            self.weight_activated_mom = self._fused_state
+        return self._fused_state
+
     def _fused_step(self, w, n, d, dwn, wn_out):
         ws, o = self._ws, self._opt_args
-        if self.sample_rate < 1:
-            mom = self.weight_activated_mom
-        else:
-            if self._fused_state is None:
-                self._fused_state = torch.zeros_like(w)
-                self.weight_activated_mom = self._fused_state
-            mom = self._fused_state
-        K.dw_sgd(dwn, w, mom, ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], 1.0, wn_out, ws.inv_w)
+        K.dw_sgd(dwn, w, self._momentum(w), ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], 1.0, wn_out, ws.inv_w)
         self._wn_valid = True             # the update wrote next step's normalised bf16 rows and 1/norm in place
+
+    def _fused_dw_step(self, w, n, n_pad, d):
+        ws, o = self._ws, self._opt_args
+        K.backward_dw_sgd(ws.E, n_pad, ws.xs, ws.B, n, d, w, self._momentum(w), ws.inv_w, o["lr"], o["momentum"],
+                          o["wd"], 1.0, ws.wn, ws.inv_w)
+        self._wn_valid = True
 
 
 class PartialFCAdamW(_PartialFCBase):

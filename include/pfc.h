@@ -126,6 +126,13 @@ int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, c
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                 float inv_grad_scale, void* wn_next_bf16, float* inv_norm_next, void* stream);
 
+/* pfc_backward_dw + pfc_dw_sgd in ONE kernel: the un-normalised gradient stays in tensor memory and the update is the
+ * GEMM's epilogue (no dWn spill).  d must be 512 (PFC_ERR_SHAPE otherwise: use the two-kernel path); w, mom and
+ * wn_next 32-byte aligned.  Same argument meaning as pfc_dw_sgd; wn_next may alias the shard pfc_backward_dx read. */
+int pfc_backward_dw_sgd(const void* E_bf16, int n_pad, const void* xs_bf16, int B, int n, int d, float* w, float* mom,
+                        const float* inv_norm_w, float lr, float momentum, float weight_decay, float inv_grad_scale,
+                        void* wn_next_bf16, float* inv_norm_next, void* stream);
+
 /* ---- (5b) the three exchanges of the step over peer memory (NVLink / NVSwitch), fused into the producing kernels.
  * They replace all_gather (nets/PartialFC.py:182-186), the softmax all_reduces (:448, :453, :459) and the dX
  * reduce (:505-522).  peer_* arguments are HOST arrays of W device pointers: entry q is rank q's symmetric buffer as

@@ -140,3 +140,10 @@ class FakeKernels:
         w[:rows] = w_new
         mom[:rows] = m_new
         self.l2norm_rows(w, None, rows, wn_next, inv_norm_next)
+
+    def backward_dw_sgd(self, E, n_pad, xs, B, n, d, w, mom, inv_norm_w, lr, momentum, wd, inv_grad_scale, wn_next,
+                        inv_norm_next):
+        dwn = torch.empty(n, d)
+        self.backward_dw(E, n_pad, xs, B, n, d, dwn)
+        self.dw_sgd(dwn, w, mom, inv_norm_w, n, d, lr, momentum, wd, inv_grad_scale, wn_next, inv_norm_next)
+

@@ -126,7 +126,8 @@ def test_overlap_update_is_bit_identical_to_serial(pfc):
     outs = []
     for overlap in (False, True):
         conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
-                                     loss_m=cfg["m"], fused_optimizer=True, overlap_update=overlap)
+                                     loss_m=cfg["m"], fused_optimizer=True, overlap_update=overlap,
+                                     fused_dw_update=False)
         head = pfc.PartialFC(conf, cfg["C"])
         head.load_state_dict({"weight": weights[0].clone()})
         head = head.train().cuda()
@@ -145,6 +146,56 @@ def test_overlap_update_is_bit_identical_to_serial(pfc):
         assert torch.equal(a, b)
     assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
     assert outs[0][0][4] < outs[0][0][0]            # and the fused SGD actually trains
+
+
+@pytest.mark.parametrize("shape", ["golden_d512", "cfg2_full"])
+def test_fused_dw_update_matches_two_kernel_path(pfc, shape):
+    """conf.fused_dw_update (dW GEMM with the SGD update as its epilogue, CTA-pair split of d) against the
+    pfc_backward_dw + pfc_dw_sgd pair: same losses, same weights / momentum up to the bf16 rounding of the
+    gradient spill that the two-kernel path has and the fused one does not."""
+    if shape == "golden_d512":
+        cfg, z = load_case("head_w1_d512")
+        weights, xs, ls = case_inputs(cfg)
+        x0, l0, steps = xs[0], ls[0], 4
+    else:
+        C, d, B = 93431, 512, 1024          # n % 128 != 0: exercises the class-tail rows of the last tile
+        w = torch.normal(0, 0.01, (C, d), generator=torch.Generator().manual_seed(1234))
+        l0 = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(7))
+        x0 = torch.nn.functional.normalize(torch.nn.functional.normalize(w[l0]) +
+                                           torch.randn(B, d, generator=torch.Generator().manual_seed(42)) / d ** 0.5)
+        cfg = dict(C=C, d=d, s=64.0, m=0.5, lr=0.1, momentum=0.9, wd=5e-4)
+        weights, steps = [w], 3
+    outs = []
+    for fuse in (False, True):
+        conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
+                                     loss_m=cfg["m"], fused_optimizer=True, fused_dw_update=fuse)
+        head = pfc.PartialFC(conf, cfg["C"])
+        head.load_state_dict({"weight": weights[0].clone()})
+        head = head.train().cuda()
+        opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
+        losses = []
+        for s in range(steps):
+            x = x0.clone().cuda().requires_grad_(True)
+            loss = head(x, l0.clone().cuda(), opt)
+            loss.backward()
+            losses.append(float(loss.detach()))
+        torch.cuda.synchronize()
+        outs.append((losses, head.weight_activated.data.clone(), head.weight_activated_mom.clone(),
+                     head._ws.wn.clone(), head._ws.inv_w.clone()))
+    w0 = weights[0].cuda()
+    (la, wa, ma, wna, ia), (lb, wb, mb, wnb, ib) = outs
+    assert la[0] == lb[0]                                   # identical first forward
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 2e-3 * abs(a)
+    assert la[-1] < la[0]
+    assert torch.isfinite(wb).all() and torch.isfinite(mb).all()
+    assert cosine((wa - w0).cpu(), (wb - w0).cpu()) >= 0.9995
+    assert cosine(ma.cpu(), mb.cpu()) >= 0.9995
+    assert abs(float(mb.norm()) / float(ma.norm()) - 1) < 1e-2
+    # next step's operand: normalised rows of the NEW weights and their inverse norms, for every row incl. the tail
+    ref_wn = torch.nn.functional.normalize(wb)
+    assert float((wnb.float() - ref_wn).abs().max()) <= 2 ** -8
+    torch.testing.assert_close(ib, 1.0 / wb.norm(dim=1), rtol=1e-5, atol=0)
 
 
 def test_batch_size_change_asserts(pfc):
