@@ -91,10 +91,10 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in self.rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
@@ -103,7 +103,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         load = [v for v in sm if v > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw) if pw else None}
 
 
 def run_reference(args, rank, world):
@@ -199,6 +200,7 @@ def main():
     ap.add_argument("--sgd-warps", type=int, default=0, help="with --overlap: persistent SGD grid, warps per SM")
     ap.add_argument("--gemm-mode", type=int, default=0, help="0 auto, 1 single CTA, 2 multicast pair, 3 cta_group::2")
     ap.add_argument("--unfused", action="store_true", help="hand dW to torch.optim.SGD instead of the fused update")
+    ap.add_argument("--fused-dw", action="store_true", help="dW GEMM with the SGD update as its epilogue (one kernel)")
     ap.add_argument("--no-peer", action="store_true",
                     help="N>1: NCCL collectives instead of the peer-memory (NVLink) exchanges fused into the kernels")
     args = ap.parse_args()
@@ -231,7 +233,7 @@ def main():
     b = GLOBAL_BATCH // world
     conf = types.SimpleNamespace(emd_size=EMB, sample_rate=1.0, mixed_precision=False, loss_s=S, loss_m=M,
                                  fused_optimizer=not args.unfused, overlap_update=bool(args.overlap) and not args.unfused,
-                                 peer_collectives=False if args.no_peer else "auto")
+                                 peer_collectives=False if args.no_peer else "auto", fused_dw_update=bool(args.fused_dw))
     head = pfc.PartialFC(conf, C_CLASSES)
     head.load_state_dict({"weight": w_shard})
     head = head.train().cuda()
@@ -241,11 +243,6 @@ def main():
     x_dev = [x.to(dev).requires_grad_(True) for x in xs]
     l_dev = [l.to(dev) for l in ls]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
-
-    # two static input slots / two graphs: with overlap_update the normalised shard ping-pongs between two buffers,
-    # so consecutive steps are two different graphs that are replayed alternately
-    static_x = [x_dev[0].detach().clone().requires_grad_(True) for _ in range(2)]
-    static_l = [l_dev[0].clone() for _ in range(2)]
 
     def step_eager(x, lab):
         loss = head(x, lab, opt)
@@ -265,49 +262,20 @@ def main():
         step_eager(x_dev[i % n_data], l_dev[i % n_data])
     torch.cuda.synchronize()
 
-    graphs = None
-    ws = head._ws
-    wn_ptr0 = ws.wn.data_ptr()
-
-    def parity():
-        return 0 if ws.wn.data_ptr() == wn_ptr0 else 1
-
+    # CUDA-graph replay through the package's own public wrapper (face_recognition_pytorch_b200.GraphedHeadStep)
+    gstep = None
     if not args.no_graph and not args.unfused:
         try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for k in range(2):
-                    static_x[k].grad = None
-                    step_eager(static_x[k], static_l[k])
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graphs = {}
-            for _ in range(2):
-                k = parity()
-                g = torch.cuda.CUDAGraph()
-                static_x[k].grad = None
-                with torch.cuda.graph(g):
-                    step_eager(static_x[k], static_l[k])    # capturing flips the ping-pong on the host side only
-                graphs[k] = g
-                if ws.wn_alt is None:                       # no ping-pong: one graph serves every step
-                    graphs[1 - k] = g
-                    break
-            torch.cuda.synchronize()
+            gstep = pfc.GraphedHeadStep(head, opt, b, EMB)
         except Exception as e:   # report, fall back to eager launches (still the CUDA path)
             if rank == 0:
                 print(f"# CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
-            graphs = None
+            gstep = None
             torch.cuda.synchronize()
 
     def run_step(i):
-        if graphs is not None:
-            k = parity()
-            static_x[k].data.copy_(x_dev[i % n_data].data)
-            static_l[k].copy_(l_dev[i % n_data])
-            graphs[k].replay()
-            if ws.wn_alt is not None:
-                ws.wn, ws.wn_alt = ws.wn_alt, ws.wn         # what the replayed step did on the device
+        if gstep is not None:
+            gstep(x_dev[i % n_data].data, l_dev[i % n_data])
         else:
             x_dev[i % n_data].grad = None
             step_eager(x_dev[i % n_data], l_dev[i % n_data])
@@ -353,6 +321,10 @@ def main():
     dx_host = torch.empty(b, EMB, dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
+        if gstep is not None:         # pinned host -> static device buffers -> graph replay -> pinned host
+            loss, dx = gstep(hx[i % n_data], hl[i % n_data])
+            dx_host.copy_(dx, non_blocking=True)
+            return float(loss.item())
         x = hx[i % n_data].to(dev, non_blocking=True).requires_grad_(True)
         lab = hl[i % n_data].to(dev, non_blocking=True)
         loss = head(x, lab, opt)
@@ -426,7 +398,7 @@ def main():
         "config": {"workload": "configs[1]: PartialFC C=93431 d=512 global_batch=1024 sample_rate=1.0 s=64 m=0.5, "
                                "fwd+bwd+" + ("torch SGD step" if args.unfused else "fused SGD update"),
                    "classes_per_gpu": nl, "local_batch": b, "parallelism": f"class-sharded x{world}",
-                   "launch": "cuda-graph replay" if graphs is not None else "eager",
+                   "launch": "cuda-graph replay (GraphedHeadStep)" if gstep is not None else "eager",
                    "overlap_update": bool(conf.overlap_update),
                    "exchange": ("none (1 GPU)" if world == 1 else
                                 "peer-memory stores + flag barriers (NVLink)" if head._peer is not None else
@@ -438,7 +410,9 @@ def main():
                           "peak_source": pk["kind"] + " burst bf16"},
         "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in kern.items()},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * EMB * 4 + b * 8,
-                "d2h_bytes_per_step": 4 + b * EMB * 4, "steps": e2e_steps, "timing": "host wall clock, max over ranks"},
+                "d2h_bytes_per_step": 4 + b * EMB * 4, "steps": e2e_steps, "timing": "host wall clock, max over ranks",
+                "api": ("GraphedHeadStep(head, opt)(x_pinned_host, labels_pinned_host) + dx D2H + loss.item()"
+                        if gstep is not None else "head(x, labels, opt); loss.backward() + dx D2H + loss.item()")},
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "wall_ms_per_step": t_wall / args.steps * 1e3,

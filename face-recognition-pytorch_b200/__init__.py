@@ -8,7 +8,8 @@ from . import _lib                                    # noqa: F401  (fails loudl
 from .arcface import ArcFace, CosFace, CombinedMarginLoss
 from .partial_fc import PartialFC, PartialFCAdamW, shard_range
 from .eval import pair_score, cross_score, performance_roc, performance_acc, kfold_accuracy
+from .graph import GraphedHeadStep
 
 __all__ = ["ArcFace", "CosFace", "CombinedMarginLoss", "PartialFC", "PartialFCAdamW", "shard_range", "pair_score",
-           "cross_score", "performance_roc", "performance_acc", "kfold_accuracy"]
+           "cross_score", "performance_roc", "performance_acc", "kfold_accuracy", "GraphedHeadStep"]
 __version__ = "0.1.0"

@@ -198,6 +198,41 @@ def test_fused_dw_update_matches_two_kernel_path(pfc, shape):
     torch.testing.assert_close(ib, 1.0 / wb.norm(dim=1), rtol=1e-5, atol=0)
 
 
+def test_graphed_head_step_replays_the_eager_step_bit_for_bit(pfc):
+    """GraphedHeadStep (CUDA-graph replay of forward + backward + fused update, pinned-host or device inputs) gives
+    the same losses, dX and weights as the eager module calls it captured."""
+    cfg, z = load_case("head_w1_d512")
+    weights, xs, ls = case_inputs(cfg)
+    outs = []
+    for graphed in (False, True):
+        conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
+                                     loss_m=cfg["m"], fused_optimizer=True)
+        head = pfc.PartialFC(conf, cfg["C"])
+        head.load_state_dict({"weight": weights[0].clone()})
+        head = head.train().cuda()
+        opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
+        losses, grads = [], []
+        if graphed:          # construction runs warm-up steps but restores weights / momentum afterwards
+            step = pfc.GraphedHeadStep(head, opt, xs[0].shape[0], cfg["d"])
+        for s in range(4):
+            xh, lh = xs[s % len(xs)], ls[s % len(ls)]
+            if graphed:
+                loss, dx = step(xh.pin_memory(), lh.pin_memory())
+            else:
+                x = xh.clone().cuda().requires_grad_(True)
+                loss = head(x, lh.clone().cuda(), opt)
+                loss.backward()
+                dx = x.grad
+            losses.append(float(loss.detach()))
+            grads.append(dx.detach().clone())
+        torch.cuda.synchronize()
+        outs.append((losses, grads, head.weight_activated.data.clone()))
+    assert outs[0][0] == outs[1][0]
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[0][2], outs[1][2])
+
+
 def test_batch_size_change_asserts(pfc):
     cfg, z = load_case("head_w1_full")
     weights, xs, ls = case_inputs(cfg)
