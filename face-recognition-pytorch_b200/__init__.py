@@ -9,7 +9,9 @@ from .arcface import ArcFace, CosFace, CombinedMarginLoss
 from .partial_fc import PartialFC, PartialFCAdamW, shard_range
 from .eval import pair_score, cross_score, performance_roc, performance_acc, kfold_accuracy
 from .graph import GraphedHeadStep
+from .checkpoint import head_shard_state, load_head_shard, reshard
 
 __all__ = ["ArcFace", "CosFace", "CombinedMarginLoss", "PartialFC", "PartialFCAdamW", "shard_range", "pair_score",
-           "cross_score", "performance_roc", "performance_acc", "kfold_accuracy", "GraphedHeadStep"]
+           "cross_score", "performance_roc", "performance_acc", "kfold_accuracy", "GraphedHeadStep", "head_shard_state",
+           "load_head_shard", "reshard"]
 __version__ = "0.1.0"

@@ -66,7 +66,9 @@ _SIGS = {
     "pfc_peer_barrier": (c_int, [POINTER(c_void_p), p, c_int, c_int, p]),
     "pfc_peer_l2norm_gather": (c_int, [p, p, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), p, p]),
     "pfc_peer_row_stats": (c_int, [p, c_int, c_int, p, p, c_int, c_int, POINTER(c_void_p), p]),
-    "pfc_peer_loss": (c_int, [p, c_int, c_int, p, p, p, p]),
+    "pfc_peer_loss": (c_int, [POINTER(c_void_p), p, c_int, p, c_int, c_int, p, p, p, p]),
+    "pfc_peer_localize_labels": (c_int, [POINTER(c_void_p), p, c_int, c_int, p, c_int, ctypes.c_int64, c_int, p, p]),
+    "pfc_peer_dx_finalize": (c_int, [POINTER(c_void_p), p, c_int, c_int, p, p, p, c_float, c_int, c_int, p, p]),
     "pfc_peer_dx_scatter": (c_int, [p, c_int, p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p), p]),
     "pfc_eval_hist_bins": (c_int, []),
     "fr_pair_score": (c_int, [p, p, p, c_int, c_int, p, p, p, p, p]),

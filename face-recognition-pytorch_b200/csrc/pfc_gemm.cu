@@ -169,6 +169,7 @@ struct StoreParams {
     int m_tiles, n_tiles, splits;
     int k_stages_total, k_stages_per_split;
     int n_fastest;
+    int m_reverse;          // 1: walk the M tiles from the last to the first (most recently written rows of A first)
     int rows_valid, cols_valid;
     int ld;                 // row stride of out (elements)
     size_t split_stride;    // elements between split slabs
@@ -195,6 +196,7 @@ struct StorePolicy {
         int mt, nt;
         if (p.n_fastest) { mt = r / p.n_tiles; nt = r - mt * p.n_tiles; }
         else             { nt = r / p.m_tiles; mt = r - nt * p.m_tiles; }
+        if (p.m_reverse) mt = p.m_tiles - 1 - mt;
         tc.m0 = mt * BM;
         tc.n0 = nt * BN;
         tc.k0 = z * p.k_stages_per_split;
@@ -486,6 +488,7 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     if (p.splits != splits) return PFC_ERR_SHAPE;
     p.num_tiles = p.m_tiles * p.n_tiles * p.splits;
     p.n_fastest = 0;
+    p.m_reverse = 0;
     p.rows_valid = B; p.cols_valid = d; p.ld = d;
     p.split_stride = static_cast<size_t>(B) * d;
     p.out = partial;
@@ -518,6 +521,9 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.k_stages_per_split = p.k_stages_total;
     p.num_tiles = p.m_tiles * p.n_tiles;
     p.n_fastest = mode == MODE_PAIR ? 0 : 1;
+    // the forward wrote E' class tile by class tile: its last tiles are still in L2, so start with them; the
+    // gradient rows written LAST are then the low ones, which is where the row-ordered update kernel starts
+    p.m_reverse = 1;
     p.rows_valid = n; p.cols_valid = d; p.ld = d;
     p.split_stride = 0;
     p.out = reinterpret_cast<float*>(dwn);

@@ -10,6 +10,9 @@
 //   pfc_peer_dx_scatter    : c_i * sum_z partial[z][i,:] for the rows owned by rank r -> slot `rank` of rank r's
 //                            dx_slots[W][b][d]   (the consumer is pfc_dx_finalize with splits = W)
 //   pfc_peer_barrier       : all ranks' previous stores are visible everywhere after it (one tiny kernel per rank)
+// The consumers of the exchanged data take the barrier at their OWN start instead of behind a separate launch
+// (pfc_peer_localize_labels, pfc_peer_loss, pfc_peer_dx_finalize): CTA 0 signals the peers, every CTA polls this
+// rank's flags, and the last CTA through advances the epoch -- three launches fewer per step.
 //
 // Peer buffers come from torch's symmetric-memory allocator (host code passes the mapped device pointers); the
 // barrier uses one uint32 flag per (receiver, sender) pair and a per-rank epoch counter kept in device memory, so the
@@ -60,6 +63,56 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, uint32_t* counter, int rank,
         }
     }
     __threadfence_system();
+}
+
+// Entry barrier of a consumer kernel (every thread of every CTA calls it first).  The producing kernel of THIS rank
+// has completed (stream order), so its stores only need the system-scope fence before the flags go out.
+// state[0] = epoch counter, state[1] = ticket of the CTAs that have passed (both zeroed once by the host).
+__device__ __forceinline__ void peer_entry_barrier(const PeerPtrs& flags, uint32_t* state, int rank, int W) {
+    __shared__ uint32_t ep_s;
+    if (threadIdx.x == 0) ep_s = *reinterpret_cast<volatile uint32_t*>(state) + 1;
+    __syncthreads();
+    const uint32_t ep = ep_s;
+    if (blockIdx.x == 0 && threadIdx.x < W) {
+        __threadfence_system();
+        uint32_t* remote = static_cast<uint32_t*>(flags.p[threadIdx.x]) + rank;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(ep) : "memory");
+    }
+    if (threadIdx.x < W) {
+        const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + threadIdx.x;
+        uint32_t v;
+        const long long t0 = clock64();
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+            if (static_cast<int32_t>(v - ep) >= 0) break;
+            if (clock64() - t0 > 20000000000LL) {
+                printf("pfc: peer barrier timed out (rank %d waiting for %d, epoch %u, saw %u)\n", rank,
+                       (int)threadIdx.x, ep, v);
+                __trap();
+            }
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // every CTA has read the epoch before it takes a ticket, so the last one may advance it
+        if (atomicAdd(state + 1, 1u) == gridDim.x - 1) {
+            state[1] = 0;
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t*>(state) = ep;
+        }
+    }
+}
+
+// barrier + labels -> shard-local ids (-1 for classes of another rank), nets/PartialFC.py:188-193
+__global__ void __launch_bounds__(256)
+peer_localize_labels_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, const int64_t* labels, int B,
+                            int64_t class_start, int num_local, int32_t* __restrict__ out) {
+    peer_entry_barrier(flags, state, rank, W);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int64_t l = reinterpret_cast<const volatile int64_t*>(labels)[i] - class_start;
+    out[i] = (l >= 0 && l < num_local) ? static_cast<int32_t>(l) : -1;
 }
 
 // warp per row; lane l handles float4 #l, #l+32, ... (d <= 1024)
@@ -128,15 +181,20 @@ peer_row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, in
 }
 
 // stats[i] = sum_r slots[r][i] (rank order), row_L, loss -- the local half of the exchange + pfc_loss
+template <bool kBarrier>
 __global__ void __launch_bounds__(1024)
-peer_loss_kernel(const float* __restrict__ slots, int W, int B, float* __restrict__ stats, float* __restrict__ row_L,
-                 float* __restrict__ loss) {
+peer_loss_kernel(PeerPtrs flags, uint32_t* state, int rank, const float* slots, int W, int B, float* __restrict__ stats,
+                 float* __restrict__ row_L, float* __restrict__ loss) {
     __shared__ float red[32];
+    if (kBarrier) peer_entry_barrier(flags, state, rank, W);
     float acc = 0.f;
     for (int i = threadIdx.x; i < B; i += 1024) {
         float others = 0.f, te = 0.f;
         for (int r = 0; r < W; ++r) {
-            const float2 v = reinterpret_cast<const float2*>(slots + static_cast<size_t>(r) * B * 2)[i];
+            // peers wrote the slots: plain (not read-only-cache) loads
+            float2 v;
+            asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];"
+                         : "=f"(v.x), "=f"(v.y) : "l"(slots + (static_cast<size_t>(r) * B + i) * 2));
             others += v.x;
             te += v.y;
         }
@@ -173,6 +231,51 @@ peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t spl
         }
         a.x *= c; a.y *= c; a.z *= c; a.w *= c;
         *reinterpret_cast<float4*>(out + 4 * k) = a;
+    }
+}
+
+// barrier + dx = W * normalize_backward(sum over the W slots of this rank's dx_slots [W][b][d])   (:505-522)
+__global__ void __launch_bounds__(256)
+peer_dx_finalize_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, const float* slots, const float* __restrict__ x,
+                        const float* __restrict__ inv_norm, float scale, int b, int d, float* __restrict__ out) {
+    peer_entry_barrier(flags, state, rank, W);
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= b) return;
+    const int nv = d >> 2;
+    const float inv = inv_norm[row];
+    float4 g[8], xv[8];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = lane + 32 * j;
+        if (k < nv) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int z = 0; z < W; ++z) {
+                const float* p = slots + (static_cast<size_t>(z) * b + row) * d + 4 * k;
+                float4 q;
+                asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(p));
+                a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+            }
+            g[j] = a;
+            float4 q = *reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * d + 4 * k);
+            q.x *= inv; q.y *= inv; q.z *= inv; q.w *= inv;
+            xv[j] = q;
+            dot += q.x * a.x + q.y * a.y + q.z * a.z + q.w * a.w;
+        }
+    }
+    dot = warp_sum_p(dot);
+    const float m = scale * inv;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = lane + 32 * j;
+        if (k < nv) {
+            float4 a = g[j];
+            a.x = (a.x - xv[j].x * dot) * m; a.y = (a.y - xv[j].y * dot) * m;
+            a.z = (a.z - xv[j].z * dot) * m; a.w = (a.w - xv[j].w * dot) * m;
+            *reinterpret_cast<float4*>(out + static_cast<size_t>(row) * d + 4 * k) = a;
+        }
     }
 }
 
@@ -223,9 +326,40 @@ int pfc_peer_row_stats(const float* part_sum, int n_tiles, int B, const int32_t*
     return launched();
 }
 
-int pfc_peer_loss(const float* slots, int W, int B, float* stats, float* row_L, float* loss, void* stream) {
+int pfc_peer_loss(void* const* peer_flags, uint32_t* barrier_state, int rank, const float* slots, int W, int B,
+                  float* stats, float* row_L, float* loss, void* stream) {
     if (B <= 0 || W < 1) return PFC_ERR_SHAPE;
-    peer_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(slots, W, B, stats, row_L, loss);
+    PeerPtrs f = {};
+    if (peer_flags) {
+        int rc = fill_peers(&f, peer_flags, W);
+        if (rc) return rc;
+        if (!barrier_state) return PFC_ERR_SHAPE;
+        peer_loss_kernel<true><<<1, 1024, 0, (cudaStream_t)stream>>>(f, barrier_state, rank, slots, W, B, stats, row_L, loss);
+    } else {
+        peer_loss_kernel<false><<<1, 1024, 0, (cudaStream_t)stream>>>(f, nullptr, rank, slots, W, B, stats, row_L, loss);
+    }
+    return launched();
+}
+
+int pfc_peer_localize_labels(void* const* peer_flags, uint32_t* barrier_state, int rank, int W, const int64_t* labels,
+                             int B, int64_t class_start, int num_local, int32_t* labels_local, void* stream) {
+    if (B <= 0 || !barrier_state) return PFC_ERR_SHAPE;
+    PeerPtrs f;
+    int rc = fill_peers(&f, peer_flags, W);
+    if (rc) return rc;
+    peer_localize_labels_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(f, barrier_state, rank, W, labels, B,
+                                                                                   class_start, num_local, labels_local);
+    return launched();
+}
+
+int pfc_peer_dx_finalize(void* const* peer_flags, uint32_t* barrier_state, int rank, int W, const float* dx_slots,
+                         const float* x, const float* inv_norm, float scale, int b, int d, float* out, void* stream) {
+    if (b <= 0 || d <= 0 || (d & 7) || d > 1024 || !barrier_state || !x || !inv_norm) return PFC_ERR_SHAPE;
+    PeerPtrs f;
+    int rc = fill_peers(&f, peer_flags, W);
+    if (rc) return rc;
+    peer_dx_finalize_kernel<<<(b + 7) / 8, 256, 0, (cudaStream_t)stream>>>(f, barrier_state, rank, W, dx_slots, x, inv_norm,
+                                                                          scale, b, d, out);
     return launched();
 }
 

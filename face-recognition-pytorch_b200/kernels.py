@@ -227,9 +227,22 @@ def peer_row_stats(part_sum, n_tiles, B, labels_local, tgt_e, rank, W, peer_slot
 
 
 @_timed("pfc_peer_loss")
-def peer_loss(slots, W, B, stats, row_L, out):
-    check(lib.pfc_peer_loss(_p(slots, F32), W, B, _p(stats, F32), _p(row_L, F32), _p(out, F32), _stream()),
-          "pfc_peer_loss")
+def peer_loss(peer_flags, state, rank, slots, W, B, stats, row_L, out):
+    """peer_flags / state None: no barrier (the caller ran pfc_peer_barrier); else the kernel takes it at its start."""
+    check(lib.pfc_peer_loss(peer_flags, _p(state, I32), rank, _p(slots, F32), W, B, _p(stats, F32), _p(row_L, F32),
+                            _p(out, F32), _stream()), "pfc_peer_loss")
+
+
+@_timed("pfc_peer_localize_labels")
+def peer_localize_labels(peer_flags, state, rank, W, labels, class_start, num_local, out):
+    check(lib.pfc_peer_localize_labels(peer_flags, _p(state, I32), rank, W, _p(labels, I64), labels.numel(), class_start,
+                                       num_local, _p(out, I32), _stream()), "pfc_peer_localize_labels")
+
+
+@_timed("pfc_peer_dx_finalize")
+def peer_dx_finalize(peer_flags, state, rank, W, dx_slots, x, inv_norm, scale, b, d, out):
+    check(lib.pfc_peer_dx_finalize(peer_flags, _p(state, I32), rank, W, _p(dx_slots, F32), _p(x, F32), _p(inv_norm, F32),
+                                   scale, b, d, _p(out, F32), _stream()), "pfc_peer_dx_finalize")
 
 
 @_timed("pfc_peer_dx_scatter")

@@ -120,6 +120,7 @@ class _PartialFCBase(torch.nn.Module):
         self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
         self.overlap_update = bool(getattr(conf, "overlap_update", False))
         self.fused_dw_update = bool(getattr(conf, "fused_dw_update", False))
+        self._num_classes = int(num_classes)
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
         self.last_batch_size: int = 0
@@ -271,8 +272,8 @@ class _PartialFCBase(torch.nn.Module):
         peer = self._peer
         if peer is not None:
             # normalise + all-gather in one kernel: every rank stores its bf16 rows and labels into every peer
+            # (the barrier that publishes the rows is taken by the consumer of the labels, below)
             K.peer_l2norm_gather(x, labels_in, self.rank, W, peer.ptrs("xn_all"), peer.ptrs("labels_all"), ws.inv_x)
-            K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
             labels_all = peer.labels_all
         elif W > 1:
             K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
@@ -288,7 +289,11 @@ class _PartialFCBase(torch.nn.Module):
         else:
             K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
             labels_all = labels_in
-        K.localize_labels(labels_all, self.class_start, self.num_local, ws.labels_local)   # :188-193
+        if peer is not None:
+            K.peer_localize_labels(peer.ptrs("flags"), peer.counter, self.rank, W, labels_all, self.class_start,
+                                   self.num_local, ws.labels_local)               # barrier + :188-193
+        else:
+            K.localize_labels(labels_all, self.class_start, self.num_local, ws.labels_local)   # :188-193
         if self.sample_rate < 1:
             self.sample(ws.labels_local, None, optimizer, perm)                   # :195-196
         else:
@@ -311,8 +316,8 @@ class _PartialFCBase(torch.nn.Module):
             # statistics straight into every peer's slot, then a rank-ordered local sum (identical bits on all ranks)
             K.peer_row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, self.rank, W,
                              peer.ptrs("slots"))
-            K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
-            K.peer_loss(peer.slots, W, B, ws.stats, ws.row_L, ws.loss)            # replaces :448, :453, :459, :461
+            K.peer_loss(peer.ptrs("flags"), peer.counter, self.rank, peer.slots, W, B, ws.stats, ws.row_L,
+                        ws.loss)                                                  # barrier + :448, :453, :459, :461
         else:
             K.row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats)
             if W > 1:
@@ -382,9 +387,11 @@ class _PartialFCBase(torch.nn.Module):
             K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)        # :521
         if peer is not None:
             # also the fence that keeps a fast rank's NEXT gather out of xn_all while a slow rank still reads it
-            K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
             if dx is not None:
-                K.dx_finalize(peer.dx_slots, W, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)    # :521
+                K.peer_dx_finalize(peer.ptrs("flags"), peer.counter, self.rank, W, peer.dx_slots, self._x_local,
+                                   ws.inv_x, float(W), b, d, dx)                  # barrier + :521
+            else:
+                K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         return dx, dw
@@ -399,7 +406,7 @@ class _PartialFCBase(torch.nn.Module):
             destination._metadata = collections.OrderedDict()
         for name, module in self._modules.items():
             if module is not None:
-                module.state_dict(destination, prefix + name + ".", keep_vars=keep_vars)
+                module.state_dict(destination=destination, prefix=prefix + name + ".", keep_vars=keep_vars)
         if self.sample_rate < 1:
             destination["weight"] = self.weight.detach()
         else:

@@ -51,7 +51,7 @@ class PeerExchange:
         self.labels_all = view("labels_all", torch.int64, (B,))
         self.slots = view("slots", torch.float32, (world, B, 2))
         self.dx_slots = view("dx_slots", torch.float32, (world, b, d))
-        self.counter = torch.zeros(1, dtype=torch.int32, device=device)   # this rank's barrier epoch
+        self.counter = torch.zeros(2, dtype=torch.int32, device=device)   # this rank's barrier state {epoch, ticket}
 
     def ptrs(self, name):
         return self._ptrs[name]

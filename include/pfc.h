@@ -143,6 +143,10 @@ int pfc_backward_dw_sgd(const void* E_bf16, int n_pad, const void* xs_bf16, int 
  *   xn_all [W*b, d] bf16, plus the local labels into every rank's labels_all [W*b] int64.
  * pfc_peer_row_stats: pfc_row_stats, written into slot `rank` of every rank's slots [W][B][2] fp32.
  * pfc_peer_loss: stats = sum over the W slots (rank order, so every rank gets identical bits) + pfc_loss.
+ * pfc_peer_localize_labels / pfc_peer_loss (peer_flags != NULL) / pfc_peer_dx_finalize take the barrier at their own
+ *   start instead of behind a separate pfc_peer_barrier launch: barrier_state -> this rank's uint32[2] {epoch, ticket}
+ *   (zeroed once; the same epoch word pfc_peer_barrier uses).  pfc_peer_dx_finalize = barrier + pfc_dx_finalize over
+ *   this rank's dx_slots (splits = W, no coefficients).
  * pfc_peer_dx_scatter: coef[i] * sum_z partial[z][i,:] of global row i -> slot `rank` of rank i/b's dx_slots
  *   [W][b][d] fp32; the owner then runs pfc_dx_finalize(dx_slots, splits = W, coef = NULL, ...). */
 int pfc_peer_max_ranks(void);
@@ -151,7 +155,12 @@ int pfc_peer_l2norm_gather(const float* x, const int64_t* labels, int b, int d, 
                            void* const* peer_xn_all, void* const* peer_labels_all, float* inv_norm, void* stream);
 int pfc_peer_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
                        int rank, int W, void* const* peer_slots, void* stream);
-int pfc_peer_loss(const float* slots, int W, int B, float* stats, float* row_L, float* loss, void* stream);
+int pfc_peer_loss(void* const* peer_flags, uint32_t* barrier_state, int rank, const float* slots, int W, int B,
+                  float* stats, float* row_L, float* loss, void* stream);
+int pfc_peer_localize_labels(void* const* peer_flags, uint32_t* barrier_state, int rank, int W, const int64_t* labels,
+                             int B, int64_t class_start, int num_local, int32_t* labels_local, void* stream);
+int pfc_peer_dx_finalize(void* const* peer_flags, uint32_t* barrier_state, int rank, int W, const float* dx_slots,
+                         const float* x, const float* inv_norm, float scale, int b, int d, float* out, void* stream);
 int pfc_peer_dx_scatter(const float* partial, int splits, const float* coef, int B, int b, int d, int rank, int W,
                         void* const* peer_dx_slots, void* stream);
 

@@ -233,6 +233,41 @@ def test_graphed_head_step_replays_the_eager_step_bit_for_bit(pfc):
     assert torch.equal(outs[0][2], outs[1][2])
 
 
+@pytest.mark.parametrize("name", ["head_w1_d512", "head_w1_sampled"])
+def test_checkpoint_resume_continues_bit_for_bit(pfc, name):
+    """head_shard_state / load_head_shard: a head rebuilt from the per-rank checkpoint (weights + momentum rows)
+    continues exactly like the one that kept running."""
+    cfg, z = load_case(name)
+    weights, xs, ls = case_inputs(cfg)
+
+    def make():
+        h = _make_head(pfc, cfg, weights, fused=True)
+        o = torch.optim.SGD(h.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
+        return h, o
+
+    def run(h, o, s):
+        s = s % cfg["steps"]                 # the fixtures hold cfg["steps"] batches / sampling draws
+        perms = case_perms(cfg, z, s)
+        perm = perms[0].cuda() if perms is not None and perms[0].numel() else None
+        x = xs[s].clone().cuda().requires_grad_(True)
+        loss = h(x, ls[s].clone().cuda(), o, perm=perm)
+        loss.backward()
+        return float(loss.detach()), x.grad.clone()
+
+    a, oa = make()
+    for s in range(2):
+        run(a, oa, s)
+    sd = pfc.head_shard_state(a)
+    assert set(sd) == {"weight", "weight_mom", "meta"} and sd["weight"].device.type == "cpu"
+    b, ob = make()
+    pfc.load_head_shard(b, sd)
+    la, ga = run(a, oa, 2)
+    lb, gb = run(b, ob, 2)
+    assert la == lb and torch.equal(ga, gb)
+    sa, sb = pfc.head_shard_state(a), pfc.head_shard_state(b)
+    assert torch.equal(sa["weight"], sb["weight"]) and torch.equal(sa["weight_mom"], sb["weight_mom"])
+
+
 def test_batch_size_change_asserts(pfc):
     cfg, z = load_case("head_w1_full")
     weights, xs, ls = case_inputs(cfg)
