@@ -22,6 +22,9 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
   conf.fused_dw_update (bool, default False; needs fused_optimizer, SGD, emd_size == 512): run the update as the EPILOGUE
       of the dW GEMM (pfc_backward_dw_sgd): the un-normalised gradient never leaves tensor memory.  Parity-tested;
       measured 246 us against 233 us for the two-kernel path at cfg-2, hence opt-in.
+  conf.device_sampling (bool, default False): draw the PartialFC sampling scores with the CUDA generator on the device
+      instead of `torch.rand` on the CPU generator + H2D copy (nets/PartialFC.py:110).  Removes a host round trip per
+      step; the sampled index set is then NOT the reference's for the same seed (same distribution, other stream).
   conf.overlap_update (bool, default False; needs fused_optimizer): run the fused update on a side stream underneath
       the dX GEMM.  The normalised shard is then double-buffered and the two buffers swap roles every step, so a
       CUDA graph of the step must capture an EVEN number of steps (bench.py captures two).
@@ -120,6 +123,7 @@ class _PartialFCBase(torch.nn.Module):
         self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
         self.overlap_update = bool(getattr(conf, "overlap_update", False))
         self.fused_dw_update = bool(getattr(conf, "fused_dw_update", False))
+        self.device_sampling = bool(getattr(conf, "device_sampling", False))
         self._num_classes = int(num_classes)
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
@@ -174,9 +178,12 @@ class _PartialFCBase(torch.nn.Module):
         is implied by it and only kept for signature parity).  `perm` defaults to torch.rand on the CPU generator exactly like the reference
         (:110) -- one H2D copy per step; pass a device tensor to replay a recorded draw."""
         ws = self._ws
-        if perm is None:
-            perm = torch.rand(size=[self.num_local])
-        ws.perm.copy_(perm, non_blocking=True)
+        if perm is None and self.device_sampling and ws.perm.is_cuda:
+            ws.perm.uniform_()                       # [0, 1) from the CUDA generator, no host round trip
+        else:
+            if perm is None:
+                perm = torch.rand(size=[self.num_local])
+            ws.perm.copy_(perm, non_blocking=True)
         K.sample(ws.perm, labels_local, self.num_local, self.num_sample, ws.index, ws.n_out, ws.labels_act,
                  ws.sample_ws)
         if self.num_sample >= ws.B:

@@ -63,6 +63,35 @@ def test_sampled_rank_shapes(pfc, name, nl, rate, B, fused):
     assert cosine(head.weight_mom.cpu(), mf[0]) >= 0.999
 
 
+def test_device_sampling_keeps_the_sampling_invariants(pfc):
+    """conf.device_sampling draws the scores on the GPU: the index set is no longer the reference's for a seed, but the
+    invariants of nets/PartialFC.py:108-118 hold -- every positive class kept, exactly num_sample rows, strictly
+    ascending, labels remapped onto positions of the index list."""
+    nl, d, B, rate = 5000, 512, 256, 0.1
+    w = torch.normal(0, 0.01, (nl, d), generator=torch.Generator().manual_seed(3))
+    conf = types.SimpleNamespace(emd_size=d, sample_rate=rate, mixed_precision=False, loss_s=64.0, loss_m=0.5,
+                                 device_sampling=True)
+    head = pfc.PartialFC(conf, nl)
+    head.load_state_dict({"weight": w.clone()})
+    head = head.train().cuda()
+    opt = torch.optim.SGD(head.parameters(), lr=0.1, momentum=0.9)
+    seen = []
+    for s in range(2):
+        lab = torch.randint(0, nl, (B,), generator=torch.Generator().manual_seed(11 + s))
+        x = torch.nn.functional.normalize(torch.randn(B, d, generator=torch.Generator().manual_seed(5 + s)))
+        loss = head(x.cuda().requires_grad_(True), lab.clone().cuda(), opt)
+        loss.backward()
+        opt.step()
+        idx = head.weight_index.cpu()
+        assert idx.numel() == head.num_sample == int(rate * nl)
+        assert bool((idx[1:] > idx[:-1]).all())
+        assert set(lab.tolist()) <= set(idx.tolist())
+        assert torch.equal(idx[head._ws.labels_act.cpu().long()], lab)
+        assert torch.isfinite(loss)
+        seen.append(idx)
+    assert not torch.equal(seen[0], seen[1])
+
+
 def _oracle_step(orc, x, lab_local_or_minus1, perm):
     """PartialFCOracle.step with labels already localised (-1 = foreign): feed global ids that map to themselves."""
     lab = lab_local_or_minus1.clone()
