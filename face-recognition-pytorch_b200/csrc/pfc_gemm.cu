@@ -20,6 +20,13 @@ namespace pfc {
 
 // ============================================================================ G1: forward
 struct FwdPolicy {
+    // 8 epilogue warps x 128 columns, 4-stage operand ring.  Measured alternative (EPI_WARPS_ = 16, 64 columns each,
+    // which costs one operand stage for the extra staging buffers and caps the kernel at 96 registers): 123 us
+    // against 102 us -- the deeper ring matters more than the extra warps for this K = 512 contraction.
+    static constexpr int EPI_WARPS_ = 8;
+    static constexpr int STAGES_ = 4;
+    static constexpr int PAIR_STAGES_ = 6;
+    static constexpr int COLS = BN / (EPI_WARPS_ / 4);
     static constexpr bool A_MN = false;
     static constexpr bool B_MN = false;
     static constexpr bool SHARE_B = true;    // a CTA pair = two sample tiles sharing one class (W) stage
@@ -34,7 +41,7 @@ struct FwdPolicy {
         int margin_kind;         // 0 = ArcFace-style (cos(theta+m)), 1 = CosFace-style (t - m3)
         float filter_thr;        // CombinedMarginLoss.interclass_filtering_threshold (0 = off)
         __nv_bfloat16* E;        // [B, n_pad]
-        float* part_sum;         // [2 * n_tiles_n, B_pad] sum of non-target e over each 128-class half tile
+        float* part_sum;         // [4 * n_tiles_n, B_pad] sum of non-target e over each 64-class quarter tile
         float* tgt_raw;          // [B] raw (unclamped) target cosine, written by the owning tile only
         float* tgt_e;            // [B] e of the margin-adjusted target logit
         float* tgt_z;            // [B] margin-adjusted target logit (already * s)
@@ -138,8 +145,8 @@ struct FwdPolicy {
         uint32_t va[32], vb[32];
         tmem_ld_32x32(taddr, va);
 #pragma unroll
-        for (int cc = 0; cc < EPI_COLS / 64; ++cc) {
-            const int tile_col = half * EPI_COLS + cc * 64;
+        for (int cc = 0; cc < COLS / 64; ++cc) {
+            const int tile_col = half * COLS + cc * 64;
             const int col64 = tc.n0 + tile_col;
             if (col64 >= p.n) break;                     // warp-uniform: nothing valid from here on
             uint32_t o[32];
@@ -147,7 +154,7 @@ struct FwdPolicy {
             tmem_ld_32x32(taddr + cc * 64 + 32, vb);     // next chunk in flight during the math below
             sum += chunk32<0>(p, va, o, col64, row, tgt_off, tile_col);
             tmem_ld_wait();                              // vb ready
-            if (cc + 1 < EPI_COLS / 64) tmem_ld_32x32(taddr + (cc + 1) * 64, va);
+            if (cc + 1 < COLS / 64) tmem_ld_32x32(taddr + (cc + 1) * 64, va);
             if (col64 + 32 < p.n) {
                 sum += chunk32<16>(p, vb, o, col64 + 32, row, tgt_off, tile_col + 32);
             } else {
@@ -158,7 +165,7 @@ struct FwdPolicy {
             warp_tma_store_rows(stage, lane, o, tmc, col64, row0, 0);
         }
         tmem_ld_wait();                                  // nothing may be outstanding when the accumulator is released
-        if (row_ok) p.part_sum[static_cast<size_t>(tc.aux * 2 + half) * p.B_pad + row] = sum;
+        if (row_ok) p.part_sum[static_cast<size_t>(tc.aux * (BN / COLS) + half) * p.B_pad + row] = sum;
     }
 };
 
@@ -180,6 +187,10 @@ struct StoreParams {
 
 template <bool kAMN>
 struct StorePolicy {
+    static constexpr int EPI_WARPS_ = 8;
+    static constexpr int STAGES_ = 4;
+    static constexpr int PAIR_STAGES_ = 6;
+    static constexpr int EPI_COLS = BN / (EPI_WARPS_ / 4);
     static constexpr bool A_MN = kAMN;
     static constexpr bool B_MN = true;
     // dX (A K-major): a CTA pair = two sample tiles sharing the Wn stage.
@@ -348,8 +359,8 @@ static int pick_mode(int m_tiles, int mcast_dim_tiles) {
 }
 
 template <class Kern, class Params>
-static int launch_cluster(Kern kern, int cluster, int smem_bytes, const CUtensorMap& ta, const CUtensorMap& tb,
-                          const CUtensorMap& tc, const Params& prm, cudaStream_t stream) {
+static int launch_cluster(Kern kern, int cluster, int threads, int smem_bytes, const CUtensorMap& ta,
+                          const CUtensorMap& tb, const CUtensorMap& tc, const Params& prm, cudaStream_t stream) {
     const int sms = num_sms();
     if (sms <= 0) return PFC_ERR_CUDA;
     if (prm.num_tiles <= 0) return PFC_OK;
@@ -358,7 +369,7 @@ static int launch_cluster(Kern kern, int cluster, int smem_bytes, const CUtensor
     grid = grid / cluster * cluster;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
     cudaLaunchAttribute at[1];
@@ -375,17 +386,20 @@ static int launch_cluster(Kern kern, int cluster, int smem_bytes, const CUtensor
 template <class P>
 static int launch_gemm(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                        const typename P::Params& prm, cudaStream_t stream) {
+    using C = GemmCfg<P>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(umma_gemm_kernel<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(umma_gemm_kernel<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(umma_gemm_pair_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(umma_gemm_kernel<P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(umma_gemm_kernel<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM) != cudaSuccess ||
+            cudaFuncSetAttribute(umma_gemm_pair_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::PAIR_SMEM) != cudaSuccess)
             return PFC_ERR_CUDA;
         attr_set = true;
     }
-    if (mode == MODE_PAIR) return launch_cluster(umma_gemm_pair_kernel<P>, 2, PAIR_SMEM_BYTES, ta, tb, tc, prm, stream);
-    if (mode == MODE_MCAST) return launch_cluster(umma_gemm_kernel<P, 2>, 2, GEMM_SMEM_BYTES, ta, tb, tc, prm, stream);
-    return launch_cluster(umma_gemm_kernel<P, 1>, 1, GEMM_SMEM_BYTES, ta, tb, tc, prm, stream);
+    if (mode == MODE_PAIR)
+        return launch_cluster(umma_gemm_pair_kernel<P>, 2, C::THREADS, C::PAIR_SMEM, ta, tb, tc, prm, stream);
+    if (mode == MODE_MCAST)
+        return launch_cluster(umma_gemm_kernel<P, 2>, 2, C::THREADS, C::SMEM, ta, tb, tc, prm, stream);
+    return launch_cluster(umma_gemm_kernel<P, 1>, 1, C::THREADS, C::SMEM, ta, tb, tc, prm, stream);
 }
 
 static int even_up(int v) { return (v + 1) / 2 * 2; }
@@ -406,7 +420,8 @@ void pfc_debug_mn_desc(unsigned lbo, unsigned sbo, unsigned kstep) {
 void pfc_debug_cluster(int mode) { g_gemm_mode = mode; }
 
 int pfc_padded_classes(int n) { return (n + 63) / 64 * 64; }
-int pfc_num_class_tiles(int n) { return 2 * ((n + BN - 1) / BN); }   // one part_sum slab per 128-column half tile
+int pfc_num_class_tiles(int n) { return (BN / FwdPolicy::COLS) * ((n + BN - 1) / BN); }   // part_sum slabs
+int pfc_part_sum_cols(void) { return FwdPolicy::COLS; }   // classes per part_sum slab
 int pfc_padded_batch(int B) { return (B + BM - 1) / BM * BM; }
 
 int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int B, int n, int d, float s,

@@ -29,6 +29,23 @@ constexpr int GEMM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int EPI_STAGE_BYTES = 32 * 128;   // per epilogue warp: 32 rows x 128 B
 constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_WARPS * EPI_STAGE_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
+constexpr int PAIR_STAGE_BYTES_ = A_STAGE_BYTES + B_STAGE_BYTES / 2;
+
+// Per-policy launch geometry.  A policy picks the number of epilogue warps (8: two per TMEM lane quarter, 128 columns
+// each; 16: four per quarter, 64 columns each -- for epilogues whose dependent chains need more warps per scheduler to
+// hide latency) and the depth of the operand ring; 4 KB of staging per epilogue warp comes out of the same 227 KB.
+template <class P>
+struct GemmCfg {
+    static constexpr int EW = P::EPI_WARPS_;
+    static constexpr int COLS = BN / (EW / 4);
+    static constexpr int ST = P::STAGES_;
+    static constexpr int THREADS = 64 + 32 * EW;
+    static constexpr int SMEM = ST * (A_STAGE_BYTES + B_STAGE_BYTES) + EW * EPI_STAGE_BYTES + 1024;
+    static constexpr int PAIR_ST = P::PAIR_STAGES_;
+    static constexpr int PAIR_SMEM = PAIR_ST * PAIR_STAGE_BYTES_ + EW * EPI_STAGE_BYTES + 1024;
+    static_assert(EW == 8 || EW == 16, "epilogue warps: 8 or 16");
+    static_assert(SMEM <= 232448 && PAIR_SMEM <= 232448, "shared memory budget");
+};
 
 struct TileCoord {
     int m0;    // first row of the A-side (TMEM lane) dimension
@@ -78,17 +95,22 @@ __device__ __forceinline__ void warp_tma_store_rows(uint32_t stage, int lane, co
 //   static void epilogue(const Params&, const TileCoord&, uint32_t taddr, int quarter, int half, int lane,
 //                        uint32_t stage, const CUtensorMap* tma_c);
 //        stage = shared-memory address of this warp's 4 KB staging buffer, tma_c = the output's store tensor map;
-//        taddr = TMEM address of this warp's lane quarter at column (half * EPI_COLS) of the tile's accumulator;
-//        the warp owns rows [32*quarter, 32*quarter+32) x columns [half*EPI_COLS, (half+1)*EPI_COLS) of the tile.
+//        COLS = GemmCfg<P>::COLS; `half` = index of the warp's column group;
+//        taddr = TMEM address of this warp's lane quarter at column (half * COLS) of the tile's accumulator;
+//        the warp owns rows [32*quarter, 32*quarter+32) x columns [half*COLS, (half+1)*COLS) of the tile.
 //
 // CL = 2 runs CTA pairs as a thread-block cluster working on two adjacent tiles that share one operand stage
 // (P::SHARE_B: the pair differs in m0 and shares B; otherwise it differs in n0 and shares A).  Each CTA fetches
 // half of the shared stage and TMA-multicasts it into both CTAs' shared memory, halving that operand's L2 traffic;
 // a stage is recycled only after BOTH CTAs' MMAs have retired (multicast tcgen05.commit on the empty barrier).
 template <class P, int CL>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<P>::THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_c, const typename P::Params prm) {
+    using C = GemmCfg<P>;
+    constexpr int STAGES = C::ST;
+    constexpr int EPI_WARPS = C::EW;
+    constexpr int EPI_COLS = C::COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;

@@ -18,16 +18,19 @@
 
 namespace pfc {
 
-constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_B_STAGE_BYTES = B_STAGE_BYTES / 2;
 constexpr int PAIR_STAGE_BYTES = A_STAGE_BYTES + PAIR_B_STAGE_BYTES;
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024;
+static_assert(PAIR_STAGE_BYTES == PAIR_STAGE_BYTES_, "pair stage size");
 
 // Tiles 2T and 2T+1 (T = pair index) must share n0 and the K range and differ only in m0.
 template <class P>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GemmCfg<P>::THREADS, 1)
 umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                       const __grid_constant__ CUtensorMap tma_c, const typename P::Params prm) {
+    using C = GemmCfg<P>;
+    constexpr int PAIR_STAGES = C::PAIR_ST;
+    constexpr int EPI_WARPS = C::EW;
+    constexpr int EPI_COLS = C::COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;

@@ -80,6 +80,7 @@ exp_top = lib.pfc_exp_top
 padded_classes = lib.pfc_padded_classes
 padded_batch = lib.pfc_padded_batch
 num_class_tiles = lib.pfc_num_class_tiles
+part_sum_cols = lib.pfc_part_sum_cols
 dx_splits = lib.pfc_dx_splits
 dx_max_splits = lib.pfc_dx_max_splits
 sample_workspace_bytes = lib.pfc_sample_workspace_bytes

@@ -39,7 +39,8 @@ const char* pfc_error_string(int code);           /* host string */
 int pfc_exp_top(void);                            /* exponent offset of the spilled e terms (see pfc_forward) */
 int pfc_padded_classes(int n);                    /* row stride (elements) of the E' spill for n active classes */
 int pfc_padded_batch(int B);                      /* row count the part_sum slabs are padded to */
-int pfc_num_class_tiles(int n);                   /* number of 128-class half tiles = leading dim of part_sum */
+int pfc_num_class_tiles(int n);                   /* number of part_sum slabs (column groups) = leading dim of part_sum */
+int pfc_part_sum_cols(void);                      /* classes per part_sum slab (64) */
 int pfc_dx_splits(int B, int n, int d);           /* class splits pfc_backward_dx will use for this shape */
 int pfc_dx_max_splits(int B, int d);              /* upper bound of pfc_dx_splits over all n (sizes `partial`) */
 

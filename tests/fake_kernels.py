@@ -20,7 +20,8 @@ class FakeKernels:
     def __init__(self, real):
         self._real = real
         # host-only helpers come from the real library (no GPU needed)
-        for name in ("exp_top", "padded_classes", "padded_batch", "num_class_tiles", "dx_splits", "dx_max_splits",
+        for name in ("exp_top", "padded_classes", "padded_batch", "num_class_tiles", "part_sum_cols", "dx_splits",
+                     "dx_max_splits",
                      "sample_workspace_bytes", "hist_bins"):
             setattr(self, name, getattr(real, name))
 
@@ -84,8 +85,9 @@ class FakeKernels:
         Ev[:, :n] = torch.where(keep, e, torch.zeros_like(e)).to(torch.bfloat16)
         nt, Bp = self.num_class_tiles(n), self.padded_batch(B)
         ps = part_sum[: nt * Bp].view(nt, Bp)
+        cw = self.part_sum_cols()
         for tix in range(nt):
-            ps[tix, :B] = e[:, tix * 128:(tix + 1) * 128].sum(1)      # one slab per 128-class half tile
+            ps[tix, :B] = e[:, tix * cw:(tix + 1) * cw].sum(1)       # one slab per `cw`-class column group
 
     def row_stats(self, part_sum, n_tiles, B, labels, tgt_e, stats):
         Bp = self.padded_batch(B)
