@@ -157,23 +157,34 @@ peer_l2norm_gather_kernel(const float* __restrict__ x, const int64_t* __restrict
     }
 }
 
-// same reduction as row_stats_kernel (pfc_rows.cu), result stored into slot `rank` of every peer
-__global__ void __launch_bounds__(256)
+// same reduction as row_stats_kernel (pfc_rows.cu: 8 rows x 32 slab groups per CTA, fixed summation order), result
+// stored into slot `rank` of every peer
+constexpr int PRS_ROWS = 8, PRS_GROUPS = 32;
+__global__ void __launch_bounds__(PRS_ROWS * PRS_GROUPS)
 peer_row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                       const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, int rank, int W,
                       PeerPtrs slots) {
-    __shared__ float red[8][33];
-    const int r = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int row = blockIdx.x * 32 + r;
+    __shared__ float red[PRS_GROUPS][PRS_ROWS + 1];
+    const int r = threadIdx.x & (PRS_ROWS - 1), g = threadIdx.x / PRS_ROWS;
+    const int row = blockIdx.x * PRS_ROWS + r;
     float s = 0.f;
-    if (row < B)
-        for (int t = g; t < n_tiles; t += 8) s += part_sum[static_cast<size_t>(t) * B_pad + row];
+    if (row < B) {
+        int t = g;
+        for (; t + 3 * PRS_GROUPS < n_tiles; t += 4 * PRS_GROUPS) {
+            const float a = part_sum[static_cast<size_t>(t) * B_pad + row];
+            const float b = part_sum[static_cast<size_t>(t + PRS_GROUPS) * B_pad + row];
+            const float c = part_sum[static_cast<size_t>(t + 2 * PRS_GROUPS) * B_pad + row];
+            const float d = part_sum[static_cast<size_t>(t + 3 * PRS_GROUPS) * B_pad + row];
+            s += a; s += b; s += c; s += d;
+        }
+        for (; t < n_tiles; t += PRS_GROUPS) s += part_sum[static_cast<size_t>(t) * B_pad + row];
+    }
     red[g][r] = s;
     __syncthreads();
     if (g == 0 && row < B) {
         float tot = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) tot += red[k][r];
+        for (int k = 0; k < PRS_GROUPS; ++k) tot += red[k][r];
         const float2 v = make_float2(tot, (labels[row] >= 0) ? tgt_e[row] : 0.f);
         for (int q = 0; q < W; ++q)
             reinterpret_cast<float2*>(static_cast<float*>(slots.p[q]) + static_cast<size_t>(rank) * B * 2)[row] = v;
@@ -225,9 +236,15 @@ peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t spl
     const float c = coef[row];
     for (int k = lane; k < (d >> 2); k += 32) {
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int z = 0; z < splits; ++z) {
-            const float4 p = *reinterpret_cast<const float4*>(partial + z * split_stride + static_cast<size_t>(row) * d + 4 * k);
-            a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+        const float* pp = partial + static_cast<size_t>(row) * d + 4 * k;
+        for (int z = 0; z < splits; z += 4) {                // four split slabs in flight, summed in slab order
+            float4 p[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                p[u] = (z + u < splits) ? *reinterpret_cast<const float4*>(pp + (z + u) * split_stride)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
         }
         a.x *= c; a.y *= c; a.z *= c; a.w *= c;
         *reinterpret_cast<float4*>(out + 4 * k) = a;
@@ -321,8 +338,8 @@ int pfc_peer_row_stats(const float* part_sum, int n_tiles, int B, const int32_t*
     int rc = fill_peers(&s, peer_slots, W);
     if (rc) return rc;
     const int B_pad = (B + 127) / 128 * 128;
-    peer_row_stats_kernel<<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(part_sum, n_tiles, B, B_pad, labels_local,
-                                                                          tgt_e, rank, W, s);
+    peer_row_stats_kernel<<<(B + PRS_ROWS - 1) / PRS_ROWS, PRS_ROWS * PRS_GROUPS, 0, (cudaStream_t)stream>>>(
+        part_sum, n_tiles, B, B_pad, labels_local, tgt_e, rank, W, s);
     return launched();
 }
 

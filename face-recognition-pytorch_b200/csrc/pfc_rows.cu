@@ -88,23 +88,43 @@ __global__ void localize_labels_kernel(const int64_t* __restrict__ labels, int B
     out[i] = (l >= 0 && l < num_local) ? static_cast<int32_t>(l) : -1;
 }
 
-// stats[i] = { sum over class tiles of part_sum[t][i],  target e (0 when the target lives on another rank) }
-// Fixed summation order -> bit-reproducible.  CTA = 32 rows x 8 tile groups.
-__global__ void __launch_bounds__(256)
-row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
-                 const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* __restrict__ stats) {
-    __shared__ float red[8][33];
-    const int r = threadIdx.x & 31, g = threadIdx.x >> 5;
-    const int row = blockIdx.x * 32 + r;
+// stats[i] = { sum over the part_sum slabs of part_sum[t][i],  target e (0 when the target lives on another rank) }
+// Fixed summation order -> bit-reproducible.  CTA = 8 rows x 32 slab groups (a first version with 32 rows per CTA had
+// only B/32 CTAs in flight and took 14 us for 3 MB).
+constexpr int RS_ROWS = 8, RS_GROUPS = 32;
+__device__ __forceinline__ float row_stats_sum(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
+                                               float (*red)[RS_ROWS + 1]) {
+    const int r = threadIdx.x & (RS_ROWS - 1), g = threadIdx.x / RS_ROWS;
+    const int row = blockIdx.x * RS_ROWS + r;
     float s = 0.f;
-    if (row < B)
-        for (int t = g; t < n_tiles; t += 8) s += part_sum[static_cast<size_t>(t) * B_pad + row];
+    if (row < B) {
+        int t = g;
+        for (; t + 3 * RS_GROUPS < n_tiles; t += 4 * RS_GROUPS) {        // four independent loads in flight
+            const float a = part_sum[static_cast<size_t>(t) * B_pad + row];
+            const float b = part_sum[static_cast<size_t>(t + RS_GROUPS) * B_pad + row];
+            const float c = part_sum[static_cast<size_t>(t + 2 * RS_GROUPS) * B_pad + row];
+            const float d = part_sum[static_cast<size_t>(t + 3 * RS_GROUPS) * B_pad + row];
+            s += a; s += b; s += c; s += d;
+        }
+        for (; t < n_tiles; t += RS_GROUPS) s += part_sum[static_cast<size_t>(t) * B_pad + row];
+    }
     red[g][r] = s;
     __syncthreads();
-    if (g == 0 && row < B) {
-        float tot = 0.f;
+    float tot = 0.f;
+    if (g == 0) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) tot += red[k][r];
+        for (int k = 0; k < RS_GROUPS; ++k) tot += red[k][r];
+    }
+    return tot;      // valid for g == 0
+}
+
+__global__ void __launch_bounds__(RS_ROWS * RS_GROUPS)
+row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
+                 const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* __restrict__ stats) {
+    __shared__ float red[RS_GROUPS][RS_ROWS + 1];
+    const float tot = row_stats_sum(part_sum, n_tiles, B, B_pad, red);
+    const int row = blockIdx.x * RS_ROWS + (threadIdx.x & (RS_ROWS - 1));
+    if (threadIdx.x < RS_ROWS && row < B) {
         stats[2 * row] = tot;
         stats[2 * row + 1] = (labels[row] >= 0) ? tgt_e[row] : 0.f;
     }
@@ -190,9 +210,14 @@ dx_finalize_kernel(const float* __restrict__ partial, int splits, size_t split_s
         const int k = lane + 32 * j;
         if (k < nv) {
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int z = 0; z < splits; ++z) {
-                const float4 p = ld4(partial + z * split_stride + static_cast<size_t>(row) * d + 4 * k);
-                a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+            const float* pp = partial + static_cast<size_t>(row) * d + 4 * k;
+            for (int z = 0; z < splits; z += 4) {            // four split slabs in flight, summed in slab order
+                float4 p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    p[u] = (z + u < splits) ? ld4_stream(pp + (z + u) * split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
             }
             a.x *= c; a.y *= c; a.z *= c; a.w *= c;
             g[j] = a;
@@ -497,8 +522,8 @@ int pfc_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labe
                   float* stats, void* stream) {
     if (B <= 0 || n_tiles <= 0) return PFC_ERR_SHAPE;
     const int B_pad = (B + 127) / 128 * 128;
-    row_stats_kernel<<<(B + 31) / 32, 256, 0, (cudaStream_t)stream>>>(part_sum, n_tiles, B, B_pad, labels_local,
-                                                                     tgt_e, stats);
+    row_stats_kernel<<<(B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0, (cudaStream_t)stream>>>(
+        part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats);
     return check_launch();
 }
 
