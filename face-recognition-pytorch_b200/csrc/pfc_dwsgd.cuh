@@ -66,6 +66,11 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c_inne
                  "r"(c_inner), "r"(c_outer)
                  : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_saddr(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c_inner,
                                                   int c_outer) {
     asm volatile(
@@ -180,14 +185,14 @@ dw_sgd_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
                 const int m0_next = (ct + ct_stride < prm.num_class_tiles) ? (ct + ct_stride) * BM : -1;
                 for (int kc = 0; kc < prm.k_stages; ++kc) {
                     // E' comes from HBM: this CTA's half of the NEXT tile's stage goes to L2 a whole tile ahead
-                    if (m0_next >= 0 && (prm.prefetch & 1)) tma_prefetch_2d(&tma_a, m0_next + crank * 64, kc * DWS_BK);
+                    if (m0_next >= 0 && (prm.prefetch & 1)) tma_prefetch_3d(&tma_a, 0, kc * DWS_BK, (m0_next >> 6) + crank);
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], DWS_A_STAGE + DWS_B_STAGE);
                     uint8_t* a_dst = sA + stage * DWS_A_STAGE;
                     uint8_t* b_dst = sB + stage * DWS_B_STAGE;
                     const int kel = kc * DWS_BK;
                     // E'^T stage (128 classes x 32 samples) = two 64-class boxes: this CTA fetches one, both get both
-                    tma_load_2d_mcast(a_dst + crank * DWS_MN_BOX, &tma_a, &full_bar[stage], m0 + crank * 64, kel, kMask);
+                    tma_load_a_mcast<true>(a_dst + crank * DWS_MN_BOX, &tma_a, &full_bar[stage], m0 + crank * 64, kel, kMask);
 #pragma unroll
                     for (int j = 0; j < BN / 64; ++j)
                         tma_load_2d(b_dst + j * DWS_MN_BOX, &tma_b, &full_bar[stage], n0 + j * 64, kel);

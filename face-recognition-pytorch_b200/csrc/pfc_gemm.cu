@@ -29,6 +29,7 @@ struct FwdPolicy {
     static constexpr int COLS = BN / (EPI_WARPS_ / 4);
     static constexpr bool A_MN = false;
     static constexpr bool B_MN = false;
+    static constexpr bool A_BLOCKED = false;
     static constexpr bool SHARE_B = true;    // a CTA pair = two sample tiles sharing one class (W) stage
     struct Params {
         int num_tiles;
@@ -161,8 +162,9 @@ struct FwdPolicy {
 #pragma unroll
                 for (int j = 16; j < 32; ++j) o[j] = 0u;
             }
-            // E'[row0 .. row0+32) x [col64, col64+64): the store map clips rows >= B (n_pad is a multiple of 64)
-            warp_tma_store_rows(stage, lane, o, tmc, col64, row0, 0);
+            // E'[col64 / 64][row0 .. row0+32)[0..64): one contiguous 4 KB piece of the class-blocked spill; the store
+            // map clips rows >= B
+            warp_tma_store_rows(stage, lane, o, tmc, 0, row0, col64 >> 6);
         }
         tmem_ld_wait();                                  // nothing may be outstanding when the accumulator is released
         if (row_ok) p.part_sum[static_cast<size_t>(tc.aux * (BN / COLS) + half) * p.B_pad + row] = sum;
@@ -193,6 +195,7 @@ struct StorePolicy {
     static constexpr int EPI_COLS = BN / (EPI_WARPS_ / 4);
     static constexpr bool A_MN = kAMN;
     static constexpr bool B_MN = true;
+    static constexpr bool A_BLOCKED = true;  // A is the spill E' (dX: K-major, dW: MN-major), stored class-blocked
     // dX (A K-major): a CTA pair = two sample tiles sharing the Wn stage.
     // dW (A MN-major): a CTA pair = the two D halves of one class tile sharing the E'^T stage.
     static constexpr bool SHARE_B = !kAMN;
@@ -302,6 +305,23 @@ static int make_store_tmap(CUtensorMap* map, void* ptr, bool is_bf16, uint64_t i
     CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, ptr, gdim, gstr,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PFC_OK : PFC_ERR_TENSORMAP;
+}
+
+// Load map of the class-blocked spill E'[n_pad/64][B][64] (bf16): dims {64, B, n_pad/64}, boxes {64, box_rows, 1} in
+// SWIZZLE_128B -- the same shared-memory image as a {64, box_rows} box of the row-major matrix, but every box is ONE
+// contiguous piece of global memory (box_rows x 128 B) instead of box_rows pieces 2*n_pad bytes apart.
+static int make_blocked_tmap(CUtensorMap* map, const void* ptr, uint64_t B, uint64_t n_pad, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return PFC_ERR_DRIVER;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || n_pad % 64) return PFC_ERR_ALIGNMENT;
+    cuuint64_t gdim[3] = {64, B, n_pad / 64};
+    cuuint64_t gstr[2] = {128, B * 128};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? PFC_OK : PFC_ERR_TENSORMAP;
 }
 
@@ -440,7 +460,7 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     // in both pair modes each CTA fetches half of the 256 class rows of a stage
     rc = make_tmap(&tb, wn, d, n, d, BK, mode == MODE_SINGLE ? BN : BN / 2);
     if (rc) return rc;
-    rc = make_store_tmap(&tc, E, true, n_pad, B, 1, n_pad, 0);
+    rc = make_store_tmap(&tc, E, true, 64, B, n_pad / 64, 64, static_cast<uint64_t>(B) * 64);
     if (rc) return rc;
     FwdPolicy::Params p;
     p.B = B; p.n = n; p.n_pad = n_pad; p.B_pad = pfc_padded_batch(B);
@@ -488,7 +508,8 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
                     void* stream) {
     if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 8 || splits <= 0) return PFC_ERR_SHAPE;
     CUtensorMap ta, tb;
-    int rc = make_tmap(&ta, E, n, B, n_pad, BK, BM);       // A: [B, n] K-major (K = classes)
+    if (n_pad % 64) return PFC_ERR_SHAPE;
+    int rc = make_blocked_tmap(&ta, E, B, n_pad, BM);      // A: E' K-major (K = classes), one 64-class block per stage
     if (rc) return rc;
     rc = make_tmap(&tb, wn, d, n, d, 64, BK);              // B: Wn [n(K), d(N)] MN-major boxes 64(N) x 64(K)
     if (rc) return rc;
@@ -520,7 +541,8 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
                     void* stream) {
     if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 8) return PFC_ERR_SHAPE;
     CUtensorMap ta, tb;
-    int rc = make_tmap(&ta, E, n, B, n_pad, 64, BK);       // A: E' [B(K), n(M)] MN-major boxes 64(M) x 64(K)
+    if (n_pad % 64) return PFC_ERR_SHAPE;
+    int rc = make_blocked_tmap(&ta, E, B, n_pad, BK);      // A: E'^T MN-major boxes 64(M = classes) x 64(K = samples)
     if (rc) return rc;
     rc = make_tmap(&tb, xs, d, B, d, 64, BK);              // B: Xs [B(K), d(N)] MN-major
     if (rc) return rc;
@@ -561,7 +583,8 @@ int pfc_backward_dw_sgd(const void* E, int n_pad, const void* xs, int B, int n, 
     if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(mom) | reinterpret_cast<uintptr_t>(wn_next)) & 31)
         return PFC_ERR_ALIGNMENT;
     CUtensorMap ta, tb, tw, tm, twn;
-    int rc = make_tmap(&ta, E, n, B, n_pad, 64, DWS_BK);   // A: E' [B(K), n(M)] MN-major boxes 64(M) x 32(K)
+    if (n_pad % 64) return PFC_ERR_SHAPE;
+    int rc = make_blocked_tmap(&ta, E, B, n_pad, DWS_BK);  // A: E'^T MN-major boxes 64(M) x 32(K)
     if (rc) return rc;
     rc = make_tmap(&tb, xs, d, B, d, 64, DWS_BK);          // B: Xs [B(K), d(N)] MN-major boxes 64(N) x 32(K)
     if (rc) return rc;

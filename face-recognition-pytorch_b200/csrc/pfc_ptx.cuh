@@ -108,6 +108,36 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     return v;
 }
 
+// 3-D variants for the class-blocked spill E'[n_pad/64][B][64] (see pfc_gemm.cu): a box never crosses a 64-class block.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                  int c2, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+        : "memory");
+}
+// Operand loads that take LOGICAL 2-D coordinates (c_inner = class, c_outer = sample row) and, for a class-blocked
+// tensor (kBlocked), turn them into (0, row, class / 64).  c_inner is a multiple of 64 in every caller.
+template <bool kBlocked>
+__device__ __forceinline__ void tma_load_a(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c_inner, int c_outer) {
+    if constexpr (kBlocked) tma_load_3d(smem_dst, m, bar, 0, c_outer, c_inner >> 6);
+    else tma_load_2d(smem_dst, m, bar, c_inner, c_outer);
+}
+template <bool kBlocked>
+__device__ __forceinline__ void tma_load_a_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c_inner,
+                                                 int c_outer, uint16_t cta_mask) {
+    if constexpr (kBlocked) tma_load_3d_mcast(smem_dst, m, bar, 0, c_outer, c_inner >> 6, cta_mask);
+    else tma_load_2d_mcast(smem_dst, m, bar, c_inner, c_outer, cta_mask);
+}
+
 // ----------------------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -192,6 +222,20 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar_addr), "r"(c_inner), "r"(c_outer)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorMap* m, uint32_t cluster_bar_addr, int c0,
+                                                 int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+template <bool kBlocked>
+__device__ __forceinline__ void tma_load_a_pair(void* smem_dst, const CUtensorMap* m, uint32_t cluster_bar_addr, int c_inner,
+                                                int c_outer) {
+    if constexpr (kBlocked) tma_load_3d_pair(smem_dst, m, cluster_bar_addr, 0, c_outer, c_inner >> 6);
+    else tma_load_2d_pair(smem_dst, m, cluster_bar_addr, c_inner, c_outer);
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {   // one warp in EACH CTA of the pair
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),

@@ -185,7 +185,8 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
             const float t = fminf(fmaxf(raw, -1.f), 1.f);
             float dm = 1.f;
             if (margin_kind == 0 && t > theta) dm = cos_m + sin_m * t / sqrtf(fmaxf(1.f - t * t, 1e-12f));
-            E[static_cast<size_t>(row) * n_pad + lbl] = __float2bfloat16_rn(-dm * mask * stats[2 * row]);
+            // class-blocked spill: E'[class / 64][row][class % 64]
+            E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = __float2bfloat16_rn(-dm * mask * stats[2 * row]);
         }
     }
 }

@@ -89,6 +89,7 @@ __device__ __forceinline__ void warp_tma_store_rows(uint32_t stage, int lane, co
 
 // Policy contract:
 //   static constexpr bool A_MN, B_MN;           operand major-ness in shared memory
+//   static constexpr bool A_BLOCKED;            A is the class-blocked spill E'[n_pad/64][B][64] (3-D tensor map)
 //   struct Params { int num_tiles; ... };
 //   static DescCfg desc(const Params&);         smem descriptor geometry (default_desc_cfg(A_MN, B_MN))
 //   static TileCoord tile(const Params&, int t);
@@ -173,16 +174,16 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         for (int jj = 0; jj < nb; ++jj) {
                             const int j = kShareA ? crank * nb + jj : jj;
                             if constexpr (kShareA)
-                                tma_load_2d_mcast(a_dst + j * MN_BOX_BYTES, &tma_a, &full_bar[stage], tc.m0 + j * 64, kel, kMask);
+                                tma_load_a_mcast<P::A_BLOCKED>(a_dst + j * MN_BOX_BYTES, &tma_a, &full_bar[stage], tc.m0 + j * 64, kel, kMask);
                             else
-                                tma_load_2d(a_dst + j * MN_BOX_BYTES, &tma_a, &full_bar[stage], tc.m0 + j * 64, kel);
+                                tma_load_a<P::A_BLOCKED>(a_dst + j * MN_BOX_BYTES, &tma_a, &full_bar[stage], tc.m0 + j * 64, kel);
                         }
                     } else {
                         if constexpr (kShareA)     // tensor map box = BM/CL rows
-                            tma_load_2d_mcast(a_dst + crank * (A_STAGE_BYTES / CL), &tma_a, &full_bar[stage], kel,
-                                              tc.m0 + crank * (BM / CL), kMask);
+                            tma_load_a_mcast<P::A_BLOCKED>(a_dst + crank * (A_STAGE_BYTES / CL), &tma_a, &full_bar[stage], kel,
+                                                           tc.m0 + crank * (BM / CL), kMask);
                         else
-                            tma_load_2d(a_dst, &tma_a, &full_bar[stage], kel, tc.m0);
+                            tma_load_a<P::A_BLOCKED>(a_dst, &tma_a, &full_bar[stage], kel, tc.m0);
                     }
                     if constexpr (P::B_MN) {
                         constexpr int nb = BN / 64 / (kShareB ? CL : 1);

@@ -88,9 +88,9 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                     if constexpr (P::A_MN) {
 #pragma unroll
                         for (int j = 0; j < BM / 64; ++j)
-                            tma_load_2d_pair(a_dst + j * MN_BOX_BYTES, &tma_a, lbar, tc.m0 + j * 64, kel);
+                            tma_load_a_pair<P::A_BLOCKED>(a_dst + j * MN_BOX_BYTES, &tma_a, lbar, tc.m0 + j * 64, kel);
                     } else {
-                        tma_load_2d_pair(a_dst, &tma_a, lbar, kel, tc.m0);
+                        tma_load_a_pair<P::A_BLOCKED>(a_dst, &tma_a, lbar, kel, tc.m0);
                     }
                     if constexpr (P::B_MN) {
 #pragma unroll

@@ -87,6 +87,18 @@ sample_workspace_bytes = lib.pfc_sample_workspace_bytes
 hist_bins = lib.pfc_eval_hist_bins
 
 
+def spill_to_rowmajor(E, B, n_pad):
+    """The class-blocked spill E'[n_pad/64][B][64] (include/pfc.h, pfc_forward) as a row-major [B, n_pad] matrix
+    (a copy; for tests and tools -- the kernels only ever see the blocked layout)."""
+    return E.reshape(-1)[: B * n_pad].view(n_pad // 64, B, 64).permute(1, 0, 2).reshape(B, n_pad)
+
+
+def spill_from_rowmajor(M):
+    """Inverse of spill_to_rowmajor: a row-major [B, n_pad] bf16 matrix -> flat class-blocked buffer."""
+    B, n_pad = M.shape
+    return M.view(B, n_pad // 64, 64).permute(1, 0, 2).contiguous().reshape(-1)
+
+
 @_timed("pfc_l2norm_rows")
 def l2norm_rows(x, index, rows, xn, inv_norm):
     d = x.shape[1]

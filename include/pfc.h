@@ -76,10 +76,13 @@ int pfc_scatter_rows(const float* const* src, float* const* dst, int count, cons
  * nets/ArcFace.py:76-91 (or :100-105), nets/PartialFC.py:446-458.  tcgen05 GEMM Xn[B,d] . Wn[n,d]^T whose epilogue
  * never writes logits: for every (sample i, class c) it forms e_ic = 2^(log2e*(z_ic - s) + pfc_exp_top()) with
  * z = s*clamp(cos,-1,1) (margin applied on the target column), accumulates the per-row sum of the NON-target terms
- * per 128-class half tile into part_sum[slab][i] and spills e (zeroed where the inter-class filter fires; the clamp's gradient gate is applied on the target
- * column by pfc_backward_prepare) as bf16
- * into E[i*n_pad + c].  For rows whose target class is local it also writes the raw target cosine, the target's
- * e term and the target logit.  labels_local: -1 = target on another rank. */
+ * per part_sum slab (pfc_part_sum_cols() classes) into part_sum[slab][i] and spills e (zeroed where the inter-class
+ * filter fires; the clamp's gradient gate is applied on the target column by pfc_backward_prepare) as bf16 into the
+ * CLASS-BLOCKED array E[(c / 64) * B + i][c % 64] (n_pad = pfc_padded_classes(n), a multiple of 64; B * n_pad
+ * elements): every 64-class column block is contiguous over the samples, so the forward's stores and both gradient
+ * GEMMs' loads are multi-KB contiguous pieces.  E is opaque to callers: only pfc_backward_* read it, with the same
+ * B and n_pad.  For rows whose target class is local it also writes the raw target cosine, the target's e term
+ * and the target logit.  labels_local: -1 = target on another rank. */
 int pfc_forward(const void* xn_bf16, const void* wn_bf16, const int32_t* labels_local, int B, int n, int d, float s,
                 int margin_kind, float m2, float m3, float interclass_filtering_threshold, void* E_bf16, int n_pad,
                 float* part_sum, float* tgt_raw, float* tgt_e, float* tgt_z, void* stream);

@@ -78,7 +78,7 @@ def _fwd(B, n, d, s=64.0, m=0.5):
     e_nt[rows, cols] = 0
     L_ref = e_nt.sum(1)
     r1, _ = _stats("row sum (non-target)", part.sum(0)[:B], L_ref)
-    Eg = E[:, :n].float()
+    Eg = K.spill_to_rowmajor(E, B, n_pad)[:, :n].float()
     Eg_cmp = Eg.clone()
     Eg_cmp[rows, cols] = 0
     r2, c2 = _stats("E spill (non-target)", torch.log2(Eg_cmp.clamp_min(1e-30)), torch.log2(e_nt.clamp_min(1e-30)))
@@ -126,6 +126,7 @@ def _dx(B, n, d, try_alts=True):
     E[:, :n] = torch.rand(B, n, generator=g).cuda().to(torch.bfloat16)
     wn = torch.nn.functional.normalize(torch.randn(n, d, generator=g)).cuda().to(torch.bfloat16).contiguous()
     ref = E[:, :n].float() @ wn.float()
+    E = K.spill_from_rowmajor(E)                 # the kernels read the class-blocked layout
     splits = K.dx_splits(B, n, d)
     print(f"  dx B={B} n={n} d={d} splits={splits} max={K.dx_max_splits(B, d)}", flush=True)
     for cfg in (ALT_DESCS if try_alts else ALT_DESCS[:1]):
@@ -152,6 +153,7 @@ def _dw(B, n, d, try_alts=True):
     E[:, :n] = torch.rand(B, n, generator=g).cuda().to(torch.bfloat16)
     xs = (torch.randn(B, d, generator=g) * 0.05).cuda().to(torch.bfloat16).contiguous()
     ref = E[:, :n].float().t() @ xs.float()
+    E = K.spill_from_rowmajor(E)                 # the kernels read the class-blocked layout
     for cfg in (ALT_DESCS if try_alts else ALT_DESCS[:1]):
         _set_desc(*cfg)
         dwn = torch.zeros(n, d, device="cuda")
