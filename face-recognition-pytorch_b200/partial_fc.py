@@ -341,9 +341,11 @@ class _PartialFCBase(torch.nn.Module):
         g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
                            ws.coef, ws.E, n_pad)
-        # Rank-local dW first.  With conf.overlap_update its HBM-bound optimizer kernel then runs on a side stream
-        # underneath the tensor-bound dX GEMM (the row kernel needs no shared memory, so its CTAs co-reside with the
-        # GEMM's); it writes next step's normalised rows into the OTHER wn buffer because dX still reads this one.
+        # Order.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the reduce-scatter /
+        # peer stores have the whole dW + update to complete.  N = 1: dW GEMM first (it walks the class tiles from the
+        # end, where the forward's spill is still in L2), then dX, then the update -- measured 0.4266 ms against
+        # 0.4293 ms for the other order.  conf.overlap_update needs dW first as well: its update runs on a side stream
+        # underneath the dX GEMM and writes next step's rows into the OTHER wn buffer.
         w = self.weight_activated.data
         overlap = self.fused_optimizer and self.overlap_update and w.is_cuda
         # one kernel for dW GEMM + update (after the dX GEMM, which still reads this step's normalised shard)
@@ -351,10 +353,11 @@ class _PartialFCBase(torch.nn.Module):
                    and not overlap)
         spill_bf16 = self.fused_optimizer and self._optimizer_kind == "sgd" and d % 128 == 0
         dwn = ws.dwn_bf16 if spill_bf16 else ws.dwn
-        if not fuse_dw:
-            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         dw, side = None, None
         wn_now = ws.wn
+        dw_first = (W == 1 and not fuse_dw) or overlap
+        if dw_first:
+            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         if overlap:
             cur = torch.cuda.current_stream()
             if self._side_stream is None:
@@ -364,10 +367,6 @@ class _PartialFCBase(torch.nn.Module):
             with torch.cuda.stream(side):
                 self._fused_step(w, n, d, dwn, ws.wn_alt)
             ws.wn, ws.wn_alt = ws.wn_alt, ws.wn       # ping-pong: the next forward reads what the update wrote
-        elif not self.fused_optimizer:
-            dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
-            K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
-            self._wn_valid = False        # an external optimizer is about to change the weights
         dx, rs_work = None, None
         peer = self._peer
         if x_in.requires_grad:
@@ -387,8 +386,15 @@ class _PartialFCBase(torch.nn.Module):
                                                             async_op=True)
         if fuse_dw:
             self._fused_dw_step(w, n, n_pad, d)       # dW GEMM + update in place, after the dX GEMM has consumed wn
-        elif self.fused_optimizer and not overlap:
-            self._fused_step(w, n, d, dwn, ws.wn)     # in place, after the dX GEMM has consumed wn
+        elif not overlap:
+            if not dw_first:
+                K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
+            if self.fused_optimizer:
+                self._fused_step(w, n, d, dwn, ws.wn)     # in place, after the dX GEMM has consumed wn
+            else:
+                dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
+                K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
+                self._wn_valid = False    # an external optimizer is about to change the weights
         if rs_work is not None:
             rs_work.wait()
             K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)        # :521
