@@ -331,6 +331,9 @@ def main():
     st_l = [torch.empty(b, dtype=torch.int64, device=dev) for _ in range(2)]
     st_dx = [torch.empty(b, EMB, device=dev) for _ in range(2)]
     dx_hosts = [torch.empty(b, EMB, dtype=torch.float32).pin_memory() for _ in range(2)]
+    st_loss = [torch.zeros(1, device=dev) for _ in range(2)]
+    loss_hosts = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    losses_seen = []
     ev_in = [torch.cuda.Event() for _ in range(2)]       # inputs of slot k are on the device
     ev_used = [torch.cuda.Event() for _ in range(2)]     # the step has consumed slot k's inputs / produced its dX
     ev_out = [torch.cuda.Event() for _ in range(2)]      # dX of slot k has reached the host
@@ -354,8 +357,16 @@ def main():
             loss = head(x, hl[i % n_data].to(dev, non_blocking=True), opt)
             loss.backward()
             dx = x.grad
-        dx_hosts[0].copy_(dx, non_blocking=True)
-        return float(loss.item())
+        # same lagged read as the pipelined loop, on one stream: step i's dX and loss go to pinned memory asynchronously
+        # and the host reads them while step i+1 runs
+        k = i % 2
+        dx_hosts[k].copy_(dx, non_blocking=True)
+        loss_hosts[k].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev_out[k].record(torch.cuda.current_stream())
+        if i >= 1:
+            ev_out[1 - k].synchronize()
+            losses_seen.append(float(loss_hosts[1 - k][0]))
+        return None
 
     def e2e_step(i):
         if not pipelined:
@@ -371,14 +382,21 @@ def main():
             loss = head(x, st_l[k].clone(), opt)
             loss.backward()
             dx = x.grad
-        cur.wait_event(ev_out[k])                        # slot k's previous dX has left the staging buffer
+        cur.wait_event(ev_out[k])                        # slot k's previous dX / loss have left the staging buffers
         st_dx[k].copy_(dx, non_blocking=True)
+        st_loss[k].copy_(loss.detach().reshape(1), non_blocking=True)
         ev_used[k].record(cur)
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_used[k])
             dx_hosts[k].copy_(st_dx[k], non_blocking=True)
+            loss_hosts[k].copy_(st_loss[k], non_blocking=True)
             ev_out[k].record(copy_stream)
-        return float(loss.item())                        # the step's result on the host: one sync per step
+        # every step's loss and dX reach the host; the host READS them one step late (while the next step runs), as a
+        # training loop that logs the previous step's loss does -- no pipeline bubble for a 4-byte read
+        if i >= 1:
+            ev_out[1 - k].synchronize()
+            losses_seen.append(float(loss_hosts[1 - k][0]))
+        return None
 
     for k in range(2):
         ev_used[k].record(torch.cuda.current_stream())
@@ -392,6 +410,9 @@ def main():
     for i in range(3, 3 + e2e_steps):
         e2e_step(i)
     torch.cuda.synchronize()
+    if True:
+        losses_seen.append(float(loss_hosts[(3 + e2e_steps - 1) % 2][0]))    # the last step's loss
+        assert all(v == v and v > 0 for v in losses_seen[-e2e_steps:]), "e2e losses must be finite"
     dist.barrier()
     te = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
     dist.all_reduce(te, dist.ReduceOp.MAX)
@@ -467,7 +488,8 @@ def main():
         "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in kern.items()},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * EMB * 4 + b * 8,
                 "d2h_bytes_per_step": 4 + b * EMB * 4, "steps": e2e_steps, "timing": "host wall clock, max over ranks" +
-                          ("; H2D of step i+1 and dX D2H of step i on a copy stream" if pipelined else ""),
+                          ("; H2D of step i+1 and D2H of step i's dX + loss on a copy stream, host reads them one step late"
+                           if pipelined else "; D2H of step i's dX + loss asynchronous, host reads them one step late"),
                 "api": ("GraphedHeadStep(head, opt)(x_pinned_host, labels_pinned_host) + dx D2H + loss.item()"
                         if gstep is not None else "head(x, labels, opt); loss.backward() + dx D2H + loss.item()")},
         "gpu_launches": launches,
