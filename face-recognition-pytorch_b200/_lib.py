@@ -40,6 +40,8 @@ _SIGS = {
     "pfc_padded_batch": (c_int, [c_int]),
     "pfc_num_class_tiles": (c_int, [c_int]),
     "pfc_part_sum_cols": (c_int, []),
+    "pfc_row_stats_loss": (c_int, [p, c_int, c_int, p, p, p, p, p, p, p]),
+    "pfc_l2norm_rows_localize": (c_int, [p, c_int, c_int, p, p, p, c_int64, c_int, p, p]),
     "pfc_dx_splits": (c_int, [c_int, c_int, c_int]),
     "pfc_dx_max_splits": (c_int, [c_int, c_int]),
     "pfc_l2norm_rows": (c_int, [p, p, c_int, c_int, p, p, p]),

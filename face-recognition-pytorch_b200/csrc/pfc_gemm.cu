@@ -364,15 +364,15 @@ static DescCfg store_desc_cfg(bool a_mn) {
 }
 
 // GEMM launch mode (pfc_debug_cluster): 0 = auto, 1 = single-CTA kernel, 2 = CTA pair sharing one operand stage by
-// TMA multicast, 3 = cta_group::2 pair kernel (pfc_umma2.cuh).  Measured on B200 at cfg-2 (profiles/README.md): all
-// three run within a few percent of each other because under sustained load the GEMMs are power-capped (~1.6 GHz),
-// not shared-memory- or L2-bound; the single-CTA kernel is the fastest for the forward (heavier epilogue) and is
-// what auto selects.  The pair kernels stay selectable and are covered by the GPU tests.
+// TMA multicast, 3 = cta_group::2 pair kernel (pfc_umma2.cuh).  Measured on B200 at cfg-2 (ncu, isolated launches,
+// profiles/README.md): forward 93.6 us single / 89.7 us pair, dW 87.6 / 86.4, dX 77.9 / 80.6 -- auto takes the pair
+// kernel for the forward and dW and the single-CTA kernel for dX.  (Before the pair kernel's accumulator hand-back was
+// changed from a release.cluster arrive to a relaxed one it lost everywhere: 28 % of its stall samples were MEMBAR.)
 static int g_gemm_mode = 0;
 enum { MODE_SINGLE = 1, MODE_MCAST = 2, MODE_PAIR = 3 };
 
-static int pick_mode(int m_tiles, int mcast_dim_tiles) {
-    int mode = g_gemm_mode == 0 ? MODE_SINGLE : g_gemm_mode;
+static int pick_mode(int m_tiles, int mcast_dim_tiles, int auto_mode) {
+    int mode = g_gemm_mode == 0 ? auto_mode : g_gemm_mode;
     if (mode == MODE_PAIR && m_tiles < 2) mode = MODE_SINGLE;
     if (mode == MODE_MCAST && (mcast_dim_tiles % 2)) mode = MODE_SINGLE;
     return mode;
@@ -452,7 +452,7 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     // every representable term must stay a normal bf16/fp32 number: 2*s*log2e <= TOP + 126
     if (!(s > 0.f) || 2.f * s * log2e > PFC_EXP_TOP + 126.f) return PFC_ERR_SCALE_RANGE;
     const int m_tiles = (B + BM - 1) / BM;
-    const int mode = pick_mode(m_tiles, m_tiles);   // pairs of sample tiles share the class (W) stage
+    const int mode = pick_mode(m_tiles, m_tiles, MODE_PAIR);   // pairs of sample tiles share the class (W) stage
     if (n_pad % 64) return PFC_ERR_SHAPE;              // the spill is stored in 64-column (128-byte) boxes
     CUtensorMap ta, tb, tc;
     int rc = make_tmap(&ta, xn, d, B, d, BK, BM);
@@ -515,7 +515,7 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     if (rc) return rc;
     StoreParams p;
     const int m_tiles = (B + BM - 1) / BM;
-    const int mode = pick_mode(m_tiles, m_tiles);          // pairs of sample tiles share the Wn stage
+    const int mode = pick_mode(m_tiles, m_tiles, MODE_SINGLE);   // pairs of sample tiles share the Wn stage
     p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;
     p.n_tiles = (d + BN - 1) / BN;
     p.k_stages_total = (n + BK - 1) / BK;
@@ -551,7 +551,7 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.n_tiles = (d + BN - 1) / BN;
     // cta_group::2: pairs of CLASS tiles share the Xs stage (m fastest); multicast mode: the two D halves of one
     // class tile share the E'^T stage (n fastest)
-    const int mode = pick_mode(m_tiles, p.n_tiles);
+    const int mode = pick_mode(m_tiles, p.n_tiles, MODE_PAIR);
     p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;
     p.splits = 1;
     p.k_stages_total = (B + BK - 1) / BK;

@@ -213,6 +213,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {   // arrive on a (possibly remote) barrier
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// Same without the release fence.  Used to hand a TMEM accumulator back to the pair leader's MMA warp: the data the
+// arrive "publishes" are tcgen05.ld results that tcgen05.wait::ld has already landed in registers (plus
+// tcgen05.fence::before_thread_sync), so nothing in memory has to become visible -- and the release form costs a
+// MEMBAR.ALL + ERRBAR per warp and tile that waits for the warp's outstanding global / TMA stores (28 % of the pair
+// kernels' stall samples).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
 // TMA load into OWN shared memory whose completion bytes are counted on the barrier at `cluster_bar_addr`
 // (the pair leader's barrier, see mapa_u32).
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t cluster_bar_addr,

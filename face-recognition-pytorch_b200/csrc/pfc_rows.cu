@@ -46,12 +46,19 @@ __device__ __forceinline__ float4 unpack4_bf16(uint2 r) {
 // ---------------------------------------------------------------------------------------------------------
 // xn = x / max(||x||, 1e-12) as bf16, inv = 1 / max(||x||, 1e-12)          (nets/PartialFC.py:199-200)
 // optional gather: row r reads x[index[r]]                                   (nets/PartialFC.py:120)
+// optional label localisation of the same rows (single-GPU step: one launch fewer), nets/PartialFC.py:188-193
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 l2norm_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ index, int rows, int d,
-                   __nv_bfloat16* __restrict__ xn, float* __restrict__ inv_norm) {
+                   __nv_bfloat16* __restrict__ xn, float* __restrict__ inv_norm,
+                   const int64_t* __restrict__ labels, int64_t class_start, int num_local,
+                   int32_t* __restrict__ labels_local) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
+    if (labels != nullptr && lane == 0) {
+        const int64_t l = labels[row] - class_start;
+        labels_local[row] = (l >= 0 && l < num_local) ? static_cast<int32_t>(l) : -1;
+    }
     const int64_t src = index ? index[row] : row;
     const float* xr = x + src * d;
     const int nv = d >> 2;
@@ -127,6 +134,52 @@ row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_p
     if (threadIdx.x < RS_ROWS && row < B) {
         stats[2 * row] = tot;
         stats[2 * row + 1] = (labels[row] >= 0) ? tgt_e[row] : 0.f;
+    }
+}
+
+// Single-GPU step: row statistics AND the loss in one launch.  Every CTA writes the stats of its rows, then takes a
+// ticket; the last CTA through sees all of them (threadfence + L2 loads) and forms row_L and the loss exactly like
+// loss_kernel (same per-thread row assignment and reduction tree -> same bits as the two-kernel path).
+__global__ void __launch_bounds__(RS_ROWS * RS_GROUPS)
+row_stats_loss_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
+                      const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* stats,
+                      float* __restrict__ row_L, float* __restrict__ loss, unsigned int* ticket) {
+    __shared__ float red[RS_GROUPS][RS_ROWS + 1];
+    __shared__ bool last;
+    const float tot = row_stats_sum(part_sum, n_tiles, B, B_pad, red);
+    const int row = blockIdx.x * RS_ROWS + (threadIdx.x & (RS_ROWS - 1));
+    if (threadIdx.x < RS_ROWS && row < B) {
+        stats[2 * row] = tot;
+        stats[2 * row + 1] = (labels[row] >= 0) ? tgt_e[row] : 0.f;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // 256 threads stand in for loss_kernel's 1024: thread t covers the rows of loss_kernel's threads t, t+256, ...
+    // in the same order, and the partial sums are combined in loss_kernel's order (warp tree, then 32 warp sums)
+    __shared__ float wsum[32];
+    for (int v = 0; v < 4; ++v) {
+        const int vt = threadIdx.x + 256 * v;            // virtual thread id of loss_kernel
+        float acc = 0.f;
+        for (int i = vt; i < B; i += 1024) {
+            const float others = __ldcg(stats + 2 * i), te = __ldcg(stats + 2 * i + 1);
+            const float L = others + te;
+            row_L[i] = L;
+            acc -= logf(fmaxf(te / L, 1e-30f));
+        }
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) wsum[vt >> 5] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = warp_sum(wsum[threadIdx.x]);
+        if (threadIdx.x == 0) {
+            loss[0] = v / static_cast<float>(B);
+            *ticket = 0;
+        }
     }
 }
 
@@ -507,7 +560,16 @@ int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void*
     if (rows < 0 || bad_d(d)) return PFC_ERR_SHAPE;
     if (rows == 0) return PFC_OK;
     l2norm_rows_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        x, index, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm);
+        x, index, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm, nullptr, 0, 0, nullptr);
+    return check_launch();
+}
+
+int pfc_l2norm_rows_localize(const float* x, int rows, int d, void* xn, float* inv_norm, const int64_t* labels,
+                             int64_t class_start, int num_local, int32_t* labels_local, void* stream) {
+    if (rows <= 0 || bad_d(d) || !labels || !labels_local) return PFC_ERR_SHAPE;
+    l2norm_rows_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+        x, nullptr, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm, labels, class_start, num_local,
+        labels_local);
     return check_launch();
 }
 
@@ -525,6 +587,15 @@ int pfc_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labe
     const int B_pad = (B + 127) / 128 * 128;
     row_stats_kernel<<<(B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0, (cudaStream_t)stream>>>(
         part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats);
+    return check_launch();
+}
+
+int pfc_row_stats_loss(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
+                       float* stats, float* row_L, float* loss, unsigned int* ticket, void* stream) {
+    if (B <= 0 || n_tiles <= 0 || !ticket) return PFC_ERR_SHAPE;
+    const int B_pad = (B + 127) / 128 * 128;
+    row_stats_loss_kernel<<<(B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0, (cudaStream_t)stream>>>(
+        part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats, row_L, loss, ticket);
     return check_launch();
 }
 

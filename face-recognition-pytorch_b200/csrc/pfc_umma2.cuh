@@ -154,7 +154,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             P::epilogue(prm, tc, taddr, quarter, half, lane, stage_buf, &tma_c);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+            if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
         }
         if (lane == 0) tma_store_wait_all();
     }

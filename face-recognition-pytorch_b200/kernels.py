@@ -106,6 +106,14 @@ def l2norm_rows(x, index, rows, xn, inv_norm):
           "pfc_l2norm_rows")
 
 
+@_timed("pfc_l2norm_rows_localize")
+def l2norm_rows_localize(x, rows, xn, inv_norm, labels, class_start, num_local, labels_local):
+    d = x.shape[1]
+    check(lib.pfc_l2norm_rows_localize(_p(x, F32), rows, d, _p(xn, BF16), _p(inv_norm, F32), _p(labels, I64),
+                                       class_start, num_local, _p(labels_local, I32), _stream()),
+          "pfc_l2norm_rows_localize")
+
+
 @_timed("pfc_localize_labels")
 def localize_labels(labels, class_start, num_local, out):
     check(lib.pfc_localize_labels(_p(labels, I64), labels.numel(), class_start, num_local, _p(out, I32), _stream()),
@@ -154,6 +162,12 @@ def margin_apply(logits, labels, margin_kind, s, m2, m3, filter_thr, out, gate):
 def row_stats(part_sum, n_tiles, B, labels_local, tgt_e, stats):
     check(lib.pfc_row_stats(_p(part_sum, F32), n_tiles, B, _p(labels_local, I32), _p(tgt_e, F32), _p(stats, F32),
                             _stream()), "pfc_row_stats")
+
+
+@_timed("pfc_row_stats_loss")
+def row_stats_loss(part_sum, n_tiles, B, labels_local, tgt_e, stats, row_L, out, ticket):
+    check(lib.pfc_row_stats_loss(_p(part_sum, F32), n_tiles, B, _p(labels_local, I32), _p(tgt_e, F32), _p(stats, F32),
+                                 _p(row_L, F32), _p(out, F32), _p(ticket, I32), _stream()), "pfc_row_stats_loss")
 
 
 @_timed("pfc_loss")

@@ -72,6 +72,7 @@ class _Workspace:
         self.stats = z(B, 2)
         self.row_L = z(B)
         self.loss = z(1)
+        self.ticket = z(1, dt=i32)
         self.coef = z(B)
         self.xs = z(B, d, dt=bf16)
         self.max_splits = max(1, K.dx_max_splits(B, d))
@@ -294,9 +295,13 @@ class _PartialFCBase(torch.nn.Module):
                 distributed.all_gather_into_tensor(ws.labels_all, labels_in)
             labels_all = ws.labels_all
         else:
-            K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
-            labels_all = labels_in
-        if peer is not None:
+            # one rank: normalise + label localisation (:188-193) in one launch
+            K.l2norm_rows_localize(x, ws.b, ws.xn_local, ws.inv_x, labels_in, self.class_start, self.num_local,
+                                   ws.labels_local)
+            labels_all = None
+        if labels_all is None:
+            pass
+        elif peer is not None:
             K.peer_localize_labels(peer.ptrs("flags"), peer.counter, self.rank, W, labels_all, self.class_start,
                                    self.num_local, ws.labels_local)               # barrier + :188-193
         else:
@@ -325,10 +330,12 @@ class _PartialFCBase(torch.nn.Module):
                              peer.ptrs("slots"))
             K.peer_loss(peer.ptrs("flags"), peer.counter, self.rank, peer.slots, W, B, ws.stats, ws.row_L,
                         ws.loss)                                                  # barrier + :448, :453, :459, :461
+        elif W == 1:
+            K.row_stats_loss(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats, ws.row_L,
+                             ws.loss, ws.ticket)                                  # :446-461 in one launch
         else:
             K.row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats)
-            if W > 1:
-                distributed.all_reduce(ws.stats, distributed.ReduceOp.SUM)        # replaces :448, :453, :459
+            distributed.all_reduce(ws.stats, distributed.ReduceOp.SUM)            # replaces :448, :453, :459
             K.loss(ws.stats, B, ws.row_L, ws.loss)                                # :461
         if self.fused_optimizer:
             self._opt_args = self._read_optimizer(self._optimizer)

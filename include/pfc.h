@@ -100,6 +100,13 @@ int pfc_margin_apply(const float* logits, const int64_t* labels, int B, int n, i
 int pfc_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
                   float* stats, void* stream);
 int pfc_loss(const float* stats, int B, float* row_L, float* loss, void* stream);
+/* One-rank shortcuts (no exchange between the two halves): pfc_row_stats + pfc_loss in one launch (ticket -> a uint32
+ * zeroed once; the last CTA through forms the loss, same bits as the two calls), and pfc_l2norm_rows +
+ * pfc_localize_labels of the same rows in one launch. */
+int pfc_row_stats_loss(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
+                       float* stats, float* row_L, float* loss, unsigned int* ticket, void* stream);
+int pfc_l2norm_rows_localize(const float* x, int rows, int d, void* xn_bf16, float* inv_norm, const int64_t* labels,
+                             int64_t class_start, int num_local, int32_t* labels_local, void* stream);
 
 /* ---- (5) backward, nets/PartialFC.py:464-484 (DistCrossEntropyFunc.backward) + autograd of :199-206.
  * pfc_backward_prepare: coef[i] = g*s/(B*row_L[i]) (g = grad_loss[0], device scalar, NULL = 1), xs = bf16(coef*xn),

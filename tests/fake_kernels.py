@@ -32,6 +32,14 @@ class FakeKernels:
         xn[:rows] = (src / denom).to(torch.bfloat16)
         inv_norm[:rows] = (1.0 / denom).reshape(-1)
 
+    def l2norm_rows_localize(self, x, rows, xn, inv_norm, labels, class_start, num_local, labels_local):
+        self.l2norm_rows(x, None, rows, xn, inv_norm)
+        self.localize_labels(labels, class_start, num_local, labels_local)
+
+    def row_stats_loss(self, part_sum, n_tiles, B, labels, tgt_e, stats, row_L, out, ticket):
+        self.row_stats(part_sum, n_tiles, B, labels, tgt_e, stats)
+        self.loss(stats, B, row_L, out)
+
     def localize_labels(self, labels, class_start, num_local, out):
         out.copy_(ho.localize_labels(labels, class_start, num_local).to(torch.int32))
 
