@@ -201,34 +201,36 @@ dw_sgd_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 1, 1);
-            const DescCfg dc = prm.dc;
-            uint32_t stage = 0, phase = 0;
-            int tl = 0;
-            for (int ct = first_ct; ct < prm.num_class_tiles; ct += ct_stride, ++tl) {
-                const int acc = tl & 1;
-                const uint32_t acc_phase = (tl >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        // ------------------------------------------------------------------ MMA issuer (uniform loops, elected lane)
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 1, 1);
+        const DescCfg dc = prm.dc;
+        const uint64_t a_tmpl = umma_smem_desc_sw128(smem_u32(sA), dc.a_lbo, dc.a_sbo);
+        const uint64_t b_tmpl = umma_smem_desc_sw128(smem_u32(sB), dc.b_lbo, dc.b_sbo);
+        const uint32_t a_kstep = dc.a_kstep >> 4, b_kstep = dc.b_kstep >> 4;
+        uint32_t stage = 0, phase = 0;
+        int tl = 0;
+        for (int ct = first_ct; ct < prm.num_class_tiles; ct += ct_stride, ++tl) {
+            const int acc = tl & 1;
+            const uint32_t acc_phase = (tl >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kc = 0; kc < prm.k_stages; ++kc) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kc = 0; kc < prm.k_stages; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(sA + stage * DWS_A_STAGE);
-                    const uint32_t b_base = smem_u32(sB + stage * DWS_B_STAGE);
+                if (elect_one_sync()) {
+                    const uint64_t adesc = a_tmpl + stage * (DWS_A_STAGE >> 4);
+                    const uint64_t bdesc = b_tmpl + stage * (DWS_B_STAGE >> 4);
 #pragma unroll
-                    for (int k = 0; k < DWS_BK / UMMA_K; ++k) {
-                        const uint64_t adesc = umma_smem_desc_sw128(a_base + k * dc.a_kstep, dc.a_lbo, dc.a_sbo);
-                        const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * dc.b_kstep, dc.b_lbo, dc.b_sbo);
-                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < DWS_BK / UMMA_K; ++k)
+                        umma_bf16_ss(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                     umma_commit_mcast(&empty_bar[stage], kMask);   // the peer multicasts into this slot too
-                    if (++stage == DWS_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full_bar[acc]);
+                __syncwarp();
+                if (++stage == DWS_STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one_sync()) umma_commit(&tmem_full_bar[acc]);
+            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ epilogue: fused update (8 warps)

@@ -364,10 +364,12 @@ static DescCfg store_desc_cfg(bool a_mn) {
 }
 
 // GEMM launch mode (pfc_debug_cluster): 0 = auto, 1 = single-CTA kernel, 2 = CTA pair sharing one operand stage by
-// TMA multicast, 3 = cta_group::2 pair kernel (pfc_umma2.cuh).  Measured on B200 at cfg-2 (ncu, isolated launches,
-// profiles/README.md): forward 93.6 us single / 89.7 us pair, dW 87.6 / 86.4, dX 77.9 / 80.6 -- auto takes the pair
-// kernel for the forward and dW and the single-CTA kernel for dX.  (Before the pair kernel's accumulator hand-back was
-// changed from a release.cluster arrive to a relaxed one it lost everywhere: 28 % of its stall samples were MEMBAR.)
+// TMA multicast, 3 = cta_group::2 pair kernel (pfc_umma2.cuh).  Measured on B200 at cfg-2 (event-timed in the bench
+// step, us; single / pair): forward 92.9 / 80.5, dX 76.3 / 69.7, dW 85.1 / 88.7 -- auto takes the pair kernel for the
+// forward and dX and the single-CTA kernel for dW.  Two fixes made the pair kernel win: its accumulator hand-back is
+// a RELAXED cluster arrive (the release form cost a MEMBAR.ALL per warp and tile, 28 % of the stall samples), and the
+// MMA warp walks its loops warp-uniformly with one elected lane issuing (one thread then feeds two SMs' tensor cores
+// with 4 back-to-back UTCHMMA per stage instead of ~20 dependent instructions per UTCHMMA).
 static int g_gemm_mode = 0;
 enum { MODE_SINGLE = 1, MODE_MCAST = 2, MODE_PAIR = 3 };
 
@@ -515,7 +517,7 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     if (rc) return rc;
     StoreParams p;
     const int m_tiles = (B + BM - 1) / BM;
-    const int mode = pick_mode(m_tiles, m_tiles, MODE_SINGLE);   // pairs of sample tiles share the Wn stage
+    const int mode = pick_mode(m_tiles, m_tiles, MODE_PAIR);     // pairs of sample tiles share the Wn stage
     p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;
     p.n_tiles = (d + BN - 1) / BN;
     p.k_stages_total = (n + BK - 1) / BK;
@@ -551,7 +553,7 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.n_tiles = (d + BN - 1) / BN;
     // cta_group::2: pairs of CLASS tiles share the Xs stage (m fastest); multicast mode: the two D halves of one
     // class tile share the E'^T stage (n fastest)
-    const int mode = pick_mode(m_tiles, p.n_tiles, MODE_PAIR);
+    const int mode = pick_mode(m_tiles, p.n_tiles, MODE_SINGLE);
     p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;
     p.splits = 1;
     p.k_stages_total = (B + BK - 1) / BK;

@@ -272,6 +272,20 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
         : "memory");
 }
 
+// One lane of a CONVERGED warp (the same one every time).  Used instead of `if (lane == 0)` around the TMA / MMA
+// issue so that the surrounding loops stay warp-uniform: the compiler then keeps barrier addresses, stage counters
+// and the shared-memory descriptors in uniform registers instead of rebuilding them per UMMA through R2UR chains
+// inside an "elect loop" (20 dependent instructions per tcgen05.mma in the first version).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ----------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (tcgen05), 128-byte swizzle. Offsets are encoded >>4.
 //   bits [0,14)  start address      bits [16,30) leading-dim byte offset

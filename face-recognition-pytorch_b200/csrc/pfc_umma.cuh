@@ -155,13 +155,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1);
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer (uniform loops, elected lane)
+        {
             uint32_t stage = 0, phase = 0;
             for (int t = first_tile; t < prm.num_tiles; t += tile_stride) {
                 const TileCoord tc = P::tile(prm, t);
                 for (int kc = tc.k0; kc < tc.k1; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one_sync()) {
                     mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES + B_STAGE_BYTES);
                     uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
                     uint8_t* b_dst = sB + stage * B_STAGE_BYTES;
@@ -202,45 +203,52 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         else
                             tma_load_2d(b_dst, &tma_b, &full_bar[stage], kel, tc.n0);
                     }
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
-            uint32_t stage = 0, phase = 0;
-            int tl = 0;
-            for (int t = first_tile; t < prm.num_tiles; t += tile_stride, ++tl) {
-                const TileCoord tc = P::tile(prm, t);
-                const int acc = tl & 1;
-                const uint32_t acc_phase = (tl >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        // The whole warp walks the tile / stage loops (uniform control flow), one elected lane issues.  The
+        // descriptors are "template + start address": only the 14-bit address field changes, so a K step is one add.
+        // K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per 16-element K step.
+        // MN-major: 64(MN) x 8(K) atoms of 1024 B; next 64-wide MN block one box (8 KB) further,
+        //           next 8 K rows 1024 B further; +2048 B per 16-row K step.
+        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
+        const DescCfg dc = P::desc(prm);
+        const uint64_t a_tmpl = umma_smem_desc_sw128(smem_u32(sA), dc.a_lbo, dc.a_sbo);
+        const uint64_t b_tmpl = umma_smem_desc_sw128(smem_u32(sB), dc.b_lbo, dc.b_sbo);
+        const uint32_t a_kstep = dc.a_kstep >> 4, b_kstep = dc.b_kstep >> 4;
+        uint32_t stage = 0, phase = 0;
+        int tl = 0;
+        for (int t = first_tile; t < prm.num_tiles; t += tile_stride, ++tl) {
+            const TileCoord tc = P::tile(prm, t);
+            const int acc = tl & 1;
+            const uint32_t acc_phase = (tl >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int kc = tc.k0; kc < tc.k1; ++kc) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kc = tc.k0; kc < tc.k1; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
-                    const uint32_t b_base = smem_u32(sB + stage * B_STAGE_BYTES);
-                    // K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per 16-element K step.
-                    // MN-major: 64(MN) x 8(K) atoms of 1024 B; next 64-wide MN block one box (8 KB) further,
-                    //           next 8 K rows 1024 B further; +2048 B per 16-row K step.
-                    const DescCfg dc = P::desc(prm);
+                if (elect_one_sync()) {
+                    const uint64_t adesc = a_tmpl + stage * (A_STAGE_BYTES >> 4);
+                    const uint64_t bdesc = b_tmpl + stage * (B_STAGE_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adesc = umma_smem_desc_sw128(a_base + k * dc.a_kstep, dc.a_lbo, dc.a_sbo);
-                        const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * dc.b_kstep, dc.b_lbo, dc.b_sbo);
-                        umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kc > tc.k0 || k > 0) ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16_ss(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
+                                     (kc > tc.k0 || k > 0) ? 1u : 0u);
                     // smem slot reusable once these MMAs retire (in every CTA that multicasts into it)
                     if constexpr (CL > 1) umma_commit_mcast(&empty_bar[stage], kMask);
                     else umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full_bar[acc]);     // accumulator complete -> epilogue
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one_sync()) umma_commit(&tmem_full_bar[acc]);     // accumulator complete -> epilogue
+            __syncwarp();
         }
     } else {
         // ------------------------------------------------------------------ epilogue (8 warps)

@@ -73,15 +73,17 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     const int tile_stride = gridDim.x;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int t = first_tile; t < prm.num_tiles; t += tile_stride) {
-                const TileCoord tc = P::tile(prm, t);
-                for (int kc = tc.k0; kc < tc.k1; ++kc) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+        // ------------------------------------------------------------------ TMA producer (both CTAs; uniform loops,
+        // one elected lane issues)
+        uint32_t stage = 0, phase = 0;
+        const uint32_t lbar0 = mapa_u32(smem_u32(&full_bar[0]), 0);          // the leader's full barriers
+        for (int t = first_tile; t < prm.num_tiles; t += tile_stride) {
+            const TileCoord tc = P::tile(prm, t);
+            for (int kc = tc.k0; kc < tc.k1; ++kc) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one_sync()) {
                     if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * PAIR_STAGE_BYTES);
-                    const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
+                    const uint32_t lbar = lbar0 + stage * 8;
                     uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
                     uint8_t* b_dst = sB + stage * PAIR_B_STAGE_BYTES;
                     const int kel = kc * BK;
@@ -101,14 +103,20 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                     } else {                                         // tensor map box = 128 B rows
                         tma_load_2d_pair(b_dst, &tma_b, lbar, kel, tc.n0 + crank * (BN / 2));
                     }
-                    if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (leader && lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only; the whole
+        // warp walks the loops, one elected lane issues; descriptors = template + start address, see pfc_umma.cuh)
+        if (leader) {
             constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
+            const DescCfg dc = P::desc(prm);
+            const uint64_t a_tmpl = umma_smem_desc_sw128(smem_u32(sA), dc.a_lbo, dc.a_sbo);
+            const uint64_t b_tmpl = umma_smem_desc_sw128(smem_u32(sB), dc.b_lbo, dc.b_sbo);
+            const uint32_t a_kstep = dc.a_kstep >> 4, b_kstep = dc.b_kstep >> 4;
             uint32_t stage = 0, phase = 0;
             int tl = 0;
             for (int t = first_tile; t < prm.num_tiles; t += tile_stride, ++tl) {
@@ -118,22 +126,23 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                const DescCfg dc = P::desc(prm);
                 for (int kc = tc.k0; kc < tc.k1; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(sA + stage * A_STAGE_BYTES);
-                    const uint32_t b_base = smem_u32(sB + stage * PAIR_B_STAGE_BYTES);
+                    if (elect_one_sync()) {
+                        const uint64_t adesc = a_tmpl + stage * (A_STAGE_BYTES >> 4);
+                        const uint64_t bdesc = b_tmpl + stage * (PAIR_B_STAGE_BYTES >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adesc = umma_smem_desc_sw128(a_base + k * dc.a_kstep, dc.a_lbo, dc.a_sbo);
-                        const uint64_t bdesc = umma_smem_desc_sw128(b_base + k * dc.b_kstep, dc.b_lbo, dc.b_sbo);
-                        umma_bf16_ss_pair(d_tmem, adesc, bdesc, idesc, (kc > tc.k0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16_ss_pair(d_tmem, adesc + k * a_kstep, bdesc + k * b_kstep, idesc,
+                                              (kc > tc.k0 || k > 0) ? 1u : 0u);
+                        umma_commit_pair(&empty_bar[stage], 0b11);      // frees the slot in BOTH CTAs
                     }
-                    umma_commit_pair(&empty_bar[stage], 0b11);      // frees the slot in BOTH CTAs
+                    __syncwarp();
                     if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_pair(&tmem_full_bar[acc], 0b11);        // both CTAs' epilogues may start
+                if (elect_one_sync()) umma_commit_pair(&tmem_full_bar[acc], 0b11);   // both CTAs' epilogues may start
+                __syncwarp();
             }
         }
     } else {
