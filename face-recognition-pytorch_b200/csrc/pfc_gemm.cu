@@ -203,13 +203,19 @@ struct StorePolicy {
     __device__ static __forceinline__ DescCfg desc(const Params& p) { return p.dc; }
     __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
         // n_fastest=0: m fastest (CTAs running together share the B stage in L2);
-        // n_fastest=1: the N tiles of one M tile run side by side (they share the A stage in L2)
+        // n_fastest=1: the N tiles of one M tile run side by side (they share the A stage in L2);
+        // n_fastest=2: the same for the CTA-pair kernel (see below)
         TileCoord tc;
         const int z = t / (p.m_tiles * p.n_tiles);
         const int r = t - z * (p.m_tiles * p.n_tiles);
         int mt, nt;
-        if (p.n_fastest) { mt = r / p.n_tiles; nt = r - mt * p.n_tiles; }
-        else             { nt = r / p.m_tiles; mt = r - nt * p.m_tiles; }
+        if (p.n_fastest == 2) {          // CTA-pair kernel: tiles 2P, 2P+1 = the two M tiles of pair P; the N tiles of one
+            const int pr = r >> 1;       // M pair run on neighbouring clusters (they share the A stage in L2)
+            const int mp = pr / p.n_tiles;
+            nt = pr - mp * p.n_tiles;
+            mt = 2 * mp + (r & 1);
+        } else if (p.n_fastest) { mt = r / p.n_tiles; nt = r - mt * p.n_tiles; }
+        else                    { nt = r / p.m_tiles; mt = r - nt * p.m_tiles; }
         if (p.m_reverse) mt = p.m_tiles - 1 - mt;
         tc.m0 = mt * BM;
         tc.n0 = nt * BN;
@@ -553,13 +559,13 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.n_tiles = (d + BN - 1) / BN;
     // cta_group::2: pairs of CLASS tiles share the Xs stage (m fastest); multicast mode: the two D halves of one
     // class tile share the E'^T stage (n fastest)
-    const int mode = pick_mode(m_tiles, p.n_tiles, MODE_SINGLE);
+    const int mode = pick_mode(m_tiles, p.n_tiles, MODE_PAIR);
     p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;
     p.splits = 1;
     p.k_stages_total = (B + BK - 1) / BK;
     p.k_stages_per_split = p.k_stages_total;
     p.num_tiles = p.m_tiles * p.n_tiles;
-    p.n_fastest = mode == MODE_PAIR ? 0 : 1;
+    p.n_fastest = mode == MODE_PAIR ? 2 : 1;
     // the forward wrote E' class tile by class tile: its last tiles are still in L2, so start with them; the
     // gradient rows written LAST are then the low ones, which is where the row-ordered update kernel starts
     p.m_reverse = 1;
