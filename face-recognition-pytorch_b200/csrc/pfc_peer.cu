@@ -159,7 +159,7 @@ peer_l2norm_gather_kernel(const float* __restrict__ x, const int64_t* __restrict
 
 // same reduction as row_stats_kernel (pfc_rows.cu: 8 rows x 32 slab groups per CTA, fixed summation order), result
 // stored into slot `rank` of every peer
-constexpr int PRS_ROWS = 8, PRS_GROUPS = 32;
+constexpr int PRS_ROWS = 8, PRS_GROUPS = 64;
 __global__ void __launch_bounds__(PRS_ROWS * PRS_GROUPS)
 peer_row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                       const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, int rank, int W,

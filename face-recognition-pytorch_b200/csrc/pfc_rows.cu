@@ -98,7 +98,7 @@ __global__ void localize_labels_kernel(const int64_t* __restrict__ labels, int B
 // stats[i] = { sum over the part_sum slabs of part_sum[t][i],  target e (0 when the target lives on another rank) }
 // Fixed summation order -> bit-reproducible.  CTA = 8 rows x 32 slab groups (a first version with 32 rows per CTA had
 // only B/32 CTAs in flight and took 14 us for 3 MB).
-constexpr int RS_ROWS = 8, RS_GROUPS = 32;
+constexpr int RS_ROWS = 8, RS_GROUPS = 64;
 __device__ __forceinline__ float row_stats_sum(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                                                float (*red)[RS_ROWS + 1]) {
     const int r = threadIdx.x & (RS_ROWS - 1), g = threadIdx.x / RS_ROWS;
@@ -158,11 +158,13 @@ row_stats_loss_kernel(const float* __restrict__ part_sum, int n_tiles, int B, in
     __syncthreads();
     if (!last) return;
     __threadfence();
-    // 256 threads stand in for loss_kernel's 1024: thread t covers the rows of loss_kernel's threads t, t+256, ...
-    // in the same order, and the partial sums are combined in loss_kernel's order (warp tree, then 32 warp sums)
+    // this CTA's threads stand in for loss_kernel's 1024: thread t covers the rows of loss_kernel's threads t,
+    // t + blockDim, ... in the same order, and the partial sums are combined in loss_kernel's order (warp tree, then
+    // 32 warp sums)
     __shared__ float wsum[32];
-    for (int v = 0; v < 4; ++v) {
-        const int vt = threadIdx.x + 256 * v;            // virtual thread id of loss_kernel
+    constexpr int kThreads = RS_ROWS * RS_GROUPS;
+    for (int v = 0; v < 1024 / kThreads; ++v) {
+        const int vt = threadIdx.x + kThreads * v;       // virtual thread id of loss_kernel
         float acc = 0.f;
         for (int i = vt; i < B; i += 1024) {
             const float others = __ldcg(stats + 2 * i), te = __ldcg(stats + 2 * i + 1);
