@@ -457,12 +457,15 @@ def main():
         else:
             ach, peak, unit = work / (ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
         # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
-        # (profiles/r01_final_ncu_full_summary.txt), valid for the single-GPU shape only
-        ncu_traffic = {"pfc_dw_sgd": 478.76e6 + 421.98e6, "pfc_forward": 96.85e6 + 144.27e6,
-                       "pfc_backward_dw": 192.51e6 + 69.82e6, "pfc_backward_dx": 287.64e6 + 5.10e6}
+        # (profiles/r01c_ncu_full_summary.txt), valid for the single-GPU shape only
+        ncu_traffic = {"pfc_dw_sgd": 478.76e6 + 422.58e6, "pfc_forward": 96.82e6 + 140.65e6,
+                       "pfc_backward_dw": 192.44e6 + 68.39e6, "pfc_backward_dx": 287.07e6 + 5.48e6}
         roof = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                 "traffic": ncu_traffic.get(dom) if world == 1 else None, "algorithmic_work": work, "peak_source": pk["kind"] + (" sustained bf16" if bound == "tensor" else " copy"),
-                "ms_per_launch": ms}
+                "ms_per_launch": ms,
+                "note": ("achieved = algorithmic bytes / time; the update re-reads part of the bf16 gradient from L2, so DRAM "
+                         "traffic (ncu) is below the algorithmic bytes and the fraction can exceed 1") if bound == "hbm" else
+                        "achieved = 2*B*n*d / time of this GEMM alone"}
     step_tf = 3 * flops_gemm / (ms_per_step * 1e-3) / 1e12
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -490,8 +493,9 @@ def main():
                 "d2h_bytes_per_step": 4 + b * EMB * 4, "steps": e2e_steps, "timing": "host wall clock, max over ranks" +
                           ("; H2D of step i+1 and D2H of step i's dX + loss on a copy stream, host reads them one step late"
                            if pipelined else "; D2H of step i's dX + loss asynchronous, host reads them one step late"),
-                "api": ("GraphedHeadStep(head, opt)(x_pinned_host, labels_pinned_host) + dx D2H + loss.item()"
-                        if gstep is not None else "head(x, labels, opt); loss.backward() + dx D2H + loss.item()")},
+                "api": ("GraphedHeadStep(head, opt)(x, labels) fed from pinned host buffers; dX and loss copied to pinned host "
+                        "memory every step" if gstep is not None else
+                        "head(x, labels, opt); loss.backward(); dX and loss copied to pinned host memory every step")},
         "gpu_launches": launches,
         "clocks": clk.summary(),
         "wall_ms_per_step": t_wall / args.steps * 1e3,

@@ -68,3 +68,16 @@ def test_state_of_a_head_keeps_the_reference_layout(pfc):
     assert torch.equal(head2.state_dict()["weight"], sd["weight"])
     with pytest.raises(ValueError):
         pfc.load_head_shard(pfc.PartialFC(conf, 38), sd)
+
+
+def test_spill_layout_helpers_round_trip(pfc):
+    """kernels.spill_from_rowmajor / spill_to_rowmajor: the class-blocked E'[n_pad/64][B][64] layout of include/pfc.h."""
+    from face_recognition_pytorch_b200 import kernels as K
+    B, n_pad = 5, 192
+    M = torch.arange(B * n_pad, dtype=torch.float32).view(B, n_pad).to(torch.bfloat16)
+    flat = K.spill_from_rowmajor(M)
+    assert flat.shape == (B * n_pad,)
+    # element (row i, class c) sits at ((c // 64) * B + i) * 64 + c % 64
+    for i, c in [(0, 0), (3, 63), (4, 64), (2, 130), (4, 191)]:
+        assert flat[((c // 64) * B + i) * 64 + c % 64] == M[i, c]
+    assert torch.equal(K.spill_to_rowmajor(flat, B, n_pad), M)
