@@ -63,6 +63,33 @@ def test_sampled_rank_shapes(pfc, name, nl, rate, B, fused):
     assert cosine(head.weight_mom.cpu(), mf[0]) >= 0.999
 
 
+@pytest.mark.parametrize("B,C", [(320, 3100), (136, 700), (1, 129)])
+def test_odd_tile_counts_through_the_pair_kernels(pfc, B, C):
+    """The cta_group::2 kernels work on PAIRS of tiles: an odd number of sample tiles (B = 320 -> 3) or class tiles
+    (C = 3100 -> 25) gets an all-padding partner tile; B = 136 / 1 exercise the ragged last tile and the single-CTA
+    fallback.  Loss, dX and dW against the fp32 oracle."""
+    d = 512
+    g = torch.Generator().manual_seed(9)
+    w = torch.normal(0, 0.01, (C, d), generator=g)
+    lab = torch.randint(0, C, (B,), generator=g)
+    # noise 1.6: target cosines ~0.5, loss O(1) -- with few classes and cleaner embeddings the loss is ~1e-3 and its
+    # RELATIVE error is dominated by bf16 operand rounding (SURVEY.md section 7)
+    x = torch.nn.functional.normalize(torch.nn.functional.normalize(w[lab]) + 1.6 * torch.randn(B, d, generator=g) / d ** 0.5)
+    conf = types.SimpleNamespace(emd_size=d, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5)
+    head = pfc.PartialFC(conf, C)
+    head.load_state_dict({"weight": w.clone()})
+    head = head.train().cuda()
+    opt = torch.optim.SGD(head.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+    xg = x.clone().cuda().requires_grad_(True)
+    loss = head(xg, lab.clone().cuda(), opt)
+    loss.backward()
+    res = ho.head_step([x], [lab], [w], C, ho.Margin("arcface", 64.0, 0.5), dtype=torch.float32)
+    assert abs(float(loss.detach()) - float(res.loss)) <= 1e-3 * abs(float(res.loss))
+    assert cosine(xg.grad.cpu(), res.dx_local[0]) >= 0.999
+    assert cosine(head.weight_activated.grad.cpu(), res.dw[0]) >= 0.999
+    assert abs(float(head.weight_activated.grad.norm()) / float(res.dw[0].norm()) - 1) < 2e-2
+
+
 def test_device_sampling_keeps_the_sampling_invariants(pfc):
     """conf.device_sampling draws the scores on the GPU: the index set is no longer the reference's for a seed, but the
     invariants of nets/PartialFC.py:108-118 hold -- every positive class kept, exactly num_sample rows, strictly
