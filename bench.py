@@ -486,7 +486,8 @@ def main():
                           "per-step CUDA events summed (--flush-l2 adds an explicit flush)")},
         "roofline": roof,
         "step_roofline": {"bound": "tensor", "achieved": step_tf / world, "peak": pk["tf_burst"], "unit": "TFLOP/s/GPU",
-                          "frac": step_tf / world / pk["tf_burst"], "work": "6*B*n*D per step (3 GEMMs, no recompute credited)",
+                          "frac": step_tf / world / pk["tf_burst"], "frac_of_sustained": step_tf / world / pk["tf_sust"],
+                          "work": "6*B*n*D per step (3 GEMMs, no recompute credited); the HBM-bound update is inside the step",
                           "peak_source": pk["kind"] + " burst bf16"},
         "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in kern.items()},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * EMB * 4 + b * 8,
