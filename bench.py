@@ -206,6 +206,9 @@ def main():
     ap.add_argument("--fused-dw", action="store_true", help="dW GEMM with the SGD update as its epilogue (one kernel)")
     ap.add_argument("--no-peer", action="store_true",
                     help="N>1: NCCL collectives instead of the peer-memory (NVLink) exchanges fused into the kernels")
+    ap.add_argument("--pdl", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="programmatic dependent launch of the step kernels: 0 off, 1 on, 2 on + deferred GEMM waits, "
+                         "-1 library default / PFC_PDL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -227,6 +230,8 @@ def main():
     import face_recognition_pytorch_b200 as pfc
     from face_recognition_pytorch_b200 import kernels as K
 
+    if args.pdl >= 0:
+        K.set_pdl(args.pdl)
     if args.sgd_warps:
         pfc._lib.lib.pfc_debug_sgd_persistent(int(args.sgd_warps))
     if args.gemm_mode:
@@ -476,6 +481,7 @@ def main():
                    "classes_per_gpu": nl, "local_batch": b, "parallelism": f"class-sharded x{world}",
                    "launch": "cuda-graph replay (GraphedHeadStep)" if gstep is not None else "eager",
                    "overlap_update": bool(conf.overlap_update),
+                   "pdl": K.get_pdl(),
                    "exchange": ("none (1 GPU)" if world == 1 else
                                 "peer-memory stores + flag barriers (NVLink)" if head._peer is not None else
                                 "NCCL all-gather / all-reduce / reduce-scatter"),

@@ -35,6 +35,9 @@ p = c_void_p
 _SIGS = {
     "pfc_version": (c_int, []),
     "pfc_error_string": (c_char_p, [c_int]),
+    "pfc_set_pdl": (None, [c_int]),
+    "pfc_get_pdl": (c_int, []),
+    "pfc_pdl_independent_next": (None, []),
     "pfc_exp_top": (c_int, []),
     "pfc_padded_classes": (c_int, [c_int]),
     "pfc_padded_batch": (c_int, [c_int]),

@@ -47,6 +47,7 @@ struct FwdPolicy {
         float* tgt_e;            // [B] e of the margin-adjusted target logit
         float* tgt_z;            // [B] margin-adjusted target logit (already * s)
         float s;
+        int pdl_defer;           // always 0: the forward depends on the kernel before it
     };
     __device__ static __forceinline__ DescCfg desc(const Params&) { return default_desc_cfg(false, false); }
     __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
@@ -185,6 +186,7 @@ struct StoreParams {
     float* out;
     int out_bf16;           // 1: `out` is a bf16 matrix (same ld in elements); used for the dWn spill in fused mode
     DescCfg dc;             // descriptor geometry (runtime so that tools/gpu_probe.py can try alternatives)
+    int pdl_defer;          // 1: griddepcontrol.wait at the END of the kernel (pfc_launch.cuh, deferred wait)
 };
 
 template <bool kAMN>
@@ -387,7 +389,7 @@ static int pick_mode(int m_tiles, int mcast_dim_tiles, int auto_mode) {
 }
 
 template <class Kern, class Params>
-static int launch_cluster(Kern kern, int cluster, int threads, int smem_bytes, const CUtensorMap& ta,
+static int launch_cluster(int pdl_id, Kern kern, int cluster, int threads, int smem_bytes, const CUtensorMap& ta,
                           const CUtensorMap& tb, const CUtensorMap& tc, const Params& prm, cudaStream_t stream) {
     const int sms = num_sms();
     if (sms <= 0) return PFC_ERR_CUDA;
@@ -400,19 +402,19 @@ static int launch_cluster(Kern kern, int cluster, int threads, int smem_bytes, c
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cluster;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 1 + pdl_attr(&at[1], pdl_id);   // the GEMM kernels start with pdl_entry() after their CTA-local setup
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, prm);
     return e == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 
 template <class P>
-static int launch_gemm(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+static int launch_gemm(int pdl_id, int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                        const typename P::Params& prm, cudaStream_t stream) {
     using C = GemmCfg<P>;
     static bool attr_set = false;
@@ -424,10 +426,10 @@ static int launch_gemm(int mode, const CUtensorMap& ta, const CUtensorMap& tb, c
         attr_set = true;
     }
     if (mode == MODE_PAIR)
-        return launch_cluster(umma_gemm_pair_kernel<P>, 2, C::THREADS, C::PAIR_SMEM, ta, tb, tc, prm, stream);
+        return launch_cluster(pdl_id, umma_gemm_pair_kernel<P>, 2, C::THREADS, C::PAIR_SMEM, ta, tb, tc, prm, stream);
     if (mode == MODE_MCAST)
-        return launch_cluster(umma_gemm_kernel<P, 2>, 2, C::THREADS, C::SMEM, ta, tb, tc, prm, stream);
-    return launch_cluster(umma_gemm_kernel<P, 1>, 1, C::THREADS, C::SMEM, ta, tb, tc, prm, stream);
+        return launch_cluster(pdl_id, umma_gemm_kernel<P, 2>, 2, C::THREADS, C::SMEM, ta, tb, tc, prm, stream);
+    return launch_cluster(pdl_id, umma_gemm_kernel<P, 1>, 1, C::THREADS, C::SMEM, ta, tb, tc, prm, stream);
 }
 
 static int even_up(int v) { return (v + 1) / 2 * 2; }
@@ -489,7 +491,9 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     p.m3 = m3; p.margin_kind = margin_kind; p.filter_thr = filter_thr;
     p.E = reinterpret_cast<__nv_bfloat16*>(E);
     p.part_sum = part_sum; p.tgt_raw = tgt_raw; p.tgt_e = tgt_e; p.tgt_z = tgt_z; p.s = s;
-    return launch_gemm<FwdPolicy>(mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
+    p.pdl_defer = 0;
+    (void)pdl_take_independent();
+    return launch_gemm<FwdPolicy>(PDL_FORWARD, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // Number of class splits the dX contraction uses for a given shape (callers size `partial` with it).
@@ -538,10 +542,11 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     p.out = partial;
     p.out_bf16 = 0;
     p.dc = store_desc_cfg(false);
+    p.pdl_defer = pdl_take_independent() ? 1 : 0;
     CUtensorMap tc;
     rc = make_store_tmap(&tc, partial, false, d, B, p.splits, d, static_cast<uint64_t>(B) * d);
     if (rc) return rc;
-    return launch_gemm<StorePolicy<false>>(mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
+    return launch_gemm<StorePolicy<false>>(PDL_DX, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // dwn[n][d] = E'^T . Xs,   Xs = c_i * Xn_i (bf16, [B, d]);  dwn fp32 or (dwn_bf16) bf16
@@ -574,10 +579,11 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.out = reinterpret_cast<float*>(dwn);
     p.out_bf16 = dwn_bf16 ? 1 : 0;
     p.dc = store_desc_cfg(true);
+    p.pdl_defer = pdl_take_independent() ? 1 : 0;
     CUtensorMap tc;
     rc = make_store_tmap(&tc, dwn, dwn_bf16 != 0, d, n, 1, d, 0);
     if (rc) return rc;
-    return launch_gemm<StorePolicy<true>>(mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
+    return launch_gemm<StorePolicy<true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // dW GEMM + normalise-backward + SGD/momentum step + next step's bf16 shard in ONE kernel (pfc_dwsgd.cuh).

@@ -22,6 +22,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include "pfc_internal.h"
+#include "pfc_launch.cuh"
 
 namespace pfc {
 
@@ -38,6 +39,7 @@ __device__ __forceinline__ float warp_sum_p(float v) {
 
 // One CTA, W threads.  flags.p[q] -> rank q's flag array uint32[W]; counter -> this rank's epoch (device memory).
 __global__ void peer_barrier_kernel(PeerPtrs flags, uint32_t* counter, int rank, int W) {
+    pdl_entry();
     __shared__ uint32_t ep_s;
     if (threadIdx.x == 0) {
         ep_s = *counter + 1;
@@ -108,6 +110,7 @@ __device__ __forceinline__ void peer_entry_barrier(const PeerPtrs& flags, uint32
 __global__ void __launch_bounds__(256)
 peer_localize_labels_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, const int64_t* labels, int B,
                             int64_t class_start, int num_local, int32_t* __restrict__ out) {
+    pdl_entry();
     peer_entry_barrier(flags, state, rank, W);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
@@ -119,6 +122,7 @@ peer_localize_labels_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, co
 __global__ void __launch_bounds__(256)
 peer_l2norm_gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, int b, int d, int rank, int W,
                           PeerPtrs xn_all, PeerPtrs labels_all, float* __restrict__ inv_norm) {
+    pdl_entry();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= b) return;
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(PRS_ROWS * PRS_GROUPS)
 peer_row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                       const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, int rank, int W,
                       PeerPtrs slots) {
+    pdl_entry();
     __shared__ float red[PRS_GROUPS][PRS_ROWS + 1];
     const int r = threadIdx.x & (PRS_ROWS - 1), g = threadIdx.x / PRS_ROWS;
     const int row = blockIdx.x * PRS_ROWS + r;
@@ -196,6 +201,7 @@ template <bool kBarrier>
 __global__ void __launch_bounds__(1024)
 peer_loss_kernel(PeerPtrs flags, uint32_t* state, int rank, const float* slots, int W, int B, float* __restrict__ stats,
                  float* __restrict__ row_L, float* __restrict__ loss) {
+    pdl_entry();
     __shared__ float red[32];
     if (kBarrier) peer_entry_barrier(flags, state, rank, W);
     float acc = 0.f;
@@ -228,6 +234,7 @@ peer_loss_kernel(PeerPtrs flags, uint32_t* state, int rank, const float* slots, 
 __global__ void __launch_bounds__(256)
 peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t split_stride,
                        const float* __restrict__ coef, int B, int b, int d, int rank, PeerPtrs dx_slots) {
+    pdl_entry();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -255,6 +262,7 @@ peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t spl
 __global__ void __launch_bounds__(256)
 peer_dx_finalize_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, const float* slots, const float* __restrict__ x,
                         const float* __restrict__ inv_norm, float scale, int b, int d, float* __restrict__ out) {
+    pdl_entry();
     peer_entry_barrier(flags, state, rank, W);
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -315,7 +323,8 @@ int pfc_peer_barrier(void* const* peer_flags, uint32_t* epoch_counter, int rank,
     PeerPtrs f;
     int rc = fill_peers(&f, peer_flags, W);
     if (rc) return rc;
-    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, epoch_counter, rank, W);
+    launch_step_kernel(PDL_LABELS, peer_barrier_kernel, 1, 32, 0, (cudaStream_t)stream,
+                       f, epoch_counter, rank, W);
     return launched();
 }
 
@@ -327,7 +336,8 @@ int pfc_peer_l2norm_gather(const float* x, const int64_t* labels, int b, int d, 
     if (rc) return rc;
     rc = fill_peers(&la, peer_labels_all, W);
     if (rc) return rc;
-    peer_l2norm_gather_kernel<<<(b + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, labels, b, d, rank, W, xa, la, inv_norm);
+    launch_step_kernel(PDL_NORMALISE, peer_l2norm_gather_kernel, (b + 7) / 8, 256, 0, (cudaStream_t)stream,
+                       x, labels, b, d, rank, W, xa, la, inv_norm);
     return launched();
 }
 
@@ -338,8 +348,8 @@ int pfc_peer_row_stats(const float* part_sum, int n_tiles, int B, const int32_t*
     int rc = fill_peers(&s, peer_slots, W);
     if (rc) return rc;
     const int B_pad = (B + 127) / 128 * 128;
-    peer_row_stats_kernel<<<(B + PRS_ROWS - 1) / PRS_ROWS, PRS_ROWS * PRS_GROUPS, 0, (cudaStream_t)stream>>>(
-        part_sum, n_tiles, B, B_pad, labels_local, tgt_e, rank, W, s);
+    launch_step_kernel(PDL_STATS, peer_row_stats_kernel, (B + PRS_ROWS - 1) / PRS_ROWS, PRS_ROWS * PRS_GROUPS, 0,
+                       (cudaStream_t)stream, part_sum, n_tiles, B, B_pad, labels_local, tgt_e, rank, W, s);
     return launched();
 }
 
@@ -351,9 +361,11 @@ int pfc_peer_loss(void* const* peer_flags, uint32_t* barrier_state, int rank, co
         int rc = fill_peers(&f, peer_flags, W);
         if (rc) return rc;
         if (!barrier_state) return PFC_ERR_SHAPE;
-        peer_loss_kernel<true><<<1, 1024, 0, (cudaStream_t)stream>>>(f, barrier_state, rank, slots, W, B, stats, row_L, loss);
+        launch_step_kernel(PDL_STATS, peer_loss_kernel<true>, 1, 1024, 0, (cudaStream_t)stream,
+                       f, barrier_state, rank, slots, W, B, stats, row_L, loss);
     } else {
-        peer_loss_kernel<false><<<1, 1024, 0, (cudaStream_t)stream>>>(f, nullptr, rank, slots, W, B, stats, row_L, loss);
+        launch_step_kernel(PDL_STATS, peer_loss_kernel<false>, 1, 1024, 0, (cudaStream_t)stream,
+                       f, nullptr, rank, slots, W, B, stats, row_L, loss);
     }
     return launched();
 }
@@ -364,8 +376,8 @@ int pfc_peer_localize_labels(void* const* peer_flags, uint32_t* barrier_state, i
     PeerPtrs f;
     int rc = fill_peers(&f, peer_flags, W);
     if (rc) return rc;
-    peer_localize_labels_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(f, barrier_state, rank, W, labels, B,
-                                                                                   class_start, num_local, labels_local);
+    launch_step_kernel(PDL_LABELS, peer_localize_labels_kernel, (B + 255) / 256, 256, 0, (cudaStream_t)stream,
+                       f, barrier_state, rank, W, labels, B, class_start, num_local, labels_local);
     return launched();
 }
 
@@ -375,8 +387,8 @@ int pfc_peer_dx_finalize(void* const* peer_flags, uint32_t* barrier_state, int r
     PeerPtrs f;
     int rc = fill_peers(&f, peer_flags, W);
     if (rc) return rc;
-    peer_dx_finalize_kernel<<<(b + 7) / 8, 256, 0, (cudaStream_t)stream>>>(f, barrier_state, rank, W, dx_slots, x, inv_norm,
-                                                                          scale, b, d, out);
+    launch_step_kernel(PDL_DX_FINAL, peer_dx_finalize_kernel, (b + 7) / 8, 256, 0, (cudaStream_t)stream,
+                       f, barrier_state, rank, W, dx_slots, x, inv_norm, scale, b, d, out);
     return launched();
 }
 
@@ -386,8 +398,8 @@ int pfc_peer_dx_scatter(const float* partial, int splits, const float* coef, int
     PeerPtrs s;
     int rc = fill_peers(&s, peer_dx_slots, W);
     if (rc) return rc;
-    peer_dx_scatter_kernel<<<(B + 7) / 8, 256, 0, (cudaStream_t)stream>>>(partial, splits, static_cast<size_t>(B) * d,
-                                                                         coef, B, b, d, rank, s);
+    launch_step_kernel(PDL_DX_FINAL, peer_dx_scatter_kernel, (B + 7) / 8, 256, 0, (cudaStream_t)stream,
+                       partial, splits, static_cast<size_t>(B) * d, coef, B, b, d, rank, s);
     return launched();
 }
 

@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "pfc_internal.h"
+#include "pfc_launch.cuh"
 
 namespace pfc {
 
@@ -52,6 +53,7 @@ l2norm_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ inde
                    __nv_bfloat16* __restrict__ xn, float* __restrict__ inv_norm,
                    const int64_t* __restrict__ labels, int64_t class_start, int num_local,
                    int32_t* __restrict__ labels_local) {
+    pdl_entry();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -89,6 +91,7 @@ l2norm_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ inde
 // labels -> shard-local ids, -1 for classes owned by another rank           (nets/PartialFC.py:188-193)
 __global__ void localize_labels_kernel(const int64_t* __restrict__ labels, int B, int64_t class_start,
                                        int num_local, int32_t* __restrict__ out) {
+    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const int64_t l = labels[i] - class_start;
@@ -128,6 +131,7 @@ __device__ __forceinline__ float row_stats_sum(const float* __restrict__ part_su
 __global__ void __launch_bounds__(RS_ROWS * RS_GROUPS)
 row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                  const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* __restrict__ stats) {
+    pdl_entry();
     __shared__ float red[RS_GROUPS][RS_ROWS + 1];
     const float tot = row_stats_sum(part_sum, n_tiles, B, B_pad, red);
     const int row = blockIdx.x * RS_ROWS + (threadIdx.x & (RS_ROWS - 1));
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(RS_ROWS * RS_GROUPS)
 row_stats_loss_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                       const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* stats,
                       float* __restrict__ row_L, float* __restrict__ loss, unsigned int* ticket) {
+    pdl_entry();
     __shared__ float red[RS_GROUPS][RS_ROWS + 1];
     __shared__ bool last;
     const float tot = row_stats_sum(part_sum, n_tiles, B, B_pad, red);
@@ -189,6 +194,7 @@ row_stats_loss_kernel(const float* __restrict__ part_sum, int n_tiles, int B, in
 // stats is the (all-reduced) [B][2] array; also emits L_i = stats[i][0] + stats[i][1].
 __global__ void __launch_bounds__(1024)
 loss_kernel(const float* __restrict__ stats, int B, float* __restrict__ row_L, float* __restrict__ loss) {
+    pdl_entry();
     __shared__ float red[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < B; i += 1024) {
@@ -219,6 +225,7 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
                         float cos_m, float sin_m, float theta, const __nv_bfloat16* __restrict__ xn,
                         __nv_bfloat16* __restrict__ xs, float* __restrict__ coef, __nv_bfloat16* __restrict__ E,
                         int n_pad) {
+    pdl_entry();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -252,6 +259,7 @@ __global__ void __launch_bounds__(256)
 dx_finalize_d512_kernel(const float* __restrict__ partial, int splits, size_t split_stride, const float* __restrict__ coef,
                         const float* __restrict__ x, const float* __restrict__ inv_norm, float scale, int rows,
                         float* __restrict__ out) {
+    pdl_entry();
     __shared__ float part[2][4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = warp >> 2, q = warp & 3;
@@ -299,6 +307,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 dx_finalize_kernel(const float* __restrict__ partial, int splits, size_t split_stride, const float* __restrict__ coef,
                    const float* __restrict__ x, const float* __restrict__ inv_norm, float scale, int rows, int d,
                    float* __restrict__ out) {
+    pdl_entry();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -364,6 +373,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const float* inv_norm_w,
                    int rows, int d, OptArgs opt, float* __restrict__ dw_out, float* __restrict__ st1,
                    float* __restrict__ st2, __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
+    pdl_entry();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -458,6 +468,7 @@ __global__ void __launch_bounds__(128)
 dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* __restrict__ mom,
                    const float* inv_norm_w, int rows, float lr, float momentum, float wd, float inv_grad_scale,
                    __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
+    pdl_entry();
     constexpr int d = 128 * NV;
     const int lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
@@ -536,11 +547,11 @@ static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom,
         if (grid > need) grid = need;
     }
     if (bf16)
-        dw_sgd_rows_kernel<NV, true><<<grid, block, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd, igs,
-                                                              wn_next, inv_next);
+        launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
+                           wd, igs, wn_next, inv_next);
     else
-        dw_sgd_rows_kernel<NV, false><<<grid, block, 0, st>>>(dwn, w, mom, inv_norm_w, rows, lr, momentum, wd, igs,
-                                                               wn_next, inv_next);
+        launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, false>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
+                           wd, igs, wn_next, inv_next);
 }
 
 // dst[r] = src[index[r]]  /  dst[index[r]] = src[r]   (nets/PartialFC.py:120-121, :142-143), up to 3 tensors at once
@@ -607,7 +618,7 @@ void pfc_debug_sgd_persistent(int warps_per_sm) { g_sgd_persistent_warps = warps
 int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void* xn, float* inv_norm, void* stream) {
     if (rows < 0 || bad_d(d)) return PFC_ERR_SHAPE;
     if (rows == 0) return PFC_OK;
-    l2norm_rows_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_NORMALISE, l2norm_rows_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         x, index, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm, nullptr, 0, 0, nullptr);
     return check_launch();
 }
@@ -615,7 +626,7 @@ int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void*
 int pfc_l2norm_rows_localize(const float* x, int rows, int d, void* xn, float* inv_norm, const int64_t* labels,
                              int64_t class_start, int num_local, int32_t* labels_local, void* stream) {
     if (rows <= 0 || bad_d(d) || !labels || !labels_local) return PFC_ERR_SHAPE;
-    l2norm_rows_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_NORMALISE, l2norm_rows_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         x, nullptr, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm, labels, class_start, num_local,
         labels_local);
     return check_launch();
@@ -624,8 +635,8 @@ int pfc_l2norm_rows_localize(const float* x, int rows, int d, void* xn, float* i
 int pfc_localize_labels(const int64_t* labels, int B, int64_t class_start, int num_local, int32_t* labels_local,
                         void* stream) {
     if (B <= 0) return PFC_ERR_SHAPE;
-    localize_labels_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(labels, B, class_start, num_local,
-                                                                              labels_local);
+    launch_step_kernel(PDL_LABELS, localize_labels_kernel, (B + 255) / 256, 256, 0, (cudaStream_t)stream,
+        labels, B, class_start, num_local, labels_local);
     return check_launch();
 }
 
@@ -633,7 +644,7 @@ int pfc_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labe
                   float* stats, void* stream) {
     if (B <= 0 || n_tiles <= 0) return PFC_ERR_SHAPE;
     const int B_pad = (B + 127) / 128 * 128;
-    row_stats_kernel<<<(B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_STATS, row_stats_kernel, (B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0, (cudaStream_t)stream,
         part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats);
     return check_launch();
 }
@@ -642,14 +653,15 @@ int pfc_row_stats_loss(const float* part_sum, int n_tiles, int B, const int32_t*
                        float* stats, float* row_L, float* loss, unsigned int* ticket, void* stream) {
     if (B <= 0 || n_tiles <= 0 || !ticket) return PFC_ERR_SHAPE;
     const int B_pad = (B + 127) / 128 * 128;
-    row_stats_loss_kernel<<<(B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_STATS, row_stats_loss_kernel, (B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0, (cudaStream_t)stream,
         part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats, row_L, loss, ticket);
     return check_launch();
 }
 
 int pfc_loss(const float* stats, int B, float* row_L, float* loss, void* stream) {
     if (B <= 0) return PFC_ERR_SHAPE;
-    loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(stats, B, row_L, loss);
+    launch_step_kernel(PDL_STATS, loss_kernel, 1, 1024, 0, (cudaStream_t)stream,
+        stats, B, row_L, loss);
     return check_launch();
 }
 
@@ -658,7 +670,7 @@ int pfc_backward_prepare(const float* stats, const float* row_L, const float* gr
                          const void* xn, void* xs, float* coef, void* E, int n_pad, void* stream) {
     if (B <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
     const double pi = 3.14159265358979323846;
-    backward_prepare_kernel<<<row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_PREPARE, backward_prepare_kernel, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
         (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
         reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad);
@@ -669,11 +681,11 @@ int pfc_dx_finalize(const float* partial, int splits, const float* coef, const f
                     float scale, int rows, int rows_total, int d, float* out, void* stream) {
     if (rows <= 0 || bad_d(d) || splits <= 0 || rows_total < rows) return PFC_ERR_SHAPE;
     if (d == 512) {
-        dx_finalize_d512_kernel<<<(rows + 1) / 2, 256, 0, (cudaStream_t)stream>>>(
-            partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, out);
+        launch_step_kernel(PDL_DX_FINAL, dx_finalize_d512_kernel, (rows + 1) / 2, 256, 0, (cudaStream_t)stream,
+        partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, out);
         return check_launch();
     }
-    dx_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_DX_FINAL, dx_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, d, out);
     return check_launch();
 }
@@ -684,7 +696,7 @@ int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, i
     OptArgs o = {};
     o.kind = OPT_NONE;
     o.inv_grad_scale = inv_grad_scale;
-    dw_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         dwn, const_cast<float*>(w), inv_norm_w, rows, d, o, dw, nullptr, nullptr, nullptr, nullptr);
     return check_launch();
 }
@@ -717,7 +729,7 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
     OptArgs o = {};
     o.kind = OPT_SGD;
     o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.inv_grad_scale = inv_grad_scale;
-    dw_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         static_cast<const float*>(dwn), w, inv_norm_w, rows, d, o, nullptr, mom, nullptr,
         reinterpret_cast<__nv_bfloat16*>(wn_next), inv_norm_next);
     return check_launch();
@@ -733,7 +745,7 @@ int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, c
     o.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     o.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     o.inv_grad_scale = inv_grad_scale;
-    dw_finalize_kernel<<<row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         dwn, w, inv_norm_w, rows, d, o, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(wn_next),
         inv_norm_next);
     return check_launch();

@@ -30,6 +30,24 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def set_pdl(mode):
+    """Programmatic dependent launch of the step kernels (pfc_set_pdl, include/pfc.h): 0 off, 1 on, 2 on + deferred
+    waits for the GEMMs declared independent of their predecessor.  Process-wide, takes effect for the launches (and
+    CUDA-graph captures) that follow.  Returns the previous mode."""
+    prev = int(lib.pfc_get_pdl())
+    lib.pfc_set_pdl(int(mode))
+    return prev
+
+
+def get_pdl():
+    return int(lib.pfc_get_pdl())
+
+
+def pdl_independent_next():
+    """The next backward_dx / backward_dw does not depend on the kernel launched just before it (include/pfc.h)."""
+    lib.pfc_pdl_independent_next()
+
+
 # ---- accounting used by bench.py: how many kernels were launched, and (optionally) their device time
 _LAUNCHES_PER_CALL = {"pfc_sample": 11}
 _count = 0

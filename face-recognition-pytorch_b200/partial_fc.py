@@ -378,6 +378,8 @@ class _PartialFCBase(torch.nn.Module):
         peer = self._peer
         if x_in.requires_grad:
             splits = K.dx_splits(B, n, d)
+            if dw_first and not overlap:
+                K.pdl_independent_next()          # dX reads E' / wn and writes dx_partial: nothing the dW GEMM touches
             K.backward_dx(ws.E, n_pad, wn_now, B, n, d, ws.dx_partial, splits)
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
             if W == 1:
@@ -395,6 +397,10 @@ class _PartialFCBase(torch.nn.Module):
             self._fused_dw_step(w, n, n_pad, d)       # dW GEMM + update in place, after the dX GEMM has consumed wn
         elif not overlap:
             if not dw_first:
+                if dx is not None and rs_work is None:
+                    # the kernel just launched is the dX finalize / peer scatter (reads dx_partial + coef, writes dX
+                    # slots); the dW GEMM reads E' / xs and writes dwn
+                    K.pdl_independent_next()
                 K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
             if self.fused_optimizer:
                 self._fused_step(w, n, d, dwn, ws.wn)     # in place, after the dX GEMM has consumed wn

@@ -35,6 +35,22 @@ extern "C" {
 int pfc_version(void);
 const char* pfc_error_string(int code);           /* host string */
 
+/* Programmatic dependent launch of the step kernels (every pfc_* kernel of one forward + backward; not the sampler or
+ * the fr_* scorer).  mode 1: each kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization and
+ * starts with griddepcontrol.wait: its CTAs are scheduled while the preceding kernel of the stream still runs, do
+ * their CTA-local setup, and touch global memory only after that kernel has completed -- same results, shorter gaps
+ * between the 8-12 dependent launches of a step (the reference's step is ~60 stream-ordered launches,
+ * nets/PartialFC.py:146-208).  mode 2: additionally honours pfc_pdl_independent_next().  mode 0: plain launches.
+ * Process-wide; the initial value comes from the environment variable PFC_PDL. */
+void pfc_set_pdl(int mode);
+int pfc_get_pdl(void);
+/* Hint for the NEXT launch on the calling thread, honoured by pfc_backward_dx / pfc_backward_dw in mode 2 and ignored
+ * (and cleared) by every other launch: that GEMM neither reads nor overwrites anything the kernel launched just before
+ * it writes or reads, and that kernel is a pfc_* step kernel which was not itself launched under this hint.  The GEMM
+ * then runs concurrently with the tail of its predecessor and still completes after it (it waits at its end), so
+ * later launches need no extra care.  Valid uses in the step: dX after dW, dW after the dX finalize / scatter. */
+void pfc_pdl_independent_next(void);
+
 /* ---- shape helpers (host only, no CUDA calls except pfc_dx_splits' SM-count query) ---------------------- */
 int pfc_exp_top(void);                            /* exponent offset of the spilled e terms (see pfc_forward) */
 int pfc_padded_classes(int n);                    /* row stride (elements) of the E' spill for n active classes */
