@@ -482,6 +482,7 @@ def main():
                    "launch": "cuda-graph replay (GraphedHeadStep)" if gstep is not None else "eager",
                    "overlap_update": bool(conf.overlap_update),
                    "pdl": K.get_pdl(),
+                   "dx_side_stream": bool(world > 1 and head._peer is not None),
                    "exchange": ("none (1 GPU)" if world == 1 else
                                 "peer-memory stores + flag barriers (NVLink)" if head._peer is not None else
                                 "NCCL all-gather / all-reduce / reduce-scatter"),

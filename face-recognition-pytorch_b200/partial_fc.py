@@ -25,11 +25,18 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
   conf.device_sampling (bool, default False): draw the PartialFC sampling scores with the CUDA generator on the device
       instead of `torch.rand` on the CPU generator + H2D copy (nets/PartialFC.py:110).  Removes a host round trip per
       step; the sampled index set is then NOT the reference's for the same seed (same distribution, other stream).
+  conf.dx_side_stream (True / False / "auto", default "auto" = on when world_size > 1): after the dX GEMM the step
+      forks -- the peer scatter + barrier + normalise-backward of dX (one GPU: just the normalise-backward) on a side
+      stream, the rank-local dW GEMM / update on the main one -- and joins before backward returns.  The branches
+      share no buffer; in a CUDA graph they become parallel branches.  Measured (graph replay, cfg-2): 2 GPUs 0.276 ->
+      0.251 ms per step (the barrier wait and two small kernels leave the critical path), 1 GPU 0.383 -> 0.384 ms
+      (neutral, hence off there).  The NCCL path overlaps its reduce-scatter with async_op instead.
   conf.overlap_update (bool, default False; needs fused_optimizer): run the fused update on a side stream underneath
       the dX GEMM.  The normalised shard is then double-buffered and the two buffers swap roles every step, so a
       CUDA graph of the step must capture an EVEN number of steps (bench.py captures two).
 """
 import collections
+import contextlib
 from typing import Callable
 
 import torch
@@ -125,6 +132,9 @@ class _PartialFCBase(torch.nn.Module):
         self.overlap_update = bool(getattr(conf, "overlap_update", False))
         self.fused_dw_update = bool(getattr(conf, "fused_dw_update", False))
         self.device_sampling = bool(getattr(conf, "device_sampling", False))
+        # run the tail of the dX path (finalize / peer scatter + finalize) on a side stream next to the rank-local
+        # dW GEMM + update, which it does not depend on; may be flipped between steps (before a graph capture)
+        self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto" (= world_size > 1)
         self._num_classes = int(num_classes)
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
@@ -376,28 +386,44 @@ class _PartialFCBase(torch.nn.Module):
             ws.wn, ws.wn_alt = ws.wn_alt, ws.wn       # ping-pong: the next forward reads what the update wrote
         dx, rs_work = None, None
         peer = self._peer
+        # fork: the tail of the dX path runs on a side stream next to the dW GEMM / update (see conf.dx_side_stream)
+        want_fork = (W > 1) if self.dx_side_stream == "auto" else bool(self.dx_side_stream)
+        fork = (want_fork and w.is_cuda and not overlap and not fuse_dw and x_in.requires_grad
+                and (W == 1 or peer is not None))
+        tail = None
         if x_in.requires_grad:
             splits = K.dx_splits(B, n, d)
             if dw_first and not overlap:
                 K.pdl_independent_next()          # dX reads E' / wn and writes dx_partial: nothing the dW GEMM touches
             K.backward_dx(ws.E, n_pad, wn_now, B, n, d, ws.dx_partial, splits)
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
-            if W == 1:
-                K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
-            elif peer is not None:
-                # :505-522 -- every rank stores its scaled partial of row i into the owner's slot; the owner sums
-                # the W slots in rank order inside the normalise-backward kernel (x W, :521)
-                K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
-            else:
-                K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
-                # :505-519 -- asynchronous: it overlaps the rank-local update below / on the side stream
-                rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
-                                                            async_op=True)
+            if fork:
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(device=w.device)
+                tail = self._side_stream
+                tail.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():
+                if W == 1:
+                    K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
+                elif peer is not None:
+                    # :505-522 -- every rank stores its scaled partial of row i into the owner's slot; the owner sums
+                    # the W slots in rank order inside the normalise-backward kernel (x W, :521)
+                    K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
+                    if tail is not None:
+                        # barrier + :521; also the fence that keeps a fast rank's NEXT gather out of xn_all while a
+                        # slow rank still reads it (this rank signals after its own dX GEMM, i.e. after its last read)
+                        K.peer_dx_finalize(peer.ptrs("flags"), peer.counter, self.rank, W, peer.dx_slots,
+                                           self._x_local, ws.inv_x, float(W), b, d, dx)
+                else:
+                    K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
+                    # :505-519 -- asynchronous: it overlaps the rank-local update below / on the side stream
+                    rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
+                                                                async_op=True)
         if fuse_dw:
             self._fused_dw_step(w, n, n_pad, d)       # dW GEMM + update in place, after the dX GEMM has consumed wn
         elif not overlap:
             if not dw_first:
-                if dx is not None and rs_work is None:
+                if dx is not None and rs_work is None and tail is None:
                     # the kernel just launched is the dX finalize / peer scatter (reads dx_partial + coef, writes dX
                     # slots); the dW GEMM reads E' / xs and writes dwn
                     K.pdl_independent_next()
@@ -411,13 +437,15 @@ class _PartialFCBase(torch.nn.Module):
         if rs_work is not None:
             rs_work.wait()
             K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)        # :521
-        if peer is not None:
+        if peer is not None and tail is None:
             # also the fence that keeps a fast rank's NEXT gather out of xn_all while a slow rank still reads it
             if dx is not None:
                 K.peer_dx_finalize(peer.ptrs("flags"), peer.counter, self.rank, W, peer.dx_slots, self._x_local,
                                    ws.inv_x, float(W), b, d, dx)                  # barrier + :521
             else:
                 K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
+        if tail is not None:
+            torch.cuda.current_stream().wait_stream(tail)                          # join
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         return dx, dw

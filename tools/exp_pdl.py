@@ -5,7 +5,7 @@ CUDA graph of the step is re-captured and 40 replays are timed with CUDA events 
 ranks).  Mask bits are PdlId of pfc_launch.cuh: 0 normalise, 1 forward GEMM, 2 row stats / loss, 3 backward_prepare,
 4 dW GEMM, 5 dX GEMM, 6 dX finalize / scatter, 7 update rows, 8 label localisation / barrier.
 
-    python tools/exp_pdl.py [--configs 0:0,1:0x1ff,2:0x1ff,...] [--steps 40]
+    python tools/exp_pdl.py [--configs mode:mask[:fork],...] [--steps 40]      (fork = conf.dx_side_stream, default auto)
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/exp_pdl.py
 """
 import argparse
@@ -62,8 +62,9 @@ def main():
 
     results = []
     for cfg in args.configs.split(","):
-        mode, mask = cfg.split(":")
-        mode, mask = int(mode), int(mask, 0)
+        f = cfg.split(":")
+        mode, mask, fork = int(f[0]), int(f[1], 0), (int(f[2]) if len(f) > 2 else -1)
+        head.dx_side_stream = "auto" if fork < 0 else bool(fork)
         K.set_pdl(mode)
         pfc._lib.lib.pfc_debug_pdl_mask(mask)
         gstep.recapture()
@@ -86,7 +87,7 @@ def main():
             best.append(float(t))
         results.append((mode, mask, best))
         if rank == 0:
-            print(f"mode {mode} mask {mask:#05x}: " + " ".join(f"{v:.4f}" for v in best) + " ms/step", flush=True)
+            print(f"mode {mode} mask {mask:#05x} fork {fork}: " + " ".join(f"{v:.4f}" for v in best) + " ms/step", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
