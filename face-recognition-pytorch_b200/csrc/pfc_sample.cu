@@ -13,6 +13,7 @@
 // compared bit-for-bit with the reference given the same draw.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "pfc_internal.h"
 
 namespace pfc {
@@ -94,6 +95,69 @@ __global__ void pick_kernel(SelState* st, int num_sample, int nl) {
     }
     st->prefix |= static_cast<uint32_t>(b) << radix_shift(PASS);
     st->k_rem = rem;
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t& total);
+
+// Same result as pick_kernel with the whole CTA: the serial walk "from the top bin down until the running count reaches
+// k_rem" stops at b* = max{ b >= 1 : I(b) >= k_rem } (0 if there is none), I(b) = sum of hist[j] over j >= b, and leaves
+// k_rem - (I(b*) - hist[b*]).  I is an inclusive scan over the bins in reversed order; the first reversed position that
+// reaches k_rem is taken with an atomicMin.  pick_kernel's single thread pays one dependent L2 load per bin walked
+// (~500-1000 bins per pass: 50-100 us of the sampler's 190 us); this is one scan.
+template <int PASS>
+__global__ void __launch_bounds__(1024)
+pick_parallel_kernel(SelState* st, int num_sample, int nl) {
+    constexpr int bins = 1 << radix_bits(PASS);
+    constexpr int per = (bins + 1023) / 1024;
+    __shared__ uint32_t wt[33];
+    __shared__ uint32_t incl[MAX_BINS];
+    __shared__ uint32_t hs[MAX_BINS];
+    __shared__ uint32_t rstar, rem_s;
+    if (threadIdx.x == 0) {
+        if (PASS == 0) {
+            uint32_t k = st->n_pos > (uint32_t)num_sample ? st->n_pos : (uint32_t)num_sample;
+            if (k > (uint32_t)nl) k = nl;
+            st->k_eff = k;
+            st->k_rem = k;
+            st->prefix = 0;
+            rem_s = k;
+        } else {
+            rem_s = st->k_rem;
+        }
+        rstar = bins - 1;                     // reversed position of bin 0: the walk's default
+    }
+    __syncthreads();
+    const uint32_t rem = rem_s;
+    if (rem == 0) {                           // nothing to select: threshold above every key (CTA-uniform branch)
+        if (threadIdx.x == 0) st->prefix = 0xFFFFFFFFu;
+        return;
+    }
+    uint32_t v[per], sum = 0;
+#pragma unroll
+    for (int u = 0; u < per; ++u) {
+        const int r = threadIdx.x * per + u;  // reversed bin index: r = 0 is the top bin
+        const uint32_t c = r < bins ? st->hist[PASS][bins - 1 - r] : 0u;
+        v[u] = c;
+        sum += c;
+        if (r < bins) hs[r] = c;
+    }
+    uint32_t tot;
+    uint32_t run = block_excl_scan(sum, wt, tot);
+#pragma unroll
+    for (int u = 0; u < per; ++u) {
+        const int r = threadIdx.x * per + u;
+        run += v[u];
+        if (r < bins) {
+            incl[r] = run;
+            if (run >= rem && r < bins - 1) atomicMin(&rstar, static_cast<uint32_t>(r));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t r = rstar;
+        st->prefix |= static_cast<uint32_t>(bins - 1 - r) << radix_shift(PASS);
+        st->k_rem = rem - (incl[r] - hs[r]);
+    }
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t& total) {
@@ -224,6 +288,22 @@ __global__ void remap_labels_kernel(const int32_t* __restrict__ labels, int B, c
     out[j] = l >= 0 ? slot_of[l] : -1;
 }
 
+// Which pick kernel the sampler uses: the CTA-wide scan (1, default) or the serial single-thread walk (0, kept as the
+// cross-check).  Measured on B200, whole sampler, eager launches: 184 -> 72 us at the cfg-3 rank shape (nl = 45 029),
+// 160 -> 73 us at cfg-4 (nl = 257 489); identical index sets on the six oracle cases (tools/check_pick.py).
+// PFC_SAMPLE_PICK=parallel|serial in the environment, pfc_debug_sample_pick() at run time.
+#ifndef PFC_SAMPLE_PICK_DEFAULT
+#define PFC_SAMPLE_PICK_DEFAULT 1
+#endif
+static int g_pick_parallel = -1;
+static bool pick_parallel() {
+    if (g_pick_parallel < 0) {
+        const char* e = getenv("PFC_SAMPLE_PICK");
+        g_pick_parallel = e ? (e[0] == 'p' || e[0] == '1') : PFC_SAMPLE_PICK_DEFAULT;
+    }
+    return g_pick_parallel != 0;
+}
+
 struct SelLayout {
     size_t flags, state, gt, eq, slot, total;
     int tiles;
@@ -248,6 +328,9 @@ using namespace pfc;
 
 extern "C" {
 
+// not part of the public header: 1 = CTA-wide pick kernel, 0 = serial walk (see pick_parallel())
+void pfc_debug_sample_pick(int parallel) { g_pick_parallel = parallel ? 1 : 0; }
+
 size_t pfc_sample_workspace_bytes(int num_local) { return num_local > 0 ? sel_layout(num_local).total : 0; }
 
 int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_local, int num_sample,
@@ -268,11 +351,15 @@ int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_lo
     mark_positive_kernel<<<(B + 255) / 256, 256, 0, stream>>>(labels_local, B, flags);
     int hb = L.tiles;   // one CTA per SEL_TILE keys keeps every SM busy for the big shards, 1 CTA for small ones
     hist_kernel<0><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    pick_kernel<0><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    const bool par = pick_parallel();
+    if (par) pick_parallel_kernel<0><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
+    else pick_kernel<0><<<1, 32, 0, stream>>>(st, num_sample, num_local);
     hist_kernel<1><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    pick_kernel<1><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    if (par) pick_parallel_kernel<1><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
+    else pick_kernel<1><<<1, 32, 0, stream>>>(st, num_sample, num_local);
     hist_kernel<2><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    pick_kernel<2><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    if (par) pick_parallel_kernel<2><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
+    else pick_kernel<2><<<1, 32, 0, stream>>>(st, num_sample, num_local);
     count_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq);
     scan_tiles_kernel<<<1, SEL_THREADS, 0, stream>>>(gt, eq, L.tiles);
     compact_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq, index_out, slot, n_out);
