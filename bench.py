@@ -206,6 +206,8 @@ def main():
     ap.add_argument("--fused-dw", action="store_true", help="dW GEMM with the SGD update as its epilogue (one kernel)")
     ap.add_argument("--no-peer", action="store_true",
                     help="N>1: NCCL collectives instead of the peer-memory (NVLink) exchanges fused into the kernels")
+    ap.add_argument("--no-autograd", action="store_true",
+                    help="capture head.fused_step (forward + backward without autograd) instead of forward + loss.backward()")
     ap.add_argument("--pdl", type=int, default=-1, choices=[-1, 0, 1, 2],
                     help="programmatic dependent launch of the step kernels: 0 off, 1 on, 2 on + deferred GEMM waits, "
                          "-1 library default / PFC_PDL")
@@ -274,7 +276,7 @@ def main():
     gstep = None
     if not args.no_graph and not args.unfused:
         try:
-            gstep = pfc.GraphedHeadStep(head, opt, b, EMB)
+            gstep = pfc.GraphedHeadStep(head, opt, b, EMB, autograd=not args.no_autograd)
         except Exception as e:   # report, fall back to eager launches (still the CUDA path)
             if rank == 0:
                 print(f"# CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
@@ -479,7 +481,8 @@ def main():
         "config": {"workload": "configs[1]: PartialFC C=93431 d=512 global_batch=1024 sample_rate=1.0 s=64 m=0.5, "
                                "fwd+bwd+" + ("torch SGD step" if args.unfused else "fused SGD update"),
                    "classes_per_gpu": nl, "local_batch": b, "parallelism": f"class-sharded x{world}",
-                   "launch": "cuda-graph replay (GraphedHeadStep)" if gstep is not None else "eager",
+                   "launch": ("cuda-graph replay (GraphedHeadStep" + (", no autograd)" if args.no_autograd else ")")
+                              if gstep is not None else "eager"),
                    "overlap_update": bool(conf.overlap_update),
                    "pdl": K.get_pdl(),
                    "dx_side_stream": bool(world > 1 and head._peer is not None),

@@ -135,6 +135,9 @@ class _PartialFCBase(torch.nn.Module):
         # run the tail of the dX path (finalize / peer scatter + finalize) on a side stream next to the rank-local
         # dW GEMM + update, which it does not depend on; may be flipped between steps (before a graph capture)
         self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto" (= world_size > 1)
+        # experiment (not measured yet): create that side stream with high priority, so that its small kernels are
+        # scheduled ahead of the update's thousands of CTAs
+        self.dx_side_priority = bool(getattr(conf, "dx_side_priority", False))
         self._num_classes = int(num_classes)
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
@@ -281,6 +284,36 @@ class _PartialFCBase(torch.nn.Module):
         raise NotImplementedError
 
     @torch.no_grad()
+    def fused_step(self, local_embeddings: torch.Tensor, local_labels: torch.Tensor,
+                   optimizer: torch.optim.Optimizer, perm: torch.Tensor = None):
+        """forward + backward of one step WITHOUT autograd: the same kernel sequence as `forward(...)` followed by
+        `loss.backward()` with d loss = 1 (nets/PartialFC.py:146-208 + :464-522), minus the three small torch kernels
+        autograd puts between them (clone of the loss, ones_like for its gradient, gradient accumulation).  Returns
+        (loss, dx): `loss` is a 0-dim VIEW of the head's static loss buffer (overwritten by the next step), `dx`
+        [b, d] = world_size * dL/d local_embeddings.  With conf.fused_optimizer the update has been applied; otherwise
+        dL/d weight_activated is left in `weight_activated.grad` for optimizer.step().  For callers that own the
+        training loop (GraphedHeadStep(autograd=False)); GradScaler users keep the autograd path."""
+        local_labels.squeeze_()
+        local_labels = local_labels.long()
+        self.update()
+        batch_size = local_embeddings.size(0)
+        if self.last_batch_size == 0:
+            self.last_batch_size = batch_size
+        assert self.last_batch_size == batch_size, (
+            "last batch size do not equal current batch size: {} vs {}".format(self.last_batch_size, batch_size))
+        if local_embeddings.dtype != torch.float32:
+            local_embeddings = local_embeddings.float()
+        self._ensure_workspace(batch_size, local_embeddings.device)
+        self._optimizer = optimizer
+        self._step_id += 1
+        self._prepare(local_embeddings, local_labels.contiguous(), optimizer, perm)
+        loss = self._forward_impl(local_embeddings, clone_loss=False)
+        dx, dw = self._backward_impl(local_embeddings, None, need_dx=True)
+        if dw is not None:
+            self.weight_activated.grad = dw
+        return loss, dx
+
+    @torch.no_grad()
     def _prepare(self, local_embeddings, labels_in, optimizer, perm):
         """Everything that precedes the differentiable part: normalise + gather the batch, localise the labels,
         sample the active classes (nets/PartialFC.py:175-196)."""
@@ -321,7 +354,7 @@ class _PartialFCBase(torch.nn.Module):
         else:
             self._n = self.num_local
 
-    def _forward_impl(self, local_embeddings):
+    def _forward_impl(self, local_embeddings, clone_loss=True):
         ws, W, d = self._ws, self.world_size, self.embedding_size
         b, B = ws.b, ws.B
         n = self._n
@@ -349,13 +382,15 @@ class _PartialFCBase(torch.nn.Module):
             K.loss(ws.stats, B, ws.row_L, ws.loss)                                # :461
         if self.fused_optimizer:
             self._opt_args = self._read_optimizer(self._optimizer)
-        return ws.loss[0].clone()
+        return ws.loss[0].clone() if clone_loss else ws.loss[0]
 
-    def _backward_impl(self, x_in, grad_loss):
+    def _backward_impl(self, x_in, grad_loss, need_dx=None):
+        """grad_loss None: d loss = 1 (no GradScaler); need_dx None: x_in.requires_grad."""
         ws, W, d = self._ws, self.world_size, self.embedding_size
         b, B, n, n_pad = ws.b, ws.B, self._n, self._n_pad
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
-        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        need_dx = x_in.requires_grad if need_dx is None else bool(need_dx)
+        g = None if grad_loss is None else grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
                            ws.coef, ws.E, n_pad)
         # Order.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the reduce-scatter /
@@ -388,10 +423,10 @@ class _PartialFCBase(torch.nn.Module):
         peer = self._peer
         # fork: the tail of the dX path runs on a side stream next to the dW GEMM / update (see conf.dx_side_stream)
         want_fork = (W > 1) if self.dx_side_stream == "auto" else bool(self.dx_side_stream)
-        fork = (want_fork and w.is_cuda and not overlap and not fuse_dw and x_in.requires_grad
+        fork = (want_fork and w.is_cuda and not overlap and not fuse_dw and need_dx
                 and (W == 1 or peer is not None))
         tail = None
-        if x_in.requires_grad:
+        if need_dx:
             splits = K.dx_splits(B, n, d)
             if dw_first and not overlap:
                 K.pdl_independent_next()          # dX reads E' / wn and writes dx_partial: nothing the dW GEMM touches
@@ -399,7 +434,7 @@ class _PartialFCBase(torch.nn.Module):
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
             if fork:
                 if self._side_stream is None:
-                    self._side_stream = torch.cuda.Stream(device=w.device)
+                    self._side_stream = torch.cuda.Stream(device=w.device, priority=-1 if self.dx_side_priority else 0)
                 tail = self._side_stream
                 tail.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _rank_main(rank, W, port, name, fused, q):
+def _rank_main(rank, W, port, name, fused, q, direct=False):
     for p in (ROOT, HERE, os.path.join(HERE, "golden")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -43,8 +43,12 @@ def _rank_main(rank, W, port, name, fused, q):
         lab = ls[s][rank * b:(rank + 1) * b].clone()
         perms = case_perms(cfg, z, s)
         opt.zero_grad()
-        loss = head(x, lab, opt, perm=None if perms is None else perms[rank])
-        loss.backward()
+        if direct:       # same step without autograd (PartialFC.fused_step)
+            loss, dx = head.fused_step(x.detach(), lab, opt, perm=None if perms is None else perms[rank])
+            x.grad = dx
+        else:
+            loss = head(x, lab, opt, perm=None if perms is None else perms[rank])
+            loss.backward()
         out[f"loss_{s}"] = float(loss.detach())
         out[f"dx_{s}"] = x.grad.numpy().copy()
         if not fused:
@@ -68,16 +72,20 @@ def _cos(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
 
 
-@pytest.mark.parametrize("name,fused,port", [("head_w2_full", False, 29821), ("head_w2_sampled", False, 29822),
-                                             ("head_w2_full", True, 29823), ("head_w2_sampled", True, 29824)])
-def test_two_rank_host_logic_matches_reference(name, fused, port):
+@pytest.mark.parametrize("name,fused,port,direct", [("head_w2_full", False, 29821, False),
+                                                    ("head_w2_sampled", False, 29822, False),
+                                                    ("head_w2_full", True, 29823, False),
+                                                    ("head_w2_sampled", True, 29824, False),
+                                                    ("head_w2_sampled", False, 29825, True),
+                                                    ("head_w2_full", True, 29826, True)])
+def test_two_rank_host_logic_matches_reference(name, fused, port, direct):
     sys.path.insert(0, HERE)
     from helpers import load_case
     cfg, z = load_case(name)
     W = cfg["W"]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, q)) for r in range(W)]
+    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, q, direct)) for r in range(W)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=240) for _ in range(W))

@@ -1,12 +1,16 @@
-"""EXPERIMENT: which step kernels profit from programmatic dependent launch (csrc/pfc_launch.cuh)?
+"""EXPERIMENT: launch-structure variants of the step -- programmatic dependent launch (csrc/pfc_launch.cuh), the dX-tail
+fork (conf.dx_side_stream), a high-priority side stream for it, and the graph without autograd (head.fused_step).
 
 One process (or one per GPU under torchrun), the bench workload (BASELINE configs[1]); for every (mode, mask) pair the
 CUDA graph of the step is re-captured and 40 replays are timed with CUDA events (L2 flushed between replays, max over
 ranks).  Mask bits are PdlId of pfc_launch.cuh: 0 normalise, 1 forward GEMM, 2 row stats / loss, 3 backward_prepare,
 4 dW GEMM, 5 dX GEMM, 6 dX finalize / scatter, 7 update rows, 8 label localisation / barrier.
 
-    python tools/exp_pdl.py [--configs mode:mask[:fork],...] [--steps 40]      (fork = conf.dx_side_stream, default auto)
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/exp_pdl.py
+    python tools/exp_step.py [--configs mode:mask[:fork[:direct[:prio]]],...] [--steps 40]
+        fork   -1 auto / 0 / 1   conf.dx_side_stream
+        direct 0 / 1             GraphedHeadStep(autograd=False): head.fused_step instead of forward + loss.backward()
+        prio   0 / 1             high-priority side stream for the dX tail
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/exp_step.py
 """
 import argparse
 import os
@@ -58,15 +62,23 @@ def main():
         x = x_dev[i % n_data].clone().requires_grad_(True)
         head(x, l_dev[i % n_data], opt).backward()
     torch.cuda.synchronize()
-    gstep = pfc.GraphedHeadStep(head, opt, b, bench.EMB)
+    gsteps = {}
 
     results = []
     for cfg in args.configs.split(","):
         f = cfg.split(":")
         mode, mask, fork = int(f[0]), int(f[1], 0), (int(f[2]) if len(f) > 2 else -1)
+        direct = int(f[3]) if len(f) > 3 else 0
+        prio = int(f[4]) if len(f) > 4 else 0
         head.dx_side_stream = "auto" if fork < 0 else bool(fork)
+        if bool(prio) != head.dx_side_priority:
+            head.dx_side_priority = bool(prio)
+            head._side_stream = None                      # re-created with the new priority at the next step
         K.set_pdl(mode)
         pfc._lib.lib.pfc_debug_pdl_mask(mask)
+        if direct not in gsteps:
+            gsteps[direct] = pfc.GraphedHeadStep(head, opt, b, bench.EMB, autograd=not direct)
+        gstep = gsteps[direct]
         gstep.recapture()
         best = []
         for _ in range(args.repeat):
@@ -87,7 +99,7 @@ def main():
             best.append(float(t))
         results.append((mode, mask, best))
         if rank == 0:
-            print(f"mode {mode} mask {mask:#05x} fork {fork}: " + " ".join(f"{v:.4f}" for v in best) + " ms/step", flush=True)
+            print(f"mode {mode} mask {mask:#05x} fork {fork} direct {direct} prio {prio}: " + " ".join(f"{v:.4f}" for v in best) + " ms/step", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
