@@ -599,7 +599,10 @@ class PartialFCAdamW(_PartialFCBase):
         ws, o = self._ws, self._opt_args
         if self.sample_rate < 1:
             m, v = self.weight_activated_exp_avg, self.weight_activated_exp_avg_sq
-            step = self.step
+            # The reference hands torch.optim.AdamW state["step"] = self.step BEFORE optimizer.step(), which increments it
+            # once more: forward call t is bias-corrected with t + 1 (nets/PartialFC.py:306, :327; pinned by
+            # tests/golden/head_w*_adamw_sampled.npz).  The un-fused path inherits that from torch; mirror it here.
+            step = self.step + 1
         else:
             if self._fused_state is None:
                 self._fused_state = (torch.zeros_like(w), torch.zeros_like(w))

@@ -246,42 +246,67 @@ class PartialFCOracle:
     """
 
     def __init__(self, weights: Sequence[torch.Tensor], num_classes: int, margin: Margin, sample_rate: float,
-                 lr: float, momentum: float, weight_decay: float, dtype=torch.float64):
+                 lr: float, momentum: float, weight_decay: float, dtype=torch.float64, optimizer: str = "sgd",
+                 betas=(0.9, 0.999), eps: float = 1e-8):
+        """optimizer "sgd": PartialFC + torch.optim.SGD; "adamw": PartialFCAdamW + torch.optim.AdamW
+        (nets/PartialFC.py:235-432), `mom` then holds exp_avg and `mom2` exp_avg_sq."""
         self.W = len(weights)
         self.num_classes, self.margin, self.sample_rate = num_classes, margin, sample_rate
         self.lr, self.momentum, self.wd, self.dtype = lr, momentum, weight_decay, dtype
+        self.optimizer, self.betas, self.eps = optimizer, betas, eps
+        self.t = 0            # forward calls so far == PartialFCAdamW.step (:306)
         self.weight = [w.clone().to(dtype) for w in weights]
         self.mom = [torch.zeros_like(w) for w in self.weight]
-        self.pending = None   # (index per rank, activated weights, activated momentum) awaiting scatter-back
+        self.mom2 = [torch.zeros_like(w) for w in self.weight]
+        self.pending = None   # (index per rank, activated weights, activated state...) awaiting scatter-back
 
     def _flush(self):
         if self.pending is None:
             return
-        for r, (idx, w_act, m_act) in enumerate(self.pending):
+        for r, (idx, w_act, m_act, v_act) in enumerate(self.pending):
             if idx is None:
                 self.weight[r], self.mom[r] = w_act, m_act
+                if v_act is not None:
+                    self.mom2[r] = v_act
             else:
                 self.weight[r][idx] = w_act
                 self.mom[r][idx] = m_act
+                if v_act is not None:
+                    self.mom2[r][idx] = v_act
         self.pending = None
 
     def step(self, local_embeddings, local_labels, perms=None) -> StepResult:
         self._flush()                                                          # update() (:166)
         res = head_step(local_embeddings, local_labels, self.weight, self.num_classes, self.margin,
                         self.sample_rate, perms, dtype=self.dtype)
+        self.t += 1
         pend = []
         for r in range(self.W):
             idx = res.index[r]
             w_act = self.weight[r] if idx is None else self.weight[r][idx]
             m_act = self.mom[r] if idx is None else self.mom[r][idx]
-            w_new, m_new = sgd_update(w_act, m_act, res.dw[r], self.lr, self.momentum, self.wd)
-            pend.append((idx, w_new, m_new))
+            if self.optimizer == "adamw":
+                v_act = self.mom2[r] if idx is None else self.mom2[r][idx]
+                # Sampled: sample() writes state["step"] = self.step (= t) BEFORE optimizer.step(), which increments it
+                # once more -- the bias correction of forward call t uses t + 1 (nets/PartialFC.py:306, :327 + torch's
+                # `step += 1`).  Full (sample_rate == 1): sample() never runs and the optimizer counts by itself: t.
+                step = self.t + 1 if idx is not None else self.t
+                w_new, m_new, v_new = adamw_update(w_act, m_act, v_act, res.dw[r], step, self.lr, self.betas[0],
+                                                   self.betas[1], self.eps, self.wd)
+                pend.append((idx, w_new, m_new, v_new))
+            else:
+                w_new, m_new = sgd_update(w_act, m_act, res.dw[r], self.lr, self.momentum, self.wd)
+                pend.append((idx, w_new, m_new, None))
         self.pending = pend
         return res
 
     def full_weights(self):
         self._flush()
         return self.weight, self.mom
+
+    def full_adam_state(self):
+        self._flush()
+        return self.mom, self.mom2
 
 
 # ----------------------------------------------------------------------------------------------- timed CPU baseline

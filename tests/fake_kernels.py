@@ -25,6 +25,9 @@ class FakeKernels:
                      "sample_workspace_bytes", "hist_bins"):
             setattr(self, name, getattr(real, name))
 
+    def pdl_independent_next(self):
+        """launch-scheduling hint (include/pfc.h): nothing to do on the CPU"""
+
     # ---- rows
     def l2norm_rows(self, x, index, rows, xn, inv_norm):
         src = x[index[:rows]] if index is not None else x[:rows]
@@ -149,6 +152,17 @@ class FakeKernels:
         w_new, m_new = ho.sgd_update(w[:rows], mom[:rows], g, lr, momentum, wd)
         w[:rows] = w_new
         mom[:rows] = m_new
+        self.l2norm_rows(w, None, rows, wn_next, inv_norm_next)
+
+    def dw_adam(self, dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, wd, step, decoupled,
+                inv_grad_scale, wn_next, inv_norm_next):
+        g = torch.empty(rows, d)
+        self.dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, g)
+        w_new, m_new, v_new = ho.adamw_update(w[:rows], exp_avg[:rows], exp_avg_sq[:rows], g, step, lr, beta1, beta2,
+                                              eps, wd, decoupled=bool(decoupled))
+        w[:rows] = w_new
+        exp_avg[:rows] = m_new
+        exp_avg_sq[:rows] = v_new
         self.l2norm_rows(w, None, rows, wn_next, inv_norm_next)
 
     def backward_dw_sgd(self, E, n_pad, xs, B, n, d, w, mom, inv_norm_w, lr, momentum, wd, inv_grad_scale, wn_next,

@@ -26,17 +26,18 @@ sys.path.insert(0, HERE)
 from inputs import synth_inputs, shard, eval_inputs_cfg5   # noqa: E402
 
 
-def _import_reference():
+def _import_reference(adamw=False):
     sys.path.insert(0, REF)
     torch.Tensor.cuda = lambda self, *a, **k: self
-    from nets.PartialFC import PartialFC                      # noqa
+    from nets.PartialFC import PartialFC, PartialFCAdamW      # noqa
     from nets.ArcFace import ArcFace, CosFace, CombinedMarginLoss   # noqa
-    return PartialFC, ArcFace, CosFace, CombinedMarginLoss
+    return (PartialFCAdamW if adamw else PartialFC), ArcFace, CosFace, CombinedMarginLoss
 
 
 def run_head_rank(rank, W, port, cfg, out_q):
     """One reference rank: builds PartialFC, loads its shard, runs `steps` of forward/backward/SGD."""
-    PartialFC, ArcFace, CosFace, CombinedMarginLoss = _import_reference()
+    adamw = cfg.get("optimizer", "sgd") == "adamw"
+    PartialFC, ArcFace, CosFace, CombinedMarginLoss = _import_reference(adamw)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=W)
     C, d, b, steps, r = cfg["C"], cfg["d"], cfg["b"], cfg["steps"], cfg["sample_rate"]
     B = b * W
@@ -47,8 +48,12 @@ def run_head_rank(rank, W, port, cfg, out_q):
     nl, cs = shard(C, rank, W)
     head.load_state_dict({"weight": w_full[cs:cs + nl].clone()})
     dummy = torch.nn.Parameter(torch.zeros(1))                # stands for the encoder param group
-    opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
-                          momentum=cfg["momentum"], weight_decay=cfg["wd"])
+    if adamw:
+        opt = torch.optim.AdamW([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
+                                weight_decay=cfg["wd"])
+    else:
+        opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
+                              momentum=cfg["momentum"], weight_decay=cfg["wd"])
     draws = []
     real_rand = torch.rand
 
@@ -77,8 +82,25 @@ def run_head_rank(rank, W, port, cfg, out_q):
             rec[f"index_{s}"] = head.weight_index.numpy().copy()
             # n_pos > num_sample: no draw is made (nets/PartialFC.py:109,114-115)
             rec[f"perm_{s}"] = draws[-1].numpy().copy() if len(draws) > n_before else np.zeros(0, np.float32)
+        if adamw and r < 1:
+            # The ONLY adaptation: PartialFCAdamW.sample stores a Python int in optimizer.state[...]["step"]
+            # (nets/PartialFC.py:327); torch >= 2.0 rejects that ("state_steps must contain singleton tensors"), so the
+            # unmodified reference cannot take an AdamW step on this torch.  Same number, as a tensor.
+            st = opt.state[head.weight_activated]
+            if not torch.is_tensor(st["step"]):
+                st["step"] = torch.tensor(float(st["step"]))
         opt.step()
-    if r < 1:
+    if adamw and r < 1:
+        head.update()
+        rec["weight_final"] = head.weight.numpy().copy()
+        rec["exp_avg_final"] = head.weight_exp_avg.numpy().copy()
+        rec["exp_avg_sq_final"] = head.weight_exp_avg_sq.numpy().copy()
+    elif adamw:
+        rec["weight_final"] = head.weight_activated.detach().numpy().copy()
+        st = opt.state[head.weight_activated]
+        rec["exp_avg_final"] = st["exp_avg"].numpy().copy()
+        rec["exp_avg_sq_final"] = st["exp_avg_sq"].numpy().copy()
+    elif r < 1:
         head.update()                                          # flush the last step's rows (reference quirk)
         rec["weight_final"] = head.weight.numpy().copy()
         rec["mom_final"] = head.weight_mom.numpy().copy()
@@ -175,7 +197,19 @@ def make_eval_case():
     print("eval: small th", th, "cfg5 th", out["cfg5_th"], "cfg5 acc", out["cfg5_acc"])
 
 
+def make_adamw_cases():
+    """PartialFCAdamW (nets/PartialFC.py:235-432): sampled (exp_avg / exp_avg_sq rows gathered and scattered back, the
+    step count patched into the optimizer) and full."""
+    base = dict(d=64, s=64.0, m=0.5, lr=1e-3, momentum=0.0, wd=0.05, steps=3, optimizer="adamw")
+    make_head_case("head_w1_adamw_sampled", 1, dict(base, C=400, b=32, sample_rate=0.25), 29619)
+    make_head_case("head_w2_adamw_sampled", 2, dict(base, C=401, b=16, sample_rate=0.5), 29620)
+    make_head_case("head_w1_adamw_full", 1, dict(base, C=300, b=32, sample_rate=1.0), 29621)
+
+
 if __name__ == "__main__":
+    if "--adamw-only" in sys.argv:      # added after the other fixtures: leaves them untouched
+        make_adamw_cases()
+        sys.exit(0)
     base = dict(d=64, s=64.0, m=0.5, lr=0.1, momentum=0.9, wd=5e-4, steps=3)
     make_head_case("head_w1_full", 1, dict(base, C=300, b=32, sample_rate=1.0), 29611)
     make_head_case("head_w1_s30", 1, dict(base, C=300, b=32, sample_rate=1.0, s=30.0, m=0.35, sigma=0.6), 29612)
@@ -185,5 +219,6 @@ if __name__ == "__main__":
     make_head_case("head_w2_full", 2, dict(base, C=301, b=16, sample_rate=1.0), 29616)
     make_head_case("head_w2_sampled", 2, dict(base, C=401, b=16, sample_rate=0.5), 29617)
     make_head_case("head_w1_d512", 1, dict(base, C=520, b=64, d=512, sample_rate=1.0, steps=1), 29618)
+    make_adamw_cases()
     make_margin_case()
     make_eval_case()

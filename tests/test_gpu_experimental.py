@@ -5,6 +5,8 @@ are off by default.  Enable a feature by default only after this file has passed
   * GraphedHeadStep(autograd=False) / PartialFC.fused_step: same kernels as forward + loss.backward() with d loss = 1,
     so the results must be bit-identical (host logic already covered on CPU by tests/test_dist_gloo.py).
   * conf.dx_side_priority: high-priority side stream for the dX tail -- scheduling only, results unchanged.
+  * PartialFCAdamW with sampling, fused update: bias correction with the reference's step count (t + 1, pinned on the CPU
+    by tests/test_oracle_golden.py and tests/test_dist_gloo.py against fixtures of the reference's PartialFCAdamW).
 """
 import os
 import types
@@ -87,3 +89,36 @@ def test_high_priority_side_stream_changes_nothing(pfc):
     b = _graph_run(pfc, True, dx_side_stream=True, dx_side_priority=True)
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+def test_adamw_sampled_fused_matches_unfused_and_reference(pfc):
+    import numpy as np
+    from helpers import load_case, case_inputs, case_perms, cosine
+    cfg, z = load_case("head_w1_adamw_sampled")
+    weights, xs, ls = case_inputs(cfg)
+    finals = []
+    for fused in (False, True):
+        conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
+                                     loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused)
+        head = pfc.PartialFCAdamW(conf, cfg["C"])
+        head.load_state_dict({"weight": weights[0].clone()})
+        head = head.train().cuda()
+        dummy = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+        opt = torch.optim.AdamW([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"], weight_decay=cfg["wd"])
+        for s in range(cfg["steps"]):
+            x = xs[s].clone().cuda().requires_grad_(True)
+            opt.zero_grad()
+            loss = head(x, ls[s].clone().cuda(), opt, perm=case_perms(cfg, z, s)[0].cuda())
+            loss.backward()
+            assert np.array_equal(head.weight_index.cpu().numpy(), z[f"r0_index_{s}"])
+            opt.step()
+        head.update()
+        finals.append(head.weight.cpu().numpy().astype(np.float64))
+    w0 = weights[0].numpy().astype(np.float64)
+    ref = z["r0_weight_final"] - w0
+    m_ref = np.abs(z["r0_exp_avg_final"])
+    well = m_ref > 0.05 * m_ref.max()
+    for f in finals:
+        err = np.abs((f - w0) - ref)[well].mean() / np.abs(ref).max()
+        assert err <= 5e-3, err
+    assert cosine(finals[0] - w0, finals[1] - w0) >= 0.9999
