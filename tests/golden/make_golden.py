@@ -43,7 +43,13 @@ def run_head_rank(rank, W, port, cfg, out_q):
     B = b * W
     w_full, xs, ls = synth_inputs(C, d, B, steps, sigma=cfg.get("sigma", 1.0))
     conf = types.SimpleNamespace(emd_size=d, sample_rate=r, mixed_precision=False, loss_s=cfg["s"], loss_m=cfg["m"])
-    margin_cls = {"arcface": ArcFace, "cosface": CosFace}[cfg.get("margin", "arcface")]
+    if cfg.get("margin", "arcface") == "combined_filter":
+        # CombinedMarginLoss in its ArcFace form with inter-class filtering (nets/ArcFace.py:30-52); the head calls
+        # margin_loss(conf.loss_s, conf.loss_m) (nets/PartialFC.py:88), so the extra arguments are bound here
+        thr = cfg["filter_thr"]
+        margin_cls = lambda s, m: CombinedMarginLoss(s, 1.0, m, 0.0, interclass_filtering_threshold=thr)   # noqa: E731
+    else:
+        margin_cls = {"arcface": ArcFace, "cosface": CosFace}[cfg.get("margin", "arcface")]
     head = PartialFC(conf, C, margin_loss=margin_cls)
     nl, cs = shard(C, rank, W)
     head.load_state_dict({"weight": w_full[cs:cs + nl].clone()})
@@ -206,9 +212,25 @@ def make_adamw_cases():
     make_head_case("head_w1_adamw_full", 1, dict(base, C=300, b=32, sample_rate=1.0), 29621)
 
 
+def make_filter_case():
+    base = dict(d=64, s=64.0, m=0.5, lr=0.1, momentum=0.9, wd=5e-4, steps=3)
+    # non-target cosines at d = 64 are ~N(0, 0.125): a threshold of 0.25 filters ~2 % of them
+    make_head_case("head_w1_filter", 1, dict(base, C=300, b=32, sample_rate=1.0, margin="combined_filter",
+                                             filter_thr=0.25), 29622)
+    # The filter is a step function of the cosine: with bf16 operands (the CUDA path) a logit within ~2e-3 of the
+    # threshold can land on the other side and move the loss by e^(64*thr).  The first case (dozens of such logits)
+    # pins the fp64 oracle; this one, whose non-target cosines all stay >= 0.02 away from the threshold over the three
+    # steps (two logits filtered), is the one bf16-operand implementations are compared with.
+    make_head_case("head_w1_filter_wide", 1, dict(base, C=300, b=32, sample_rate=1.0, margin="combined_filter",
+                                                  filter_thr=0.47), 29623)
+
+
 if __name__ == "__main__":
     if "--adamw-only" in sys.argv:      # added after the other fixtures: leaves them untouched
         make_adamw_cases()
+        sys.exit(0)
+    if "--filter-only" in sys.argv:
+        make_filter_case()
         sys.exit(0)
     base = dict(d=64, s=64.0, m=0.5, lr=0.1, momentum=0.9, wd=5e-4, steps=3)
     make_head_case("head_w1_full", 1, dict(base, C=300, b=32, sample_rate=1.0), 29611)
@@ -220,5 +242,6 @@ if __name__ == "__main__":
     make_head_case("head_w2_sampled", 2, dict(base, C=401, b=16, sample_rate=0.5), 29617)
     make_head_case("head_w1_d512", 1, dict(base, C=520, b=64, d=512, sample_rate=1.0, steps=1), 29618)
     make_adamw_cases()
+    make_filter_case()
     make_margin_case()
     make_eval_case()

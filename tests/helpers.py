@@ -9,7 +9,7 @@ from oracle import head_oracle as ho
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HEAD_CASES = ["head_w1_full", "head_w1_s30", "head_w1_cosface", "head_w1_sampled", "head_w1_manypos",
-              "head_w2_full", "head_w2_sampled", "head_w1_d512"]
+              "head_w2_full", "head_w2_sampled", "head_w1_d512", "head_w1_filter", "head_w1_filter_wide"]
 
 
 def load_case(name):
@@ -31,6 +31,8 @@ def case_inputs(cfg):
 
 
 def case_margin(cfg):
+    if cfg["margin"] == "combined_filter":      # CombinedMarginLoss(s, 1, m, 0, interclass_filtering_threshold)
+        return ho.Margin(kind="arcface", s=cfg["s"], m=cfg["m"], filter_thr=cfg["filter_thr"])
     return ho.Margin(kind=cfg["margin"], s=cfg["s"], m=cfg["m"])
 
 

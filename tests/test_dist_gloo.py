@@ -31,7 +31,12 @@ def _rank_main(rank, W, port, name, fused, q, direct=False):
     b = cfg["b"]
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
                                  loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused)
-    head = pfc.PartialFC(conf, cfg["C"])
+    if cfg["margin"] == "combined_filter":
+        thr = cfg["filter_thr"]
+        margin = lambda s_, m_: pfc.CombinedMarginLoss(s_, 1.0, m_, 0.0, interclass_filtering_threshold=thr)  # noqa: E731
+    else:
+        margin = {"arcface": pfc.ArcFace, "cosface": pfc.CosFace}[cfg["margin"]]
+    head = pfc.PartialFC(conf, cfg["C"], margin_loss=margin)
     assert (head.num_local, head.class_start) == pfc.shard_range(cfg["C"], rank, W)
     head.load_state_dict({"weight": weights[rank].clone()})
     dummy = torch.nn.Parameter(torch.zeros(1))
@@ -165,7 +170,10 @@ def _cos(a, b):
                                                     ("head_w2_full", True, 29823, False),
                                                     ("head_w2_sampled", True, 29824, False),
                                                     ("head_w2_sampled", False, 29825, True),
-                                                    ("head_w2_full", True, 29826, True)])
+                                                    ("head_w2_full", True, 29826, True),
+                                                    # one rank: CombinedMarginLoss with inter-class filtering
+                                                    ("head_w1_filter_wide", False, 29827, False),
+                                                    ("head_w1_filter_wide", True, 29828, True)])
 def test_two_rank_host_logic_matches_reference(name, fused, port, direct):
     sys.path.insert(0, HERE)
     from helpers import load_case
@@ -181,7 +189,8 @@ def test_two_rank_host_logic_matches_reference(name, fused, port, direct):
         p.join(timeout=60)
         assert p.exitcode == 0
     for s in range(cfg["steps"]):
-        assert res[0][f"loss_{s}"] == res[1][f"loss_{s}"]                    # every rank returns the global loss
+        if W > 1:
+            assert res[0][f"loss_{s}"] == res[1][f"loss_{s}"]                # every rank returns the global loss
         for r in range(W):
             ref_loss = float(z[f"r{r}_loss_{s}"])
             assert abs(res[r][f"loss_{s}"] - ref_loss) <= 6e-3 * abs(ref_loss)   # bf16 operands at d = 64 (see test_gpu_head.py)

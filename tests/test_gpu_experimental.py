@@ -7,6 +7,8 @@ are off by default.  Enable a feature by default only after this file has passed
   * conf.dx_side_priority: high-priority side stream for the dX tail -- scheduling only, results unchanged.
   * PartialFCAdamW with sampling, fused update: bias correction with the reference's step count (t + 1, pinned on the CPU
     by tests/test_oracle_golden.py and tests/test_dist_gloo.py against fixtures of the reference's PartialFCAdamW).
+  * CombinedMarginLoss with inter-class filtering INSIDE the head (the kFilter branch of the forward epilogue): until now
+    only the stand-alone margin kernel was compared with the reference on the GPU.
 """
 import os
 import types
@@ -122,3 +124,35 @@ def test_adamw_sampled_fused_matches_unfused_and_reference(pfc):
         err = np.abs((f - w0) - ref)[well].mean() / np.abs(ref).max()
         assert err <= 5e-3, err
     assert cosine(finals[0] - w0, finals[1] - w0) >= 0.9999
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_head_with_interclass_filter_matches_reference(pfc, fused):
+    """tests/golden/head_w1_filter_wide.npz: every non-target cosine stays >= 0.02 away from the threshold, so bf16
+    operand rounding cannot flip a filter decision."""
+    import numpy as np
+    from helpers import load_case, case_inputs, cosine
+    cfg, z = load_case("head_w1_filter_wide")
+    weights, xs, ls = case_inputs(cfg)
+    thr = cfg["filter_thr"]
+    conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
+                                 loss_m=cfg["m"], fused_optimizer=fused)
+    head = pfc.PartialFC(conf, cfg["C"], margin_loss=lambda s_, m_: pfc.CombinedMarginLoss(
+        s_, 1.0, m_, 0.0, interclass_filtering_threshold=thr))
+    head.load_state_dict({"weight": weights[0].clone()})
+    head = head.train().cuda()
+    opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
+    for s in range(cfg["steps"]):
+        x = xs[s].clone().cuda().requires_grad_(True)
+        opt.zero_grad()
+        loss = head(x, ls[s].clone().cuda(), opt)
+        loss.backward()
+        ref_loss = float(z[f"r0_loss_{s}"])
+        assert abs(float(loss.detach()) - ref_loss) <= 6e-3 * abs(ref_loss), (s, float(loss.detach()), ref_loss)
+        assert cosine(x.grad.cpu(), z[f"r0_dx_{s}"]) >= 0.999
+        if not fused:
+            assert cosine(head.weight_activated.grad.cpu(), z[f"r0_dw_{s}"]) >= 0.999
+        opt.step()
+    w0 = weights[0].double()
+    assert cosine(head.weight_activated.data.cpu().double() - w0,
+                  torch.from_numpy(z["r0_weight_final"]).double() - w0) >= 0.999
