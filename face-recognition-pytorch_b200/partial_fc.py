@@ -31,6 +31,12 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       share no buffer; in a CUDA graph they become parallel branches.  Measured (graph replay, cfg-2): 2 GPUs 0.276 ->
       0.251 ms per step (the barrier wait and two small kernels leave the critical path), 1 GPU 0.383 -> 0.384 ms
       (neutral, hence off there).  The NCCL path overlaps its reduce-scatter with async_op instead.
+  conf.early_dx (bool, default False; written after the round's GPU budget was spent -- host logic covered on CPU, kernels
+      behind tests/test_gpu_experimental.py): the forward GEMM leaves 0 in the target column of the spill, so the dX
+      GEMM does not need the target patch (a rank-1 term added when the partials are summed) nor the per-row coefficients
+      (applied afterwards).  It is launched on its own stream straight after the forward GEMM and overlaps the row
+      statistics, their exchange, the loss and backward_prepare; backward joins it, writes the patch into the spill
+      and goes on with the dW GEMM.
   conf.overlap_update (bool, default False; needs fused_optimizer): run the fused update on a side stream underneath
       the dX GEMM.  The normalised shard is then double-buffered and the two buffers swap roles every step, so a
       CUDA graph of the step must capture an EVEN number of steps (bench.py captures two).
@@ -81,6 +87,7 @@ class _Workspace:
         self.loss = z(1)
         self.ticket = z(1, dt=i32)
         self.coef = z(B)
+        self.patch = z(B)                         # deferred target values of E' (conf.early_dx)
         self.xs = z(B, d, dt=bf16)
         self.max_splits = max(1, K.dx_max_splits(B, d))
         self.dx_partial = z(self.max_splits * B * d)
@@ -104,7 +111,7 @@ class _HeadFunction(torch.autograd.Function):
         ctx.head = head
         ctx.x = local_embeddings
         ctx.step_id = head._step_id
-        return head._forward_impl(local_embeddings)
+        return head._forward_impl(local_embeddings, need_dx=ctx.needs_input_grad[0])
 
     @staticmethod
     def backward(ctx, grad_loss):
@@ -135,6 +142,11 @@ class _PartialFCBase(torch.nn.Module):
         # run the tail of the dX path (finalize / peer scatter + finalize) on a side stream next to the rank-local
         # dW GEMM + update, which it does not depend on; may be flipped between steps (before a graph capture)
         self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto" (= world_size > 1)
+        # experiment (not measured yet): launch the dX GEMM right after the forward GEMM, on the unpatched spill and on
+        # its own stream, so that it runs NEXT TO row statistics -> exchange -> loss -> prepare instead of behind them
+        self.early_dx = bool(getattr(conf, "early_dx", False))
+        self._early = None              # (stream or None, splits) of an early dX GEMM that has not been joined yet
+        self._early_stream = None
         # experiment (not measured yet): create that side stream with high priority, so that its small kernels are
         # scheduled ahead of the update's thousands of CTAs
         self.dx_side_priority = bool(getattr(conf, "dx_side_priority", False))
@@ -307,7 +319,7 @@ class _PartialFCBase(torch.nn.Module):
         self._optimizer = optimizer
         self._step_id += 1
         self._prepare(local_embeddings, local_labels.contiguous(), optimizer, perm)
-        loss = self._forward_impl(local_embeddings, clone_loss=False)
+        loss = self._forward_impl(local_embeddings, clone_loss=False, need_dx=True)
         dx, dw = self._backward_impl(local_embeddings, None, need_dx=True)
         if dw is not None:
             self.weight_activated.grad = dw
@@ -354,7 +366,15 @@ class _PartialFCBase(torch.nn.Module):
         else:
             self._n = self.num_local
 
-    def _forward_impl(self, local_embeddings, clone_loss=True):
+    def _join_early(self):
+        """Order the current stream after an early dX GEMM that is still outstanding (also when backward never ran)."""
+        if self._early is not None:
+            stream, _ = self._early
+            if stream is not None:
+                torch.cuda.current_stream().wait_stream(stream)
+            self._early = None
+
+    def _forward_impl(self, local_embeddings, clone_loss=True, need_dx=False):
         ws, W, d = self._ws, self.world_size, self.embedding_size
         b, B = ws.b, ws.B
         n = self._n
@@ -364,8 +384,22 @@ class _PartialFCBase(torch.nn.Module):
             self._wn_valid = True
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
         self._n_pad = K.padded_classes(n)
+        self._join_early()              # a previous step's early dX GEMM (backward skipped) must not read the new spill
         K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
                   ws.tgt_raw, ws.tgt_e, ws.tgt_z)                                 # :201-207
+        if (self.early_dx and need_dx and not (self.fused_optimizer and self.overlap_update)
+                and not (self.fused_optimizer and self.fused_dw_update)):
+            # dX partials from the spill as the forward wrote it (target column = 0), next to everything below
+            splits = K.dx_splits(B, n, d)
+            stream = None
+            if w.is_cuda:
+                if self._early_stream is None:
+                    self._early_stream = torch.cuda.Stream(device=w.device)
+                stream = self._early_stream
+                stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
+                K.backward_dx(ws.E, self._n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
+            self._early = (stream, splits)
         peer = self._peer
         if peer is not None:
             # statistics straight into every peer's slot, then a rank-ordered local sum (identical bits on all ranks)
@@ -391,8 +425,16 @@ class _PartialFCBase(torch.nn.Module):
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
         need_dx = x_in.requires_grad if need_dx is None else bool(need_dx)
         g = None if grad_loss is None else grad_loss.detach().to(torch.float32).reshape(1).contiguous()
-        K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
-                           ws.coef, ws.E, n_pad)
+        early = self._early
+        if early is not None:
+            # the dX GEMM is (or was) reading the unpatched spill: keep the target values aside, join, then patch
+            K.backward_prepare_deferred(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all,
+                                        ws.xs, ws.coef, ws.patch)
+            self._join_early()
+            K.apply_target_patch(ws.E, n_pad, B, ws.labels_act, ws.patch)
+        else:
+            K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
+                               ws.coef, ws.E, n_pad)
         # Order.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the reduce-scatter /
         # peer stores have the whole dW + update to complete.  N = 1: dW GEMM first (it walks the class tiles from the
         # end, where the forward's spill is still in L2), then dX, then the update -- measured 0.4266 ms against
@@ -427,10 +469,13 @@ class _PartialFCBase(torch.nn.Module):
                 and (W == 1 or peer is not None))
         tail = None
         if need_dx:
-            splits = K.dx_splits(B, n, d)
-            if dw_first and not overlap:
-                K.pdl_independent_next()          # dX reads E' / wn and writes dx_partial: nothing the dW GEMM touches
-            K.backward_dx(ws.E, n_pad, wn_now, B, n, d, ws.dx_partial, splits)
+            if early is not None:
+                splits = early[1]                 # the partials are there already; their target term is added below
+            else:
+                splits = K.dx_splits(B, n, d)
+                if dw_first and not overlap:
+                    K.pdl_independent_next()      # dX reads E' / wn and writes dx_partial: nothing the dW GEMM touches
+                K.backward_dx(ws.E, n_pad, wn_now, B, n, d, ws.dx_partial, splits)
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
             if fork:
                 if self._side_stream is None:
@@ -439,18 +484,30 @@ class _PartialFCBase(torch.nn.Module):
                 tail.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():
                 if W == 1:
-                    K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
+                    if early is not None:
+                        K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx,
+                                              ws.patch, ws.labels_act, wn_now)
+                    else:
+                        K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
                 elif peer is not None:
                     # :505-522 -- every rank stores its scaled partial of row i into the owner's slot; the owner sums
                     # the W slots in rank order inside the normalise-backward kernel (x W, :521)
-                    K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
+                    if early is not None:
+                        K.peer_dx_scatter_patched(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W,
+                                                  peer.ptrs("dx_slots"), ws.patch, ws.labels_act, wn_now)
+                    else:
+                        K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
                     if tail is not None:
                         # barrier + :521; also the fence that keeps a fast rank's NEXT gather out of xn_all while a
                         # slow rank still reads it (this rank signals after its own dX GEMM, i.e. after its last read)
                         K.peer_dx_finalize(peer.ptrs("flags"), peer.counter, self.rank, W, peer.dx_slots,
                                            self._x_local, ws.inv_x, float(W), b, d, dx)
                 else:
-                    K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
+                    if early is not None:
+                        K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all,
+                                              ws.patch, ws.labels_act, wn_now)
+                    else:
+                        K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
                     # :505-519 -- asynchronous: it overlaps the rank-local update below / on the side stream
                     rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
                                                                 async_op=True)

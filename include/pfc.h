@@ -141,6 +141,22 @@ int pfc_backward_dx(const void* E_bf16, int n_pad, const void* wn_bf16, int B, i
                     int splits, void* stream);
 int pfc_dx_finalize(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
                     float scale, int rows, int rows_total, int d, float* out, void* stream);
+/* Early-dX variants (conf.early_dx): pfc_forward leaves 0 in the target column of E, so pfc_backward_dx may run on the
+ * spill BEFORE the statistics exchange and the patch -- next to them instead of behind them.
+ * pfc_backward_prepare_deferred = pfc_backward_prepare that leaves E alone and writes the target value to patch[i]
+ * (the bf16-rounded -dm_i*mask_i*stats[i][0]; 0 for rows whose class is on another rank);
+ * pfc_apply_target_patch writes it into E (after the early dX GEMM, before pfc_backward_dw);
+ * pfc_dx_finalize_patched / pfc_peer_dx_scatter_patched add the missing rank-1 term patch[i] * Wn[labels_local[i], :]
+ * to row i of the summed partials before scaling (bf16 x bf16 products are exact in fp32: the result differs from the
+ * patched GEMM only by the position of that term in the sum). */
+int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
+                                  const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
+                                  const void* xn_bf16, void* xs_bf16, float* coef, float* patch, void* stream);
+int pfc_apply_target_patch(void* E_bf16, int n_pad, int B, const int32_t* labels_local, const float* patch,
+                           void* stream);
+int pfc_dx_finalize_patched(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
+                            float scale, int rows, int rows_total, int d, float* out, const float* patch,
+                            const int32_t* labels_local, const void* wn_bf16, void* stream);
 /* dwn_bf16 != 0: dwn is a bf16 [n,d] matrix (halves the spill that pfc_dw_sgd re-reads; fused-SGD mode only). */
 int pfc_backward_dw(const void* E_bf16, int n_pad, const void* xs_bf16, int B, int n, int d, void* dwn, int dwn_bf16,
                     void* stream);
@@ -190,6 +206,9 @@ int pfc_peer_dx_finalize(void* const* peer_flags, uint32_t* barrier_state, int r
                          const float* x, const float* inv_norm, float scale, int b, int d, float* out, void* stream);
 int pfc_peer_dx_scatter(const float* partial, int splits, const float* coef, int B, int b, int d, int rank, int W,
                         void* const* peer_dx_slots, void* stream);
+int pfc_peer_dx_scatter_patched(const float* partial, int splits, const float* coef, int B, int b, int d, int rank, int W,
+                                void* const* peer_dx_slots, const float* patch, const int32_t* labels_local,
+                                const void* wn_bf16, void* stream);
 
 /* ---- (6) pair verification, utils/eval.py.
  * fr_pair_score  (:68-99): scores[i] = 1 - ||e1_i - e2_i||^2/4 (fp32 difference, fp64 accumulation), optional

@@ -124,6 +124,30 @@ class FakeKernels:
         Ev = E[: B * n_pad].view(B, n_pad)
         Ev[rows, labels[rows].long()] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16)
 
+    def backward_prepare_deferred(self, stats, row_L, grad_loss, s, B, d, labels, tgt_raw, kind, m2, xn, xs, coef,
+                                  patch):
+        g = float(grad_loss[0]) if grad_loss is not None else 1.0
+        c = g * s / (B * row_L)
+        coef.copy_(c)
+        xs[:B] = (xn[:B].float() * c.reshape(-1, 1)).to(torch.bfloat16)
+        rows = torch.nonzero(labels[:B] >= 0).reshape(-1)
+        raw = tgt_raw[rows]
+        _, dm = self._margin(kind, raw.clamp(-1, 1), m2, 0.0)
+        mask = (raw.abs() <= 1).float()
+        patch.zero_()
+        patch[rows] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16).float()
+
+    def apply_target_patch(self, E, n_pad, B, labels, patch):
+        rows = torch.nonzero(labels[:B] >= 0).reshape(-1)
+        E[: B * n_pad].view(B, n_pad)[rows, labels[rows].long()] = patch[rows].to(torch.bfloat16)
+
+    def dx_finalize_patched(self, partial, splits, coef, x, inv_norm, scale, rows, rows_total, d, out, patch, labels, wn):
+        p = partial.reshape(-1)[: splits * rows_total * d].view(splits, rows_total, d)
+        own = torch.nonzero(labels[:rows_total] >= 0).reshape(-1)
+        fixed = p.clone()
+        fixed[0, own] += patch[own].reshape(-1, 1) * wn[labels[own].long()].float()
+        self.dx_finalize(fixed, splits, coef, x, inv_norm, scale, rows, rows_total, d, out)
+
     def backward_dx(self, E, n_pad, wn, B, n, d, partial, splits):
         p = partial[: splits * B * d].view(splits, B, d)
         p.zero_()

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _rank_main(rank, W, port, name, fused, q, direct=False):
+def _rank_main(rank, W, port, name, fused, q, direct=False, early=False):
     for p in (ROOT, HERE, os.path.join(HERE, "golden")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -30,7 +30,7 @@ def _rank_main(rank, W, port, name, fused, q, direct=False):
     weights, xs, ls = case_inputs(cfg)
     b = cfg["b"]
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
-                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused)
+                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused, early_dx=early)
     if cfg["margin"] == "combined_filter":
         thr = cfg["filter_thr"]
         margin = lambda s_, m_: pfc.CombinedMarginLoss(s_, 1.0, m_, 0.0, interclass_filtering_threshold=thr)  # noqa: E731
@@ -165,23 +165,27 @@ def _cos(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
 
 
-@pytest.mark.parametrize("name,fused,port,direct", [("head_w2_full", False, 29821, False),
-                                                    ("head_w2_sampled", False, 29822, False),
-                                                    ("head_w2_full", True, 29823, False),
-                                                    ("head_w2_sampled", True, 29824, False),
-                                                    ("head_w2_sampled", False, 29825, True),
-                                                    ("head_w2_full", True, 29826, True),
-                                                    # one rank: CombinedMarginLoss with inter-class filtering
-                                                    ("head_w1_filter_wide", False, 29827, False),
-                                                    ("head_w1_filter_wide", True, 29828, True)])
-def test_two_rank_host_logic_matches_reference(name, fused, port, direct):
+@pytest.mark.parametrize("name,fused,port,direct,early", [("head_w2_full", False, 29821, False, False),
+                                                          ("head_w2_sampled", False, 29822, False, False),
+                                                          ("head_w2_full", True, 29823, False, False),
+                                                          ("head_w2_sampled", True, 29824, False, False),
+                                                          ("head_w2_sampled", False, 29825, True, False),
+                                                          ("head_w2_full", True, 29826, True, False),
+                                                          # one rank: CombinedMarginLoss with inter-class filtering
+                                                          ("head_w1_filter_wide", False, 29827, False, False),
+                                                          ("head_w1_filter_wide", True, 29828, True, False),
+                                                          # conf.early_dx: dX GEMM on the unpatched spill + rank-1 fix-up
+                                                          ("head_w2_sampled", False, 29829, False, True),
+                                                          ("head_w2_full", True, 29830, True, True),
+                                                          ("head_w1_full", True, 29834, False, True)])
+def test_two_rank_host_logic_matches_reference(name, fused, port, direct, early):
     sys.path.insert(0, HERE)
     from helpers import load_case
     cfg, z = load_case(name)
     W = cfg["W"]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, q, direct)) for r in range(W)]
+    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, q, direct, early)) for r in range(W)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=240) for _ in range(W))

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(HERE)
 pytestmark = pytest.mark.gpu
 
 
-def _rank_main(rank, W, port, name, fused, peer, q):
+def _rank_main(rank, W, port, name, fused, peer, q, extra=None):
     for p in (ROOT, HERE, os.path.join(HERE, "golden")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -29,7 +29,7 @@ def _rank_main(rank, W, port, name, fused, peer, q):
     b = cfg["b"]
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
                                  loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused,
-                                 peer_collectives=peer)
+                                 peer_collectives=peer, **(extra or {}))
     head = pfc.PartialFC(conf, cfg["C"])
     head.load_state_dict({"weight": weights[rank].clone()})
     head = head.train().cuda()
@@ -75,6 +75,21 @@ def _cos(a, b):
     ("head_w2_full", False, 29845, True), ("head_w2_sampled", True, 29846, True),
     ("head_w2_full", True, 29847, True)])
 def test_two_rank_nccl_matches_reference(name, fused, port, peer):
+    _run_case(name, fused, port, peer, None)
+
+
+# features written after the round's GPU budget was spent (see tests/test_gpu_experimental.py): opt-in
+@pytest.mark.skipif(os.environ.get("PFC_EXPERIMENTAL") != "1", reason="opt-in: PFC_EXPERIMENTAL=1")
+@pytest.mark.parametrize("name,fused,port,peer,extra", [
+    ("head_w2_full", False, 29851, True, {"early_dx": True}),
+    ("head_w2_sampled", True, 29852, True, {"early_dx": True}),
+    ("head_w2_full", True, 29853, False, {"early_dx": True}),
+    ("head_w2_full", True, 29854, True, {"early_dx": True, "dx_side_priority": True})])
+def test_two_rank_experimental_variants(name, fused, port, peer, extra):
+    _run_case(name, fused, port, peer, extra)
+
+
+def _run_case(name, fused, port, peer, extra):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     sys.path.insert(0, HERE)
@@ -83,7 +98,7 @@ def test_two_rank_nccl_matches_reference(name, fused, port, peer):
     W = cfg["W"]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, peer, q)) for r in range(W)]
+    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, peer, q, extra)) for r in range(W)]
     for p in procs:
         p.start()
     res = dict(q.get(timeout=300) for _ in range(W))

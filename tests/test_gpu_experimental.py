@@ -9,6 +9,8 @@ are off by default.  Enable a feature by default only after this file has passed
     by tests/test_oracle_golden.py and tests/test_dist_gloo.py against fixtures of the reference's PartialFCAdamW).
   * CombinedMarginLoss with inter-class filtering INSIDE the head (the kFilter branch of the forward epilogue): until now
     only the stand-alone margin kernel was compared with the reference on the GPU.
+  * conf.early_dx: dX GEMM on the unpatched spill, launched on its own stream right after the forward GEMM; the
+    target's rank-1 term is added when the partials are summed.  Same loss bits, dX equal up to fp32 summation order.
 """
 import os
 import types
@@ -156,3 +158,55 @@ def test_head_with_interclass_filter_matches_reference(pfc, fused):
     w0 = weights[0].double()
     assert cosine(head.weight_activated.data.cpu().double() - w0,
                   torch.from_numpy(z["r0_weight_final"]).double() - w0) >= 0.999
+
+
+@pytest.mark.parametrize("B,C,d,fused", [(1024, 20000, 512, True), (320, 3100, 512, False), (96, 1500, 64, True)])
+def test_early_dx_matches_the_serial_order(pfc, B, C, d, fused):
+    from helpers import cosine
+    g0 = torch.Generator().manual_seed(44)
+    w = torch.normal(0, 0.01, (C, d), generator=g0)
+    outs = []
+    for early in (False, True):
+        g = torch.Generator().manual_seed(45)
+        conf = types.SimpleNamespace(emd_size=d, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5,
+                                     fused_optimizer=fused, early_dx=early)
+        head = pfc.PartialFC(conf, C)
+        head.load_state_dict({"weight": w.clone()})
+        head = head.train().cuda()
+        opt = torch.optim.SGD(head.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+        rec = []
+        for s in range(3):
+            lab = torch.randint(0, C, (B,), generator=g).cuda()
+            x = torch.nn.functional.normalize(torch.nn.functional.normalize(w[lab.cpu()]) +
+                                              1.5 * torch.randn(B, d, generator=g) / d ** 0.5).cuda().requires_grad_(True)
+            opt.zero_grad()
+            loss = head(x, lab, opt)
+            loss.backward()
+            rec.append((loss.detach().clone(), x.grad.clone(),
+                        None if fused else head.weight_activated.grad.clone()))
+            if not fused:
+                opt.step()
+        rec.append(head.weight_activated.data.clone())
+        torch.cuda.synchronize()
+        outs.append(rec)
+    a, b = outs
+    for s in range(3):
+        # step 0 starts from identical weights: identical loss bits; later steps inherit dW differences of ~1 ulp
+        if s == 0:
+            assert torch.equal(a[s][0], b[s][0])
+        assert abs(float(a[s][0]) - float(b[s][0])) <= 1e-5 * abs(float(a[s][0]))
+        assert cosine(a[s][1].cpu(), b[s][1].cpu()) >= 0.999999
+        torch.testing.assert_close(a[s][1], b[s][1], rtol=1e-3, atol=1e-6 * float(a[s][1].abs().max()) + 1e-12)
+        if not fused:
+            assert cosine(a[s][2].cpu(), b[s][2].cpu()) >= 0.999999     # dW sees the SAME patched spill
+    assert cosine((a[3] - w.cuda()).cpu(), (b[3] - w.cuda()).cpu()) >= 0.99999
+
+
+def test_early_dx_graph_replay(pfc):
+    a = _graph_run(pfc, True)
+    b = _graph_run(pfc, True, early_dx=True)
+    c = _graph_run(pfc, False, early_dx=True)
+    from helpers import cosine
+    for u, v, w_ in zip(a, b, c):
+        assert cosine(u.cpu().reshape(-1), v.cpu().reshape(-1)) >= 0.999999
+        assert torch.equal(v, w_)            # autograd or not: same kernels, same order
