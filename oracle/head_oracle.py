@@ -248,8 +248,8 @@ class PartialFCOracle:
     def __init__(self, weights: Sequence[torch.Tensor], num_classes: int, margin: Margin, sample_rate: float,
                  lr: float, momentum: float, weight_decay: float, dtype=torch.float64, optimizer: str = "sgd",
                  betas=(0.9, 0.999), eps: float = 1e-8):
-        """optimizer "sgd": PartialFC + torch.optim.SGD; "adamw": PartialFCAdamW + torch.optim.AdamW
-        (nets/PartialFC.py:235-432), `mom` then holds exp_avg and `mom2` exp_avg_sq."""
+        """optimizer "sgd": PartialFC + torch.optim.SGD; "adamw" / "adam": PartialFCAdamW + torch.optim.AdamW / Adam
+        (nets/PartialFC.py:235-432, :320), `mom` then holds exp_avg and `mom2` exp_avg_sq."""
         self.W = len(weights)
         self.num_classes, self.margin, self.sample_rate = num_classes, margin, sample_rate
         self.lr, self.momentum, self.wd, self.dtype = lr, momentum, weight_decay, dtype
@@ -285,14 +285,15 @@ class PartialFCOracle:
             idx = res.index[r]
             w_act = self.weight[r] if idx is None else self.weight[r][idx]
             m_act = self.mom[r] if idx is None else self.mom[r][idx]
-            if self.optimizer == "adamw":
+            if self.optimizer in ("adamw", "adam"):
                 v_act = self.mom2[r] if idx is None else self.mom2[r][idx]
                 # Sampled: sample() writes state["step"] = self.step (= t) BEFORE optimizer.step(), which increments it
                 # once more -- the bias correction of forward call t uses t + 1 (nets/PartialFC.py:306, :327 + torch's
                 # `step += 1`).  Full (sample_rate == 1): sample() never runs and the optimizer counts by itself: t.
                 step = self.t + 1 if idx is not None else self.t
                 w_new, m_new, v_new = adamw_update(w_act, m_act, v_act, res.dw[r], step, self.lr, self.betas[0],
-                                                   self.betas[1], self.eps, self.wd)
+                                                   self.betas[1], self.eps, self.wd,
+                                                   decoupled=self.optimizer == "adamw")
                 pend.append((idx, w_new, m_new, v_new))
             else:
                 w_new, m_new = sgd_update(w_act, m_act, res.dw[r], self.lr, self.momentum, self.wd)

@@ -36,7 +36,7 @@ def _import_reference(adamw=False):
 
 def run_head_rank(rank, W, port, cfg, out_q):
     """One reference rank: builds PartialFC, loads its shard, runs `steps` of forward/backward/SGD."""
-    adamw = cfg.get("optimizer", "sgd") == "adamw"
+    adamw = cfg.get("optimizer", "sgd") in ("adamw", "adam")        # both drive PartialFCAdamW (:320)
     PartialFC, ArcFace, CosFace, CombinedMarginLoss = _import_reference(adamw)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=W)
     C, d, b, steps, r = cfg["C"], cfg["d"], cfg["b"], cfg["steps"], cfg["sample_rate"]
@@ -55,8 +55,8 @@ def run_head_rank(rank, W, port, cfg, out_q):
     head.load_state_dict({"weight": w_full[cs:cs + nl].clone()})
     dummy = torch.nn.Parameter(torch.zeros(1))                # stands for the encoder param group
     if adamw:
-        opt = torch.optim.AdamW([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
-                                weight_decay=cfg["wd"])
+        opt_cls = torch.optim.AdamW if cfg["optimizer"] == "adamw" else torch.optim.Adam   # Adam: coupled weight decay
+        opt = opt_cls([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"], weight_decay=cfg["wd"])
     else:
         opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
                               momentum=cfg["momentum"], weight_decay=cfg["wd"])
@@ -210,6 +210,9 @@ def make_adamw_cases():
     make_head_case("head_w1_adamw_sampled", 1, dict(base, C=400, b=32, sample_rate=0.25), 29619)
     make_head_case("head_w2_adamw_sampled", 2, dict(base, C=401, b=16, sample_rate=0.5), 29620)
     make_head_case("head_w1_adamw_full", 1, dict(base, C=300, b=32, sample_rate=1.0), 29621)
+    if "--adam-only" in sys.argv or "--adamw-only" not in sys.argv:
+        make_head_case("head_w1_adam_sampled", 1, dict(base, C=400, b=32, sample_rate=0.25, optimizer="adam", wd=5e-2),
+                       29624)
 
 
 def make_filter_case():
@@ -228,6 +231,10 @@ def make_filter_case():
 if __name__ == "__main__":
     if "--adamw-only" in sys.argv:      # added after the other fixtures: leaves them untouched
         make_adamw_cases()
+        sys.exit(0)
+    if "--adam-only" in sys.argv:
+        make_head_case("head_w1_adam_sampled", 1, dict(d=64, s=64.0, m=0.5, lr=1e-3, momentum=0.0, wd=5e-2, steps=3,
+                                                       optimizer="adam", C=400, b=32, sample_rate=0.25), 29624)
         sys.exit(0)
     if "--filter-only" in sys.argv:
         make_filter_case()

@@ -92,7 +92,8 @@ def _adamw_rank_main(rank, W, port, name, fused, q):
     head = pfc.PartialFCAdamW(conf, cfg["C"])
     head.load_state_dict({"weight": weights[rank].clone()})
     dummy = torch.nn.Parameter(torch.zeros(1))
-    opt = torch.optim.AdamW([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"], weight_decay=cfg["wd"])
+    opt_cls = torch.optim.AdamW if cfg["optimizer"] == "adamw" else torch.optim.Adam      # Adam: coupled weight decay
+    opt = opt_cls([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"], weight_decay=cfg["wd"])
     out = {}
     for s in range(cfg["steps"]):
         x = xs[s][rank * b:(rank + 1) * b].clone().requires_grad_(True)
@@ -118,7 +119,8 @@ def _adamw_rank_main(rank, W, port, name, fused, q):
 
 
 @pytest.mark.parametrize("name,fused,port", [("head_w2_adamw_sampled", False, 29831), ("head_w2_adamw_sampled", True, 29832),
-                                             ("head_w1_adamw_full", True, 29833)])
+                                             ("head_w1_adamw_full", True, 29833), ("head_w1_adam_sampled", True, 29835),
+                                             ("head_w1_adam_sampled", False, 29836)])
 def test_adamw_host_logic_matches_reference(name, fused, port):
     """Against fixtures of the reference's PartialFCAdamW: same sampled rows, the Adam state of re-sampled rows carried
     across steps, and the reference's step count (sampled: bias correction with t + 1) in the un-fused AND fused path."""

@@ -41,7 +41,8 @@ def test_head_steps_match_reference(name):
         _close(mf[r], z[f"r{r}_mom_final"], 2e-4)
 
 
-@pytest.mark.parametrize("name", ["head_w1_adamw_sampled", "head_w2_adamw_sampled", "head_w1_adamw_full"])
+@pytest.mark.parametrize("name", ["head_w1_adamw_sampled", "head_w2_adamw_sampled", "head_w1_adamw_full",
+                                  "head_w1_adam_sampled"])
 def test_adamw_head_steps_match_reference(name):
     """PartialFCAdamW + torch.optim.AdamW (nets/PartialFC.py:235-432): exp_avg / exp_avg_sq rows gathered and scattered
     back around every step, and the reference's step-count quirk (the sampled path corrects the bias with t + 1)."""
@@ -49,7 +50,7 @@ def test_adamw_head_steps_match_reference(name):
     weights, xs, ls = case_inputs(cfg)
     W, b = cfg["W"], cfg["b"]
     orc = ho.PartialFCOracle(weights, cfg["C"], case_margin(cfg), cfg["sample_rate"], cfg["lr"], 0.0, cfg["wd"],
-                             optimizer="adamw")
+                             optimizer=cfg["optimizer"])
     for s in range(cfg["steps"]):
         xl = [xs[s][r * b:(r + 1) * b] for r in range(W)]
         ll = [ls[s][r * b:(r + 1) * b] for r in range(W)]
