@@ -67,6 +67,8 @@ def _rank_main(rank, W, port, name, fused, q, direct=False, early=False):
     else:
         out["weight_final"] = head.weight_activated.detach().numpy().copy()
     out["state_dict_shape"] = tuple(head.state_dict()["weight"].shape)
+    out["state_dict_keys"] = list(head.state_dict().keys())
+    out["state_dict_weight"] = head.state_dict()["weight"].detach().numpy().copy()
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -211,5 +213,8 @@ def test_two_rank_host_logic_matches_reference(name, fused, port, direct, early)
     for r in range(W):
         nl, cs = shard(cfg["C"], r, W)
         assert res[r]["state_dict_shape"] == (nl, cfg["d"])
+        assert res[r]["state_dict_keys"] == ["weight"]                      # nets/PartialFC.py:210-221: no prefix, one key
         w0 = w_full[cs:cs + nl].numpy()
+        if f"r{r}_state_dict_weight" in z.files:
+            assert _cos(res[r]["state_dict_weight"] - w0, z[f"r{r}_state_dict_weight"] - w0) >= 0.999
         assert _cos(res[r]["weight_final"] - w0, z[f"r{r}_weight_final"] - w0) >= 0.999
