@@ -15,17 +15,54 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _rank_main(rank, W, port, name, fused, q, direct=False, early=False):
+# (name, fused, direct = PartialFC.fused_step instead of autograd, early = conf.early_dx)
+SGD_CASES = [("head_w2_full", False, False, False), ("head_w2_sampled", False, False, False),
+             ("head_w2_full", True, False, False), ("head_w2_sampled", True, False, False),
+             ("head_w2_sampled", False, True, False), ("head_w2_full", True, True, False),
+             # one rank: CombinedMarginLoss with inter-class filtering
+             ("head_w1_filter_wide", False, False, False), ("head_w1_filter_wide", True, True, False),
+             # conf.early_dx: dX GEMM on the unpatched spill + rank-1 fix-up
+             ("head_w2_sampled", False, False, True), ("head_w2_full", True, True, True),
+             ("head_w1_full", True, False, True)]
+# (name, fused)
+ADAM_CASES = [("head_w2_adamw_sampled", False), ("head_w2_adamw_sampled", True), ("head_w1_adamw_full", True),
+              ("head_w1_adam_sampled", True), ("head_w1_adam_sampled", False)]
+
+
+def _world_of(name):
+    return 2 if "_w2_" in name else 1
+
+
+def _group_main(rank, W, port, q):
+    """One process per rank and WORLD SIZE: every case of that world size runs in the same process group (spawning a
+    pair of interpreters per case made this file the slowest of the CPU suite)."""
     for p in (ROOT, HERE, os.path.join(HERE, "golden")):
         if p not in sys.path:
             sys.path.insert(0, p)
     import torch.distributed as dist
-    from helpers import load_case, case_inputs, case_perms
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=W)
-    import face_recognition_pytorch_b200 as pfc
     from face_recognition_pytorch_b200 import partial_fc, kernels
     from fake_kernels import FakeKernels
     partial_fc.K = FakeKernels(kernels)            # test-only substitution of the kernel layer
+    for case in SGD_CASES:
+        if _world_of(case[0]) == W:
+            try:
+                q.put((rank, ("sgd",) + case, _run_sgd_case(rank, W, *case)))
+            except Exception as e:     # report per case: the others still run
+                q.put((rank, ("sgd",) + case, {"error": f"{type(e).__name__}: {e}"}))
+    for case in ADAM_CASES:
+        if _world_of(case[0]) == W:
+            try:
+                q.put((rank, ("adam",) + case, _run_adam_case(rank, W, *case)))
+            except Exception as e:
+                q.put((rank, ("adam",) + case, {"error": f"{type(e).__name__}: {e}"}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_sgd_case(rank, W, name, fused, direct, early):
+    from helpers import load_case, case_inputs, case_perms
+    import face_recognition_pytorch_b200 as pfc
     cfg, z = load_case(name)
     weights, xs, ls = case_inputs(cfg)
     b = cfg["b"]
@@ -69,23 +106,13 @@ def _rank_main(rank, W, port, name, fused, q, direct=False, early=False):
     out["state_dict_shape"] = tuple(head.state_dict()["weight"].shape)
     out["state_dict_keys"] = list(head.state_dict().keys())
     out["state_dict_weight"] = head.state_dict()["weight"].detach().numpy().copy()
-    q.put((rank, out))
-    dist.barrier()
-    dist.destroy_process_group()
+    return out
 
 
-def _adamw_rank_main(rank, W, port, name, fused, q):
+def _run_adam_case(rank, W, name, fused):
     """PartialFCAdamW host logic (state rows gathered / scattered, step patched into the optimizer, fused update)."""
-    for p in (ROOT, HERE, os.path.join(HERE, "golden")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    import torch.distributed as dist
     from helpers import load_case, case_inputs, case_perms
-    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=W)
     import face_recognition_pytorch_b200 as pfc
-    from face_recognition_pytorch_b200 import partial_fc, kernels
-    from fake_kernels import FakeKernels
-    partial_fc.K = FakeKernels(kernels)
     cfg, z = load_case(name)
     weights, xs, ls = case_inputs(cfg)
     b = cfg["b"]
@@ -115,30 +142,45 @@ def _adamw_rank_main(rank, W, port, name, fused, q):
         out["exp_avg_sq_final"] = head.weight_exp_avg_sq.numpy().copy()
     else:
         out["weight_final"] = head.weight_activated.detach().numpy().copy()
-    q.put((rank, out))
-    dist.barrier()
-    dist.destroy_process_group()
+    return out
 
 
-@pytest.mark.parametrize("name,fused,port", [("head_w2_adamw_sampled", False, 29831), ("head_w2_adamw_sampled", True, 29832),
-                                             ("head_w1_adamw_full", True, 29833), ("head_w1_adam_sampled", True, 29835),
-                                             ("head_w1_adam_sampled", False, 29836)])
-def test_adamw_host_logic_matches_reference(name, fused, port):
+@pytest.fixture(scope="module")
+def group_results():
+    """{(kind, name, ...): {rank: out}} for every case, from ONE spawn per world size."""
+    results = {}
+    ctx = mp.get_context("spawn")
+    for W, port in ((2, 29821), (1, 29822)):
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_group_main, args=(r, W, port, q)) for r in range(W)]
+        for p in procs:
+            p.start()
+        n_cases = sum(_world_of(c[0]) == W for c in SGD_CASES) + sum(_world_of(c[0]) == W for c in ADAM_CASES)
+        for _ in range(n_cases * W):
+            rank, key, out = q.get(timeout=600)
+            results.setdefault(key, {})[rank] = out
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    return results
+
+
+def _case_result(group_results, key):
+    res = group_results[key]
+    for r, out in res.items():
+        assert "error" not in out, f"rank {r}: {out.get('error')}"
+    return res
+
+
+@pytest.mark.parametrize("name,fused", ADAM_CASES)
+def test_adamw_host_logic_matches_reference(group_results, name, fused):
     """Against fixtures of the reference's PartialFCAdamW: same sampled rows, the Adam state of re-sampled rows carried
     across steps, and the reference's step count (sampled: bias correction with t + 1) in the un-fused AND fused path."""
     sys.path.insert(0, HERE)
     from helpers import load_case
     cfg, z = load_case(name)
     W = cfg["W"]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_adamw_rank_main, args=(r, W, port, name, fused, q)) for r in range(W)]
-    for p in procs:
-        p.start()
-    res = dict(q.get(timeout=240) for _ in range(W))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _case_result(group_results, ("adam", name, fused))
     from inputs import synth_inputs, shard
     w_full, _, _ = synth_inputs(cfg["C"], cfg["d"], cfg["b"] * W, 1)
     for r in range(W):
@@ -169,33 +211,13 @@ def _cos(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
 
 
-@pytest.mark.parametrize("name,fused,port,direct,early", [("head_w2_full", False, 29821, False, False),
-                                                          ("head_w2_sampled", False, 29822, False, False),
-                                                          ("head_w2_full", True, 29823, False, False),
-                                                          ("head_w2_sampled", True, 29824, False, False),
-                                                          ("head_w2_sampled", False, 29825, True, False),
-                                                          ("head_w2_full", True, 29826, True, False),
-                                                          # one rank: CombinedMarginLoss with inter-class filtering
-                                                          ("head_w1_filter_wide", False, 29827, False, False),
-                                                          ("head_w1_filter_wide", True, 29828, True, False),
-                                                          # conf.early_dx: dX GEMM on the unpatched spill + rank-1 fix-up
-                                                          ("head_w2_sampled", False, 29829, False, True),
-                                                          ("head_w2_full", True, 29830, True, True),
-                                                          ("head_w1_full", True, 29834, False, True)])
-def test_two_rank_host_logic_matches_reference(name, fused, port, direct, early):
+@pytest.mark.parametrize("name,fused,direct,early", SGD_CASES)
+def test_two_rank_host_logic_matches_reference(group_results, name, fused, direct, early):
     sys.path.insert(0, HERE)
     from helpers import load_case
     cfg, z = load_case(name)
     W = cfg["W"]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, W, port, name, fused, q, direct, early)) for r in range(W)]
-    for p in procs:
-        p.start()
-    res = dict(q.get(timeout=240) for _ in range(W))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = _case_result(group_results, ("sgd", name, fused, direct, early))
     for s in range(cfg["steps"]):
         if W > 1:
             assert res[0][f"loss_{s}"] == res[1][f"loss_{s}"]                # every rank returns the global loss
