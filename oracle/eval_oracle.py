@@ -106,7 +106,8 @@ def performance_acc(scores: np.ndarray, labels: np.ndarray, th) -> float:
 
 
 def kfold_accuracy(dist: np.ndarray, labels: np.ndarray, folds: int = 10, n_thr: int = 400, step: float = 0.01):
-    """Standard LFW protocol (UNPINNED by the reference): contiguous KFold(folds) over the pair list, thresholds
+    """Standard LFW protocol (not in the reference; pinned against an sklearn-KFold restatement of the public LFW
+    evaluation in tests/test_oracle_golden.py): contiguous KFold(folds) over the pair list, thresholds
     k*step on the squared distance, the threshold with the best training-fold accuracy (first maximum) is applied
     to the held-out fold.  Returns (per-fold accuracy, per-fold best threshold index)."""
     n = len(dist)
