@@ -2,7 +2,8 @@
 
 NumPy restatement; pinned by tests/test_oracle_golden.py against fixtures produced by the reference's own numba /
 Python functions (tests/golden/make_golden.py).  The 10-fold protocol (`kfold_accuracy`) does not exist in the
-reference (discrepancy 1): its parity is UNPINNED and it is defined here.
+reference (discrepancy 1): its parity is UNPINNED by the reference; it is pinned against the public
+LFW evaluation (sklearn KFold restatement) in tests/test_oracle_golden.py.
 """
 from __future__ import annotations
 
