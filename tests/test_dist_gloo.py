@@ -56,8 +56,36 @@ def _group_main(rank, W, port, q):
                 q.put((rank, ("adam",) + case, _run_adam_case(rank, W, *case)))
             except Exception as e:
                 q.put((rank, ("adam",) + case, {"error": f"{type(e).__name__}: {e}"}))
+    if W == 1:
+        try:
+            q.put((rank, ("scale",), _run_scale_case()))
+        except Exception as e:
+            q.put((rank, ("scale",), {"error": f"{type(e).__name__}: {e}"}))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _run_scale_case():
+    """A scaled loss (GradScaler: model/FR_PartialFC.py:178-180 calls amp.scale(loss).backward(), then unscale_) must give
+    scale x the same gradients: DistCrossEntropyFunc.backward multiplies by loss_gradient.item() (nets/PartialFC.py:474)."""
+    from helpers import load_case, case_inputs
+    import face_recognition_pytorch_b200 as pfc
+    cfg, z = load_case("head_w1_full")
+    weights, xs, ls = case_inputs(cfg)
+    out = {}
+    for tag, scale in (("plain", 1.0), ("scaled", 1024.0)):
+        conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
+                                     loss_m=cfg["m"])
+        head = pfc.PartialFC(conf, cfg["C"])
+        head.load_state_dict({"weight": weights[0].clone()})
+        opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
+        x = xs[0].clone().requires_grad_(True)
+        loss = head(x, ls[0].clone(), opt)
+        (loss * scale).backward()
+        out[tag + "_loss"] = float(loss.detach())
+        out[tag + "_dx"] = x.grad.numpy().copy()
+        out[tag + "_dw"] = head.weight_activated.grad.numpy().copy()
+    return out
 
 
 def _run_sgd_case(rank, W, name, fused, direct, early):
@@ -155,7 +183,8 @@ def group_results():
         procs = [ctx.Process(target=_group_main, args=(r, W, port, q)) for r in range(W)]
         for p in procs:
             p.start()
-        n_cases = sum(_world_of(c[0]) == W for c in SGD_CASES) + sum(_world_of(c[0]) == W for c in ADAM_CASES)
+        n_cases = (sum(_world_of(c[0]) == W for c in SGD_CASES) + sum(_world_of(c[0]) == W for c in ADAM_CASES)
+                   + (1 if W == 1 else 0))
         for _ in range(n_cases * W):
             rank, key, out = q.get(timeout=600)
             results.setdefault(key, {})[rank] = out
@@ -170,6 +199,15 @@ def _case_result(group_results, key):
     for r, out in res.items():
         assert "error" not in out, f"rank {r}: {out.get('error')}"
     return res
+
+
+def test_scaled_loss_scales_the_gradients(group_results):
+    res = _case_result(group_results, ("scale",))[0]
+    assert res["plain_loss"] == res["scaled_loss"]
+    for k in ("dx", "dw"):
+        a, b = res["plain_" + k].astype(np.float64) * 1024.0, res["scaled_" + k].astype(np.float64)
+        # bf16 rounding of xs = c_i * xn is scale-invariant for a power-of-two scale: the two runs agree to fp32 rounding
+        assert np.abs(a - b).max() <= 1e-5 * np.abs(a).max()
 
 
 @pytest.mark.parametrize("name,fused", ADAM_CASES)
