@@ -45,3 +45,8 @@ def eval_inputs_cfg5(N=6000, d=512):
     rho = np.where(lab, rng.normal(0.55, 0.18, N), rng.normal(0.08, 0.12, N)).clip(-0.99, 0.99)
     b = rho[:, None] * a + np.sqrt(1 - rho ** 2)[:, None] * n
     return a.astype(np.float32), b.astype(np.float32), lab
+
+
+def proj_matrix(d, k=16, seed=99):
+    """Fixed random projection that keeps the [C, d] arrays of the cfg-1 fixture small: X -> X @ R, R [d, k]."""
+    return torch.randn(d, k, generator=torch.Generator().manual_seed(seed)).numpy().astype(np.float64)

@@ -23,7 +23,7 @@ REF = os.environ.get("PFC_REFERENCE", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 warnings.filterwarnings("ignore")
 sys.path.insert(0, HERE)
-from inputs import synth_inputs, shard, eval_inputs_cfg5   # noqa: E402
+from inputs import synth_inputs, shard, eval_inputs_cfg5, proj_matrix   # noqa: E402
 
 
 def _import_reference(adamw=False):
@@ -139,6 +139,29 @@ def make_head_case(name, W, cfg, port):
     print(name, {k: v.shape for k, v in out.items() if not k.startswith("cfg_")})
 
 
+def make_cfg1_case():
+    """BASELINE.json configs[0]: ArcFace margin loss (s=64, m=0.5), 512-d embeddings, batch 128, 10 000 classes, one
+    process.  dW / final weights / momentum are [10000, 512]: stored as their norm and a 16-column random projection."""
+    cfg = dict(d=512, s=64.0, m=0.5, lr=0.1, momentum=0.9, wd=5e-4, steps=2, C=10000, b=128, sample_rate=1.0)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    p = ctx.Process(target=run_head_rank, args=(0, 1, 29625, cfg, q))
+    p.start()
+    _, rec = q.get()
+    p.join()
+    R = proj_matrix(cfg["d"])
+    out = {"cfg_" + k: np.array(v) for k, v in cfg.items()}
+    out["cfg_W"] = np.array(1)
+    for k, v in rec.items():
+        if v.ndim == 2 and v.shape[0] == cfg["C"]:
+            out[f"r0_{k}_proj"] = (v.astype(np.float64) @ R).astype(np.float32)
+            out[f"r0_{k}_norm"] = np.array(np.linalg.norm(v.astype(np.float64)))
+        else:
+            out[f"r0_{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "head_cfg1.npz"), **out)
+    print("head_cfg1", {k: v.shape for k, v in out.items() if not k.startswith("cfg_")})
+
+
 def make_margin_case():
     _, ArcFace, CosFace, CombinedMarginLoss = _import_reference()
     g = torch.Generator().manual_seed(5)
@@ -236,6 +259,9 @@ if __name__ == "__main__":
         make_head_case("head_w1_adam_sampled", 1, dict(d=64, s=64.0, m=0.5, lr=1e-3, momentum=0.0, wd=5e-2, steps=3,
                                                        optimizer="adam", C=400, b=32, sample_rate=0.25), 29624)
         sys.exit(0)
+    if "--cfg1-only" in sys.argv:
+        make_cfg1_case()
+        sys.exit(0)
     if "--filter-only" in sys.argv:
         make_filter_case()
         sys.exit(0)
@@ -250,5 +276,6 @@ if __name__ == "__main__":
     make_head_case("head_w1_d512", 1, dict(base, C=520, b=64, d=512, sample_rate=1.0, steps=1), 29618)
     make_adamw_cases()
     make_filter_case()
+    make_cfg1_case()
     make_margin_case()
     make_eval_case()

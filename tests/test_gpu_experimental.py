@@ -107,7 +107,7 @@ def test_adamw_sampled_fused_matches_unfused_and_reference(pfc):
         head = pfc.PartialFCAdamW(conf, cfg["C"])
         head.load_state_dict({"weight": weights[0].clone()})
         head = head.train().cuda()
-        dummy = torch.nn.Parameter(torch.zeros(1, device="cuda"))
+        dummy = torch.nn.Parameter(torch.zeros(1).cuda())
         opt = torch.optim.AdamW([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"], weight_decay=cfg["wd"])
         for s in range(cfg["steps"]):
             x = xs[s].clone().cuda().requires_grad_(True)

@@ -78,6 +78,26 @@ def test_adamw_head_steps_match_reference(name):
         _close(v[r], z[f"r{r}_exp_avg_sq_final"], 2e-4)
 
 
+def test_cfg1_shape_matches_reference():
+    """BASELINE.json configs[0] (batch 128, 10 000 classes, d = 512, one process): the [C, d] arrays of the fixture are
+    stored as norm + 16-column random projection (tests/golden/make_golden.py::make_cfg1_case)."""
+    from inputs import proj_matrix
+    cfg, z = load_case("head_cfg1")
+    weights, xs, ls = case_inputs(cfg)
+    R = proj_matrix(cfg["d"])
+    orc = ho.PartialFCOracle(weights, cfg["C"], case_margin(cfg), 1.0, cfg["lr"], cfg["momentum"], cfg["wd"])
+    for s in range(cfg["steps"]):
+        res = orc.step([xs[s]], [ls[s]])
+        ref_loss = float(z[f"r0_loss_{s}"])
+        assert abs(float(res.loss) - ref_loss) <= 2e-6 * abs(ref_loss)
+        _close(res.dx_local[0], z[f"r0_dx_{s}"], 5e-5)
+        _close(res.dw[0].numpy() @ R, z[f"r0_dw_{s}_proj"], 5e-5)
+        assert abs(float(res.dw[0].norm()) / float(z[f"r0_dw_{s}_norm"]) - 1) <= 2e-5
+    wf, mf = orc.full_weights()
+    _close(wf[0].numpy() @ R, z["r0_weight_final_proj"], 5e-5)
+    _close(mf[0].numpy() @ R, z["r0_mom_final_proj"], 2e-4)
+
+
 def test_shard_arithmetic_covers_all_classes():
     for C in (10, 301, 93431, 360232):
         for W in (1, 2, 3, 8):

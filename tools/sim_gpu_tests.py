@@ -1,0 +1,47 @@
+"""DEV TOOL: run the BODIES of selected GPU tests on the CPU, with tests/fake_kernels.py standing in for the CUDA
+kernels and .cuda() patched to the identity.  It catches Python-level mistakes in GPU tests (and in the host logic they
+drive) when no GPU is at hand; it says nothing about the kernels.  Not part of the test-suite.
+
+    python tools/sim_gpu_tests.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "tests")
+for p in (ROOT, HERE, os.path.join(HERE, "golden")):
+    sys.path.insert(0, p)
+
+import torch                                   # noqa: E402
+import torch.distributed as dist               # noqa: E402
+
+torch.Tensor.cuda = lambda self, *a, **k: self
+torch.nn.Module.cuda = lambda self, *a, **k: self
+torch.cuda.synchronize = lambda *a, **k: None
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29879", rank=0, world_size=1)
+import face_recognition_pytorch_b200 as pfc    # noqa: E402
+from face_recognition_pytorch_b200 import partial_fc, kernels   # noqa: E402
+from fake_kernels import FakeKernels           # noqa: E402
+
+partial_fc.K = FakeKernels(kernels)
+os.environ["PFC_EXPERIMENTAL"] = "1"
+import test_gpu_configs as tc                  # noqa: E402
+import test_gpu_experimental as te             # noqa: E402
+
+RUNS = [
+    (tc.test_cfg1_shape_against_the_reference_fixture, [(pfc, False), (pfc, True)]),
+    (te.test_fused_step_eager_matches_autograd, [(pfc,)]),
+    (te.test_adamw_sampled_fused_matches_unfused_and_reference, [(pfc,)]),
+    (te.test_head_with_interclass_filter_matches_reference, [(pfc, False), (pfc, True)]),
+    (te.test_early_dx_matches_the_serial_order, [(pfc, 320, 3100, 512, False), (pfc, 96, 1500, 64, True)]),
+]
+failed = 0
+for fn, arglists in RUNS:
+    for args in arglists:
+        try:
+            fn(*args)
+            print("ok    ", fn.__name__, args[1:], flush=True)
+        except Exception as e:   # noqa: BLE001
+            failed += 1
+            print("FAILED", fn.__name__, args[1:], type(e).__name__, str(e)[:300], flush=True)
+sys.exit(1 if failed else 0)
