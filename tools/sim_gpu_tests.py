@@ -25,7 +25,7 @@ from fake_kernels import FakeKernels           # noqa: E402
 
 partial_fc.K = FakeKernels(kernels)
 os.environ["PFC_EXPERIMENTAL"] = "1"
-import test_gpu_configs as tc                  # noqa: E402
+import test_gpu_z_cfg1 as tc                   # noqa: E402
 import test_gpu_experimental as te             # noqa: E402
 
 RUNS = [
