@@ -189,7 +189,9 @@ struct StoreParams {
     int pdl_defer;          // 1: griddepcontrol.wait at the END of the kernel (pfc_launch.cuh, deferred wait)
 };
 
-template <bool kAMN>
+// kKeep (dW GEMM only, PFC_L2_GRAD): the bf16 gradient tiles are stored with an L2 evict_last hint so that the update
+// kernel, which runs next, reads them from L2 (and then discards them) instead of HBM.
+template <bool kAMN, bool kKeep = false>
 struct StorePolicy {
     static constexpr int EPI_WARPS_ = 8;
     static constexpr int STAGES_ = 4;
@@ -248,7 +250,7 @@ struct StorePolicy {
                     for (int j = 0; j < 16; ++j)
                         o[h2 * 16 + j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
                 }
-                warp_tma_store_rows(stage, lane, o, tmc, col64, row0, 0);
+                warp_tma_store_rows<kKeep>(stage, lane, o, tmc, col64, row0, 0);
             }
             return;
         }
@@ -434,6 +436,11 @@ static int launch_gemm(int pdl_id, int mode, const CUtensorMap& ta, const CUtens
 
 static int even_up(int v) { return (v + 1) / 2 * 2; }
 
+// PFC_L2_GRAD / pfc_debug_l2_grad: keep the bf16 gradient of the dW GEMM in L2 for the update kernel (evict_last stores
+// here, evict_first streams + discard.global.L2 in dw_sgd_rows_kernel, pfc_rows.cu).  Off by default: written after the
+// round's GPU budget was spent, never run.
+static int g_l2_grad = -1;
+
 }  // namespace pfc
 
 using namespace pfc;
@@ -448,6 +455,15 @@ void pfc_debug_mn_desc(unsigned lbo, unsigned sbo, unsigned kstep) {
 }
 // not part of the public header: GEMM launch mode, see g_gemm_mode
 void pfc_debug_cluster(int mode) { g_gemm_mode = mode; }
+// not part of the public header: L2-resident bf16 gradient between pfc_backward_dw and pfc_dw_sgd (see g_l2_grad)
+void pfc_debug_l2_grad(int on) { g_l2_grad = on ? 1 : 0; }
+int pfc_l2_grad_enabled(void) {
+    if (g_l2_grad < 0) {
+        const char* e = getenv("PFC_L2_GRAD");
+        g_l2_grad = e ? (atoi(e) != 0) : 0;
+    }
+    return g_l2_grad;
+}
 
 int pfc_padded_classes(int n) { return (n + 63) / 64 * 64; }
 int pfc_num_class_tiles(int n) { return (BN / FwdPolicy::COLS) * ((n + BN - 1) / BN); }   // part_sum slabs
@@ -583,6 +599,8 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     CUtensorMap tc;
     rc = make_store_tmap(&tc, dwn, dwn_bf16 != 0, d, n, 1, d, 0);
     if (rc) return rc;
+    if (dwn_bf16 && pfc_l2_grad_enabled())
+        return launch_gemm<StorePolicy<true, true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
     return launch_gemm<StorePolicy<true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -14,3 +14,8 @@
 
 // e = 2^(log2e*(z - s) + PFC_EXP_TOP): largest possible term is 2^PFC_EXP_TOP
 #define PFC_EXP_TOP 64
+
+#ifdef __cplusplus
+// 1: keep the bf16 gradient of the dW GEMM in L2 for the update kernel (PFC_L2_GRAD / pfc_debug_l2_grad, pfc_gemm.cu)
+extern "C" int pfc_l2_grad_enabled(void);
+#endif

@@ -92,6 +92,29 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t smem
                  "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// L2 residency controls (conf / PFC_L2_GRAD, pfc_gemm.cu): a 64-bit cache policy for cache_hint operands, a TMA store
+// that carries one, and discard.global.L2, which drops a (dirty) line from L2 WITHOUT writing it back -- the data at
+// that address is undefined afterwards, so only for buffers whose content is dead.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* m, uint32_t smem_src, int c0, int c1, int c2,
+                                                  uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void discard_l2_128(const void* p) {   // p: 128-byte aligned global address
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all but the newest N bulk groups of this thread have finished READING their shared-memory source
 template <int N>

@@ -504,7 +504,26 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
 // Specialised fused SGD row kernel for d = 128 * NV: all three input streams (dwn, w, momentum) are requested
 // up front (12 x 16-byte loads per lane in flight at d = 512) so a warp is never waiting on a dependent phase,
 // arrays are sized exactly (no predicated dead registers), 4 rows per CTA for occupancy.
-template <int NV, bool kGradBf16>
+// kL2 (PFC_L2_GRAD, bf16 gradient only): the gradient rows are expected in L2 (the dW GEMM stored them evict_last), the
+// fp32 state streams through with evict_first so that it does not push them out, and each gradient row is DISCARDED
+// from L2 once its warp has consumed it -- its dirty lines never reach HBM (the next step rewrites the buffer).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld4_hint(const float* p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st4_hint(float* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
+template <int NV, bool kGradBf16, bool kL2 = false>
 __global__ void __launch_bounds__(128)
 dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* __restrict__ mom,
                    const float* inv_norm_w, int rows, float lr, float momentum, float wd, float inv_grad_scale,
@@ -529,10 +548,14 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
             g[j] = ld4_stream(static_cast<const float*>(dwn_) + base + 4 * (lane + 32 * j));
         }
     }
+    uint64_t pol = 0;
+    if constexpr (kL2) pol = l2_evict_first_policy();
 #pragma unroll
-    for (int j = 0; j < NV; ++j) wv[j] = ld4(w + base + 4 * (lane + 32 * j));
+    for (int j = 0; j < NV; ++j)
+        wv[j] = kL2 ? ld4_hint(w + base + 4 * (lane + 32 * j), pol) : ld4(w + base + 4 * (lane + 32 * j));
 #pragma unroll
-    for (int j = 0; j < NV; ++j) mv[j] = ld4(mom + base + 4 * (lane + 32 * j));
+    for (int j = 0; j < NV; ++j)
+        mv[j] = kL2 ? ld4_hint(mom + base + 4 * (lane + 32 * j), pol) : ld4(mom + base + 4 * (lane + 32 * j));
     const float inv = inv_norm_w[row];
     float dot = 0.f;
 #pragma unroll
@@ -552,10 +575,23 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
         b.x = momentum * b.x + a.x; b.y = momentum * b.y + a.y;
         b.z = momentum * b.z + a.z; b.w = momentum * b.w + a.w;
         q.x -= lr * b.x; q.y -= lr * b.y; q.z -= lr * b.z; q.w -= lr * b.w;
-        st4(mom + base + 4 * (lane + 32 * j), b);
-        st4(w + base + 4 * (lane + 32 * j), q);
+        if constexpr (kL2) {
+            st4_hint(mom + base + 4 * (lane + 32 * j), b, pol);
+            st4_hint(w + base + 4 * (lane + 32 * j), q, pol);
+        } else {
+            st4(mom + base + 4 * (lane + 32 * j), b);
+            st4(w + base + 4 * (lane + 32 * j), q);
+        }
         wv[j] = q;
         ss += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+    }
+    if constexpr (kL2 && kGradBf16) {
+        // every lane's gradient loads have returned (their values went into the update above): drop the row's lines
+        __syncwarp();
+        constexpr int kLines = d * 2 / 128;
+        if (lane < kLines)
+            asm volatile("discard.global.L2 [%0], 128;" ::"l"(static_cast<const __nv_bfloat16*>(dwn_) + base + lane * 64)
+                         : "memory");
     }
     if (wn_next == nullptr) continue;
     ss = warp_sum(ss);
@@ -587,7 +623,10 @@ static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom,
         const int need = (rows + block / 32 - 1) / (block / 32);
         if (grid > need) grid = need;
     }
-    if (bf16)
+    if (bf16 && pfc_l2_grad_enabled())
+        launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr,
+                           momentum, wd, igs, wn_next, inv_next);
+    else if (bf16)
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
                            wd, igs, wn_next, inv_next);
     else

@@ -72,6 +72,8 @@ __host__ __device__ constexpr DescCfg default_desc_cfg(bool a_mn, bool b_mn) {
 // Compared with per-thread LDS + STG this removes 16 memory instructions, their 64-bit address arithmetic and the
 // bounds predicates per box from the epilogue warps, which pace the kernel when only two of them share a scheduler.
 // (c0, c1, c2) = element coordinates of the box in the map's (inner, row, slab) dimensions.
+// kKeep: the store carries an L2 evict_last hint (the consumer of this output runs next and should find it in L2).
+template <bool kKeep = false>
 __device__ __forceinline__ void warp_tma_store_rows(uint32_t stage, int lane, const uint32_t (&v)[32],
                                                     const CUtensorMap* map, int c0, int c1, int c2) {
     if (lane == 0) tma_store_wait_read<0>();   // the previous box of this warp has left the staging buffer
@@ -83,7 +85,8 @@ __device__ __forceinline__ void warp_tma_store_rows(uint32_t stage, int lane, co
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-        tma_store_3d(map, stage, c0, c1, c2);
+        if constexpr (kKeep) tma_store_3d_hint(map, stage, c0, c1, c2, l2_policy_evict_last());
+        else tma_store_3d(map, stage, c0, c1, c2);
         tma_store_commit();
     }
 }

@@ -11,6 +11,8 @@ are off by default.  Enable a feature by default only after this file has passed
     only the stand-alone margin kernel was compared with the reference on the GPU.
   * conf.early_dx: dX GEMM on the unpatched spill, launched on its own stream right after the forward GEMM; the
     target's rank-1 term is added when the partials are summed.  Same loss bits, dX equal up to fp32 summation order.
+  * PFC_L2_GRAD / pfc_debug_l2_grad: the bf16 gradient of the dW GEMM kept in L2 for the update (evict_last TMA stores,
+    evict_first state streams, discard.global.L2 after use).  Cache hints only: bit-identical results.
 """
 import os
 import types
@@ -210,3 +212,19 @@ def test_early_dx_graph_replay(pfc):
     for u, v, w_ in zip(a, b, c):
         assert cosine(u.cpu().reshape(-1), v.cpu().reshape(-1)) >= 0.999999
         assert torch.equal(v, w_)            # autograd or not: same kernels, same order
+
+
+def test_l2_resident_gradient_is_bit_identical(pfc):
+    from face_recognition_pytorch_b200 import _lib
+    a = _graph_run(pfc, True)
+    _lib.lib.pfc_debug_l2_grad(1)
+    try:
+        b = _graph_run(pfc, True)
+        c = _graph_run(pfc, True, B=320, C=3100)          # odd tile counts, ragged last class tile
+    finally:
+        _lib.lib.pfc_debug_l2_grad(0)
+    d = _graph_run(pfc, True, B=320, C=3100)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    for u, v in zip(c, d):
+        assert torch.equal(u, v)

@@ -6,11 +6,12 @@ CUDA graph of the step is re-captured and 40 replays are timed with CUDA events 
 ranks).  Mask bits are PdlId of pfc_launch.cuh: 0 normalise, 1 forward GEMM, 2 row stats / loss, 3 backward_prepare,
 4 dW GEMM, 5 dX GEMM, 6 dX finalize / scatter, 7 update rows, 8 label localisation / barrier.
 
-    python tools/exp_step.py [--configs mode:mask[:fork[:direct[:prio[:early]]]],...] [--steps 40]
+    python tools/exp_step.py [--configs mode:mask[:fork[:direct[:prio[:early[:l2]]]]],...] [--steps 40]
         fork   -1 auto / 0 / 1   conf.dx_side_stream
         direct 0 / 1             GraphedHeadStep(autograd=False): head.fused_step instead of forward + loss.backward()
         prio   0 / 1             high-priority side stream for the dX tail
         early  0 / 1             conf.early_dx: dX GEMM on the unpatched spill, next to statistics / loss / prepare
+        l2     0 / 1             pfc_debug_l2_grad: bf16 gradient kept in L2 between the dW GEMM and the update
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/exp_step.py
 """
 import argparse
@@ -73,6 +74,8 @@ def main():
         prio = int(f[4]) if len(f) > 4 else 0
         early = int(f[5]) if len(f) > 5 else 0
         head.early_dx = bool(early)
+        l2 = int(f[6]) if len(f) > 6 else 0
+        pfc._lib.lib.pfc_debug_l2_grad(l2)
         head.dx_side_stream = "auto" if fork < 0 else bool(fork)
         if bool(prio) != head.dx_side_priority:
             head.dx_side_priority = bool(prio)
@@ -102,7 +105,7 @@ def main():
             best.append(float(t))
         results.append((mode, mask, best))
         if rank == 0:
-            print(f"mode {mode} mask {mask:#05x} fork {fork} direct {direct} prio {prio} early {early}: " + " ".join(f"{v:.4f}" for v in best) + " ms/step", flush=True)
+            print(f"mode {mode} mask {mask:#05x} fork {fork} direct {direct} prio {prio} early {early} l2 {l2}: " + " ".join(f"{v:.4f}" for v in best) + " ms/step", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
