@@ -468,6 +468,7 @@ class _PartialFCBase(torch.nn.Module):
         fork = (want_fork and w.is_cuda and not overlap and not fuse_dw and need_dx
                 and (W == 1 or peer is not None))
         tail = None
+        wn_read_done = None       # early dX + fork: the tail's patched kernel reads wn, which the update rewrites in place
         if need_dx:
             if early is not None:
                 splits = early[1]                 # the partials are there already; their target term is added below
@@ -487,6 +488,9 @@ class _PartialFCBase(torch.nn.Module):
                     if early is not None:
                         K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx,
                                               ws.patch, ws.labels_act, wn_now)
+                        if tail is not None:
+                            wn_read_done = torch.cuda.Event()
+                            wn_read_done.record()                 # on the tail stream
                     else:
                         K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
                 elif peer is not None:
@@ -497,6 +501,9 @@ class _PartialFCBase(torch.nn.Module):
                                                   peer.ptrs("dx_slots"), ws.patch, ws.labels_act, wn_now)
                     else:
                         K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
+                    if tail is not None and early is not None:
+                        wn_read_done = torch.cuda.Event()
+                        wn_read_done.record()                     # on the tail stream
                     if tail is not None:
                         # barrier + :521; also the fence that keeps a fast rank's NEXT gather out of xn_all while a
                         # slow rank still reads it (this rank signals after its own dX GEMM, i.e. after its last read)
@@ -521,6 +528,8 @@ class _PartialFCBase(torch.nn.Module):
                     K.pdl_independent_next()
                 K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
             if self.fused_optimizer:
+                if wn_read_done is not None:
+                    torch.cuda.current_stream().wait_event(wn_read_done)
                 self._fused_step(w, n, d, dwn, ws.wn)     # in place, after the dX GEMM has consumed wn
             else:
                 dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
