@@ -304,6 +304,180 @@ static bool pick_parallel() {
     return g_pick_parallel != 0;
 }
 
+// exclusive scan of a 64-bit value over the 1024 threads of the CTA (two 32-bit counters packed side by side)
+__device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long long v, unsigned long long* warp_tot,
+                                                                 unsigned long long& total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const unsigned long long t = warp_tot[lane];
+        unsigned long long ti = t;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long n = __shfl_up_sync(0xffffffffu, ti, o);
+            if (lane >= o) ti += n;
+        }
+        warp_tot[lane] = ti - t;
+        if (lane == 31) warp_tot[32] = ti;
+    }
+    __syncthreads();
+    total = warp_tot[32];
+    const unsigned long long r = warp_tot[w] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// The whole sampler in ONE launch of ONE CTA, for shards of up to FUSED_MAX_NL classes (cfg-3's rank shape: 45 029
+// scores = 180 KB, L2-resident; the 12-launch pipeline above costs ~6 us of launch latency per stage there).  Same
+// algorithm and the same tie rule, stage by stage: flags, three histogram + pick passes (CTA-wide suffix scan as in
+// pick_parallel_kernel), then an ordered compaction that walks the array in tiles of 8192 keys with ONE packed scan
+// per tile: an element's output position is (#keys > T before it) + min(#keys == T before it, need_eq).
+// Opt-in (PFC_SAMPLE_FUSED=1 / pfc_debug_sample_fused): written after the round's GPU budget was spent, never run.
+constexpr int FUSED_MAX_NL = 65536;
+__global__ void __launch_bounds__(SEL_THREADS)
+sample_fused_kernel(const float* __restrict__ perm, const int32_t* __restrict__ labels, int B, int nl, int num_sample,
+                    uint8_t* flags, int32_t* slot_of, int64_t* __restrict__ index_out, int32_t* __restrict__ n_out,
+                    int32_t* __restrict__ labels_remapped) {
+    __shared__ uint32_t h[MAX_BINS];
+    __shared__ uint32_t incl[MAX_BINS];
+    __shared__ uint32_t wt[33];
+    __shared__ unsigned long long wt64[33];
+    __shared__ uint32_t s_npos, s_prefix, s_rem, s_keff, s_rstar;
+    const int T = threadIdx.x;
+    for (int i = T; i < nl; i += SEL_THREADS) flags[i] = 0;
+    if (T == 0) { s_npos = 0; s_prefix = 0; s_rem = 0; s_keff = 0; }
+    __syncthreads();
+    for (int j = T; j < B; j += SEL_THREADS) {
+        const int l = labels[j];
+        if (l >= 0) flags[l] = 1;
+    }
+    __syncthreads();
+    uint32_t prefix = 0, rem = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        const int bits = pass == 2 ? 10 : 11;
+        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
+        const int bins = 1 << bits;
+        const uint32_t hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
+        const uint32_t dmask = (1u << bits) - 1;
+        for (int b = T; b < MAX_BINS; b += SEL_THREADS) h[b] = 0;
+        __syncthreads();
+        uint32_t np = 0;
+        for (int i = T; i < nl; i += SEL_THREADS) {
+            const uint32_t k = key_of(perm, flags, i);
+            if (pass == 0) np += flags[i];
+            if ((k & hi_mask) == prefix) atomicAdd(&h[(k >> shift) & dmask], 1u);
+        }
+        if (pass == 0) {
+            np = __reduce_add_sync(0xffffffffu, np);
+            if ((T & 31) == 0 && np) atomicAdd(&s_npos, np);
+        }
+        __syncthreads();
+        if (pass == 0) {
+            if (T == 0) {
+                uint32_t k = s_npos > (uint32_t)num_sample ? s_npos : (uint32_t)num_sample;
+                if (k > (uint32_t)nl) k = nl;
+                s_keff = k;
+                s_rem = k;
+            }
+            __syncthreads();
+        }
+        rem = s_rem;
+        if (rem == 0) {                       // nothing to select (CTA-uniform): threshold above every key
+            prefix = 0xFFFFFFFFu;
+            break;
+        }
+        // pick: largest bin b >= 1 whose inclusive suffix count reaches rem (0 if none), see pick_parallel_kernel
+        if (T == 0) s_rstar = bins - 1;
+        uint32_t v[2], sum = 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = T * 2 + u;          // reversed bin index
+            v[u] = r < bins ? h[bins - 1 - r] : 0u;
+            sum += v[u];
+        }
+        uint32_t tot;
+        uint32_t run = block_excl_scan(sum, wt, tot);     // its first barrier also publishes s_rstar
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int r = T * 2 + u;
+            run += v[u];
+            if (r < bins) {
+                incl[r] = run;
+                if (run >= rem && r < bins - 1) atomicMin(&s_rstar, static_cast<uint32_t>(r));
+            }
+        }
+        __syncthreads();
+        if (T == 0) {
+            const uint32_t r = s_rstar;
+            s_prefix = prefix | (static_cast<uint32_t>(bins - 1 - r) << shift);
+            s_rem = rem - (incl[r] - h[bins - 1 - r]);
+        }
+        __syncthreads();
+        prefix = s_prefix;
+        rem = s_rem;
+    }
+    // ordered compaction
+    const uint32_t Tkey = prefix, need_eq = rem, keff = s_keff;
+    const bool none = keff == 0;
+    if (T == 0) n_out[0] = static_cast<int32_t>(keff);
+    uint32_t gt_before = 0, eq_before = 0;
+    for (int base0 = 0; base0 < nl; base0 += SEL_TILE) {
+        const int base = base0 + T * SEL_ITEMS;
+        uint32_t isgt = 0, iseq = 0, ng = 0, ne = 0;
+#pragma unroll
+        for (int u = 0; u < SEL_ITEMS; ++u) {
+            const int i = base + u;
+            if (i < nl && !none) {
+                const uint32_t k = key_of(perm, flags, i);
+                if (k > Tkey) { isgt |= 1u << u; ++ng; }
+                if (k == Tkey) { iseq |= 1u << u; ++ne; }
+            }
+        }
+        unsigned long long total;
+        const unsigned long long ex =
+            block_excl_scan64((static_cast<unsigned long long>(ne) << 32) | ng, wt64, total);
+        uint32_t e_rank = eq_before + static_cast<uint32_t>(ex >> 32);
+        uint32_t pos = gt_before + static_cast<uint32_t>(ex & 0xffffffffu) + min(e_rank, need_eq);
+#pragma unroll
+        for (int u = 0; u < SEL_ITEMS; ++u) {
+            bool take = (isgt >> u) & 1u;
+            if ((iseq >> u) & 1u) {
+                take = e_rank < need_eq;
+                ++e_rank;
+            }
+            if (take) {
+                const int i = base + u;
+                index_out[pos] = i;
+                if (flags[i]) slot_of[i] = static_cast<int32_t>(pos);
+                ++pos;
+            }
+        }
+        gt_before += static_cast<uint32_t>(total & 0xffffffffu);
+        eq_before += static_cast<uint32_t>(total >> 32);
+    }
+    __syncthreads();                          // every slot_of entry of a positive class is written
+    for (int j = T; j < B; j += SEL_THREADS) {
+        const int l = labels[j];
+        labels_remapped[j] = l >= 0 ? slot_of[l] : -1;
+    }
+}
+
+static int g_sample_fused = -1;
+static bool sample_fused() {
+    if (g_sample_fused < 0) {
+        const char* e = getenv("PFC_SAMPLE_FUSED");
+        g_sample_fused = e ? (atoi(e) != 0) : 0;
+    }
+    return g_sample_fused != 0;
+}
+
 struct SelLayout {
     size_t flags, state, gt, eq, slot, total;
     int tiles;
@@ -328,6 +502,8 @@ using namespace pfc;
 
 extern "C" {
 
+// not part of the public header: 1 = the one-launch sampler for shards of up to 65 536 classes (sample_fused_kernel)
+void pfc_debug_sample_fused(int on) { g_sample_fused = on ? 1 : 0; }
 // not part of the public header: 1 = CTA-wide pick kernel, 0 = serial walk (see pick_parallel())
 void pfc_debug_sample_pick(int parallel) { g_pick_parallel = parallel ? 1 : 0; }
 
@@ -346,6 +522,11 @@ int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_lo
     uint32_t* gt = reinterpret_cast<uint32_t*>(ws + L.gt);
     uint32_t* eq = reinterpret_cast<uint32_t*>(ws + L.eq);
     int32_t* slot = reinterpret_cast<int32_t*>(ws + L.slot);
+    if (sample_fused() && num_local <= FUSED_MAX_NL) {
+        sample_fused_kernel<<<1, SEL_THREADS, 0, stream>>>(perm, labels_local, B, num_local, num_sample, flags, slot,
+                                                           index_out, n_out, labels_remapped);
+        return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
+    }
     // flags and the selection state are contiguous at the front of the workspace
     if (cudaMemsetAsync(ws, 0, L.gt, stream) != cudaSuccess) return PFC_ERR_CUDA;
     mark_positive_kernel<<<(B + 255) / 256, 256, 0, stream>>>(labels_local, B, flags);

@@ -13,6 +13,8 @@ are off by default.  Enable a feature by default only after this file has passed
     target's rank-1 term is added when the partials are summed.  Same loss bits, dX equal up to fp32 summation order.
   * PFC_L2_GRAD / pfc_debug_l2_grad: the bf16 gradient of the dW GEMM kept in L2 for the update (evict_last TMA stores,
     evict_first state streams, discard.global.L2 after use).  Cache hints only: bit-identical results.
+  * PFC_SAMPLE_FUSED / pfc_debug_sample_fused: the sampler as one launch of one CTA for shards of up to 65 536 classes
+    (its algorithm was checked on the CPU against the oracle with a numpy emulation; the CUDA code never ran).
 """
 import os
 import types
@@ -228,3 +230,13 @@ def test_l2_resident_gradient_is_bit_identical(pfc):
         assert torch.equal(u, v)
     for u, v in zip(c, d):
         assert torch.equal(u, v)
+
+
+def test_fused_sampler_matches_the_oracle(pfc):
+    from face_recognition_pytorch_b200 import _lib
+    from tools import gpu_probe
+    _lib.lib.pfc_debug_sample_fused(1)
+    try:
+        assert gpu_probe._case_sample_once()      # shards > 65 536 classes silently take the multi-launch path
+    finally:
+        _lib.lib.pfc_debug_sample_fused(0)

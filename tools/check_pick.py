@@ -19,8 +19,9 @@ for nl, k, B in ((45029, 4502, 1024), (257489, 51497, 4096)):
     n_out = torch.zeros(1, dtype=torch.int32, device="cuda")
     rem = torch.zeros(B, dtype=torch.int32, device="cuda")
     ws = torch.zeros(K.sample_workspace_bytes(nl), dtype=torch.uint8, device="cuda")
-    for par in (0, 1):
-        _lib.lib.pfc_debug_sample_pick(par)
+    for par in (0, 1, 2):       # 2 = the one-launch sampler (PFC_SAMPLE_FUSED, shards of up to 65 536 classes)
+        _lib.lib.pfc_debug_sample_pick(1 if par else 0)
+        _lib.lib.pfc_debug_sample_fused(1 if par == 2 else 0)
         ts = []
         for i in range(8):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,4 +30,5 @@ for nl, k, B in ((45029, 4502, 1024), (257489, 51497, 4096)):
             b.record()
             torch.cuda.synchronize()
             ts.append(a.elapsed_time(b) * 1e3)
-        print(f"pfc_sample nl={nl} k={k} pick={'parallel' if par else 'serial'}: median {sorted(ts[2:])[3]:.1f} us", flush=True)
+        print(f"pfc_sample nl={nl} k={k} pick={('serial', 'parallel', 'fused one-launch')[par]}: median {sorted(ts[2:])[3]:.1f} us", flush=True)
+_lib.lib.pfc_debug_sample_fused(0)

@@ -7,7 +7,7 @@ set -x
 if [ "$N" = "1" ]; then
   PFC_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_experimental.py tests/test_gpu_z_cfg1.py -q 2>&1 | tail -15
   timeout 300 python tools/exp_step.py --configs 0:0:-1:0:0:0:0,0:0:-1:1:0:0:0,0:0:-1:0:0:1:0,0:0:-1:1:0:1:0,0:0:-1:0:0:0:1,0:0:-1:1:0:1:1,0:0:1:1:0:1:1,0:0:-1:0:0:0:0 2>&1 | grep -E "^mode|rror"
-  timeout 120 python tools/check_pick.py 2>&1 | grep -E "PARALLEL|pfc_sample"
+  timeout 120 python tools/check_pick.py 2>&1 | grep -E "PARALLEL|pfc_sample"     # incl. the one-launch sampler's time
 else
   PFC_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_dist.py -q -k experimental 2>&1 | tail -8
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29631 \
