@@ -10,8 +10,6 @@ After the rendezvous every rank holds the device pointers of all W buffers as ma
 they are handed to the kernels as small host arrays of pointers.  Only ranks of ONE node with NVLink / P2P access
 qualify; anything else raises and the head keeps the NCCL collectives.
 """
-import ctypes
-
 import torch
 import torch.distributed as dist
 

@@ -1,6 +1,5 @@
 """CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU and exports every symbol that
 include/pfc.h declares; the Python binding table matches the header; shape helpers behave."""
-import ctypes
 import os
 import re
 
