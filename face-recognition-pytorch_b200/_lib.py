@@ -35,9 +35,6 @@ p = c_void_p
 _SIGS = {
     "pfc_version": (c_int, []),
     "pfc_error_string": (c_char_p, [c_int]),
-    "pfc_set_pdl": (None, [c_int]),
-    "pfc_get_pdl": (c_int, []),
-    "pfc_pdl_independent_next": (None, []),
     "pfc_exp_top": (c_int, []),
     "pfc_padded_classes": (c_int, [c_int]),
     "pfc_padded_batch": (c_int, [c_int]),
@@ -47,6 +44,13 @@ _SIGS = {
     "pfc_l2norm_rows_localize": (c_int, [p, c_int, c_int, p, p, p, c_int64, c_int, p, p]),
     "pfc_dx_splits": (c_int, [c_int, c_int, c_int]),
     "pfc_dx_max_splits": (c_int, [c_int, c_int]),
+    "pfc_fx_splits": (c_int, [c_int, c_int, c_int]),
+    "pfc_fx_max_splits": (c_int, [c_int, c_int]),
+    "pfc_fx_counter_words": (c_int, [c_int, c_int, c_int]),
+    "pfc_fx_tile_order": (c_int, [c_int, c_int, c_int, p]),
+    "pfc_forward_dx": (c_int, [p, p, p, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float, p, c_int, p, p,
+                               p, p, p, c_int, p, c_int, p]),
+    "pfc_dw_sgd_ordered": (c_int, [p, p, p, p, c_int, c_int, c_float, c_float, c_float, p, p, p, c_int, p, p, p]),
     "pfc_l2norm_rows": (c_int, [p, p, c_int, c_int, p, p, p]),
     "pfc_localize_labels": (c_int, [p, c_int, c_int64, c_int, p, p]),
     "pfc_sample_workspace_bytes": (c_size_t, [c_int]),
@@ -60,17 +64,15 @@ _SIGS = {
     "pfc_loss": (c_int, [p, c_int, p, p, p]),
     "pfc_backward_prepare": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, c_int, p]),
     "pfc_backward_prepare_deferred": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, p]),
-    "pfc_apply_target_patch": (c_int, [p, c_int, c_int, p, p, p]),
+    "pfc_apply_target_patch": (c_int, [p, c_int, c_int, p, p, p, p]),
     "pfc_dx_finalize_patched": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p, p, p, p]),
     "pfc_backward_dx": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dx_finalize": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p]),
     "pfc_backward_dw": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dw_finalize": (c_int, [p, p, p, c_int, c_int, c_float, p, p]),
-    "pfc_dw_sgd": (c_int, [p, c_int, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, p, p, p]),
+    "pfc_dw_sgd": (c_int, [p, c_int, p, p, p, c_int, c_int, c_float, c_float, c_float, p, p, p, p]),
     "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int,
-                            c_float, p, p, p]),
-    "pfc_backward_dw_sgd": (c_int, [p, c_int, p, c_int, c_int, c_int, p, p, p, c_float, c_float, c_float, c_float, p, p,
-                                    p]),
+                            p, p, p, p, p]),
     "pfc_peer_max_ranks": (c_int, []),
     "pfc_peer_barrier": (c_int, [POINTER(c_void_p), p, c_int, c_int, p]),
     "pfc_peer_l2norm_gather": (c_int, [p, p, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), p, p]),

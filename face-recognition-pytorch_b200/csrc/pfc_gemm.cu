@@ -13,7 +13,6 @@
 #include <stdlib.h>
 #include "pfc_umma.cuh"
 #include "pfc_umma2.cuh"
-#include "pfc_dwsgd.cuh"
 #include "pfc_internal.h"
 
 namespace pfc {
@@ -47,7 +46,6 @@ struct FwdPolicy {
         float* tgt_e;            // [B] e of the margin-adjusted target logit
         float* tgt_z;            // [B] margin-adjusted target logit (already * s)
         float s;
-        int pdl_defer;           // always 0: the forward depends on the kernel before it
     };
     __device__ static __forceinline__ DescCfg desc(const Params&) { return default_desc_cfg(false, false); }
     __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
@@ -186,7 +184,6 @@ struct StoreParams {
     float* out;
     int out_bf16;           // 1: `out` is a bf16 matrix (same ld in elements); used for the dWn spill in fused mode
     DescCfg dc;             // descriptor geometry (runtime so that tools/gpu_probe.py can try alternatives)
-    int pdl_defer;          // 1: griddepcontrol.wait at the END of the kernel (pfc_launch.cuh, deferred wait)
 };
 
 // kKeep (dW GEMM only, PFC_L2_GRAD): the bf16 gradient tiles are stored with an L2 evict_last hint so that the update
@@ -266,6 +263,10 @@ struct StorePolicy {
     }
 };
 
+}  // namespace pfc
+#include "pfc_fx.cuh"
+namespace pfc {
+
 // ============================================================================ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -335,24 +336,6 @@ static int make_blocked_tmap(CUtensorMap* map, const void* ptr, uint64_t B, uint
     return r == CUDA_SUCCESS ? PFC_OK : PFC_ERR_TENSORMAP;
 }
 
-// Generic 2-D row-major tensor map (loads and stores), bf16 or fp32, explicit box and swizzle mode.
-static int make_tmap_2d(CUtensorMap* map, void* ptr, bool is_bf16, uint64_t inner, uint64_t outer,
-                        uint64_t row_stride_elems, uint32_t box_inner, uint32_t box_outer, bool swizzle128) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return PFC_ERR_DRIVER;
-    const uint64_t es = is_bf16 ? 2 : 4;
-    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (row_stride_elems * es) % 16) return PFC_ERR_ALIGNMENT;
-    cuuint64_t gdim[2] = {inner, outer};
-    cuuint64_t gstr[1] = {row_stride_elems * es};
-    cuuint32_t box[2] = {box_inner, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, gdim, gstr,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? PFC_OK : PFC_ERR_TENSORMAP;
-}
-
 static int num_sms() {
     static int sms = 0;
     if (!sms) {
@@ -404,13 +387,14 @@ static int launch_cluster(int pdl_id, Kern kern, int cluster, int threads, int s
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute at[2];
+    cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = cluster;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1 + pdl_attr(&at[1], pdl_id);   // the GEMM kernels start with pdl_entry() after their CTA-local setup
+    cfg.numAttrs = 1;
+    (void)pdl_id;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, prm);
     return e == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
@@ -436,9 +420,35 @@ static int launch_gemm(int pdl_id, int mode, const CUtensorMap& ta, const CUtens
 
 static int even_up(int v) { return (v + 1) / 2 * 2; }
 
-// PFC_L2_GRAD / pfc_debug_l2_grad: keep the bf16 gradient of the dW GEMM in L2 for the update kernel (evict_last stores
-// here, evict_first streams + discard.global.L2 in dw_sgd_rows_kernel, pfc_rows.cu).  Off by default: written after the
-// round's GPU budget was spent, never run.
+static void fill_fwd_params(FwdPolicy::Params& p, int B, int n, int n_pad, int d, int m_tiles, float s, int margin_kind,
+                            float m2, float m3, float filter_thr, const int32_t* labels_local, void* E, float* part_sum,
+                            float* tgt_raw, float* tgt_e, float* tgt_z) {
+    const float log2e = 1.4426950408889634f;
+    p.B = B; p.n = n; p.n_pad = n_pad; p.B_pad = (B + BM - 1) / BM * BM;
+    p.m_tiles = m_tiles;                    // an odd count gets one all-padding tile in the pair kernel
+    p.k_stages = (d + BK - 1) / BK;
+    p.num_tiles = p.m_tiles * ((n + BN - 1) / BN);
+    p.labels = labels_local;
+    p.k1 = s * log2e;
+    p.k2 = s * log2e - (float)PFC_EXP_TOP;
+    p.k1x2 = 2.f * p.k1;
+    p.k12 = p.k1 + p.k2;
+    {   // same double-precision constants the reference computes with math.cos/sin (nets/ArcFace.py:69-72)
+        const double pi = 3.14159265358979323846;
+        p.cos_m = (float)cos((double)m2); p.sin_m = (float)sin((double)m2);
+        p.theta = (float)cos(pi - (double)m2);
+        p.sinmm = (float)(sin(pi - (double)m2) * (double)m2);
+    }
+    p.m3 = m3; p.margin_kind = margin_kind; p.filter_thr = filter_thr;
+    p.E = reinterpret_cast<__nv_bfloat16*>(E);
+    p.part_sum = part_sum; p.tgt_raw = tgt_raw; p.tgt_e = tgt_e; p.tgt_z = tgt_z; p.s = s;
+}
+
+// Keep the bf16 gradient of the dW GEMM in L2 for the update kernel that runs right behind it (evict_last stores here,
+// evict_first streams + discard.global.L2 in dw_sgd_rows_kernel, pfc_rows.cu).  Bit-identical results; measured on B200 at
+// cfg-2: 0.3872 -> 0.3812 ms per step on one GPU, 0.2486 -> 0.2452 on two (profiles/r02a_experimental_n*.log), hence on by
+// default.  PFC_L2_GRAD=0 / pfc_debug_l2_grad(0) switch it off (the A/B test does).  The lazy-update path consumes the
+// gradient a whole step later and does not use the hints.
 static int g_l2_grad = -1;
 
 }  // namespace pfc
@@ -460,7 +470,7 @@ void pfc_debug_l2_grad(int on) { g_l2_grad = on ? 1 : 0; }
 int pfc_l2_grad_enabled(void) {
     if (g_l2_grad < 0) {
         const char* e = getenv("PFC_L2_GRAD");
-        g_l2_grad = e ? (atoi(e) != 0) : 0;
+        g_l2_grad = e ? (atoi(e) != 0) : 1;
     }
     return g_l2_grad;
 }
@@ -489,26 +499,8 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     rc = make_store_tmap(&tc, E, true, 64, B, n_pad / 64, 64, static_cast<uint64_t>(B) * 64);
     if (rc) return rc;
     FwdPolicy::Params p;
-    p.B = B; p.n = n; p.n_pad = n_pad; p.B_pad = pfc_padded_batch(B);
-    p.m_tiles = mode == MODE_PAIR ? even_up(m_tiles) : m_tiles;   // an odd count gets one all-padding tile
-    p.k_stages = (d + BK - 1) / BK;
-    p.num_tiles = p.m_tiles * ((n + BN - 1) / BN);
-    p.labels = labels_local;
-    p.k1 = s * log2e;
-    p.k2 = s * log2e - (float)PFC_EXP_TOP;
-    p.k1x2 = 2.f * p.k1;
-    p.k12 = p.k1 + p.k2;
-    {   // same double-precision constants the reference computes with math.cos/sin (nets/ArcFace.py:69-72)
-        const double pi = 3.14159265358979323846;
-        p.cos_m = (float)cos((double)m2); p.sin_m = (float)sin((double)m2);
-        p.theta = (float)cos(pi - (double)m2);
-        p.sinmm = (float)(sin(pi - (double)m2) * (double)m2);
-    }
-    p.m3 = m3; p.margin_kind = margin_kind; p.filter_thr = filter_thr;
-    p.E = reinterpret_cast<__nv_bfloat16*>(E);
-    p.part_sum = part_sum; p.tgt_raw = tgt_raw; p.tgt_e = tgt_e; p.tgt_z = tgt_z; p.s = s;
-    p.pdl_defer = 0;
-    (void)pdl_take_independent();
+    fill_fwd_params(p, B, n, n_pad, d, mode == MODE_PAIR ? even_up(m_tiles) : m_tiles, s, margin_kind, m2, m3, filter_thr,
+                    labels_local, E, part_sum, tgt_raw, tgt_e, tgt_z);
     return launch_gemm<FwdPolicy>(PDL_FORWARD, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -558,7 +550,6 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     p.out = partial;
     p.out_bf16 = 0;
     p.dc = store_desc_cfg(false);
-    p.pdl_defer = pdl_take_independent() ? 1 : 0;
     CUtensorMap tc;
     rc = make_store_tmap(&tc, partial, false, d, B, p.splits, d, static_cast<uint64_t>(B) * d);
     if (rc) return rc;
@@ -595,64 +586,120 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.out = reinterpret_cast<float*>(dwn);
     p.out_bf16 = dwn_bf16 ? 1 : 0;
     p.dc = store_desc_cfg(true);
-    p.pdl_defer = pdl_take_independent() ? 1 : 0;
     CUtensorMap tc;
     rc = make_store_tmap(&tc, dwn, dwn_bf16 != 0, d, n, 1, d, 0);
     if (rc) return rc;
-    if (dwn_bf16 && pfc_l2_grad_enabled())
+    if (dwn_bf16 == 1 && pfc_l2_grad_enabled())   // 2: bf16 without the L2 hints (consumed a step later: lazy update)
         return launch_gemm<StorePolicy<true, true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
     return launch_gemm<StorePolicy<true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
-// dW GEMM + normalise-backward + SGD/momentum step + next step's bf16 shard in ONE kernel (pfc_dwsgd.cuh).
-// Specialised for d = 512 (the two 256-column halves of a class tile run on a CTA pair); other d: PFC_ERR_SHAPE,
-// callers then use pfc_backward_dw + pfc_dw_sgd.
-int pfc_backward_dw_sgd(const void* E, int n_pad, const void* xs, int B, int n, int d, float* w, float* mom,
-                        const float* inv_norm_w, float lr, float momentum, float weight_decay, float inv_grad_scale,
-                        void* wn_next, float* inv_norm_next, void* stream) {
-    if (B <= 0 || n <= 0 || d != DWS_D || n_pad % 8) return PFC_ERR_SHAPE;
-    if (!w || !mom || !inv_norm_w || !wn_next || !inv_norm_next) return PFC_ERR_SHAPE;
-    if ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(mom) | reinterpret_cast<uintptr_t>(wn_next)) & 31)
-        return PFC_ERR_ALIGNMENT;
-    CUtensorMap ta, tb, tw, tm, twn;
-    if (n_pad % 64) return PFC_ERR_SHAPE;
-    int rc = make_blocked_tmap(&ta, E, B, n_pad, DWS_BK);  // A: E'^T MN-major boxes 64(M) x 32(K)
+// ---------------------------------------------------------------------------------------------------------------
+// FX: forward GEMM + dX GEMM in one persistent kernel (pfc_fx.cuh)
+static void fx_geometry(int B, int n, int d, int* R, int* H, int* G, int* CT) {
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    *R = (B + 2 * BM - 1) / (2 * BM);
+    *H = (d + BN - 1) / BN;
+    *CT = (n + BN - 1) / BN;
+    int g = (sms / 2) / (*R * *H);
+    if (g < 1) g = 1;
+    if (g > *CT) g = *CT;
+    *G = g;
+}
+
+// class groups = slabs of the dX partial buffer [G][B][d] pfc_forward_dx writes
+int pfc_fx_splits(int B, int n, int d) {
+    int R, H, G, CT;
+    fx_geometry(B, n, d, &R, &H, &G, &CT);
+    return G;
+}
+int pfc_fx_max_splits(int B, int d) {
+    const int sms = num_sms() > 0 ? num_sms() : 148;
+    const int g = (sms / 2) / (((B + 2 * BM - 1) / (2 * BM)) * ((d + BN - 1) / BN));
+    return g > 1 ? g : 1;
+}
+// int32 words of the per-step counter array: [CT] wn_ready, [R * CT] e_ready (zeroed by the caller before every step)
+int pfc_fx_counter_words(int B, int n, int d) {
+    int R, H, G, CT;
+    fx_geometry(B, n, d, &R, &H, &G, &CT);
+    return CT + R * CT;
+}
+// order[i] = i-th class tile (256 classes) the FX kernel asks for: round p of every group before round p + 1.  The
+// update kernel of the lazy mode rewrites the shard in this order (host array of ceil(n / 256) ints).
+int pfc_fx_tile_order(int B, int n, int d, int32_t* order) {
+    int R, H, G, CT;
+    fx_geometry(B, n, d, &R, &H, &G, &CT);
+    int k = 0, longest = 0;
+    for (int g = 0; g < G; ++g) {
+        const int L = (int)(((long long)(g + 1) * CT) / G) - (int)(((long long)g * CT) / G);
+        if (L > longest) longest = L;
+    }
+    for (int i = 0; i < longest; ++i)
+        for (int g = 0; g < G; ++g) {
+            const int c0 = (int)(((long long)g * CT) / G), L = (int)(((long long)(g + 1) * CT) / G) - c0;
+            if (i < L) order[k++] = c0 + i;
+        }
+    return k == CT ? PFC_OK : PFC_ERR_SHAPE;
+}
+
+// pfc_forward (with the target column of E' left at 0) and pfc_backward_dx on that spill, fused: see pfc_fx.cuh.
+// partial: [pfc_fx_splits(B, n, d)][B][d] fp32; counters: pfc_fx_counter_words ints, ZERO on entry; wn_gate != 0: wait
+// for counters[ct] == rows of class tile ct (pfc_dw_sgd_ordered) before reading that tile of wn.
+int pfc_forward_dx(const void* xn, const void* wn, const int32_t* labels_local, int B, int n, int d, float s,
+                   int margin_kind, float m2, float m3, float filter_thr, void* E, int n_pad, float* part_sum,
+                   float* tgt_raw, float* tgt_e, float* tgt_z, float* partial, int splits, int* counters, int wn_gate,
+                   void* stream) {
+    if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 64 || n_pad < n || !counters || !partial) return PFC_ERR_SHAPE;
+    const float log2e = 1.4426950408889634f;
+    if (!(s > 0.f) || 2.f * s * log2e > PFC_EXP_TOP + 126.f) return PFC_ERR_SCALE_RANGE;
+    FxParams p;
+    fx_geometry(B, n, d, &p.R, &p.H, &p.G, &p.CT);
+    if (splits != p.G) return PFC_ERR_SHAPE;
+    CUtensorMap t_xn, t_wnk, t_est, t_eld, t_wnmn, t_dx;
+    int rc = make_tmap(&t_xn, xn, d, B, d, BK, BM);
     if (rc) return rc;
-    rc = make_tmap(&tb, xs, d, B, d, 64, DWS_BK);          // B: Xs [B(K), d(N)] MN-major boxes 64(N) x 32(K)
+    rc = make_tmap(&t_wnk, wn, d, n, d, BK, BN / 2);
     if (rc) return rc;
-    // state streams: boxes of 32 rows x 32 columns, loaded AND stored through the same maps
-    rc = make_tmap_2d(&tw, w, false, d, n, d, 32, 32, true);
+    rc = make_store_tmap(&t_est, E, true, 64, B, n_pad / 64, 64, static_cast<uint64_t>(B) * 64);
     if (rc) return rc;
-    rc = make_tmap_2d(&tm, mom, false, d, n, d, 32, 32, true);
+    rc = make_blocked_tmap(&t_eld, E, B, n_pad, BM);
     if (rc) return rc;
-    rc = make_tmap_2d(&twn, wn_next, true, d, n, d, 32, 32, false);
+    rc = make_tmap(&t_wnmn, wn, d, n, d, 64, BK);
     if (rc) return rc;
+    rc = make_store_tmap(&t_dx, partial, false, d, B, p.G, d, static_cast<uint64_t>(B) * d);
+    if (rc) return rc;
+    fill_fwd_params(p.f, B, n, n_pad, d, 2 * p.R, s, margin_kind, m2, m3, filter_thr, labels_local, E, part_sum, tgt_raw,
+                    tgt_e, tgt_z);
+    p.x = StoreParams{};
+    p.x.rows_valid = B; p.x.cols_valid = d; p.x.ld = d;
+    p.x.split_stride = static_cast<size_t>(B) * d;
+    p.x.out = partial;
+    p.x.out_bf16 = 0;
+    p.kf_stages = (d + BK - 1) / BK;
+    p.n_pad = n_pad;
+    p.n = n;
+    p.wn_ready = wn_gate ? counters : nullptr;
+    p.e_ready = counters + p.CT;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(dw_sgd_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWS_SMEM_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute(fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_SMEM) != cudaSuccess)
             return PFC_ERR_CUDA;
         attr_set = true;
     }
-    DwSgdParams p;
-    p.num_class_tiles = (n + BM - 1) / BM;
-    p.n = n;
-    p.k_stages = (B + DWS_BK - 1) / DWS_BK;
-    p.inv_w = inv_norm_w;
-    p.inv_next = inv_norm_next;
-    p.lr = lr; p.momentum = momentum; p.wd = weight_decay; p.inv_grad_scale = inv_grad_scale;
-    {
-        const char* e = getenv("PFC_DWS_PREFETCH");   // tuning knob, see pfc_dwsgd.cuh
-        p.prefetch = e ? atoi(e) : 0;
-    }
-    p.dc = store_desc_cfg(true);
-    p.dc.a_lbo = p.dc.b_lbo = DWS_MN_BOX;                  // 64-wide MN blocks are one 32-row box (4 KB) apart
-    const int sms = num_sms();
-    if (sms < 2) return PFC_ERR_CUDA;
-    int pairs = sms / 2;
-    if (pairs > p.num_class_tiles) pairs = p.num_class_tiles;
-    dw_sgd_gemm_kernel<<<2 * pairs, GEMM_THREADS, DWS_SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-        ta, tb, tw, tm, twn, p);
-    return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * p.R * p.H * p.G);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = FX_SMEM;
+    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, fx_kernel, t_xn, t_wnk, t_est, t_eld, t_wnmn, t_dx, p);
+    return e == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 
 }  // extern "C"

@@ -39,7 +39,6 @@ __device__ __forceinline__ float warp_sum_p(float v) {
 
 // One CTA, W threads.  flags.p[q] -> rank q's flag array uint32[W]; counter -> this rank's epoch (device memory).
 __global__ void peer_barrier_kernel(PeerPtrs flags, uint32_t* counter, int rank, int W) {
-    pdl_entry();
     __shared__ uint32_t ep_s;
     if (threadIdx.x == 0) {
         ep_s = *counter + 1;
@@ -110,7 +109,6 @@ __device__ __forceinline__ void peer_entry_barrier(const PeerPtrs& flags, uint32
 __global__ void __launch_bounds__(256)
 peer_localize_labels_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, const int64_t* labels, int B,
                             int64_t class_start, int num_local, int32_t* __restrict__ out) {
-    pdl_entry();
     peer_entry_barrier(flags, state, rank, W);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
@@ -122,7 +120,6 @@ peer_localize_labels_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, co
 __global__ void __launch_bounds__(256)
 peer_l2norm_gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, int b, int d, int rank, int W,
                           PeerPtrs xn_all, PeerPtrs labels_all, float* __restrict__ inv_norm) {
-    pdl_entry();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= b) return;
@@ -168,7 +165,6 @@ __global__ void __launch_bounds__(PRS_ROWS * PRS_GROUPS)
 peer_row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                       const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, int rank, int W,
                       PeerPtrs slots) {
-    pdl_entry();
     __shared__ float red[PRS_GROUPS][PRS_ROWS + 1];
     const int r = threadIdx.x & (PRS_ROWS - 1), g = threadIdx.x / PRS_ROWS;
     const int row = blockIdx.x * PRS_ROWS + r;
@@ -201,7 +197,6 @@ template <bool kBarrier>
 __global__ void __launch_bounds__(1024)
 peer_loss_kernel(PeerPtrs flags, uint32_t* state, int rank, const float* slots, int W, int B, float* __restrict__ stats,
                  float* __restrict__ row_L, float* __restrict__ loss) {
-    pdl_entry();
     __shared__ float red[32];
     if (kBarrier) peer_entry_barrier(flags, state, rank, W);
     float acc = 0.f;
@@ -238,7 +233,6 @@ peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t spl
                        const float* __restrict__ coef, int B, int b, int d, int rank, PeerPtrs dx_slots,
                        const float* __restrict__ patch, const int32_t* __restrict__ labels,
                        const __nv_bfloat16* __restrict__ wn) {
-    pdl_entry();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -276,7 +270,6 @@ peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t spl
 __global__ void __launch_bounds__(256)
 peer_dx_finalize_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, const float* slots, const float* __restrict__ x,
                         const float* __restrict__ inv_norm, float scale, int b, int d, float* __restrict__ out) {
-    pdl_entry();
     peer_entry_barrier(flags, state, rank, W);
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;

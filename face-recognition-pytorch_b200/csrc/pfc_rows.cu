@@ -53,7 +53,6 @@ l2norm_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ inde
                    __nv_bfloat16* __restrict__ xn, float* __restrict__ inv_norm,
                    const int64_t* __restrict__ labels, int64_t class_start, int num_local,
                    int32_t* __restrict__ labels_local) {
-    pdl_entry();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -91,7 +90,6 @@ l2norm_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ inde
 // labels -> shard-local ids, -1 for classes owned by another rank           (nets/PartialFC.py:188-193)
 __global__ void localize_labels_kernel(const int64_t* __restrict__ labels, int B, int64_t class_start,
                                        int num_local, int32_t* __restrict__ out) {
-    pdl_entry();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const int64_t l = labels[i] - class_start;
@@ -131,7 +129,6 @@ __device__ __forceinline__ float row_stats_sum(const float* __restrict__ part_su
 __global__ void __launch_bounds__(RS_ROWS * RS_GROUPS)
 row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                  const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* __restrict__ stats) {
-    pdl_entry();
     __shared__ float red[RS_GROUPS][RS_ROWS + 1];
     const float tot = row_stats_sum(part_sum, n_tiles, B, B_pad, red);
     const int row = blockIdx.x * RS_ROWS + (threadIdx.x & (RS_ROWS - 1));
@@ -148,7 +145,6 @@ __global__ void __launch_bounds__(RS_ROWS * RS_GROUPS)
 row_stats_loss_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                       const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* stats,
                       float* __restrict__ row_L, float* __restrict__ loss, unsigned int* ticket) {
-    pdl_entry();
     __shared__ float red[RS_GROUPS][RS_ROWS + 1];
     __shared__ bool last;
     const float tot = row_stats_sum(part_sum, n_tiles, B, B_pad, red);
@@ -194,7 +190,6 @@ row_stats_loss_kernel(const float* __restrict__ part_sum, int n_tiles, int B, in
 // stats is the (all-reduced) [B][2] array; also emits L_i = stats[i][0] + stats[i][1].
 __global__ void __launch_bounds__(1024)
 loss_kernel(const float* __restrict__ stats, int B, float* __restrict__ row_L, float* __restrict__ loss) {
-    pdl_entry();
     __shared__ float red[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < B; i += 1024) {
@@ -228,7 +223,6 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
                         float cos_m, float sin_m, float theta, const __nv_bfloat16* __restrict__ xn,
                         __nv_bfloat16* __restrict__ xs, float* __restrict__ coef, __nv_bfloat16* __restrict__ E,
                         int n_pad, float* __restrict__ patch) {
-    pdl_entry();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -261,10 +255,11 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
 }
 
 // E'[i, y_i] = patch[i] for the rows whose class lives on this rank (the deferred half of backward_prepare)
+// pending (lazy update, may be null): set to 1 -- the dW GEMM that follows leaves a gradient the next step applies
 __global__ void apply_target_patch_kernel(__nv_bfloat16* __restrict__ E, int B, const int32_t* __restrict__ labels,
-                                          const float* __restrict__ patch) {
-    pdl_entry();
+                                          const float* __restrict__ patch, int* __restrict__ pending) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row == 0 && pending != nullptr) *pending = 1;
     if (row >= B) return;
     const int lbl = labels[row];
     if (lbl >= 0) E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = __float2bfloat16_rn(patch[row]);
@@ -281,7 +276,6 @@ dx_finalize_d512_kernel(const float* __restrict__ partial, int splits, size_t sp
                         const float* __restrict__ x, const float* __restrict__ inv_norm, float scale, int rows,
                         float* __restrict__ out, const float* __restrict__ patch, const int32_t* __restrict__ labels,
                         const __nv_bfloat16* __restrict__ wn) {
-    pdl_entry();
     __shared__ float part[2][4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = warp >> 2, q = warp & 3;
@@ -340,7 +334,6 @@ dx_finalize_kernel(const float* __restrict__ partial, int splits, size_t split_s
                    const float* __restrict__ x, const float* __restrict__ inv_norm, float scale, int rows, int d,
                    float* __restrict__ out, const float* __restrict__ patch, const int32_t* __restrict__ labels,
                    const __nv_bfloat16* __restrict__ wn) {
-    pdl_entry();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -407,14 +400,18 @@ struct OptArgs {
     int kind;
     float lr, momentum, wd;         // SGD
     float beta1, beta2, eps, bc1, bc2_sqrt;   // Adam(W): bc1 = 1-b1^t, bc2_sqrt = sqrt(1-b2^t)
-    float inv_grad_scale;           // multiplies dw first (GradScaler unscale); 1 otherwise
+    const float* grad_scale;        // device scalar: the loss scale the gradient carries (divided out first), or null
+    const int* step_dev;            // Adam(W): device step counter (the update is step step_dev[0] + 1), or null
 };
+
+__device__ __forceinline__ float opt_inv_grad_scale(const float* grad_scale) {
+    return grad_scale ? 1.f / grad_scale[0] : 1.f;
+}
 
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const float* inv_norm_w,
                    int rows, int d, OptArgs opt, float* __restrict__ dw_out, float* __restrict__ st1,
                    float* __restrict__ st2, __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
-    pdl_entry();
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -434,7 +431,13 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
     }
     dot = warp_sum(dot) * inv;                       // wn . dwn
     const float wscale = dot * inv;                  // (wn . dwn) * wn = w * (dot * inv)
-    const float gs = inv * opt.inv_grad_scale;
+    const float gs = inv * opt_inv_grad_scale(opt.grad_scale);
+    float bc1 = opt.bc1, bc2_sqrt = opt.bc2_sqrt;
+    if (opt.step_dev != nullptr) {                   // CUDA-graph replay: the step count lives on the device
+        const float t = static_cast<float>(opt.step_dev[0] + 1);
+        bc1 = 1.f - powf(opt.beta1, t);
+        bc2_sqrt = sqrtf(1.f - powf(opt.beta2, t));
+    }
     float ss = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
@@ -475,11 +478,11 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
                 v.z = b2 * v.z + (1.f - b2) * a.z * a.z; v.w = b2 * v.w + (1.f - b2) * a.w * a.w;
                 st4(st1 + base + 4 * k, m);
                 st4(st2 + base + 4 * k, v);
-                const float step = opt.lr / opt.bc1;
-                wq.x -= step * m.x / (sqrtf(v.x) / opt.bc2_sqrt + opt.eps);
-                wq.y -= step * m.y / (sqrtf(v.y) / opt.bc2_sqrt + opt.eps);
-                wq.z -= step * m.z / (sqrtf(v.z) / opt.bc2_sqrt + opt.eps);
-                wq.w -= step * m.w / (sqrtf(v.w) / opt.bc2_sqrt + opt.eps);
+                const float step = opt.lr / bc1;
+                wq.x -= step * m.x / (sqrtf(v.x) / bc2_sqrt + opt.eps);
+                wq.y -= step * m.y / (sqrtf(v.y) / bc2_sqrt + opt.eps);
+                wq.z -= step * m.z / (sqrtf(v.z) / bc2_sqrt + opt.eps);
+                wq.w -= step * m.w / (sqrtf(v.w) / bc2_sqrt + opt.eps);
             }
             st4(w + base + 4 * k, wq);
             wv[j] = wq;
@@ -526,9 +529,9 @@ __device__ __forceinline__ void st4_hint(float* p, float4 v, uint64_t pol) {
 template <int NV, bool kGradBf16, bool kL2 = false>
 __global__ void __launch_bounds__(128)
 dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* __restrict__ mom,
-                   const float* inv_norm_w, int rows, float lr, float momentum, float wd, float inv_grad_scale,
-                   __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
-    pdl_entry();
+                   const float* inv_norm_w, int rows, float lr, float momentum, float wd,
+                   const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
+    const float inv_grad_scale = opt_inv_grad_scale(grad_scale);
     constexpr int d = 128 * NV;
     const int lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
@@ -605,12 +608,102 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
     }
 }
 
+// Lazy mode: the SAME update as dw_sgd_rows_kernel, applied at the START of the next step, co-resident with the FX
+// kernel (pfc_fx.cuh) that consumes the rewritten bf16 shard tile by tile.  Persistent (one CTA per SM, 4 warps, 64
+// registers, no shared memory: fits next to FX's one CTA per SM), rows taken in the order FX asks for its class tiles
+// (tile_order, pfc_fx_tile_order), one row per warp and trip.  wn_ready[tile] counts finished rows; a row is
+// published one trip late, behind the fence that the NEXT row's loads have to wait for anyway, so the release costs
+// the streaming warp nothing.  *pending == 0 (nothing to apply: first step, or after a flush): only the counters move.
+// grad_scale (device scalar or nullptr): the loss scale the gradient carries (GradScaler flow), divided out here.
+template <int NV>
+__global__ void __launch_bounds__(128)
+dw_sgd_ordered_kernel(const __nv_bfloat16* __restrict__ dwn, float* __restrict__ w, float* __restrict__ mom,
+                      float* inv_norm_w, int rows, float lr, float momentum, float wd, const float* __restrict__ grad_scale,
+                      __nv_bfloat16* __restrict__ wn, const int* __restrict__ tile_order, int num_tiles,
+                      int* wn_ready, const int* __restrict__ pending) {
+    constexpr int d = 128 * NV;
+    constexpr int TILE = 256;
+    const int lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    const int wid = threadIdx.x >> 5;
+    const int blocks_per_tile = TILE / warps;
+    const int total = num_tiles * blocks_per_tile;
+    const bool apply = pending == nullptr || *pending != 0;
+    const float igs = grad_scale ? 1.f / grad_scale[0] : 1.f;
+    int publish = -1;                                    // tile of the row this warp finished in the previous trip
+    for (int vb = blockIdx.x; vb < total; vb += gridDim.x) {
+        const int tile = tile_order[vb / blocks_per_tile];
+        const int row = tile * TILE + (vb % blocks_per_tile) * warps + wid;
+        if (row >= rows) continue;                       // warp-uniform
+        if (!apply) {
+            if (lane == 0) atomicAdd(wn_ready + tile, 1);
+            continue;
+        }
+        const size_t base = static_cast<size_t>(row) * d;
+        float4 g[NV], wv[NV], mv[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint2 r;
+            const __nv_bfloat16* gp = dwn + base + 4 * (lane + 32 * j);
+            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(gp));
+            g[j] = unpack4_bf16(r);
+        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) wv[j] = ld4(w + base + 4 * (lane + 32 * j));
+#pragma unroll
+        for (int j = 0; j < NV; ++j) mv[j] = ld4(mom + base + 4 * (lane + 32 * j));
+        const float inv = inv_norm_w[row];
+        if (publish >= 0) {                              // previous row: its stores were issued a whole trip ago
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(wn_ready + publish, 1);
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+            dot += wv[j].x * g[j].x + wv[j].y * g[j].y + wv[j].z * g[j].z + wv[j].w * g[j].w;
+        dot = warp_sum(dot) * inv;
+        const float wscale = dot * inv;
+        const float gs = inv * igs;
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            float4 a, b = mv[j], q = wv[j];
+            a.x = (g[j].x - q.x * wscale) * gs + wd * q.x;
+            a.y = (g[j].y - q.y * wscale) * gs + wd * q.y;
+            a.z = (g[j].z - q.z * wscale) * gs + wd * q.z;
+            a.w = (g[j].w - q.w * wscale) * gs + wd * q.w;
+            b.x = momentum * b.x + a.x; b.y = momentum * b.y + a.y;
+            b.z = momentum * b.z + a.z; b.w = momentum * b.w + a.w;
+            q.x -= lr * b.x; q.y -= lr * b.y; q.z -= lr * b.z; q.w -= lr * b.w;
+            st4(mom + base + 4 * (lane + 32 * j), b);
+            st4(w + base + 4 * (lane + 32 * j), q);
+            wv[j] = q;
+            ss += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
+        }
+        ss = warp_sum(ss);
+        const float denom = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            const float4 q = make_float4(wv[j].x / denom, wv[j].y / denom, wv[j].z / denom, wv[j].w / denom);
+            *reinterpret_cast<uint2*>(wn + base + 4 * (lane + 32 * j)) = pack4_bf16(q);
+        }
+        if (lane == 0) inv_norm_w[row] = 1.f / denom;
+        publish = tile;
+    }
+    if (publish >= 0) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(wn_ready + publish, 1);
+    }
+}
+
 static int g_sgd_persistent_warps = 0;   // 0: one row per warp, full grid; > 0: that many warps per SM, grid-stride
 
 template <int NV>
 static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom, const float* inv_norm_w, int rows,
-                               float lr, float momentum, float wd, float igs, __nv_bfloat16* wn_next, float* inv_next,
-                               cudaStream_t st) {
+                               float lr, float momentum, float wd, const float* igs, __nv_bfloat16* wn_next,
+                               float* inv_next, cudaStream_t st) {
     int grid = (rows + 3) / 4, block = 128;
     if (g_sgd_persistent_warps > 0) {
         int dev = 0, sms = 148;
@@ -769,10 +862,11 @@ int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const 
     return check_launch();
 }
 
-int pfc_apply_target_patch(void* E, int n_pad, int B, const int32_t* labels_local, const float* patch, void* stream) {
+int pfc_apply_target_patch(void* E, int n_pad, int B, const int32_t* labels_local, const float* patch, int* pending,
+                           void* stream) {
     if (B <= 0 || n_pad % 64 || !patch) return PFC_ERR_SHAPE;
     launch_step_kernel(PDL_PREPARE, apply_target_patch_kernel, (B + 255) / 256, 256, 0, (cudaStream_t)stream,
-        reinterpret_cast<__nv_bfloat16*>(E), B, labels_local, patch);
+        reinterpret_cast<__nv_bfloat16*>(E), B, labels_local, patch, pending);
     return check_launch();
 }
 
@@ -813,16 +907,16 @@ int pfc_dx_finalize_patched(const float* partial, int splits, const float* coef,
 int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, int rows, int d, float inv_grad_scale,
                     float* dw, void* stream) {
     if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
+    if (inv_grad_scale != 1.f) return PFC_ERR_SHAPE;   // the un-fused gradient keeps the loss scale (GradScaler.unscale_)
     OptArgs o = {};
     o.kind = OPT_NONE;
-    o.inv_grad_scale = inv_grad_scale;
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         dwn, const_cast<float*>(w), inv_norm_w, rows, d, o, dw, nullptr, nullptr, nullptr, nullptr);
     return check_launch();
 }
 
 int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float* inv_norm_w, int rows, int d, float lr,
-               float momentum, float weight_decay, float inv_grad_scale, void* wn_next, float* inv_norm_next,
+               float momentum, float weight_decay, const float* grad_scale, void* wn_next, float* inv_norm_next,
                void* stream) {
     if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
     if (d % 128 == 0 && mom != nullptr) {
@@ -830,7 +924,7 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
         __nv_bfloat16* wnn = reinterpret_cast<__nv_bfloat16*>(wn_next);
         const bool bf = dwn_bf16 != 0;
 #define PFC_SGD_CASE(NV) \
-    launch_dw_sgd_rows<NV>(dwn, bf, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, inv_grad_scale, wnn, \
+    launch_dw_sgd_rows<NV>(dwn, bf, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, grad_scale, wnn, \
                            inv_norm_next, st)
         switch (d / 128) {
             case 1: PFC_SGD_CASE(1); break;
@@ -848,23 +942,55 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
     if (dwn_bf16) return PFC_ERR_SHAPE;   // the generic row kernel reads an fp32 gradient
     OptArgs o = {};
     o.kind = OPT_SGD;
-    o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.inv_grad_scale = inv_grad_scale;
+    o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.grad_scale = grad_scale;
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         static_cast<const float*>(dwn), w, inv_norm_w, rows, d, o, nullptr, mom, nullptr,
         reinterpret_cast<__nv_bfloat16*>(wn_next), inv_norm_next);
     return check_launch();
 }
 
+// The fused SGD update of pfc_dw_sgd as a persistent, ordered kernel that publishes its progress per class tile
+// (lazy mode, see dw_sgd_ordered_kernel).  d must be a multiple of 128 (<= 1024); dwn is the bf16 gradient spill.
+int pfc_dw_sgd_ordered(const void* dwn_bf16, float* w, float* mom, float* inv_norm_w, int rows, int d, float lr,
+                       float momentum, float weight_decay, const float* grad_scale, void* wn, const int32_t* tile_order,
+                       int num_tiles, int* wn_ready, const int* pending, void* stream) {
+    if (rows <= 0 || d <= 0 || d % 128 || d > 128 * MAXV || num_tiles != (rows + 255) / 256) return PFC_ERR_SHAPE;
+    if (!dwn_bf16 || !w || !mom || !inv_norm_w || !wn || !tile_order || !wn_ready) return PFC_ERR_SHAPE;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(dwn_bf16);
+    __nv_bfloat16* wnp = reinterpret_cast<__nv_bfloat16*>(wn);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PFC_ORD_CASE(NV) \
+    dw_sgd_ordered_kernel<NV><<<sms, 128, 0, st>>>(g, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, grad_scale, \
+                                                   wnp, tile_order, num_tiles, wn_ready, pending)
+    switch (d / 128) {
+        case 1: PFC_ORD_CASE(1); break;
+        case 2: PFC_ORD_CASE(2); break;
+        case 3: PFC_ORD_CASE(3); break;
+        case 4: PFC_ORD_CASE(4); break;
+        case 5: PFC_ORD_CASE(5); break;
+        case 6: PFC_ORD_CASE(6); break;
+        case 7: PFC_ORD_CASE(7); break;
+        default: PFC_ORD_CASE(8); break;
+    }
+#undef PFC_ORD_CASE
+    return check_launch();
+}
+
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
-                float inv_grad_scale, void* wn_next, float* inv_norm_next, void* stream) {
-    if (rows <= 0 || bad_d(d) || step <= 0) return PFC_ERR_SHAPE;
+                const float* grad_scale, void* wn_next, float* inv_norm_next, const int* step_dev, void* stream) {
+    if (rows <= 0 || bad_d(d) || (step <= 0 && !step_dev)) return PFC_ERR_SHAPE;
+    if (step <= 0) step = 1;
     OptArgs o = {};
     o.kind = decoupled ? OPT_ADAMW : OPT_ADAM;
     o.lr = lr; o.wd = weight_decay; o.beta1 = beta1; o.beta2 = beta2; o.eps = eps;
     o.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     o.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
-    o.inv_grad_scale = inv_grad_scale;
+    o.grad_scale = grad_scale;
+    o.step_dev = step_dev;
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         dwn, w, inv_norm_w, rows, d, o, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(wn_next),
         inv_norm_next);

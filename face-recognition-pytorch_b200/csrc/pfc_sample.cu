@@ -70,40 +70,13 @@ hist_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, i
     if (PASS == 0 && threadIdx.x == 0 && npos_s) atomicAdd(&st->n_pos, npos_s);
 }
 
-// single warp: walk the bins from the top until the running count reaches k_rem
-template <int PASS>
-__global__ void pick_kernel(SelState* st, int num_sample, int nl) {
-    if (threadIdx.x != 0) return;
-    if (PASS == 0) {
-        uint32_t k = st->n_pos > (uint32_t)num_sample ? st->n_pos : (uint32_t)num_sample;
-        if (k > (uint32_t)nl) k = nl;
-        st->k_eff = k;
-        st->k_rem = k;
-        st->prefix = 0;
-    }
-    uint32_t rem = st->k_rem;
-    const int bins = 1 << radix_bits(PASS);
-    int b = bins - 1;
-    if (rem == 0) {   // nothing to select: threshold above every key
-        st->prefix = 0xFFFFFFFFu;
-        return;
-    }
-    for (; b > 0; --b) {
-        const uint32_t c = st->hist[PASS][b];
-        if (c >= rem) break;
-        rem -= c;
-    }
-    st->prefix |= static_cast<uint32_t>(b) << radix_shift(PASS);
-    st->k_rem = rem;
-}
-
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t& total);
 
-// Same result as pick_kernel with the whole CTA: the serial walk "from the top bin down until the running count reaches
-// k_rem" stops at b* = max{ b >= 1 : I(b) >= k_rem } (0 if there is none), I(b) = sum of hist[j] over j >= b, and leaves
+// Pick the digit of this pass: walking the bins from the top down until the running count reaches k_rem stops at
+// b* = max{ b >= 1 : I(b) >= k_rem } (0 if there is none), I(b) = sum of hist[j] over j >= b, and leaves
 // k_rem - (I(b*) - hist[b*]).  I is an inclusive scan over the bins in reversed order; the first reversed position that
-// reaches k_rem is taken with an atomicMin.  pick_kernel's single thread pays one dependent L2 load per bin walked
-// (~500-1000 bins per pass: 50-100 us of the sampler's 190 us); this is one scan.
+// reaches k_rem is taken with an atomicMin.  (A single-thread walk, one dependent L2 load per bin, cost 50-100 us of a
+// 190 us sampler in round 1; this is one CTA-wide scan.)
 template <int PASS>
 __global__ void __launch_bounds__(1024)
 pick_parallel_kernel(SelState* st, int num_sample, int nl) {
@@ -288,196 +261,6 @@ __global__ void remap_labels_kernel(const int32_t* __restrict__ labels, int B, c
     out[j] = l >= 0 ? slot_of[l] : -1;
 }
 
-// Which pick kernel the sampler uses: the CTA-wide scan (1, default) or the serial single-thread walk (0, kept as the
-// cross-check).  Measured on B200, whole sampler, eager launches: 184 -> 72 us at the cfg-3 rank shape (nl = 45 029),
-// 160 -> 73 us at cfg-4 (nl = 257 489); identical index sets on the six oracle cases (tools/check_pick.py).
-// PFC_SAMPLE_PICK=parallel|serial in the environment, pfc_debug_sample_pick() at run time.
-#ifndef PFC_SAMPLE_PICK_DEFAULT
-#define PFC_SAMPLE_PICK_DEFAULT 1
-#endif
-static int g_pick_parallel = -1;
-static bool pick_parallel() {
-    if (g_pick_parallel < 0) {
-        const char* e = getenv("PFC_SAMPLE_PICK");
-        g_pick_parallel = e ? (e[0] == 'p' || e[0] == '1') : PFC_SAMPLE_PICK_DEFAULT;
-    }
-    return g_pick_parallel != 0;
-}
-
-// exclusive scan of a 64-bit value over the 1024 threads of the CTA (two 32-bit counters packed side by side)
-__device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long long v, unsigned long long* warp_tot,
-                                                                 unsigned long long& total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned long long inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long n = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += n;
-    }
-    if (lane == 31) warp_tot[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        const unsigned long long t = warp_tot[lane];
-        unsigned long long ti = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long n = __shfl_up_sync(0xffffffffu, ti, o);
-            if (lane >= o) ti += n;
-        }
-        warp_tot[lane] = ti - t;
-        if (lane == 31) warp_tot[32] = ti;
-    }
-    __syncthreads();
-    total = warp_tot[32];
-    const unsigned long long r = warp_tot[w] + inc - v;
-    __syncthreads();
-    return r;
-}
-
-// The whole sampler in ONE launch of ONE CTA, for shards of up to FUSED_MAX_NL classes (cfg-3's rank shape: 45 029
-// scores = 180 KB, L2-resident; the 12-launch pipeline above costs ~6 us of launch latency per stage there).  Same
-// algorithm and the same tie rule, stage by stage: flags, three histogram + pick passes (CTA-wide suffix scan as in
-// pick_parallel_kernel), then an ordered compaction that walks the array in tiles of 8192 keys with ONE packed scan
-// per tile: an element's output position is (#keys > T before it) + min(#keys == T before it, need_eq).
-// Opt-in (PFC_SAMPLE_FUSED=1 / pfc_debug_sample_fused): written after the round's GPU budget was spent, never run.
-constexpr int FUSED_MAX_NL = 65536;
-__global__ void __launch_bounds__(SEL_THREADS)
-sample_fused_kernel(const float* __restrict__ perm, const int32_t* __restrict__ labels, int B, int nl, int num_sample,
-                    uint8_t* flags, int32_t* slot_of, int64_t* __restrict__ index_out, int32_t* __restrict__ n_out,
-                    int32_t* __restrict__ labels_remapped) {
-    __shared__ uint32_t h[MAX_BINS];
-    __shared__ uint32_t incl[MAX_BINS];
-    __shared__ uint32_t wt[33];
-    __shared__ unsigned long long wt64[33];
-    __shared__ uint32_t s_npos, s_prefix, s_rem, s_keff, s_rstar;
-    const int T = threadIdx.x;
-    for (int i = T; i < nl; i += SEL_THREADS) flags[i] = 0;
-    if (T == 0) { s_npos = 0; s_prefix = 0; s_rem = 0; s_keff = 0; }
-    __syncthreads();
-    for (int j = T; j < B; j += SEL_THREADS) {
-        const int l = labels[j];
-        if (l >= 0) flags[l] = 1;
-    }
-    __syncthreads();
-    uint32_t prefix = 0, rem = 0;
-    for (int pass = 0; pass < 3; ++pass) {
-        const int bits = pass == 2 ? 10 : 11;
-        const int shift = pass == 0 ? 21 : (pass == 1 ? 10 : 0);
-        const int bins = 1 << bits;
-        const uint32_t hi_mask = pass == 0 ? 0u : (pass == 1 ? 0xFFE00000u : 0xFFFFFC00u);
-        const uint32_t dmask = (1u << bits) - 1;
-        for (int b = T; b < MAX_BINS; b += SEL_THREADS) h[b] = 0;
-        __syncthreads();
-        uint32_t np = 0;
-        for (int i = T; i < nl; i += SEL_THREADS) {
-            const uint32_t k = key_of(perm, flags, i);
-            if (pass == 0) np += flags[i];
-            if ((k & hi_mask) == prefix) atomicAdd(&h[(k >> shift) & dmask], 1u);
-        }
-        if (pass == 0) {
-            np = __reduce_add_sync(0xffffffffu, np);
-            if ((T & 31) == 0 && np) atomicAdd(&s_npos, np);
-        }
-        __syncthreads();
-        if (pass == 0) {
-            if (T == 0) {
-                uint32_t k = s_npos > (uint32_t)num_sample ? s_npos : (uint32_t)num_sample;
-                if (k > (uint32_t)nl) k = nl;
-                s_keff = k;
-                s_rem = k;
-            }
-            __syncthreads();
-        }
-        rem = s_rem;
-        if (rem == 0) {                       // nothing to select (CTA-uniform): threshold above every key
-            prefix = 0xFFFFFFFFu;
-            break;
-        }
-        // pick: largest bin b >= 1 whose inclusive suffix count reaches rem (0 if none), see pick_parallel_kernel
-        if (T == 0) s_rstar = bins - 1;
-        uint32_t v[2], sum = 0;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int r = T * 2 + u;          // reversed bin index
-            v[u] = r < bins ? h[bins - 1 - r] : 0u;
-            sum += v[u];
-        }
-        uint32_t tot;
-        uint32_t run = block_excl_scan(sum, wt, tot);     // its first barrier also publishes s_rstar
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int r = T * 2 + u;
-            run += v[u];
-            if (r < bins) {
-                incl[r] = run;
-                if (run >= rem && r < bins - 1) atomicMin(&s_rstar, static_cast<uint32_t>(r));
-            }
-        }
-        __syncthreads();
-        if (T == 0) {
-            const uint32_t r = s_rstar;
-            s_prefix = prefix | (static_cast<uint32_t>(bins - 1 - r) << shift);
-            s_rem = rem - (incl[r] - h[bins - 1 - r]);
-        }
-        __syncthreads();
-        prefix = s_prefix;
-        rem = s_rem;
-    }
-    // ordered compaction
-    const uint32_t Tkey = prefix, need_eq = rem, keff = s_keff;
-    const bool none = keff == 0;
-    if (T == 0) n_out[0] = static_cast<int32_t>(keff);
-    uint32_t gt_before = 0, eq_before = 0;
-    for (int base0 = 0; base0 < nl; base0 += SEL_TILE) {
-        const int base = base0 + T * SEL_ITEMS;
-        uint32_t isgt = 0, iseq = 0, ng = 0, ne = 0;
-#pragma unroll
-        for (int u = 0; u < SEL_ITEMS; ++u) {
-            const int i = base + u;
-            if (i < nl && !none) {
-                const uint32_t k = key_of(perm, flags, i);
-                if (k > Tkey) { isgt |= 1u << u; ++ng; }
-                if (k == Tkey) { iseq |= 1u << u; ++ne; }
-            }
-        }
-        unsigned long long total;
-        const unsigned long long ex =
-            block_excl_scan64((static_cast<unsigned long long>(ne) << 32) | ng, wt64, total);
-        uint32_t e_rank = eq_before + static_cast<uint32_t>(ex >> 32);
-        uint32_t pos = gt_before + static_cast<uint32_t>(ex & 0xffffffffu) + min(e_rank, need_eq);
-#pragma unroll
-        for (int u = 0; u < SEL_ITEMS; ++u) {
-            bool take = (isgt >> u) & 1u;
-            if ((iseq >> u) & 1u) {
-                take = e_rank < need_eq;
-                ++e_rank;
-            }
-            if (take) {
-                const int i = base + u;
-                index_out[pos] = i;
-                if (flags[i]) slot_of[i] = static_cast<int32_t>(pos);
-                ++pos;
-            }
-        }
-        gt_before += static_cast<uint32_t>(total & 0xffffffffu);
-        eq_before += static_cast<uint32_t>(total >> 32);
-    }
-    __syncthreads();                          // every slot_of entry of a positive class is written
-    for (int j = T; j < B; j += SEL_THREADS) {
-        const int l = labels[j];
-        labels_remapped[j] = l >= 0 ? slot_of[l] : -1;
-    }
-}
-
-static int g_sample_fused = -1;
-static bool sample_fused() {
-    if (g_sample_fused < 0) {
-        const char* e = getenv("PFC_SAMPLE_FUSED");
-        g_sample_fused = e ? (atoi(e) != 0) : 0;
-    }
-    return g_sample_fused != 0;
-}
-
 struct SelLayout {
     size_t flags, state, gt, eq, slot, total;
     int tiles;
@@ -502,11 +285,6 @@ using namespace pfc;
 
 extern "C" {
 
-// not part of the public header: 1 = the one-launch sampler for shards of up to 65 536 classes (sample_fused_kernel)
-void pfc_debug_sample_fused(int on) { g_sample_fused = on ? 1 : 0; }
-// not part of the public header: 1 = CTA-wide pick kernel, 0 = serial walk (see pick_parallel())
-void pfc_debug_sample_pick(int parallel) { g_pick_parallel = parallel ? 1 : 0; }
-
 size_t pfc_sample_workspace_bytes(int num_local) { return num_local > 0 ? sel_layout(num_local).total : 0; }
 
 int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_local, int num_sample,
@@ -522,25 +300,16 @@ int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_lo
     uint32_t* gt = reinterpret_cast<uint32_t*>(ws + L.gt);
     uint32_t* eq = reinterpret_cast<uint32_t*>(ws + L.eq);
     int32_t* slot = reinterpret_cast<int32_t*>(ws + L.slot);
-    if (sample_fused() && num_local <= FUSED_MAX_NL) {
-        sample_fused_kernel<<<1, SEL_THREADS, 0, stream>>>(perm, labels_local, B, num_local, num_sample, flags, slot,
-                                                           index_out, n_out, labels_remapped);
-        return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
-    }
     // flags and the selection state are contiguous at the front of the workspace
     if (cudaMemsetAsync(ws, 0, L.gt, stream) != cudaSuccess) return PFC_ERR_CUDA;
     mark_positive_kernel<<<(B + 255) / 256, 256, 0, stream>>>(labels_local, B, flags);
     int hb = L.tiles;   // one CTA per SEL_TILE keys keeps every SM busy for the big shards, 1 CTA for small ones
     hist_kernel<0><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    const bool par = pick_parallel();
-    if (par) pick_parallel_kernel<0><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
-    else pick_kernel<0><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    pick_parallel_kernel<0><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
     hist_kernel<1><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    if (par) pick_parallel_kernel<1><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
-    else pick_kernel<1><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    pick_parallel_kernel<1><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
     hist_kernel<2><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    if (par) pick_parallel_kernel<2><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
-    else pick_kernel<2><<<1, 32, 0, stream>>>(st, num_sample, num_local);
+    pick_parallel_kernel<2><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
     count_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq);
     scan_tiles_kernel<<<1, SEL_THREADS, 0, stream>>>(gt, eq, L.tiles);
     compact_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq, index_out, slot, n_out);

@@ -153,9 +153,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    // everything above is CTA-local (overlaps the tail of the preceding kernel under PDL); global memory from here on
-    if (!prm.pdl_defer) pdl_wait();
-    pdl_launch_dependents();
     const int crank = (CL > 1) ? static_cast<int>(cluster_ctarank()) : 0;
     const int first_tile = (blockIdx.x / CL) * CL + crank;   // cluster c works on tiles CL*c .. CL*c+CL-1, then strides
     const int tile_stride = gridDim.x;                        // gridDim.x is a multiple of CL
@@ -280,7 +277,6 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) tma_store_wait_all();     // this warp's last boxes are in global memory before the CTA exits
     }
 
-    if (prm.pdl_defer) pdl_wait();               // deferred wait: this grid completes only after its predecessor
     tc_fence_before();
     if constexpr (CL > 1) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
     else __syncthreads();

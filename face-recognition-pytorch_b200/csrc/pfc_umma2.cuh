@@ -69,9 +69,6 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    // CTA-local setup above overlaps the preceding kernel's tail; global memory from here on
-    if (!prm.pdl_defer) pdl_wait();
-    pdl_launch_dependents();
     const int first_tile = (blockIdx.x / 2) * 2 + crank;
     const int tile_stride = gridDim.x;
 
@@ -171,7 +168,6 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         if (lane == 0) tma_store_wait_all();
     }
 
-    if (prm.pdl_defer) pdl_wait();               // deferred wait: this grid completes only after its predecessor
     tc_fence_before();
     cluster_sync_all();
     if (warp == 1) {

@@ -11,11 +11,14 @@ collectives included -- NCCL or the peer-memory exchanges) and replays it:
 
 `feat` / `labels` may be device tensors or PINNED host tensors (copied with non_blocking=True on the current stream);
 `loss` and `dx` are static device buffers that the next call overwrites.  Requirements (checked): the head runs with
-conf.fused_optimizer (the update is part of the captured backward), sample_rate == 1 (sampling draws host random
-numbers and patches the optimizer every step) and a constant batch size -- the configuration of BASELINE configs[1].
-Hyper-parameters (lr, momentum, weight decay) are baked in at capture time: call `recapture()` after the scheduler
-changes them.  Capturing needs a few real warm-up steps; the weights and the optimizer state of the head are saved
-before and restored after them, so constructing / recapturing does not train.
+conf.fused_optimizer (the update is part of the captured backward), sample_rate == 1 (sampling patches the optimizer on
+the host every step) and a constant batch size -- the configuration of BASELINE configs[1].  Both heads are supported:
+PartialFC (SGD, also with conf.lazy_update) and PartialFCAdamW (the bias-correction step count lives in a device scalar
+that every replay advances).  Hyper-parameters (lr, momentum / betas, weight decay) are kernel arguments and therefore
+part of the graph: every call compares optimizer.param_groups[-1] and the storage of weight_activated with what was
+captured and re-captures when the scheduler (utils/scheduler.py:87-88) or load_state_dict() changed them.  Capturing
+needs a few real warm-up steps; the weights and the optimizer state of the head are saved before and restored after
+them, so constructing / recapturing does not train.
 """
 import torch
 
@@ -23,13 +26,12 @@ from . import kernels as K
 
 
 class GraphedHeadStep:
-    def __init__(self, head, optimizer, batch, dim, device=None, warmup=2, autograd=True):
-        """autograd=False captures `head.fused_step` (no autograd between forward and backward: three small torch
-        kernels fewer per step) instead of `head(x, labels, opt)` + `loss.backward()`; same results."""
+    def __init__(self, head, optimizer, batch, dim, device=None, warmup=2, autograd=False):
+        """autograd=False (default) captures `head.fused_step` (no autograd between forward and backward: three small
+        torch kernels fewer per step); autograd=True captures `head(x, labels, opt)` + `loss.backward()`.  Same
+        results (tests/test_gpu_modes.py)."""
         if not head.fused_optimizer:
             raise RuntimeError("GraphedHeadStep needs conf.fused_optimizer = True (the update is part of the graph)")
-        if head._optimizer_kind != "sgd":
-            raise RuntimeError("GraphedHeadStep supports the SGD head (Adam's bias-correction step count is host state)")
         if head.sample_rate < 1:
             raise RuntimeError("GraphedHeadStep needs sample_rate == 1 (sampling patches the optimizer on the host)")
         self.head, self.optimizer = head, optimizer
@@ -37,79 +39,93 @@ class GraphedHeadStep:
         if dev.type != "cuda":
             raise RuntimeError("GraphedHeadStep needs a CUDA head")
         self.device = dev
-        # two slots: with conf.overlap_update the normalised shard ping-pongs between two buffers, so consecutive
-        # steps are two different graphs that are replayed alternately; otherwise one graph serves every step
-        self._x = [torch.zeros(batch, dim, device=dev).requires_grad_(True) for _ in range(2)]
-        self._labels = [torch.zeros(batch, dtype=torch.int64, device=dev) for _ in range(2)]
-        self._loss = [None, None]
-        self._dx = [None, None]
+        self._x = torch.zeros(batch, dim, device=dev).requires_grad_(True)
+        self._labels = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self._loss = None
+        self._dx = None
         self._autograd = bool(autograd)
-        self._graphs = None
+        self._graph = None
         self._warmup = warmup
+        self._captured = None
         self.recapture()
 
     # ------------------------------------------------------------------
-    def _eager(self, k):
+    def _eager(self):
         if not self._autograd:
-            loss, self._dx[k] = self.head.fused_step(self._x[k].detach(), self._labels[k], self.optimizer)
+            loss, self._dx = self.head.fused_step(self._x.detach(), self._labels, self.optimizer)
             return loss
-        self._x[k].grad = None
-        loss = self.head(self._x[k], self._labels[k], self.optimizer)
+        self._x.grad = None
+        loss = self.head(self._x, self._labels, self.optimizer)
         loss.backward()
-        self._dx[k] = self._x[k].grad
+        self._dx = self._x.grad
         return loss
 
-    def _parity(self):
-        return 0 if self.head._ws is None or self.head._ws.wn.data_ptr() == self._wn_ptr0 else 1
+    def _signature(self):
+        """What the captured kernels have baked in: the head's hyper-parameters and the storage they update."""
+        g = self.optimizer.param_groups[-1]
+        hp = tuple((k, g[k]) for k in ("lr", "momentum", "weight_decay", "betas", "eps") if k in g)
+        return hp, self.head.weight_activated.data_ptr()
+
+    def _optimizer_state(self):
+        head = self.head
+        st = head._fused_state
+        if st is None:
+            return []
+        return list(st) if isinstance(st, (tuple, list)) else [st]
 
     def recapture(self):
-        """(Re)build the graph(s) from the head's current state and the optimizer's current hyper-parameters."""
+        """(Re)build the graph from the head's current state and the optimizer's current hyper-parameters."""
         head = self.head
+        head.flush()                                   # conf.lazy_update: start from weights that owe nothing
         torch.cuda.synchronize(self.device)
         w = head.weight_activated.data
         saved_w = w.clone()
-        saved_state = None if head._fused_state is None else head._fused_state.clone()
+        had_state = head._fused_state is not None
+        saved_state = [t.clone() for t in self._optimizer_state()]
+        saved_step = head.step
+        head._graph_steps = head._optimizer_kind != "sgd"
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):                      # warm-up on a side stream, as graph capture requires
-            for i in range(max(2, self._warmup)):
-                self._eager(i % 2)
+            for _ in range(max(2, self._warmup)):
+                self._eager()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         ws = head._ws
-        self._wn_ptr0 = ws.wn.data_ptr()
-        graphs = {}
-        for _ in range(2):
-            k = self._parity()
-            g = torch.cuda.CUDAGraph()
-            self._x[k].grad = None
-            with torch.cuda.graph(g):
-                self._loss[k] = self._eager(k)              # capturing flips the ping-pong on the host side only
-            graphs[k] = g
-            if ws.wn_alt is None:
-                graphs[1 - k] = g
-                self._loss[1 - k] = self._loss[k]
-                self._dx[1 - k] = self._dx[k]
-                self._x[1 - k], self._labels[1 - k] = self._x[k], self._labels[k]
-                break
+        g = torch.cuda.CUDAGraph()
+        self._x.grad = None
+        with torch.cuda.graph(g):
+            self._loss = self._eager()
         torch.cuda.synchronize(self.device)
-        self._graphs = graphs
-        # undo the warm-up steps: weights, momentum and the normalised bf16 shard the graph's first replay will read
+        self._graph = g
+        # undo the warm-up steps: weights, optimizer state, step count, the pending lazy update and the normalised bf16
+        # shard the graph's first replay will read
         w.copy_(saved_w)
-        if saved_state is not None:
-            head._fused_state.copy_(saved_state)
-        elif head._fused_state is not None:
-            head._fused_state.zero_()
+        if had_state:
+            for t, s in zip(self._optimizer_state(), saved_state):
+                t.copy_(s)
+        else:
+            for t in self._optimizer_state():
+                t.zero_()
+        head.step = saved_step
+        ws.adam_step.fill_(saved_step)
+        ws.pending.zero_()
+        head._pending, head._pending_opt = False, None
         K.l2norm_rows(w, None, head._n, ws.wn, ws.inv_w)
         head._wn_valid = True
         torch.cuda.synchronize(self.device)
+        self._captured = self._signature()
 
     def __call__(self, feat, labels):
-        k = self._parity()
-        self._x[k].data.copy_(feat, non_blocking=True)
-        self._labels[k].copy_(labels.reshape(-1), non_blocking=True)
-        self._graphs[k].replay()
-        ws = self.head._ws
-        if ws.wn_alt is not None:
-            ws.wn, ws.wn_alt = ws.wn_alt, ws.wn             # what the replayed step did on the device
-        return self._loss[k], (self._x[k].grad if self._autograd else self._dx[k])
+        if self._signature() != self._captured:
+            self.recapture()               # the scheduler changed lr, or load_state_dict() rebound the weights
+        head = self.head
+        self._x.data.copy_(feat, non_blocking=True)
+        self._labels.copy_(labels.reshape(-1), non_blocking=True)
+        self._graph.replay()
+        # host mirrors of what the replayed step did on the device
+        if head.lazy_update:
+            head._pending = True
+        if head._optimizer_kind != "sgd":
+            head.step += 1
+        return self._loss, (self._x.grad if self._autograd else self._dx)

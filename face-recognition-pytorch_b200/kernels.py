@@ -30,24 +30,6 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def set_pdl(mode):
-    """Programmatic dependent launch of the step kernels (pfc_set_pdl, include/pfc.h): 0 off, 1 on, 2 on + deferred
-    waits for the GEMMs declared independent of their predecessor.  Process-wide, takes effect for the launches (and
-    CUDA-graph captures) that follow.  Returns the previous mode."""
-    prev = int(lib.pfc_get_pdl())
-    lib.pfc_set_pdl(int(mode))
-    return prev
-
-
-def get_pdl():
-    return int(lib.pfc_get_pdl())
-
-
-def pdl_independent_next():
-    """The next backward_dx / backward_dw does not depend on the kernel launched just before it (include/pfc.h)."""
-    lib.pfc_pdl_independent_next()
-
-
 # ---- accounting used by bench.py: how many kernels were launched, and (optionally) their device time
 _LAUNCHES_PER_CALL = {"pfc_sample": 11}
 _count = 0
@@ -101,6 +83,17 @@ num_class_tiles = lib.pfc_num_class_tiles
 part_sum_cols = lib.pfc_part_sum_cols
 dx_splits = lib.pfc_dx_splits
 dx_max_splits = lib.pfc_dx_max_splits
+fx_splits = lib.pfc_fx_splits
+fx_max_splits = lib.pfc_fx_max_splits
+fx_counter_words = lib.pfc_fx_counter_words
+
+
+def fx_tile_order(B, n, d):
+    """int32 [ceil(n / 256)] host tensor: the order in which pfc_forward_dx asks for the 256-class tiles of the shard."""
+    ct = (n + 255) // 256
+    out = torch.empty(ct, dtype=torch.int32)
+    check(lib.pfc_fx_tile_order(B, n, d, ctypes.c_void_p(out.data_ptr())), "pfc_fx_tile_order")
+    return out
 sample_workspace_bytes = lib.pfc_sample_workspace_bytes
 hist_bins = lib.pfc_eval_hist_bins
 
@@ -169,6 +162,17 @@ def forward(xn, wn, labels_local, B, n, d, s, margin_kind, m2, m3, filter_thr, E
                           _p(tgt_z, F32), _stream()), "pfc_forward")
 
 
+@_timed("pfc_forward_dx")
+def forward_dx(xn, wn, labels_local, B, n, d, s, margin_kind, m2, m3, filter_thr, E, n_pad, part_sum, tgt_raw, tgt_e,
+               tgt_z, partial, splits, counters, wn_gate):
+    """pfc_forward with the target column of E' left at 0, plus the dX partials of that spill (csrc/pfc_fx.cuh).
+    counters must be zero on entry; wn_gate: wait for pfc_dw_sgd_ordered's per-tile progress before reading wn."""
+    check(lib.pfc_forward_dx(_p(xn, BF16), _p(wn, BF16), _p(labels_local, I32), B, n, d, s, margin_kind, m2, m3,
+                             filter_thr, _p(E, BF16), n_pad, _p(part_sum, F32), _p(tgt_raw, F32), _p(tgt_e, F32),
+                             _p(tgt_z, F32), _p(partial, F32), splits, _p(counters, I32), int(bool(wn_gate)), _stream()),
+          "pfc_forward_dx")
+
+
 @_timed("pfc_margin_apply")
 def margin_apply(logits, labels, margin_kind, s, m2, m3, filter_thr, out, gate):
     B, n = logits.shape
@@ -211,9 +215,9 @@ def backward_prepare_deferred(stats, row_L, grad_loss, s, B, d, labels_local, tg
 
 
 @_timed("pfc_apply_target_patch")
-def apply_target_patch(E, n_pad, B, labels_local, patch):
-    check(lib.pfc_apply_target_patch(_p(E, BF16), n_pad, B, _p(labels_local, I32), _p(patch, F32), _stream()),
-          "pfc_apply_target_patch")
+def apply_target_patch(E, n_pad, B, labels_local, patch, pending=None):
+    check(lib.pfc_apply_target_patch(_p(E, BF16), n_pad, B, _p(labels_local, I32), _p(patch, F32), _p(pending, I32),
+                                     _stream()), "pfc_apply_target_patch")
 
 
 @_timed("pfc_dx_finalize_patched")
@@ -236,11 +240,11 @@ def dx_finalize(partial, splits, coef, x, inv_norm, scale, rows, rows_total, d, 
 
 
 @_timed("pfc_backward_dw")
-def backward_dw(E, n_pad, xs, B, n, d, dwn):
-    """dwn: fp32 [n,d], or bf16 [n,d] (fused-SGD spill)."""
+def backward_dw(E, n_pad, xs, B, n, d, dwn, keep_in_l2=True):
+    """dwn: fp32 [n,d], or bf16 [n,d] (fused-SGD spill; keep_in_l2: the update kernel runs right behind this GEMM)."""
     is_bf16 = dwn.dtype == BF16
     check(lib.pfc_backward_dw(_p(E, BF16), n_pad, _p(xs, BF16), B, n, d, _p(dwn, BF16 if is_bf16 else F32),
-                              int(is_bf16), _stream()), "pfc_backward_dw")
+                              (1 if keep_in_l2 else 2) if is_bf16 else 0, _stream()), "pfc_backward_dw")
 
 
 @_timed("pfc_dw_finalize")
@@ -250,28 +254,32 @@ def dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, dw):
 
 
 @_timed("pfc_dw_sgd")
-def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, inv_grad_scale, wn_next, inv_norm_next):
+def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_scale, wn_next, inv_norm_next):
+    """grad_scale: device scalar holding the loss scale the gradient carries (divided out first), or None."""
     is_bf16 = dwn.dtype == BF16
     check(lib.pfc_dw_sgd(_p(dwn, BF16 if is_bf16 else F32), int(is_bf16), _p(w, F32), _p(mom, F32),
-                         _p(inv_norm_w, F32), rows, d, lr, momentum, weight_decay, inv_grad_scale, _p(wn_next, BF16),
-                         _p(inv_norm_next, F32), _stream()), "pfc_dw_sgd")
+                         _p(inv_norm_w, F32), rows, d, lr, momentum, weight_decay, _p(grad_scale, F32),
+                         _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()), "pfc_dw_sgd")
 
 
-@_timed("pfc_backward_dw_sgd")
-def backward_dw_sgd(E, n_pad, xs, B, n, d, w, mom, inv_norm_w, lr, momentum, weight_decay, inv_grad_scale, wn_next,
-                    inv_norm_next):
-    """dW GEMM with normalise-backward + SGD/momentum + next bf16 shard as its epilogue (d == 512 only)."""
-    check(lib.pfc_backward_dw_sgd(_p(E, BF16), n_pad, _p(xs, BF16), B, n, d, _p(w, F32), _p(mom, F32),
-                                  _p(inv_norm_w, F32), lr, momentum, weight_decay, inv_grad_scale, _p(wn_next, BF16),
-                                  _p(inv_norm_next, F32), _stream()), "pfc_backward_dw_sgd")
+@_timed("pfc_dw_sgd_ordered")
+def dw_sgd_ordered(dwn_bf16, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_scale, wn, tile_order,
+                   counters, pending):
+    """pfc_dw_sgd as a persistent kernel that rewrites the shard in pfc_forward_dx's tile order and publishes its
+    progress in counters[0 : ceil(rows / 256)]; *pending == 0: only the counters move."""
+    check(lib.pfc_dw_sgd_ordered(_p(dwn_bf16, BF16), _p(w, F32), _p(mom, F32), _p(inv_norm_w, F32), rows, d, lr, momentum,
+                                 weight_decay, _p(grad_scale, F32), _p(wn, BF16), _p(tile_order, I32),
+                                 tile_order.numel(), _p(counters, I32), _p(pending, I32), _stream()),
+          "pfc_dw_sgd_ordered")
 
 
 @_timed("pfc_dw_adam")
 def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, weight_decay, step, decoupled,
-            inv_grad_scale, wn_next, inv_norm_next):
+            grad_scale, wn_next, inv_norm_next, step_dev=None):
+    """step_dev (int32 device scalar): the update is step step_dev[0] + 1 (CUDA-graph replay), `step` is ignored."""
     check(lib.pfc_dw_adam(_p(dwn, F32), _p(w, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), _p(inv_norm_w, F32), rows,
-                          d, lr, beta1, beta2, eps, weight_decay, step, int(decoupled), inv_grad_scale,
-                          _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()), "pfc_dw_adam")
+                          d, lr, beta1, beta2, eps, weight_decay, step, int(decoupled), _p(grad_scale, F32),
+                          _p(wn_next, BF16), _p(inv_norm_next, F32), _p(step_dev, I32), _stream()), "pfc_dw_adam")
 
 
 # ---- peer-memory exchanges (peer_* are ctypes arrays of W mapped device pointers, see partial_fc._PeerExchange)

@@ -17,29 +17,27 @@ The collectives are the naturally sharded ones issued thr
 Optional keys read from `conf` beyond the reference's five (emd_size, sample_rate, mixed_precision, loss_s, loss_m):
   conf.fused_optimizer (bool, default False): run the SGD / AdamW update of the head inside the backward and leave
       weight_activated.grad = None so optimizer.step() skips it.  Hyper-parameters are re-read from
-      optimizer.param_groups[-1] every step (the scheduler mutates lr, utils/scheduler.py:87-88).  Not valid together
-      with a GradScaler (inf-skipping cannot be honoured); the un-fused default is.
-  conf.fused_dw_update (bool, default False; needs fused_optimizer, SGD, emd_size == 512): run the update as the EPILOGUE
-      of the dW GEMM (pfc_backward_dw_sgd): the un-normalised gradient never leaves tensor memory.  Parity-tested;
-      measured 246 us against 233 us for the two-kernel path at cfg-2, hence opt-in.
+      optimizer.param_groups[-1] every step (the scheduler mutates lr, utils/scheduler.py:87-88).  A scaled loss
+      (GradScaler flow, model/FR_PartialFC.py:178-184) is honoured: dX keeps the scale autograd expects and the fused
+      update divides it out on the device; the scaler's inf-skipping cannot be (bf16 operands do not need a scaler).
+  conf.fx (bool, default True): compute the dX partials inside the forward kernel (pfc_forward_dx, csrc/pfc_fx.cuh)
+      whenever local_embeddings needs a gradient -- the spill E' and the normalised shard are then read from L2
+      instead of HBM and the two contractions share the tensor pipe.  False: separate forward / dX GEMMs.
+  conf.lazy_update (bool, default False; needs fused_optimizer, SGD, sample_rate == 1, emd_size % 128 == 0): backward
+      stops after the dW GEMM; the SGD / momentum update it feeds is applied at the START of the next forward by a
+      persistent kernel that runs underneath the forward + dX kernel (HBM-bound next to tensor-bound, same SMs) and
+      feeds it the rewritten shard tile by tile.  Same arithmetic, same order of updates; only `weight_activated` (and
+      the momentum) lag by one pending update between steps -- `flush()` applies it, and `state_dict()`,
+      `load_state_dict()` and forward passes that do not train call flush() themselves.
   conf.device_sampling (bool, default False): draw the PartialFC sampling scores with the CUDA generator on the device
       instead of `torch.rand` on the CPU generator + H2D copy (nets/PartialFC.py:110).  Removes a host round trip per
       step; the sampled index set is then NOT the reference's for the same seed (same distribution, other stream).
-  conf.dx_side_stream (True / False / "auto", default "auto" = on when world_size > 1): after the dX GEMM the step
-      forks -- the peer scatter + barrier + normalise-backward of dX (one GPU: just the normalise-backward) on a side
-      stream, the rank-local dW GEMM / update on the main one -- and joins before backward returns.  The branches
-      share no buffer; in a CUDA graph they become parallel branches.  Measured (graph replay, cfg-2): 2 GPUs 0.276 ->
-      0.251 ms per step (the barrier wait and two small kernels leave the critical path), 1 GPU 0.383 -> 0.384 ms
-      (neutral, hence off there).  The NCCL path overlaps its reduce-scatter with async_op instead.
-  conf.early_dx (bool, default False; written after the round's GPU budget was spent -- host logic covered on CPU, kernels
-      behind tests/test_gpu_experimental.py): the forward GEMM leaves 0 in the target column of the spill, so the dX
-      GEMM does not need the target patch (a rank-1 term added when the partials are summed) nor the per-row coefficients
-      (applied afterwards).  It is launched on its own stream straight after the forward GEMM and overlaps the row
-      statistics, their exchange, the loss and backward_prepare; backward joins it, writes the patch into the spill
-      and goes on with the dW GEMM.
-  conf.overlap_update (bool, default False; needs fused_optimizer): run the fused update on a side stream underneath
-      the dX GEMM.  The normalised shard is then double-buffered and the two buffers swap roles every step, so a
-      CUDA graph of the step must capture an EVEN number of steps (bench.py captures two).
+  conf.dx_side_stream (True / False / "auto", default "auto" = on when world_size > 1 or conf.fx): after the dX
+      partials exist the step forks -- the peer scatter + barrier + normalise-backward of dX (one GPU: just the
+      normalise-backward) on a side stream, the rank-local dW GEMM / update on the main one -- and joins before
+      backward returns.  The branches share no buffer; in a CUDA graph they become parallel branches.
+  conf.peer_collectives (True / False / "auto"): exchange the batch, the softmax statistics and dX through peer
+      (NVLink) memory with the stores fused into the producing kernels instead of three NCCL collectives.
 """
 import collections
 import contextlib
@@ -77,7 +75,6 @@ class _Workspace:
         self.labels_local = z(B, dt=i32)
         self.labels_act = z(B, dt=i32) if sampled else self.labels_local
         self.wn = z(n_max, d, dt=bf16)
-        self.wn_alt = None                        # second buffer, allocated when conf.overlap_update is set
         self.inv_w = z(n_max)
         self.E = z(B * self.n_pad_max, dt=bf16)
         self.part_sum = z(K.num_class_tiles(n_max) * self.B_pad)
@@ -87,19 +84,34 @@ class _Workspace:
         self.loss = z(1)
         self.ticket = z(1, dt=i32)
         self.coef = z(B)
-        self.patch = z(B)                         # deferred target values of E' (conf.early_dx)
+        self.patch = z(B)                         # target values of E' kept aside while the spill's target column is 0
         self.xs = z(B, d, dt=bf16)
-        self.max_splits = max(1, K.dx_max_splits(B, d))
+        self.max_splits = max(1, K.dx_max_splits(B, d), K.fx_max_splits(B, d))
         self.dx_partial = z(self.max_splits * B * d)
         self.dxn_all = z(B, d) if W > 1 else None
         self.dxn_local = z(b, d) if W > 1 else None
-        self.dwn = z(n_max, d)
-        self.dwn_bf16 = z(n_max, d, dt=bf16)      # fused-SGD mode spills the un-normalised dW in bf16
+        self.dwn = None                           # fp32 un-normalised dW (un-fused / AdamW), allocated on first use
+        self.dwn_bf16 = None                      # bf16 spill of it (fused SGD), allocated on first use
+        # FX kernel (pfc_forward_dx): per-step tile counters; lazy update: tile order, pending flag, loss scale
+        self.counters = z(K.fx_counter_words(B, n_max, d) + 4, dt=i32)
+        self.tile_order = None
+        self.pending = z(1, dt=i32)
+        self.gscale = torch.ones(1, dtype=f32, device=dev)
+        self.adam_step = z(1, dt=i32)
         if sampled:
             self.perm = z(nl)
             self.index = z(n_max, dt=i64)
             self.n_out = z(1, dt=i32)
             self.sample_ws = z(K.sample_workspace_bytes(nl), dt=torch.uint8)
+
+    def grad_buffer(self, bf16, d):
+        if bf16:
+            if self.dwn_bf16 is None:
+                self.dwn_bf16 = torch.zeros(self.n_max, d, dtype=torch.bfloat16, device=self.wn.device)
+            return self.dwn_bf16
+        if self.dwn is None:
+            self.dwn = torch.zeros(self.n_max, d, dtype=torch.float32, device=self.wn.device)
+        return self.dwn
 
 
 class _HeadFunction(torch.autograd.Function):
@@ -136,20 +148,14 @@ class _PartialFCBase(torch.nn.Module):
         self.sample_rate: float = conf.sample_rate
         self.fp16 = conf.mixed_precision           # kept for interface parity; the kernels always run bf16-in / fp32-acc
         self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
-        self.overlap_update = bool(getattr(conf, "overlap_update", False))
-        self.fused_dw_update = bool(getattr(conf, "fused_dw_update", False))
         self.device_sampling = bool(getattr(conf, "device_sampling", False))
+        # forward + dX partials in one kernel (csrc/pfc_fx.cuh) whenever the embeddings need a gradient
+        self.fx = bool(getattr(conf, "fx", True))
+        # apply the fused SGD update at the start of the NEXT forward, underneath the forward + dX kernel
+        self.lazy_update = bool(getattr(conf, "lazy_update", False))
         # run the tail of the dX path (finalize / peer scatter + finalize) on a side stream next to the rank-local
         # dW GEMM + update, which it does not depend on; may be flipped between steps (before a graph capture)
-        self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto" (= world_size > 1)
-        # experiment (not measured yet): launch the dX GEMM right after the forward GEMM, on the unpatched spill and on
-        # its own stream, so that it runs NEXT TO row statistics -> exchange -> loss -> prepare instead of behind them
-        self.early_dx = bool(getattr(conf, "early_dx", False))
-        self._early = None              # (stream or None, splits) of an early dX GEMM that has not been joined yet
-        self._early_stream = None
-        # experiment (not measured yet): create that side stream with high priority, so that its small kernels are
-        # scheduled ahead of the update's thousands of CTAs
-        self.dx_side_priority = bool(getattr(conf, "dx_side_priority", False))
+        self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto"
         self._num_classes = int(num_classes)
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
@@ -184,7 +190,18 @@ class _PartialFCBase(torch.nn.Module):
         self._fused_state = None        # optimizer state for the fused step when sample_rate == 1
         self._n = self.num_local        # active classes this step
         self._opt_args = None
-        self._side_stream = None
+        self._side_stream = None        # dX tail
+        self._upd_stream = None         # lazy update
+        self._fx_splits = None          # slabs of dX partials the forward of this step left in ws.dx_partial
+        self._pending = False           # lazy update: ws.dwn_bf16 holds a gradient that has not been applied yet
+        self._pending_opt = None        # ... and the hyper-parameters of the step that produced it
+        self._gscale_is_one = True
+        self._graph_steps = False       # AdamW: take the bias-correction step count from ws.adam_step (graph replay)
+        if self.lazy_update:
+            if not (self.fused_optimizer and self._optimizer_kind == "sgd" and self.sample_rate >= 1
+                    and self.embedding_size % 128 == 0 and self.embedding_size <= 1024 and self.fx):
+                raise RuntimeError("conf.lazy_update needs conf.fused_optimizer, conf.fx, the SGD head (PartialFC), "
+                                   "sample_rate == 1 and emd_size a multiple of 128 (<= 1024)")
         # True / False / "auto": exchange the batch, the softmax statistics and dX through peer (NVLink) memory with
         # the stores fused into the producing kernels (csrc/pfc_peer.cu) instead of three NCCL collectives
         self.peer_collectives = getattr(conf, "peer_collectives", "auto")
@@ -251,8 +268,6 @@ class _PartialFCBase(torch.nn.Module):
         n_max = self.num_local if not sampled else max(self.num_sample, min(B, self.num_local))
         if self._ws is None or self._ws.b != b or self._ws.xn_local.device != dev:
             self._ws = _Workspace(dev, b, self.world_size, n_max, self.num_local, d, sampled)
-            if self.fused_optimizer and self.overlap_update:
-                self._ws.wn_alt = torch.zeros_like(self._ws.wn)
             self._wn_valid = False
             if sampled:
                 k = 1 + len(self._state_names)
@@ -366,40 +381,72 @@ class _PartialFCBase(torch.nn.Module):
         else:
             self._n = self.num_local
 
-    def _join_early(self):
-        """Order the current stream after an early dX GEMM that is still outstanding (also when backward never ran)."""
-        if self._early is not None:
-            stream, _ = self._early
-            if stream is not None:
-                torch.cuda.current_stream().wait_stream(stream)
-            self._early = None
+    # ---- lazy update (conf.lazy_update)
+    def _launch_lazy_update(self):
+        """The pending SGD step as the ordered, progress-publishing kernel (pfc_dw_sgd_ordered) on the CURRENT stream;
+        ws.counters must be zero.  With nothing pending on the device only the counters move."""
+        ws, d = self._ws, self.embedding_size
+        n = self.num_local
+        w = self.weight_activated.data
+        if ws.tile_order is None:
+            ws.tile_order = K.fx_tile_order(ws.B, n, d).to(w.device)
+        o = self._pending_opt or self._opt_args or self._read_optimizer(self._optimizer)
+        K.dw_sgd_ordered(ws.grad_buffer(True, d), w, self._momentum(w), ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"],
+                         ws.gscale, ws.wn, ws.tile_order, ws.counters, ws.pending)
+
+    @torch.no_grad()
+    def flush(self):
+        """Apply the update a lazy head still owes (conf.lazy_update); a no-op otherwise."""
+        if not (self.lazy_update and self._pending):
+            return
+        ws = self._ws
+        ws.counters.zero_()
+        self._launch_lazy_update()
+        ws.pending.zero_()
+        self._pending = False
+        self._pending_opt = None
 
     def _forward_impl(self, local_embeddings, clone_loss=True, need_dx=False):
         ws, W, d = self._ws, self.world_size, self.embedding_size
         b, B = ws.b, ws.B
         n = self._n
         w = self.weight_activated.data
+        use_fx = self.fx and need_dx
+        if self.fused_optimizer:
+            self._opt_args = self._read_optimizer(self._optimizer)
+        lazy = self.lazy_update and use_fx
+        if self.lazy_update and not lazy:
+            self.flush()                # a forward that does not train sees the up-to-date shard
         if not self._wn_valid:
             K.l2norm_rows(w, None, n, ws.wn, ws.inv_w)                            # :200
             self._wn_valid = True
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
         self._n_pad = K.padded_classes(n)
-        self._join_early()              # a previous step's early dX GEMM (backward skipped) must not read the new spill
-        K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
-                  ws.tgt_raw, ws.tgt_e, ws.tgt_z)                                 # :201-207
-        if (self.early_dx and need_dx and not (self.fused_optimizer and self.overlap_update)
-                and not (self.fused_optimizer and self.fused_dw_update)):
-            # dX partials from the spill as the forward wrote it (target column = 0), next to everything below
-            splits = K.dx_splits(B, n, d)
-            stream = None
-            if w.is_cuda:
-                if self._early_stream is None:
-                    self._early_stream = torch.cuda.Stream(device=w.device)
-                stream = self._early_stream
-                stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext():
-                K.backward_dx(ws.E, self._n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
-            self._early = (stream, splits)
+        self._fx_splits = None
+        if use_fx:
+            # :201-207 plus the dX contraction on the same tiles (target column of E' = 0, fixed up in backward)
+            splits = K.fx_splits(B, n, d)
+            ws.counters.zero_()
+            upd = None
+            if lazy:
+                # the update of the previous step's gradient runs NEXT TO the kernel below and feeds it the shard
+                if w.is_cuda:
+                    if self._upd_stream is None:
+                        self._upd_stream = torch.cuda.Stream(device=w.device)
+                    upd = self._upd_stream
+                    upd.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(upd) if upd is not None else contextlib.nullcontext():
+                    self._launch_lazy_update()
+            K.forward_dx(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
+                         ws.tgt_raw, ws.tgt_e, ws.tgt_z, ws.dx_partial, splits, ws.counters, lazy)
+            if upd is not None:
+                torch.cuda.current_stream().wait_stream(upd)
+            if lazy:
+                self._pending, self._pending_opt = False, None      # consumed (the device flag is set again by backward)
+            self._fx_splits = splits
+        else:
+            K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
+                      ws.tgt_raw, ws.tgt_e, ws.tgt_z)                             # :201-207
         peer = self._peer
         if peer is not None:
             # statistics straight into every peer's slot, then a rank-ordered local sum (identical bits on all ranks)
@@ -414,8 +461,6 @@ class _PartialFCBase(torch.nn.Module):
             K.row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats)
             distributed.all_reduce(ws.stats, distributed.ReduceOp.SUM)            # replaces :448, :453, :459
             K.loss(ws.stats, B, ws.row_L, ws.loss)                                # :461
-        if self.fused_optimizer:
-            self._opt_args = self._read_optimizer(self._optimizer)
         return ws.loss[0].clone() if clone_loss else ws.loss[0]
 
     def _backward_impl(self, x_in, grad_loss, need_dx=None):
@@ -425,116 +470,95 @@ class _PartialFCBase(torch.nn.Module):
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
         need_dx = x_in.requires_grad if need_dx is None else bool(need_dx)
         g = None if grad_loss is None else grad_loss.detach().to(torch.float32).reshape(1).contiguous()
-        early = self._early
-        if early is not None:
-            # the dX GEMM is (or was) reading the unpatched spill: keep the target values aside, join, then patch
+        w = self.weight_activated.data
+        peer = self._peer
+        patched = self._fx_splits is not None      # the forward left the dX partials of the UNPATCHED spill behind
+        lazy = self.lazy_update and patched
+        if self.fused_optimizer:
+            if g is not None:
+                ws.gscale.copy_(g)                 # the fused update divides the loss scale out again
+            elif not self._gscale_is_one:
+                ws.gscale.fill_(1.0)
+            self._gscale_is_one = g is None
+        if patched:
+            # keep the target values aside for the rank-1 fix-up of dX, then write them into the spill for dW
             K.backward_prepare_deferred(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all,
                                         ws.xs, ws.coef, ws.patch)
-            self._join_early()
-            K.apply_target_patch(ws.E, n_pad, B, ws.labels_act, ws.patch)
+            K.apply_target_patch(ws.E, n_pad, B, ws.labels_act, ws.patch, ws.pending if lazy else None)
         else:
             K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
                                ws.coef, ws.E, n_pad)
-        # Order.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the reduce-scatter /
-        # peer stores have the whole dW + update to complete.  N = 1: dW GEMM first (it walks the class tiles from the
-        # end, where the forward's spill is still in L2), then dX, then the update -- measured 0.4266 ms against
-        # 0.4293 ms for the other order.  conf.overlap_update needs dW first as well: its update runs on a side stream
-        # underneath the dX GEMM and writes next step's rows into the OTHER wn buffer.
-        w = self.weight_activated.data
-        overlap = self.fused_optimizer and self.overlap_update and w.is_cuda
-        # one kernel for dW GEMM + update (after the dX GEMM, which still reads this step's normalised shard)
-        fuse_dw = (self.fused_optimizer and self.fused_dw_update and self._optimizer_kind == "sgd" and d == 512
-                   and not overlap)
         spill_bf16 = self.fused_optimizer and self._optimizer_kind == "sgd" and d % 128 == 0
-        dwn = ws.dwn_bf16 if spill_bf16 else ws.dwn
-        dw, side = None, None
-        wn_now = ws.wn
-        dw_first = (W == 1 and not fuse_dw) or overlap
+        dwn = ws.grad_buffer(spill_bf16, d)
+        dw = None
+        # Order without FX.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the
+        # reduce-scatter / peer stores have the whole dW + update to complete.  N = 1: dW GEMM first (it walks the class
+        # tiles from the end, where the forward's spill is still in L2), then dX, then the update.
+        dw_first = W == 1 and not patched
         if dw_first:
             K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
-        if overlap:
-            cur = torch.cuda.current_stream()
-            if self._side_stream is None:
-                self._side_stream = torch.cuda.Stream(device=w.device)
-            side = self._side_stream
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                self._fused_step(w, n, d, dwn, ws.wn_alt)
-            ws.wn, ws.wn_alt = ws.wn_alt, ws.wn       # ping-pong: the next forward reads what the update wrote
         dx, rs_work = None, None
-        peer = self._peer
         # fork: the tail of the dX path runs on a side stream next to the dW GEMM / update (see conf.dx_side_stream)
-        want_fork = (W > 1) if self.dx_side_stream == "auto" else bool(self.dx_side_stream)
-        fork = (want_fork and w.is_cuda and not overlap and not fuse_dw and need_dx
-                and (W == 1 or peer is not None))
+        want_fork = (W > 1 or patched) if self.dx_side_stream == "auto" else bool(self.dx_side_stream)
+        fork = want_fork and w.is_cuda and need_dx and (W == 1 or peer is not None)
         tail = None
-        wn_read_done = None       # early dX + fork: the tail's patched kernel reads wn, which the update rewrites in place
+        wn_read_done = None       # fork: the tail's patched kernel reads wn, which the fused update rewrites in place
         if need_dx:
-            if early is not None:
-                splits = early[1]                 # the partials are there already; their target term is added below
+            if patched:
+                splits = self._fx_splits
             else:
                 splits = K.dx_splits(B, n, d)
-                if dw_first and not overlap:
-                    K.pdl_independent_next()      # dX reads E' / wn and writes dx_partial: nothing the dW GEMM touches
-                K.backward_dx(ws.E, n_pad, wn_now, B, n, d, ws.dx_partial, splits)
+                K.backward_dx(ws.E, n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
             if fork:
                 if self._side_stream is None:
-                    self._side_stream = torch.cuda.Stream(device=w.device, priority=-1 if self.dx_side_priority else 0)
+                    self._side_stream = torch.cuda.Stream(device=w.device)
                 tail = self._side_stream
                 tail.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():
                 if W == 1:
-                    if early is not None:
+                    if patched:
                         K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx,
-                                              ws.patch, ws.labels_act, wn_now)
-                        if tail is not None:
-                            wn_read_done = torch.cuda.Event()
-                            wn_read_done.record()                 # on the tail stream
+                                              ws.patch, ws.labels_act, ws.wn)
                     else:
                         K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
                 elif peer is not None:
                     # :505-522 -- every rank stores its scaled partial of row i into the owner's slot; the owner sums
                     # the W slots in rank order inside the normalise-backward kernel (x W, :521)
-                    if early is not None:
+                    if patched:
                         K.peer_dx_scatter_patched(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W,
-                                                  peer.ptrs("dx_slots"), ws.patch, ws.labels_act, wn_now)
+                                                  peer.ptrs("dx_slots"), ws.patch, ws.labels_act, ws.wn)
                     else:
                         K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
-                    if tail is not None and early is not None:
-                        wn_read_done = torch.cuda.Event()
-                        wn_read_done.record()                     # on the tail stream
                     if tail is not None:
                         # barrier + :521; also the fence that keeps a fast rank's NEXT gather out of xn_all while a
-                        # slow rank still reads it (this rank signals after its own dX GEMM, i.e. after its last read)
+                        # slow rank still reads it (this rank signals after its last read of the gathered batch)
                         K.peer_dx_finalize(peer.ptrs("flags"), peer.counter, self.rank, W, peer.dx_slots,
                                            self._x_local, ws.inv_x, float(W), b, d, dx)
                 else:
-                    if early is not None:
+                    if patched:
                         K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all,
-                                              ws.patch, ws.labels_act, wn_now)
+                                              ws.patch, ws.labels_act, ws.wn)
                     else:
                         K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
-                    # :505-519 -- asynchronous: it overlaps the rank-local update below / on the side stream
+                    # :505-519 -- asynchronous: it overlaps the rank-local dW GEMM / update below
                     rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
                                                                 async_op=True)
-        if fuse_dw:
-            self._fused_dw_step(w, n, n_pad, d)       # dW GEMM + update in place, after the dX GEMM has consumed wn
-        elif not overlap:
-            if not dw_first:
-                if dx is not None and rs_work is None and tail is None:
-                    # the kernel just launched is the dX finalize / peer scatter (reads dx_partial + coef, writes dX
-                    # slots); the dW GEMM reads E' / xs and writes dwn
-                    K.pdl_independent_next()
-                K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
-            if self.fused_optimizer:
-                if wn_read_done is not None:
-                    torch.cuda.current_stream().wait_event(wn_read_done)
-                self._fused_step(w, n, d, dwn, ws.wn)     # in place, after the dX GEMM has consumed wn
-            else:
-                dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
-                K.dw_finalize(ws.dwn, w, ws.inv_w, n, d, 1.0, dw)
-                self._wn_valid = False    # an external optimizer is about to change the weights
+                if patched and tail is not None and self.fused_optimizer and not lazy:
+                    wn_read_done = torch.cuda.Event()
+                    wn_read_done.record()                     # on the tail stream
+        if not dw_first:
+            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn, keep_in_l2=not lazy)
+        if lazy:
+            self._pending, self._pending_opt = True, self._opt_args   # applied by the next forward / flush()
+        elif self.fused_optimizer:
+            if wn_read_done is not None:
+                torch.cuda.current_stream().wait_event(wn_read_done)
+            self._fused_step(w, n, d, dwn, ws.wn)         # in place, after the last reader of this step's shard
+        else:
+            dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
+            K.dw_finalize(dwn, w, ws.inv_w, n, d, 1.0, dw)
+            self._wn_valid = False    # an external optimizer is about to change the weights
         if rs_work is not None:
             rs_work.wait()
             K.dx_finalize(ws.dxn_local, 1, None, self._x_local, ws.inv_x, float(W), b, b, d, dx)        # :521
@@ -547,8 +571,7 @@ class _PartialFCBase(torch.nn.Module):
                 K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
         if tail is not None:
             torch.cuda.current_stream().wait_stream(tail)                          # join
-        if side is not None:
-            torch.cuda.current_stream().wait_stream(side)
+        self._fx_splits = None
         return dx, dw
 
     def _fused_step(self, w, n, d, dwn, wn_out):
@@ -556,6 +579,7 @@ class _PartialFCBase(torch.nn.Module):
 
     # ------------------------------------------------------------------ checkpoint layout (nets/PartialFC.py:210-232)
     def state_dict(self, destination=None, prefix="", keep_vars=False):
+        self.flush()                    # conf.lazy_update: the checkpoint holds the weights AFTER the last step
         if destination is None:
             destination = collections.OrderedDict()
             destination._metadata = collections.OrderedDict()
@@ -569,6 +593,7 @@ class _PartialFCBase(torch.nn.Module):
         return destination
 
     def load_state_dict(self, state_dict, strict: bool = True):
+        self.flush()                    # a pending lazy update belongs to the weights that are being replaced
         self._wn_valid = False
         if self.sample_rate < 1:
             self.weight = state_dict["weight"].to(self.weight.device)
@@ -617,14 +642,8 @@ class PartialFC(_PartialFCBase):
 
     def _fused_step(self, w, n, d, dwn, wn_out):
         ws, o = self._ws, self._opt_args
-        K.dw_sgd(dwn, w, self._momentum(w), ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], 1.0, wn_out, ws.inv_w)
+        K.dw_sgd(dwn, w, self._momentum(w), ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], ws.gscale, wn_out, ws.inv_w)
         self._wn_valid = True             # the update wrote next step's normalised bf16 rows and 1/norm in place
-
-    def _fused_dw_step(self, w, n, n_pad, d):
-        ws, o = self._ws, self._opt_args
-        K.backward_dw_sgd(ws.E, n_pad, ws.xs, ws.B, n, d, w, self._momentum(w), ws.inv_w, o["lr"], o["momentum"],
-                          o["wd"], 1.0, ws.wn, ws.inv_w)
-        self._wn_valid = True
 
 
 class PartialFCAdamW(_PartialFCBase):
@@ -675,6 +694,10 @@ class PartialFCAdamW(_PartialFCBase):
             m, v = self._fused_state
             self.step += 1
             step = self.step
+        # under GraphedHeadStep the step count comes from a device scalar that every replay advances
+        graphed = self._graph_steps and self.sample_rate >= 1
         K.dw_adam(dwn, w, m, v, ws.inv_w, n, d, o["lr"], o["beta1"], o["beta2"], o["eps"], o["wd"], step,
-                  o["decoupled"], 1.0, wn_out, ws.inv_w)
+                  o["decoupled"], ws.gscale, wn_out, ws.inv_w, ws.adam_step if graphed else None)
+        if graphed:
+            ws.adam_step.add_(1)
         self._wn_valid = True

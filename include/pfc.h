@@ -35,22 +35,6 @@ extern "C" {
 int pfc_version(void);
 const char* pfc_error_string(int code);           /* host string */
 
-/* Programmatic dependent launch of the step kernels (every pfc_* kernel of one forward + backward; not the sampler or
- * the fr_* scorer).  mode 1: each kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization and
- * starts with griddepcontrol.wait: its CTAs are scheduled while the preceding kernel of the stream still runs, do
- * their CTA-local setup, and touch global memory only after that kernel has completed -- same results, shorter gaps
- * between the 8-12 dependent launches of a step (the reference's step is ~60 stream-ordered launches,
- * nets/PartialFC.py:146-208).  mode 2: additionally honours pfc_pdl_independent_next().  mode 0: plain launches.
- * Process-wide; the initial value comes from the environment variable PFC_PDL. */
-void pfc_set_pdl(int mode);
-int pfc_get_pdl(void);
-/* Hint for the NEXT launch on the calling thread, honoured by pfc_backward_dx / pfc_backward_dw in mode 2 and ignored
- * (and cleared) by every other launch: that GEMM neither reads nor overwrites anything the kernel launched just before
- * it writes or reads, and that kernel is a pfc_* step kernel which was not itself launched under this hint.  The GEMM
- * then runs concurrently with the tail of its predecessor and still completes after it (it waits at its end), so
- * later launches need no extra care.  Valid uses in the step: dX after dW, dW after the dX finalize / scatter. */
-void pfc_pdl_independent_next(void);
-
 /* ---- shape helpers (host only, no CUDA calls except pfc_dx_splits' SM-count query) ---------------------- */
 int pfc_exp_top(void);                            /* exponent offset of the spilled e terms (see pfc_forward) */
 int pfc_padded_classes(int n);                    /* row stride (elements) of the E' spill for n active classes */
@@ -59,6 +43,11 @@ int pfc_num_class_tiles(int n);                   /* number of part_sum slabs (c
 int pfc_part_sum_cols(void);                      /* classes per part_sum slab (64) */
 int pfc_dx_splits(int B, int n, int d);           /* class splits pfc_backward_dx will use for this shape */
 int pfc_dx_max_splits(int B, int d);              /* upper bound of pfc_dx_splits over all n (sizes `partial`) */
+int pfc_fx_splits(int B, int n, int d);           /* slabs of dX partials pfc_forward_dx writes (its class groups) */
+int pfc_fx_max_splits(int B, int d);              /* upper bound of pfc_fx_splits over all n */
+int pfc_fx_counter_words(int B, int n, int d);    /* int32 words of pfc_forward_dx's per-step counter array */
+int pfc_fx_tile_order(int B, int n, int d, int32_t* order);   /* HOST array [ceil(n/256)]: order in which
+                                                      pfc_forward_dx asks for the 256-class tiles of the shard */
 
 /* ---- (1) fused L2 normalise: F.normalize of embeddings / of the classifier shard, nets/PartialFC.py:199-200.
  * xn[r,:] = bf16(x[src,:] / max(||x[src,:]||, 1e-12)), inv_norm[r] = 1/max(||.||, 1e-12), src = index ? index[r] : r
@@ -141,40 +130,54 @@ int pfc_backward_dx(const void* E_bf16, int n_pad, const void* wn_bf16, int B, i
                     int splits, void* stream);
 int pfc_dx_finalize(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
                     float scale, int rows, int rows_total, int d, float* out, void* stream);
-/* Early-dX variants (conf.early_dx): pfc_forward leaves 0 in the target column of E, so pfc_backward_dx may run on the
- * spill BEFORE the statistics exchange and the patch -- next to them instead of behind them.
+/* Forward + dX in one kernel (csrc/pfc_fx.cuh; replaces pfc_forward followed by pfc_backward_dx on the same step).
+ * pfc_forward_dx = pfc_forward -- same outputs, E's target column left at 0 -- plus partial[g] = E[:, group g] . Wn[group g, :]
+ * for the G = pfc_fx_splits(B,n,d) class groups, contracted tile by tile while the spill and the shard are still in
+ * L2.  dX needs neither the softmax denominator nor the target patch: those are applied when the partials are summed:
  * pfc_backward_prepare_deferred = pfc_backward_prepare that leaves E alone and writes the target value to patch[i]
  * (the bf16-rounded -dm_i*mask_i*stats[i][0]; 0 for rows whose class is on another rank);
- * pfc_apply_target_patch writes it into E (after the early dX GEMM, before pfc_backward_dw);
+ * pfc_apply_target_patch writes it into E (before pfc_backward_dw; pending != NULL: also sets *pending = 1);
  * pfc_dx_finalize_patched / pfc_peer_dx_scatter_patched add the missing rank-1 term patch[i] * Wn[labels_local[i], :]
  * to row i of the summed partials before scaling (bf16 x bf16 products are exact in fp32: the result differs from the
- * patched GEMM only by the position of that term in the sum). */
+ * patched GEMM only by the position of that term in the sum).
+ * counters: pfc_fx_counter_words ints, ZERO on entry (per step).  wn_gate != 0 (lazy update): the kernel asks for the
+ * 256-class tile t of wn only once counters[t] == rows of that tile, which pfc_dw_sgd_ordered -- launched on another
+ * stream, co-resident on the same SMs -- counts up as it rewrites the shard with the PREVIOUS step's gradient. */
+int pfc_forward_dx(const void* xn_bf16, const void* wn_bf16, const int32_t* labels_local, int B, int n, int d, float s,
+                   int margin_kind, float m2, float m3, float interclass_filtering_threshold, void* E_bf16, int n_pad,
+                   float* part_sum, float* tgt_raw, float* tgt_e, float* tgt_z, float* partial, int splits,
+                   int* counters, int wn_gate, void* stream);
 int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
                                   const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
                                   const void* xn_bf16, void* xs_bf16, float* coef, float* patch, void* stream);
 int pfc_apply_target_patch(void* E_bf16, int n_pad, int B, const int32_t* labels_local, const float* patch,
-                           void* stream);
+                           int* pending, void* stream);
 int pfc_dx_finalize_patched(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
                             float scale, int rows, int rows_total, int d, float* out, const float* patch,
                             const int32_t* labels_local, const void* wn_bf16, void* stream);
-/* dwn_bf16 != 0: dwn is a bf16 [n,d] matrix (halves the spill that pfc_dw_sgd re-reads; fused-SGD mode only). */
+/* dwn_bf16 != 0: dwn is a bf16 [n,d] matrix (halves the spill that pfc_dw_sgd re-reads; fused-SGD mode only);
+ * 1: stored with L2 evict_last hints for a pfc_dw_sgd that runs right behind it, 2: plain stores. */
 int pfc_backward_dw(const void* E_bf16, int n_pad, const void* xs_bf16, int B, int n, int d, void* dwn, int dwn_bf16,
                     void* stream);
+/* inv_grad_scale must be 1: the un-fused gradient keeps the loss scale for GradScaler.unscale_ (model/FR_PartialFC.py:180) */
 int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, int rows, int d, float inv_grad_scale,
                     float* dw, void* stream);
+/* grad_scale: device scalar with the loss scale the gradient carries (g = d loss of pfc_backward_prepare), divided out
+ * before the step; NULL = 1.  step_dev (Adam): int32 device scalar, the update is step step_dev[0] + 1 and `step` is
+ * ignored (CUDA-graph replay; the caller increments it); NULL: `step` (host, >= 1). */
 int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* momentum_buf, const float* inv_norm_w, int rows, int d,
-               float lr, float momentum, float weight_decay, float inv_grad_scale, void* wn_next_bf16,
+               float lr, float momentum, float weight_decay, const float* grad_scale, void* wn_next_bf16,
                float* inv_norm_next, void* stream);
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
-                float inv_grad_scale, void* wn_next_bf16, float* inv_norm_next, void* stream);
-
-/* pfc_backward_dw + pfc_dw_sgd in ONE kernel: the un-normalised gradient stays in tensor memory and the update is the
- * GEMM's epilogue (no dWn spill).  d must be 512 (PFC_ERR_SHAPE otherwise: use the two-kernel path); w, mom and
- * wn_next 32-byte aligned.  Same argument meaning as pfc_dw_sgd; wn_next may alias the shard pfc_backward_dx read. */
-int pfc_backward_dw_sgd(const void* E_bf16, int n_pad, const void* xs_bf16, int B, int n, int d, float* w, float* mom,
-                        const float* inv_norm_w, float lr, float momentum, float weight_decay, float inv_grad_scale,
-                        void* wn_next_bf16, float* inv_norm_next, void* stream);
+                const float* grad_scale, void* wn_next_bf16, float* inv_norm_next, const int* step_dev, void* stream);
+/* pfc_dw_sgd (bf16 gradient, d % 128 == 0) as a persistent kernel -- one small CTA per SM, no shared memory, so that it
+ * runs NEXT TO pfc_forward_dx on the same SMs -- that rewrites the shard in pfc_fx_tile_order's order and counts the
+ * finished rows of 256-class tile t in wn_ready[t] (zero on entry).  inv_norm_w is read (old norm) and rewritten (new
+ * norm) in place.  pending (device int, may be NULL = 1): 0 = nothing to apply, only the counters move. */
+int pfc_dw_sgd_ordered(const void* dwn_bf16, float* w, float* momentum_buf, float* inv_norm_w, int rows, int d, float lr,
+                       float momentum, float weight_decay, const float* grad_scale, void* wn_bf16,
+                       const int32_t* tile_order, int num_tiles, int* wn_ready, const int* pending, void* stream);
 
 /* ---- (5b) the three exchanges of the step over peer memory (NVLink / NVSwitch), fused into the producing kernels.
  * They replace all_gather (nets/PartialFC.py:182-186), the softmax all_reduces (:448, :453, :459) and the dX

@@ -21,12 +21,9 @@ class FakeKernels:
         self._real = real
         # host-only helpers come from the real library (no GPU needed)
         for name in ("exp_top", "padded_classes", "padded_batch", "num_class_tiles", "part_sum_cols", "dx_splits",
-                     "dx_max_splits",
+                     "dx_max_splits", "fx_splits", "fx_max_splits", "fx_counter_words", "fx_tile_order",
                      "sample_workspace_bytes", "hist_bins"):
             setattr(self, name, getattr(real, name))
-
-    def pdl_independent_next(self):
-        """launch-scheduling hint (include/pfc.h): nothing to do on the CPU"""
 
     # ---- rows
     def l2norm_rows(self, x, index, rows, xn, inv_norm):
@@ -137,7 +134,18 @@ class FakeKernels:
         patch.zero_()
         patch[rows] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16).float()
 
-    def apply_target_patch(self, E, n_pad, B, labels, patch):
+    def forward_dx(self, xn, wn, labels, B, n, d, s, kind, m2, m3, thr, E, n_pad, part_sum, tgt_raw, tgt_e, tgt_z,
+                   partial, splits, counters, wn_gate):
+        if wn_gate:      # the ordered update must have published every tile of the shard
+            tiles = (n + 255) // 256
+            want = torch.tensor([min(256, n - 256 * t) for t in range(tiles)], dtype=counters.dtype)
+            assert torch.equal(counters[:tiles], want), "pfc_forward_dx gate: shard tiles not published"
+        self.forward(xn, wn, labels, B, n, d, s, kind, m2, m3, thr, E, n_pad, part_sum, tgt_raw, tgt_e, tgt_z)
+        self.backward_dx(E, n_pad, wn, B, n, d, partial, splits)       # target column of E' is 0 here
+
+    def apply_target_patch(self, E, n_pad, B, labels, patch, pending=None):
+        if pending is not None:
+            pending[0] = 1
         rows = torch.nonzero(labels[:B] >= 0).reshape(-1)
         E[: B * n_pad].view(B, n_pad)[rows, labels[rows].long()] = patch[rows].to(torch.bfloat16)
 
@@ -162,24 +170,37 @@ class FakeKernels:
             g = (g - xn * (xn * g).sum(1, keepdim=True)) * inv_norm[:rows].reshape(-1, 1)
         out[:rows] = g * scale
 
-    def backward_dw(self, E, n_pad, xs, B, n, d, dwn):
-        dwn[:n] = E[: B * n_pad].view(B, n_pad)[:, :n].float().t() @ xs[:B].float()
+    def backward_dw(self, E, n_pad, xs, B, n, d, dwn, keep_in_l2=True):
+        dwn[:n] = (E[: B * n_pad].view(B, n_pad)[:, :n].float().t() @ xs[:B].float()).to(dwn.dtype)
 
     def dw_finalize(self, dwn, w, inv_norm_w, rows, d, inv_grad_scale, dw):
         wn = w[:rows] * inv_norm_w[:rows].reshape(-1, 1)
         g = dwn[:rows]
         dw[:rows] = (g - wn * (wn * g).sum(1, keepdim=True)) * inv_norm_w[:rows].reshape(-1, 1) * inv_grad_scale
 
-    def dw_sgd(self, dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, inv_grad_scale, wn_next, inv_norm_next):
+    def dw_sgd(self, dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn_next, inv_norm_next):
         g = torch.empty(rows, d)
-        self.dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, g)
+        inv_grad_scale = 1.0 if grad_scale is None else 1.0 / float(grad_scale[0])
+        self.dw_finalize(dwn.float(), w, inv_norm_w, rows, d, inv_grad_scale, g)
         w_new, m_new = ho.sgd_update(w[:rows], mom[:rows], g, lr, momentum, wd)
         w[:rows] = w_new
         mom[:rows] = m_new
         self.l2norm_rows(w, None, rows, wn_next, inv_norm_next)
 
+    def dw_sgd_ordered(self, dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn, tile_order, counters,
+                       pending):
+        tiles = (rows + 255) // 256
+        assert sorted(tile_order.tolist()) == list(range(tiles))
+        if pending is None or int(pending[0]) != 0:
+            self.dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn, inv_norm_w)
+        for t in range(tiles):
+            counters[t] += min(256, rows - 256 * t)
+
     def dw_adam(self, dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, wd, step, decoupled,
-                inv_grad_scale, wn_next, inv_norm_next):
+                grad_scale, wn_next, inv_norm_next, step_dev=None):
+        if step_dev is not None:
+            step = int(step_dev[0]) + 1
+        inv_grad_scale = 1.0 if grad_scale is None else 1.0 / float(grad_scale[0])
         g = torch.empty(rows, d)
         self.dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, g)
         w_new, m_new, v_new = ho.adamw_update(w[:rows], exp_avg[:rows], exp_avg_sq[:rows], g, step, lr, beta1, beta2,
@@ -188,10 +209,3 @@ class FakeKernels:
         exp_avg[:rows] = m_new
         exp_avg_sq[:rows] = v_new
         self.l2norm_rows(w, None, rows, wn_next, inv_norm_next)
-
-    def backward_dw_sgd(self, E, n_pad, xs, B, n, d, w, mom, inv_norm_w, lr, momentum, wd, inv_grad_scale, wn_next,
-                        inv_norm_next):
-        dwn = torch.empty(n, d)
-        self.backward_dw(E, n_pad, xs, B, n, d, dwn)
-        self.dw_sgd(dwn, w, mom, inv_norm_w, n, d, lr, momentum, wd, inv_grad_scale, wn_next, inv_norm_next)
-

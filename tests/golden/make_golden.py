@@ -259,6 +259,11 @@ if __name__ == "__main__":
         make_head_case("head_w1_adam_sampled", 1, dict(d=64, s=64.0, m=0.5, lr=1e-3, momentum=0.0, wd=5e-2, steps=3,
                                                        optimizer="adam", C=400, b=32, sample_rate=0.25), 29624)
         sys.exit(0)
+    if "--d128-only" in sys.argv:       # round 2: d a multiple of 128 and several 256-class tiles per rank, multi-step
+        b128 = dict(d=128, s=64.0, m=0.5, lr=0.1, momentum=0.9, wd=5e-4, steps=3)     # (conf.lazy_update, FX groups)
+        make_head_case("head_w1_d128", 1, dict(b128, C=777, b=48, sample_rate=1.0), 29631)
+        make_head_case("head_w2_d128", 2, dict(b128, C=1101, b=24, sample_rate=1.0), 29632)
+        sys.exit(0)
     if "--cfg1-only" in sys.argv:
         make_cfg1_case()
         sys.exit(0)

@@ -9,7 +9,8 @@ from oracle import head_oracle as ho
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 HEAD_CASES = ["head_w1_full", "head_w1_s30", "head_w1_cosface", "head_w1_sampled", "head_w1_manypos",
-              "head_w2_full", "head_w2_sampled", "head_w1_d512", "head_w1_filter", "head_w1_filter_wide"]
+              "head_w2_full", "head_w2_sampled", "head_w1_d512", "head_w1_filter", "head_w1_filter_wide", "head_w1_d128",
+              "head_w2_d128"]
 
 
 def load_case(name):

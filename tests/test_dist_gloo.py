@@ -15,15 +15,20 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-# (name, fused, direct = PartialFC.fused_step instead of autograd, early = conf.early_dx)
-SGD_CASES = [("head_w2_full", False, False, False), ("head_w2_sampled", False, False, False),
-             ("head_w2_full", True, False, False), ("head_w2_sampled", True, False, False),
-             ("head_w2_sampled", False, True, False), ("head_w2_full", True, True, False),
+# (name, fused, direct = PartialFC.fused_step instead of autograd, mode): mode "" = defaults (conf.fx: forward + dX
+# partials in one kernel, target term fixed up when they are summed), "nofx" = separate forward / dX GEMMs,
+# "lazy" = conf.lazy_update (the fused SGD step applied at the start of the next forward)
+SGD_CASES = [("head_w2_full", False, False, ""), ("head_w2_sampled", False, False, ""),
+             ("head_w2_full", True, False, ""), ("head_w2_sampled", True, False, ""),
+             ("head_w2_sampled", False, True, ""), ("head_w2_full", True, True, ""),
              # one rank: CombinedMarginLoss with inter-class filtering
-             ("head_w1_filter_wide", False, False, False), ("head_w1_filter_wide", True, True, False),
-             # conf.early_dx: dX GEMM on the unpatched spill + rank-1 fix-up
-             ("head_w2_sampled", False, False, True), ("head_w2_full", True, True, True),
-             ("head_w1_full", True, False, True)]
+             ("head_w1_filter_wide", False, False, ""), ("head_w1_filter_wide", True, True, ""),
+             ("head_w2_sampled", False, False, "nofx"), ("head_w2_full", True, True, "nofx"),
+             ("head_w1_full", True, False, "nofx"),
+             # d = 128, several 256-class tiles per rank
+             ("head_w2_d128", True, False, ""), ("head_w1_d128", False, False, ""),
+             ("head_w2_d128", True, False, "lazy"), ("head_w2_d128", True, True, "lazy"),
+             ("head_w1_d128", True, True, "lazy")]
 # (name, fused)
 ADAM_CASES = [("head_w2_adamw_sampled", False), ("head_w2_adamw_sampled", True), ("head_w1_adamw_full", True),
               ("head_w1_adam_sampled", True), ("head_w1_adam_sampled", False)]
@@ -88,14 +93,15 @@ def _run_scale_case():
     return out
 
 
-def _run_sgd_case(rank, W, name, fused, direct, early):
+def _run_sgd_case(rank, W, name, fused, direct, mode):
     from helpers import load_case, case_inputs, case_perms
     import face_recognition_pytorch_b200 as pfc
     cfg, z = load_case(name)
     weights, xs, ls = case_inputs(cfg)
     b = cfg["b"]
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
-                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused, early_dx=early)
+                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused, fx=mode != "nofx",
+                                 lazy_update=mode == "lazy")
     if cfg["margin"] == "combined_filter":
         thr = cfg["filter_thr"]
         margin = lambda s_, m_: pfc.CombinedMarginLoss(s_, 1.0, m_, 0.0, interclass_filtering_threshold=thr)  # noqa: E731
@@ -130,6 +136,7 @@ def _run_sgd_case(rank, W, name, fused, direct, early):
         head.update()
         out["weight_final"] = head.weight.numpy().copy()
     else:
+        head.flush()                                  # conf.lazy_update: the last step's update is still owed
         out["weight_final"] = head.weight_activated.detach().numpy().copy()
     out["state_dict_shape"] = tuple(head.state_dict()["weight"].shape)
     out["state_dict_keys"] = list(head.state_dict().keys())
@@ -249,13 +256,13 @@ def _cos(a, b):
     return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
 
 
-@pytest.mark.parametrize("name,fused,direct,early", SGD_CASES)
-def test_two_rank_host_logic_matches_reference(group_results, name, fused, direct, early):
+@pytest.mark.parametrize("name,fused,direct,mode", SGD_CASES)
+def test_two_rank_host_logic_matches_reference(group_results, name, fused, direct, mode):
     sys.path.insert(0, HERE)
     from helpers import load_case
     cfg, z = load_case(name)
     W = cfg["W"]
-    res = _case_result(group_results, ("sgd", name, fused, direct, early))
+    res = _case_result(group_results, ("sgd", name, fused, direct, mode))
     for s in range(cfg["steps"]):
         if W > 1:
             assert res[0][f"loss_{s}"] == res[1][f"loss_{s}"]                # every rank returns the global loss

@@ -35,9 +35,9 @@ def _margin_cls(pfc, cfg):
     return {"arcface": pfc.ArcFace, "cosface": pfc.CosFace}[cfg["margin"]]
 
 
-def _make_head(pfc, cfg, weights, fused=False, adam=False):
+def _make_head(pfc, cfg, weights, fused=False, adam=False, **extra):
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
-                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused)
+                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused, **extra)
     cls = pfc.PartialFCAdamW if adam else pfc.PartialFC
     head = cls(conf, cfg["C"], margin_loss=_margin_cls(pfc, cfg))
     head.load_state_dict({"weight": weights[0].clone()})
@@ -45,13 +45,17 @@ def _make_head(pfc, cfg, weights, fused=False, adam=False):
     return head
 
 
-@pytest.mark.parametrize("name", ["head_w1_full", "head_w1_s30", "head_w1_cosface", "head_w1_sampled",
-                                  "head_w1_manypos", "head_w1_d512"])
-@pytest.mark.parametrize("fused", [False, True])
-def test_steps_match_reference_and_oracle(pfc, name, fused):
+# mode: "unfused" (dW to torch.optim.SGD), "fused" (conf.fused_optimizer), "nofx" (fused, separate forward / dX GEMMs
+# instead of the forward + dX kernel), "lazy" (conf.lazy_update: the fused step applied under the next forward)
+@pytest.mark.parametrize("name,mode", [(n, m) for n in ["head_w1_full", "head_w1_s30", "head_w1_cosface", "head_w1_sampled",
+                                                       "head_w1_manypos", "head_w1_d512", "head_w1_d128"]
+                                       for m in ["unfused", "fused", "nofx"]] +
+                         [("head_w1_d512", "lazy"), ("head_w1_d128", "lazy")])
+def test_steps_match_reference_and_oracle(pfc, name, mode):
     cfg, z = load_case(name)
     weights, xs, ls = case_inputs(cfg)
-    head = _make_head(pfc, cfg, weights, fused=fused)
+    fused = mode != "unfused"
+    head = _make_head(pfc, cfg, weights, fused=fused, fx=mode != "nofx", lazy_update=mode == "lazy")
     dummy = torch.nn.Parameter(torch.zeros(1, device="cuda"))
     opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
                           momentum=cfg["momentum"], weight_decay=cfg["wd"])
@@ -88,6 +92,7 @@ def test_steps_match_reference_and_oracle(pfc, name, fused):
         head.update()
         w_final, m_final = head.weight, head.weight_mom
     else:
+        head.flush()                        # conf.lazy_update: the last step's update is still owed
         w_final = head.weight_activated.data
         m_final = head.weight_activated_mom if fused else opt.state[head.weight_activated]["momentum_buffer"]
     w0 = weights[0].double()
@@ -117,85 +122,6 @@ def test_adamw_fused_matches_torch_adamw(pfc):
     w0 = weights[0].cuda()
     assert cosine((a - w0).cpu(), (b - w0).cpu()) >= 0.9999
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=0, atol=2e-5)
-
-
-def test_overlap_update_is_bit_identical_to_serial(pfc):
-    """conf.overlap_update only changes scheduling (side stream + ping-pong wn buffers): same bits as the serial path."""
-    cfg, z = load_case("head_w1_d512")
-    weights, xs, ls = case_inputs(cfg)
-    outs = []
-    for overlap in (False, True):
-        conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
-                                     loss_m=cfg["m"], fused_optimizer=True, overlap_update=overlap,
-                                     fused_dw_update=False)
-        head = pfc.PartialFC(conf, cfg["C"])
-        head.load_state_dict({"weight": weights[0].clone()})
-        head = head.train().cuda()
-        opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
-        losses, grads = [], []
-        for s in range(5):
-            x = xs[0].clone().cuda().requires_grad_(True)
-            loss = head(x, ls[0].clone().cuda(), opt)
-            loss.backward()
-            losses.append(float(loss.detach()))
-            grads.append(x.grad.clone())
-        torch.cuda.synchronize()
-        outs.append((losses, grads, head.weight_activated.data.clone(), head.weight_activated_mom.clone()))
-    assert outs[0][0] == outs[1][0]
-    for a, b in zip(outs[0][1], outs[1][1]):
-        assert torch.equal(a, b)
-    assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][3], outs[1][3])
-    assert outs[0][0][4] < outs[0][0][0]            # and the fused SGD actually trains
-
-
-@pytest.mark.parametrize("shape", ["golden_d512", "cfg2_full"])
-def test_fused_dw_update_matches_two_kernel_path(pfc, shape):
-    """conf.fused_dw_update (dW GEMM with the SGD update as its epilogue, CTA-pair split of d) against the
-    pfc_backward_dw + pfc_dw_sgd pair: same losses, same weights / momentum up to the bf16 rounding of the
-    gradient spill that the two-kernel path has and the fused one does not."""
-    if shape == "golden_d512":
-        cfg, z = load_case("head_w1_d512")
-        weights, xs, ls = case_inputs(cfg)
-        x0, l0, steps = xs[0], ls[0], 4
-    else:
-        C, d, B = 93431, 512, 1024          # n % 128 != 0: exercises the class-tail rows of the last tile
-        w = torch.normal(0, 0.01, (C, d), generator=torch.Generator().manual_seed(1234))
-        l0 = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(7))
-        x0 = torch.nn.functional.normalize(torch.nn.functional.normalize(w[l0]) +
-                                           torch.randn(B, d, generator=torch.Generator().manual_seed(42)) / d ** 0.5)
-        cfg = dict(C=C, d=d, s=64.0, m=0.5, lr=0.1, momentum=0.9, wd=5e-4)
-        weights, steps = [w], 3
-    outs = []
-    for fuse in (False, True):
-        conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
-                                     loss_m=cfg["m"], fused_optimizer=True, fused_dw_update=fuse)
-        head = pfc.PartialFC(conf, cfg["C"])
-        head.load_state_dict({"weight": weights[0].clone()})
-        head = head.train().cuda()
-        opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
-        losses = []
-        for s in range(steps):
-            x = x0.clone().cuda().requires_grad_(True)
-            loss = head(x, l0.clone().cuda(), opt)
-            loss.backward()
-            losses.append(float(loss.detach()))
-        torch.cuda.synchronize()
-        outs.append((losses, head.weight_activated.data.clone(), head.weight_activated_mom.clone(),
-                     head._ws.wn.clone(), head._ws.inv_w.clone()))
-    w0 = weights[0].cuda()
-    (la, wa, ma, wna, ia), (lb, wb, mb, wnb, ib) = outs
-    assert la[0] == lb[0]                                   # identical first forward
-    for a, b in zip(la, lb):
-        assert abs(a - b) <= 2e-3 * abs(a)
-    assert la[-1] < la[0]
-    assert torch.isfinite(wb).all() and torch.isfinite(mb).all()
-    assert cosine((wa - w0).cpu(), (wb - w0).cpu()) >= 0.9995
-    assert cosine(ma.cpu(), mb.cpu()) >= 0.9995
-    assert abs(float(mb.norm()) / float(ma.norm()) - 1) < 1e-2
-    # next step's operand: normalised rows of the NEW weights and their inverse norms, for every row incl. the tail
-    ref_wn = torch.nn.functional.normalize(wb)
-    assert float((wnb.float() - ref_wn).abs().max()) <= 2 ** -8
-    torch.testing.assert_close(ib, 1.0 / wb.norm(dim=1), rtol=1e-5, atol=0)
 
 
 def test_graphed_head_step_replays_the_eager_step_bit_for_bit(pfc):
@@ -314,3 +240,69 @@ def test_full_size_properties_cfg2(pfc):
     assert float(((xg.grad * xn).sum(1)).abs().max()) <= 1e-4 * float(xg.grad.norm(dim=1).max())
     wn = torch.nn.functional.normalize(head.weight_activated.data)
     assert float(((gw * wn).sum(1)).abs().max()) <= 1e-4 * float(gw.norm(dim=1).max())
+
+
+def test_fused_update_at_full_size_matches_oracle(pfc):
+    """The fused SGD / momentum step at the BASELINE configs[1] shape against the oracle's fp32 step on the host, for
+    the in-step update and the lazy one (applied under the next forward), two steps so that momentum is exercised."""
+    C, d, B = 93431, 512, 1024
+    w = torch.normal(0, 0.01, (C, d), generator=torch.Generator().manual_seed(1234))
+    batches = []
+    for s in range(2):
+        lab = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(7 + s))
+        x = torch.nn.functional.normalize(torch.nn.functional.normalize(w[lab]) +
+                                          torch.randn(B, d, generator=torch.Generator().manual_seed(42 + s)) / d ** 0.5)
+        batches.append((x, lab))
+    orc = ho.PartialFCOracle([w], C, ho.Margin("arcface", 64.0, 0.5), 1.0, 0.1, 0.9, 5e-4, dtype=torch.float32)
+    ref_losses = [float(orc.step([x], [lab], None).loss) for x, lab in batches]
+    orc._flush()
+    w_ref = orc.weight[0].float()
+    cfg = dict(C=C, d=d, sample_rate=1.0, s=64.0, m=0.5, margin="arcface")
+    finals = {}
+    for mode in ("fused", "lazy"):
+        head = _make_head(pfc, cfg, [w], fused=True, lazy_update=mode == "lazy")
+        opt = torch.optim.SGD(head.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+        for (x, lab), ref in zip(batches, ref_losses):
+            xg = x.clone().cuda().requires_grad_(True)
+            loss = head(xg, lab.clone().cuda(), opt)
+            loss.backward()
+            assert abs(float(loss) - ref) <= LOSS_RTOL * abs(ref), (mode, float(loss), ref)
+        sd = head.state_dict()["weight"].cpu()          # flushes the lazy head
+        assert cosine(sd - w, w_ref - w) >= COS_MIN, mode
+        assert abs(float((sd - w).norm()) / float((w_ref - w).norm()) - 1) < 2e-2
+        finals[mode] = sd
+    # same arithmetic, same order of updates: the lazy head ends where the eager one does
+    torch.testing.assert_close(finals["lazy"], finals["fused"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["unfused", "fused", "lazy"])
+def test_scaled_loss_through_the_kernels(pfc, mode):
+    """GradScaler flow (model/FR_PartialFC.py:178-184: amp.scale(loss).backward(), unscale_, step): d loss = 1024 reaches
+    pfc_backward_prepare as a device scalar (nets/PartialFC.py:484's `loss_gradient.item()` without the sync); dX and the
+    un-fused dW carry the scale, the fused update divides it out on the device."""
+    cfg, z = load_case("head_w1_d128")
+    weights, xs, ls = case_inputs(cfg)
+    outs = []
+    for scale in (1.0, 1024.0):
+        head = _make_head(pfc, cfg, weights, fused=mode != "unfused", lazy_update=mode == "lazy")
+        opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
+        rec = []
+        for s in range(2):
+            x = xs[s].clone().cuda().requires_grad_(True)
+            opt.zero_grad()
+            loss = head(x, ls[s].clone().cuda(), opt)
+            (loss * scale).backward()
+            if mode == "unfused":
+                rec.append((float(loss.detach()), x.grad.clone(), head.weight_activated.grad.clone()))
+                head.weight_activated.grad /= scale          # GradScaler.unscale_
+                opt.step()
+            else:
+                rec.append((float(loss.detach()), x.grad.clone(), None))
+        outs.append((rec, head.state_dict()["weight"].clone()))
+    (ra, wa), (rb, wb) = outs
+    for (la, dxa, dwa), (lb, dxb, dwb) in zip(ra, rb):
+        assert abs(la - lb) <= 1e-6 * abs(la)
+        torch.testing.assert_close(dxb, dxa * 1024.0, rtol=1e-4, atol=1e-6 * float(dxa.abs().max()) * 1024.0)
+        if dwa is not None:
+            torch.testing.assert_close(dwb, dwa * 1024.0, rtol=1e-4, atol=1e-6 * float(dwa.abs().max()) * 1024.0)
+    torch.testing.assert_close(wb, wa, rtol=0, atol=1e-6)      # the weights do not see the loss scale

@@ -1,20 +1,15 @@
-"""GPU checks of code paths that were written after the round's GPU budget was spent and are therefore OPT-IN:
-they run only with PFC_EXPERIMENTAL=1 in the environment (the default test run skips them), and the features they cover
-are off by default.  Enable a feature by default only after this file has passed on a B200.
+"""GPU checks of the head's execution modes against each other and against fixtures of the reference:
 
   * GraphedHeadStep(autograd=False) / PartialFC.fused_step: same kernels as forward + loss.backward() with d loss = 1,
-    so the results must be bit-identical (host logic already covered on CPU by tests/test_dist_gloo.py).
-  * conf.dx_side_priority: high-priority side stream for the dX tail -- scheduling only, results unchanged.
+    so the results must be bit-identical (host logic also covered on CPU by tests/test_dist_gloo.py).
   * PartialFCAdamW with sampling, fused update: bias correction with the reference's step count (t + 1, pinned on the CPU
     by tests/test_oracle_golden.py and tests/test_dist_gloo.py against fixtures of the reference's PartialFCAdamW).
-  * CombinedMarginLoss with inter-class filtering INSIDE the head (the kFilter branch of the forward epilogue): until now
-    only the stand-alone margin kernel was compared with the reference on the GPU.
-  * conf.early_dx: dX GEMM on the unpatched spill, launched on its own stream right after the forward GEMM; the
-    target's rank-1 term is added when the partials are summed.  Same loss bits, dX equal up to fp32 summation order.
-  * PFC_L2_GRAD / pfc_debug_l2_grad: the bf16 gradient of the dW GEMM kept in L2 for the update (evict_last TMA stores,
-    evict_first state streams, discard.global.L2 after use).  Cache hints only: bit-identical results.
-  * PFC_SAMPLE_FUSED / pfc_debug_sample_fused: the sampler as one launch of one CTA for shards of up to 65 536 classes
-    (its algorithm was checked on the CPU against the oracle with a numpy emulation; the CUDA code never ran).
+  * CombinedMarginLoss with inter-class filtering INSIDE the head (the kFilter branch of the forward epilogue).
+  * conf.fx (forward + dX partials in one kernel, csrc/pfc_fx.cuh) against the separate forward / dX GEMMs: same loss
+    bits, dX equal up to fp32 summation order, at shapes with odd tile counts and ragged class tails.
+  * conf.lazy_update against the in-step fused update, eager and graph-replayed.
+  * the L2 residency hints of the bf16 gradient (pfc_debug_l2_grad): cache hints only, bit-identical results.
+  * PartialFCAdamW inside GraphedHeadStep (step count in a device scalar).
 """
 import os
 import types
@@ -22,8 +17,7 @@ import types
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PFC_EXPERIMENTAL") != "1", reason="opt-in: PFC_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
@@ -53,7 +47,7 @@ def _graph_run(pfc, autograd, B=1024, C=20000, d=512, steps=4, **conf_extra):
                                           1.5 * torch.randn(B, d, generator=g) / d ** 0.5).cuda()
         loss, dx = step(x, lab)
         out += [loss.detach().clone().reshape(()), dx.clone()]
-    out.append(head.weight_activated.data.clone())
+    out.append(head.state_dict()["weight"].clone())       # (flushes a lazy head)
     torch.cuda.synchronize()
     return out
 
@@ -89,13 +83,6 @@ def test_fused_step_eager_matches_autograd(pfc):
             dx, dw = xg.grad, head.weight_activated.grad
         res.append((loss.detach().clone().reshape(()), dx.clone(), dw.clone()))
     for u, v in zip(*res):
-        assert torch.equal(u, v)
-
-
-def test_high_priority_side_stream_changes_nothing(pfc):
-    a = _graph_run(pfc, True, dx_side_stream=True)
-    b = _graph_run(pfc, True, dx_side_stream=True, dx_side_priority=True)
-    for u, v in zip(a, b):
         assert torch.equal(u, v)
 
 
@@ -164,16 +151,18 @@ def test_head_with_interclass_filter_matches_reference(pfc, fused):
                   torch.from_numpy(z["r0_weight_final"]).double() - w0) >= 0.999
 
 
-@pytest.mark.parametrize("B,C,d,fused", [(1024, 20000, 512, True), (320, 3100, 512, False), (96, 1500, 64, True)])
-def test_early_dx_matches_the_serial_order(pfc, B, C, d, fused):
+@pytest.mark.parametrize("B,C,d,fused", [(1024, 20000, 512, True), (320, 3100, 512, False), (96, 1500, 64, True),
+                                         (200, 777, 128, True), (1024, 300, 512, False)])
+def test_fx_matches_separate_gemms(pfc, B, C, d, fused):
+    """conf.fx: forward + dX partials in one kernel, target term fixed up when the partials are summed."""
     from helpers import cosine
     g0 = torch.Generator().manual_seed(44)
     w = torch.normal(0, 0.01, (C, d), generator=g0)
     outs = []
-    for early in (False, True):
+    for fx in (False, True):
         g = torch.Generator().manual_seed(45)
         conf = types.SimpleNamespace(emd_size=d, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5,
-                                     fused_optimizer=fused, early_dx=early)
+                                     fused_optimizer=fused, fx=fx)
         head = pfc.PartialFC(conf, C)
         head.load_state_dict({"weight": w.clone()})
         head = head.train().cuda()
@@ -206,37 +195,78 @@ def test_early_dx_matches_the_serial_order(pfc, B, C, d, fused):
     assert cosine((a[3] - w.cuda()).cpu(), (b[3] - w.cuda()).cpu()) >= 0.99999
 
 
-def test_early_dx_graph_replay(pfc):
-    a = _graph_run(pfc, True)
-    b = _graph_run(pfc, True, early_dx=True)
-    c = _graph_run(pfc, False, early_dx=True)
-    from helpers import cosine
-    for u, v, w_ in zip(a, b, c):
-        assert cosine(u.cpu().reshape(-1), v.cpu().reshape(-1)) >= 0.999999
-        assert torch.equal(v, w_)            # autograd or not: same kernels, same order
+def test_fx_forward_only_and_eval_paths(pfc):
+    """No gradient wanted for the embeddings: the plain forward kernel runs and gives the loss of the training path."""
+    d, B, C = 128, 200, 777
+    g = torch.Generator().manual_seed(9)
+    w = torch.normal(0, 0.01, (C, d), generator=g)
+    lab = torch.randint(0, C, (B,), generator=g).cuda()
+    x = torch.nn.functional.normalize(torch.randn(B, d, generator=g)).cuda()
+    conf = types.SimpleNamespace(emd_size=d, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5)
+    head = pfc.PartialFC(conf, C)
+    head.load_state_dict({"weight": w.clone()})
+    head = head.train().cuda()
+    opt = torch.optim.SGD(head.parameters(), lr=0.1)
+    with torch.no_grad():
+        l0 = head(x, lab.clone(), opt).clone()
+    l1 = head(x.clone().requires_grad_(True), lab.clone(), opt)
+    assert torch.equal(l0, l1.detach())
+
+
+def test_lazy_update_graph_replay_matches_eager_fused(pfc):
+    """conf.lazy_update under GraphedHeadStep: losses / dX of every step and the flushed weights equal the in-step
+    fused update's (the same arithmetic applied one kernel later)."""
+    a = _graph_run(pfc, False)
+    b = _graph_run(pfc, False, lazy_update=True)
+    c = _graph_run(pfc, True, lazy_update=True, B=320, C=3100)
+    d = _graph_run(pfc, True, B=320, C=3100)
+    for (u, v) in list(zip(a, b)) + list(zip(c, d)):
+        torch.testing.assert_close(u, v, rtol=1e-5, atol=1e-6 * float(u.abs().max()) + 1e-12)
+
+
+def test_adamw_in_a_graph_matches_eager(pfc):
+    """PartialFCAdamW (sample_rate 1, fused) inside GraphedHeadStep: the bias-correction step count comes from a device
+    scalar, so replays advance it like eager steps do."""
+    d, B, C = 512, 256, 3000
+    g = torch.Generator().manual_seed(77)
+    w = torch.normal(0, 0.01, (C, d), generator=g)
+    data = [(torch.nn.functional.normalize(torch.randn(B, d, generator=g)), torch.randint(0, C, (B,), generator=g))
+            for _ in range(4)]
+    outs = []
+    for graphed in (False, True):
+        conf = types.SimpleNamespace(emd_size=d, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5,
+                                     fused_optimizer=True)
+        head = pfc.PartialFCAdamW(conf, C)
+        head.load_state_dict({"weight": w.clone()})
+        head = head.train().cuda()
+        opt = torch.optim.AdamW(head.parameters(), lr=1e-3, weight_decay=0.05)
+        step = pfc.GraphedHeadStep(head, opt, B, d) if graphed else None
+        losses = []
+        for x, lab in data:
+            if graphed:
+                loss, _ = step(x.cuda(), lab.cuda())
+            else:
+                xg = x.clone().cuda().requires_grad_(True)
+                loss = head(xg, lab.clone().cuda(), opt)
+                loss.backward()
+            losses.append(float(loss.detach()))
+        outs.append((losses, head.weight_activated.data.clone(), head.step))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][2] == outs[1][2] == 4
+    torch.testing.assert_close(outs[0][1], outs[1][1], rtol=0, atol=1e-7)
 
 
 def test_l2_resident_gradient_is_bit_identical(pfc):
     from face_recognition_pytorch_b200 import _lib
     a = _graph_run(pfc, True)
-    _lib.lib.pfc_debug_l2_grad(1)
+    _lib.lib.pfc_debug_l2_grad(0)
     try:
         b = _graph_run(pfc, True)
         c = _graph_run(pfc, True, B=320, C=3100)          # odd tile counts, ragged last class tile
     finally:
-        _lib.lib.pfc_debug_l2_grad(0)
+        _lib.lib.pfc_debug_l2_grad(1)
     d = _graph_run(pfc, True, B=320, C=3100)
     for u, v in zip(a, b):
         assert torch.equal(u, v)
     for u, v in zip(c, d):
         assert torch.equal(u, v)
-
-
-def test_fused_sampler_matches_the_oracle(pfc):
-    from face_recognition_pytorch_b200 import _lib
-    from tools import gpu_probe
-    _lib.lib.pfc_debug_sample_fused(1)
-    try:
-        assert gpu_probe._case_sample_once()      # shards > 65 536 classes silently take the multi-launch path
-    finally:
-        _lib.lib.pfc_debug_sample_fused(0)
