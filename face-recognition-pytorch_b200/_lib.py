@@ -20,9 +20,17 @@ class PfcError(RuntimeError):
 
 def _load():
     path = _build.LIB
-    if not os.path.exists(path) or (os.environ.get("PFC_REBUILD") == "1"):
-        # first use in a fresh checkout: compile in-tree (needs nvcc); failure here is fatal by design
-        _build.build(force=True)
+    if os.environ.get("PFC_REBUILD") == "1" or _build.needs_build():
+        # missing (fresh checkout) or older than a source under csrc/: compile in-tree.  build_locked() serialises the ranks
+        # of one node behind a file lock and re-checks staleness once it holds it, so only the first one compiles.
+        # Without nvcc a missing library is fatal by design; a merely stale one is loaded with a warning.
+        try:
+            _build.build_locked(force=os.environ.get("PFC_REBUILD") == "1")
+        except Exception:
+            if not os.path.exists(path):
+                raise
+            import warnings
+            warnings.warn("libpfc_b200.so is older than its sources and could not be rebuilt here; loading it as it is")
     try:
         return ctypes.CDLL(path)
     except OSError as e:   # pragma: no cover
@@ -63,7 +71,8 @@ _SIGS = {
     "pfc_row_stats": (c_int, [p, c_int, c_int, p, p, p, p]),
     "pfc_loss": (c_int, [p, c_int, p, p, p]),
     "pfc_backward_prepare": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, c_int, p]),
-    "pfc_backward_prepare_deferred": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, p]),
+    "pfc_backward_prepare_deferred": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, p, c_int,
+                                              p, p]),
     "pfc_apply_target_patch": (c_int, [p, c_int, c_int, p, p, p, p]),
     "pfc_dx_finalize_patched": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p, p, p, p]),
     "pfc_backward_dx": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
@@ -74,6 +83,7 @@ _SIGS = {
     "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int,
                             p, p, p, p, p]),
     "pfc_peer_max_ranks": (c_int, []),
+    "pfc_peer_set_timeout_ms": (c_int, [c_double]),
     "pfc_peer_barrier": (c_int, [POINTER(c_void_p), p, c_int, c_int, p]),
     "pfc_peer_l2norm_gather": (c_int, [p, p, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), p, p]),
     "pfc_peer_row_stats": (c_int, [p, c_int, c_int, p, p, c_int, c_int, POINTER(c_void_p), p]),

@@ -26,11 +26,25 @@ def _nvcc():
     return exe
 
 
+STAMP = LIB + ".srchash"
+
+
+def _source_hash():
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    """True when the library is missing or was built from other sources (content hash, not mtimes: a repo snapshot copied
+    to another machine does not keep them)."""
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    with open(STAMP) as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -42,7 +56,7 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     procs = []
     for src in SOURCES:
-        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", f".{os.getpid()}.o"))
         cmd = [nvcc, *NVCC_FLAGS, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -55,13 +69,33 @@ def build(force=False, verbose=False):
         if verbose:
             print(out)
         objs.append(obj)
-    tmp = LIB + ".tmp"
+    tmp = f"{LIB}.{os.getpid()}.tmp"          # per process: concurrent builders never publish a half-linked file
     link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     os.replace(tmp, LIB)
+    with open(STAMP + f".{os.getpid()}", "w") as fh:
+        fh.write(_source_hash())
+    os.replace(STAMP + f".{os.getpid()}", STAMP)
+    for obj in objs:
+        try:
+            os.remove(obj)
+        except OSError:
+            pass
     return LIB
+
+
+def build_locked(force=False, verbose=False):
+    """build() behind an exclusive file lock: the ranks of one node (torchrun starts them together) compile once."""
+    import fcntl
+    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lk:
+        fcntl.flock(lk, fcntl.LOCK_EX)
+        try:
+            return build(force=force, verbose=verbose)     # re-checks needs_build() now that the lock is held
+        finally:
+            fcntl.flock(lk, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

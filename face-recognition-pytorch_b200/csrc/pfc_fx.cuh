@@ -83,7 +83,11 @@ __device__ __forceinline__ void wait_counter(const int* p, int target) {
     fence_proxy_async_all();
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// Register cap 144 (not the 168 the forward epilogue would take): the 10 warps of this kernel sit three to a scheduler on
+// two of the SM's four sub-partitions, whose register files (16 384 each) must still take one 72-register warp of the
+// co-resident update kernel -- 3 x 144 x 32 + 72 x 32 = 16 128.  With 168 the update kernel's CTAs only found room on
+// the 4 SMs this kernel leaves idle and the lazy step took 0.69 ms (profiles/r02b_bench_modes.txt).
+__global__ void __maxnreg__(144)
 fx_kernel(const __grid_constant__ CUtensorMap tma_xn,      // Xn  [B, d]   box {64, 128}          A of F (K-major)
           const __grid_constant__ CUtensorMap tma_wn_k,    // Wn  [n, d]   box {64, 128}          B of F (K-major, this CTA's half)
           const __grid_constant__ CUtensorMap tma_e_st,    // E'  blocked  box {64, 32, 1}        F epilogue stores

@@ -61,8 +61,8 @@ struct FwdPolicy {
 
     // 32 accumulator columns -> 16 packed bf16x2 words o[kOff .. kOff+16); returns the sum of the non-target terms
     // (four independent partial sums: no 32-long dependent FADD chain)
-    template <bool kHasTarget, bool kTail, bool kFilter, int kOff>
-    __device__ static __forceinline__ float chunk(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[32],
+    template <bool kHasTarget, bool kTail, bool kFilter>
+    __device__ static __forceinline__ float chunk(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[16],
                                                   int col_base, int jt) {
         float sum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -90,14 +90,13 @@ struct FwdPolicy {
                 sum[((j >> 1) & 1) * 2 + u] += e;
                 e2[u] = keep ? e : 0.f;
             }
-            o[kOff + (j >> 1)] = pack_bf16x2(e2[0], e2[1]);
+            o[j >> 1] = pack_bf16x2(e2[0], e2[1]);
         }
         return (sum[0] + sum[1]) + (sum[2] + sum[3]);
     }
 
     // v = 32 accumulator columns already in registers
-    template <int kOff>
-    __device__ static __forceinline__ float chunk32(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[32],
+    __device__ static __forceinline__ float chunk32(const Params& p, const uint32_t (&v)[32], uint32_t (&o)[16],
                                                     int col_base, int row, int tgt_off_in_tile, int tile_col) {
         // tile_col = column of this chunk inside the 256-wide tile; tgt_off_in_tile = target column inside the tile or -1
         const bool has_t = (tgt_off_in_tile >= tile_col) && (tgt_off_in_tile < tile_col + 32);
@@ -106,11 +105,11 @@ struct FwdPolicy {
         const int jt = has_t ? (tgt_off_in_tile - tile_col) : -1;
         float sum;
         if (!has_t && !tail && !filt) {
-            sum = chunk<false, false, false, kOff>(p, v, o, col_base, jt);
+            sum = chunk<false, false, false>(p, v, o, col_base, jt);
         } else if (!filt) {
-            sum = chunk<true, true, false, kOff>(p, v, o, col_base, jt);
+            sum = chunk<true, true, false>(p, v, o, col_base, jt);
         } else {
-            sum = chunk<true, true, true, kOff>(p, v, o, col_base, jt);
+            sum = chunk<true, true, true>(p, v, o, col_base, jt);
         }
         if (has_t) {
             float raw = 0.f;
@@ -149,21 +148,24 @@ struct FwdPolicy {
             const int tile_col = half * COLS + cc * 64;
             const int col64 = tc.n0 + tile_col;
             if (col64 >= p.n) break;                     // warp-uniform: nothing valid from here on
-            uint32_t o[32];
+            uint32_t o[16];                              // 32 columns = 64 bytes of the row, staged half by half
             tmem_ld_wait();                              // va = columns [cc*64, cc*64+32)
             tmem_ld_32x32(taddr + cc * 64 + 32, vb);     // next chunk in flight during the math below
-            sum += chunk32<0>(p, va, o, col64, row, tgt_off, tile_col);
+            sum += chunk32(p, va, o, col64, row, tgt_off, tile_col);
+            warp_tma_store_begin(lane);                  // the previous box of this warp has left the staging buffer
+            warp_tma_store_half<0>(stage, lane, o);
             tmem_ld_wait();                              // vb ready
             if (cc + 1 < COLS / 64) tmem_ld_32x32(taddr + (cc + 1) * 64, va);
             if (col64 + 32 < p.n) {
-                sum += chunk32<16>(p, vb, o, col64 + 32, row, tgt_off, tile_col + 32);
+                sum += chunk32(p, vb, o, col64 + 32, row, tgt_off, tile_col + 32);
             } else {
 #pragma unroll
-                for (int j = 16; j < 32; ++j) o[j] = 0u;
+                for (int j = 0; j < 16; ++j) o[j] = 0u;
             }
+            warp_tma_store_half<1>(stage, lane, o);
             // E'[col64 / 64][row0 .. row0+32)[0..64): one contiguous 4 KB piece of the class-blocked spill; the store
             // map clips rows >= B
-            warp_tma_store_rows(stage, lane, o, tmc, 0, row0, col64 >> 6);
+            warp_tma_store_commit(stage, lane, tmc, 0, row0, col64 >> 6);
         }
         tmem_ld_wait();                                  // nothing may be outstanding when the accumulator is released
         if (row_ok) p.part_sum[static_cast<size_t>(tc.aux * (BN / COLS) + half) * p.B_pad + row] = sum;

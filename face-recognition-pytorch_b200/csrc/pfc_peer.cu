@@ -31,6 +31,31 @@ struct PeerPtrs {
     void* p[MAX_PEERS];
 };
 
+// How long a rank waits for its peers at a flag barrier before it gives up (printf + trap, which surfaces as a CUDA
+// error on this rank instead of a silent hang).  NCCL's own watchdog default is 10 minutes; a barrier here is reached by
+// every rank once per step, so the only legitimate long waits are host-side stalls of a peer (data-loader hiccup,
+// rank-0 checkpoint / validation, a debugger).  Default 10 minutes of SM clock at 2 GHz; pfc_peer_set_timeout_ms()
+// changes it (0 = wait forever).  After the first ~100 us a waiting thread backs off with nanosleep.
+__device__ long long g_peer_timeout_cycles = 1200000000000LL;
+
+__device__ __forceinline__ void peer_wait_flag(const uint32_t* mine, uint32_t ep, int rank, int from) {
+    uint32_t v;
+    const long long t0 = clock64();
+    const long long limit = *reinterpret_cast<volatile long long*>(&g_peer_timeout_cycles);
+    unsigned spins = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+        if (static_cast<int32_t>(v - ep) >= 0) break;
+        if (++spins > 256) {
+            __nanosleep(spins > 65536 ? 2000 : 100);
+            if (limit > 0 && clock64() - t0 > limit) {
+                printf("pfc: peer barrier timed out (rank %d waiting for %d, epoch %u, saw %u)\n", rank, from, ep, v);
+                __trap();
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ float warp_sum_p(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -50,18 +75,7 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, uint32_t* counter, int rank,
     if (threadIdx.x < W) {
         uint32_t* remote = static_cast<uint32_t*>(flags.p[threadIdx.x]) + rank;    // my slot in peer's array
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(ep) : "memory");
-        const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + threadIdx.x;
-        uint32_t v;
-        const long long t0 = clock64();
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-            if (static_cast<int32_t>(v - ep) >= 0) break;
-            if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; trap instead of hanging the GPU
-                printf("pfc: peer barrier timed out (rank %d waiting for %d, epoch %u, saw %u)\n", rank,
-                       (int)threadIdx.x, ep, v);
-                __trap();
-            }
-        }
+        peer_wait_flag(static_cast<const uint32_t*>(flags.p[rank]) + threadIdx.x, ep, rank, threadIdx.x);
     }
     __threadfence_system();
 }
@@ -80,18 +94,7 @@ __device__ __forceinline__ void peer_entry_barrier(const PeerPtrs& flags, uint32
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(ep) : "memory");
     }
     if (threadIdx.x < W) {
-        const uint32_t* mine = static_cast<const uint32_t*>(flags.p[rank]) + threadIdx.x;
-        uint32_t v;
-        const long long t0 = clock64();
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
-            if (static_cast<int32_t>(v - ep) >= 0) break;
-            if (clock64() - t0 > 20000000000LL) {
-                printf("pfc: peer barrier timed out (rank %d waiting for %d, epoch %u, saw %u)\n", rank,
-                       (int)threadIdx.x, ep, v);
-                __trap();
-            }
-        }
+        peer_wait_flag(static_cast<const uint32_t*>(flags.p[rank]) + threadIdx.x, ep, rank, threadIdx.x);
         __threadfence_system();
     }
     __syncthreads();
@@ -323,6 +326,12 @@ static inline int launched() { return cudaGetLastError() == cudaSuccess ? PFC_OK
 using namespace pfc;
 
 extern "C" {
+
+// Barrier timeout of the peer exchanges in milliseconds of SM time at 2 GHz (0 = never give up); see peer_wait_flag.
+int pfc_peer_set_timeout_ms(double ms) {
+    const long long cycles = ms <= 0 ? 0 : static_cast<long long>(ms * 2.0e6);
+    return cudaMemcpyToSymbol(pfc::g_peer_timeout_cycles, &cycles, sizeof(cycles)) == cudaSuccess ? PFC_OK : PFC_ERR_CUDA;
+}
 
 int pfc_peer_max_ranks(void) { return MAX_PEERS; }
 

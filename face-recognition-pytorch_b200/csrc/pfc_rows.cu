@@ -222,9 +222,10 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
                         const int32_t* __restrict__ labels, const float* __restrict__ tgt_raw, int margin_kind,
                         float cos_m, float sin_m, float theta, const __nv_bfloat16* __restrict__ xn,
                         __nv_bfloat16* __restrict__ xs, float* __restrict__ coef, __nv_bfloat16* __restrict__ E,
-                        int n_pad, float* __restrict__ patch) {
+                        int n_pad, float* __restrict__ patch, int* __restrict__ pending) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    if (kDefer && pending != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *pending = 1;   // see apply_target_patch
     if (row >= B) return;
     const float g = grad_loss ? grad_loss[0] : 1.f;
     const float c = g * s / (static_cast<float>(B) * row_L[row]);
@@ -247,7 +248,9 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
             const __nv_bfloat16 pv = __float2bfloat16_rn(-dm * mask * stats[2 * row]);
             // class-blocked spill: E'[class / 64][row][class % 64]
             if constexpr (kDefer) patch[row] = __bfloat162float(pv);
-            else E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = pv;
+            // kDefer with E given: the dX partials of the unpatched spill exist already (pfc_forward_dx), so the spill
+            // can take its target values for the dW GEMM right away
+            if (!kDefer || E != nullptr) E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = pv;
         } else if constexpr (kDefer) {
             patch[row] = 0.f;
         }
@@ -846,19 +849,20 @@ int pfc_backward_prepare(const float* stats, const float* row_L, const float* gr
     launch_step_kernel(PDL_PREPARE, backward_prepare_kernel<false>, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
         (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
-        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, nullptr);
+        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, nullptr, nullptr);
     return check_launch();
 }
 
 int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
                                   const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                                  const void* xn, void* xs, float* coef, float* patch, void* stream) {
-    if (B <= 0 || bad_d(d) || !patch) return PFC_ERR_SHAPE;
+                                  const void* xn, void* xs, float* coef, float* patch, void* E, int n_pad, int* pending,
+                                  void* stream) {
+    if (B <= 0 || bad_d(d) || !patch || (E && n_pad % 64)) return PFC_ERR_SHAPE;
     const double pi = 3.14159265358979323846;
     launch_step_kernel(PDL_PREPARE, backward_prepare_kernel<true>, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
         (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
-        reinterpret_cast<__nv_bfloat16*>(xs), coef, nullptr, 0, patch);
+        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, patch, pending);
     return check_launch();
 }
 

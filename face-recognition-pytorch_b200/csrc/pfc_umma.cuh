@@ -91,6 +91,29 @@ __device__ __forceinline__ void warp_tma_store_rows(uint32_t stage, int lane, co
     }
 }
 
+// The same store in two halves, for epilogues that produce a row's 128 bytes as two 64-byte pieces and should not keep
+// both in registers: rows_begin (staging buffer free), rows_half<0>, rows_half<1>, rows_commit.
+__device__ __forceinline__ void warp_tma_store_begin(int lane) {
+    if (lane == 0) tma_store_wait_read<0>();
+    __syncwarp();
+}
+template <int kHalf>
+__device__ __forceinline__ void warp_tma_store_half(uint32_t stage, int lane, const uint32_t (&v)[16]) {
+    const uint32_t row = stage + lane * 128;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        sts128(row + (((4 * kHalf + j) ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void warp_tma_store_commit(uint32_t stage, int lane, const CUtensorMap* map, int c0, int c1,
+                                                      int c2) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_3d(map, stage, c0, c1, c2);
+        tma_store_commit();
+    }
+}
+
 // Policy contract:
 //   static constexpr bool A_MN, B_MN;           operand major-ness in shared memory
 //   static constexpr bool A_BLOCKED;            A is the class-blocked spill E'[n_pad/64][B][64] (3-D tensor map)

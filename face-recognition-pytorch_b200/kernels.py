@@ -207,10 +207,12 @@ def backward_prepare(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, ma
 
 @_timed("pfc_backward_prepare_deferred")
 def backward_prepare_deferred(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef,
-                              patch):
+                              patch, E=None, n_pad=0, pending=None):
+    """E given: the target values also go into the spill (no separate apply_target_patch); pending: set to 1."""
     check(lib.pfc_backward_prepare_deferred(_p(stats, F32), _p(row_L, F32), _p(grad_loss, F32), s, B, d,
                                             _p(labels_local, I32), _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16),
-                                            _p(xs, BF16), _p(coef, F32), _p(patch, F32), _stream()),
+                                            _p(xs, BF16), _p(coef, F32), _p(patch, F32), _p(E, BF16), n_pad,
+                                            _p(pending, I32), _stream()),
           "pfc_backward_prepare_deferred")
 
 

@@ -38,6 +38,8 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       backward returns.  The branches share no buffer; in a CUDA graph they become parallel branches.
   conf.peer_collectives (True / False / "auto"): exchange the batch, the softmax statistics and dX through peer
       (NVLink) memory with the stores fused into the producing kernels instead of three NCCL collectives.
+  conf.peer_timeout_ms (float, default 600 000 = NCCL's watchdog default; 0 = wait forever): how long a flag barrier of
+      the peer exchange waits for a stalled rank before this rank's kernel traps (a CUDA error instead of a hang).
 """
 import collections
 import contextlib
@@ -205,6 +207,7 @@ class _PartialFCBase(torch.nn.Module):
         # True / False / "auto": exchange the batch, the softmax statistics and dX through peer (NVLink) memory with
         # the stores fused into the producing kernels (csrc/pfc_peer.cu) instead of three NCCL collectives
         self.peer_collectives = getattr(conf, "peer_collectives", "auto")
+        self.peer_timeout_ms = getattr(conf, "peer_timeout_ms", None)
         self._peer = None
 
     # ------------------------------------------------------------------ reference-visible helpers
@@ -276,7 +279,7 @@ class _PartialFCBase(torch.nn.Module):
             if self.world_size > 1 and dev.type == "cuda" and self.peer_collectives in (True, "auto"):
                 try:
                     from .peer import PeerExchange
-                    self._peer = PeerExchange(dev, self.rank, self.world_size, b, d)
+                    self._peer = PeerExchange(dev, self.rank, self.world_size, b, d, timeout_ms=self.peer_timeout_ms)
                     self._ws.xn_all = self._peer.xn_all          # peers store straight into these
                     self._ws.labels_all = self._peer.labels_all
                 except Exception as e:                            # no P2P / symmetric memory: keep the NCCL collectives
@@ -483,8 +486,7 @@ class _PartialFCBase(torch.nn.Module):
         if patched:
             # keep the target values aside for the rank-1 fix-up of dX, then write them into the spill for dW
             K.backward_prepare_deferred(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all,
-                                        ws.xs, ws.coef, ws.patch)
-            K.apply_target_patch(ws.E, n_pad, B, ws.labels_act, ws.patch, ws.pending if lazy else None)
+                                        ws.xs, ws.coef, ws.patch, ws.E, n_pad, ws.pending if lazy else None)
         else:
             K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
                                ws.coef, ws.E, n_pad)

@@ -21,8 +21,10 @@ def _align(v, a=256):
 
 
 class PeerExchange:
-    def __init__(self, device, rank, world, b, d):
+    def __init__(self, device, rank, world, b, d, timeout_ms=None):
         import torch.distributed._symmetric_memory as symm_mem
+        if timeout_ms is not None:      # how long a flag barrier waits for a stalled peer before it traps (default 10 min)
+            _lib.check(_lib.lib.pfc_peer_set_timeout_ms(float(timeout_ms)), "pfc_peer_set_timeout_ms")
         if world > _lib.lib.pfc_peer_max_ranks():
             raise RuntimeError("too many ranks for the peer-memory exchange")
         B = b * world

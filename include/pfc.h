@@ -134,9 +134,10 @@ int pfc_dx_finalize(const float* partial, int splits, const float* coef, const f
  * pfc_forward_dx = pfc_forward -- same outputs, E's target column left at 0 -- plus partial[g] = E[:, group g] . Wn[group g, :]
  * for the G = pfc_fx_splits(B,n,d) class groups, contracted tile by tile while the spill and the shard are still in
  * L2.  dX needs neither the softmax denominator nor the target patch: those are applied when the partials are summed:
- * pfc_backward_prepare_deferred = pfc_backward_prepare that leaves E alone and writes the target value to patch[i]
- * (the bf16-rounded -dm_i*mask_i*stats[i][0]; 0 for rows whose class is on another rank);
- * pfc_apply_target_patch writes it into E (before pfc_backward_dw; pending != NULL: also sets *pending = 1);
+ * pfc_backward_prepare_deferred = pfc_backward_prepare that writes the target value to patch[i] (the bf16-rounded
+ * -dm_i*mask_i*stats[i][0]; 0 for rows whose class is on another rank) and, when E_bf16 != NULL, into E as well (the dX
+ * partials exist already, the dW GEMM comes next); pending != NULL: also sets *pending = 1 (lazy update);
+ * pfc_apply_target_patch writes patch[] into E as a separate step (before pfc_backward_dw);
  * pfc_dx_finalize_patched / pfc_peer_dx_scatter_patched add the missing rank-1 term patch[i] * Wn[labels_local[i], :]
  * to row i of the summed partials before scaling (bf16 x bf16 products are exact in fp32: the result differs from the
  * patched GEMM only by the position of that term in the sum).
@@ -149,7 +150,8 @@ int pfc_forward_dx(const void* xn_bf16, const void* wn_bf16, const int32_t* labe
                    int* counters, int wn_gate, void* stream);
 int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
                                   const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                                  const void* xn_bf16, void* xs_bf16, float* coef, float* patch, void* stream);
+                                  const void* xn_bf16, void* xs_bf16, float* coef, float* patch, void* E_bf16, int n_pad,
+                                  int* pending, void* stream);
 int pfc_apply_target_patch(void* E_bf16, int n_pad, int B, const int32_t* labels_local, const float* patch,
                            int* pending, void* stream);
 int pfc_dx_finalize_patched(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
@@ -196,6 +198,9 @@ int pfc_dw_sgd_ordered(const void* dwn_bf16, float* w, float* momentum_buf, floa
  * pfc_peer_dx_scatter: coef[i] * sum_z partial[z][i,:] of global row i -> slot `rank` of rank i/b's dx_slots
  *   [W][b][d] fp32; the owner then runs pfc_dx_finalize(dx_slots, splits = W, coef = NULL, ...). */
 int pfc_peer_max_ranks(void);
+/* How long a rank waits for its peers at a flag barrier before it prints and traps (a CUDA error on this rank instead of
+ * a silent hang): milliseconds of SM clock at 2 GHz, default 600 000 (NCCL's watchdog default), 0 = wait forever. */
+int pfc_peer_set_timeout_ms(double ms);
 int pfc_peer_barrier(void* const* peer_flags, uint32_t* epoch_counter, int rank, int W, void* stream);
 int pfc_peer_l2norm_gather(const float* x, const int64_t* labels, int b, int d, int rank, int W,
                            void* const* peer_xn_all, void* const* peer_labels_all, float* inv_norm, void* stream);

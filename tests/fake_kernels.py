@@ -122,7 +122,7 @@ class FakeKernels:
         Ev[rows, labels[rows].long()] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16)
 
     def backward_prepare_deferred(self, stats, row_L, grad_loss, s, B, d, labels, tgt_raw, kind, m2, xn, xs, coef,
-                                  patch):
+                                  patch, E=None, n_pad=0, pending=None):
         g = float(grad_loss[0]) if grad_loss is not None else 1.0
         c = g * s / (B * row_L)
         coef.copy_(c)
@@ -133,6 +133,8 @@ class FakeKernels:
         mask = (raw.abs() <= 1).float()
         patch.zero_()
         patch[rows] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16).float()
+        if E is not None:
+            self.apply_target_patch(E, n_pad, B, labels, patch, pending)
 
     def forward_dx(self, xn, wn, labels, B, n, d, s, kind, m2, m3, thr, E, n_pad, part_sum, tgt_raw, tgt_e, tgt_z,
                    partial, splits, counters, wn_gate):

@@ -186,17 +186,8 @@ def case_dw_big():
 
 
 def case_sample():
-    """Both pick kernels (CTA-wide scan = default, serial walk) against the oracle."""
-    from face_recognition_pytorch_b200 import _lib
-    ok = True
-    try:
-        for par in (1, 0):
-            _lib.lib.pfc_debug_sample_pick(par)
-            print(f"  pick kernel: {'parallel' if par else 'serial'}", flush=True)
-            ok &= _case_sample_once()
-    finally:
-        _lib.lib.pfc_debug_sample_pick(1)
-    return ok
+    """The sampler against the oracle (index set and remapped labels, with forced ties)."""
+    return _case_sample_once()
 
 
 def _case_sample_once():

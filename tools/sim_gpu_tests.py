@@ -24,16 +24,20 @@ from face_recognition_pytorch_b200 import partial_fc, kernels   # noqa: E402
 from fake_kernels import FakeKernels           # noqa: E402
 
 partial_fc.K = FakeKernels(kernels)
-os.environ["PFC_EXPERIMENTAL"] = "1"
 import test_gpu_z_cfg1 as tc                   # noqa: E402
-import test_gpu_experimental as te             # noqa: E402
+import test_gpu_modes as te                    # noqa: E402
+import test_gpu_head as th                     # noqa: E402
 
 RUNS = [
     (tc.test_cfg1_shape_against_the_reference_fixture, [(pfc, False), (pfc, True)]),
     (te.test_fused_step_eager_matches_autograd, [(pfc,)]),
     (te.test_adamw_sampled_fused_matches_unfused_and_reference, [(pfc,)]),
     (te.test_head_with_interclass_filter_matches_reference, [(pfc, False), (pfc, True)]),
-    (te.test_early_dx_matches_the_serial_order, [(pfc, 320, 3100, 512, False), (pfc, 96, 1500, 64, True)]),
+    (te.test_fx_matches_separate_gemms, [(pfc, 320, 3100, 512, False), (pfc, 96, 1500, 64, True), (pfc, 200, 777, 128, True)]),
+    (te.test_fx_forward_only_and_eval_paths, [(pfc,)]),
+    (th.test_steps_match_reference_and_oracle, [(pfc, "head_w1_d128", "lazy"), (pfc, "head_w1_d128", "nofx"),
+                                                (pfc, "head_w1_sampled", "fused"), (pfc, "head_w1_full", "unfused")]),
+    (th.test_scaled_loss_through_the_kernels, [(pfc, "unfused"), (pfc, "fused"), (pfc, "lazy")]),
 ]
 failed = 0
 for fn, arglists in RUNS:
