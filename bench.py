@@ -3,7 +3,7 @@ global batch 1024 (BASELINE.json configs[1]) on N B200s of one node, with the ro
 reference head's CPU implementation timed on the host cores beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1|2|3|4] [--scaling strong|weak]
-                    [--mode lazy|fused|nofx|unfused] [--no-graph] [--no-parity] [--no-cpu-baseline]
+                    [--mode fused|late_dx|unfused] [--no-graph] [--no-parity] [--no-cpu-baseline]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
         bench.py --gpus N --steps K --warmup W
 
@@ -313,7 +313,6 @@ def parity_check(cfg, head, opt, x_local, lab_local, perm_local, w_shard, rank, 
                "ranks": world, "oracle": "oracle/head_oracle.py::head_step fp32 on rank 0's host cores, whole world, "
                f"same inputs ({time.perf_counter() - t0:.1f} s)"}
     # restore: weights, optimizer state, bookkeeping of the head
-    head.flush()
     head.load_state_dict({"weight": w_shard.clone()})
     for nm in ("weight_mom", "weight_activated_mom"):
         t = getattr(head, nm, None)
@@ -344,10 +343,10 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4], help="BASELINE.json configs[config - 1]")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the config's global batch on every N; weak: 128 samples per GPU (global batch 128 N)")
-    ap.add_argument("--mode", default="lazy", choices=["lazy", "fused", "nofx", "unfused"],
-                    help="lazy: conf.lazy_update (fused SGD step applied under the next forward + dX kernel; falls back "
-                         "to fused when sampling); fused: in-step fused update; nofx: fused, separate forward / dX "
-                         "GEMMs (the round-1 step); unfused: dW handed to torch.optim.SGD")
+    ap.add_argument("--mode", default="fused", choices=["fused", "late_dx", "unfused"],
+                    help="fused: SGD update fused into the backward, dX GEMM launched right behind the forward GEMM "
+                         "(conf.early_dx); late_dx: fused, dX after the loss (the round-1 order); unfused: dW handed to "
+                         "torch.optim.SGD")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--autograd", action="store_true", help="capture forward + loss.backward() instead of head.fused_step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -372,8 +371,6 @@ def main():
     C, GLOBAL_BATCH, rate = cfg["C"], cfg["B"], cfg["r"]
     sampled = rate < 1
     mode = args.mode
-    if sampled and mode == "lazy":
-        mode = "fused"                       # the lazy update is defined for sample_rate == 1
 
     import torch
     import torch.distributed as dist
@@ -381,9 +378,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if not dist.is_initialized():
         if "MASTER_ADDR" in os.environ and "RANK" in os.environ:
-            dist.init_process_group("nccl", device_id=dev)
+            dist.init_process_group("cpu:gloo,cuda:nccl", device_id=dev)
         else:
-            dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29541", rank=0, world_size=1, device_id=dev)
+            # gloo beside nccl: the CPU-baseline leg runs the reference's own module, which all-reduces CPU tensors
+            dist.init_process_group("cpu:gloo,cuda:nccl", init_method="tcp://127.0.0.1:29541", rank=0, world_size=1,
+                                    device_id=dev)
     import face_recognition_pytorch_b200 as pfc
     from face_recognition_pytorch_b200 import kernels as K
 
@@ -394,7 +393,7 @@ def main():
     b = GLOBAL_BATCH // world
     fused = mode != "unfused"
     conf = types.SimpleNamespace(emd_size=EMB, sample_rate=rate, mixed_precision=False, loss_s=S, loss_m=M,
-                                 fused_optimizer=fused, fx=mode != "nofx", lazy_update=mode == "lazy",
+                                 fused_optimizer=fused, early_dx=mode != "late_dx",
                                  peer_collectives=False if args.no_peer else "auto")
     head = pfc.PartialFC(conf, C)
     head.load_state_dict({"weight": w_shard.clone()})
@@ -619,8 +618,8 @@ def main():
     #   bf16 gradient spill is traffic, not algorithmic work.
     alg = {
         "pfc_forward": ("tensor", flops_gemm), "pfc_backward_dx": ("tensor", flops_gemm),
-        "pfc_backward_dw": ("tensor", flops_gemm), "pfc_forward_dx": ("tensor", 2 * flops_gemm),
-        "pfc_dw_sgd": ("hbm", n_act * EMB * 18.0), "pfc_dw_sgd_ordered": ("hbm", n_act * EMB * 18.0),
+        "pfc_backward_dw": ("tensor", flops_gemm),
+        "pfc_dw_sgd": ("hbm", n_act * EMB * 18.0),
         "pfc_dw_finalize": ("hbm", n_act * EMB * 4 * 3.0),
     }
     dom = max((k for k in kern if k in alg), key=lambda k: kern[k]["ms_total"], default=None)
@@ -636,8 +635,7 @@ def main():
                 "traffic": None, "traffic_note": "dram__bytes per launch: profiles/r02*_ncu_full_summary.txt (ncu --set full)",
                 "algorithmic_work": work, "peak_source": pk["kind"] + (" burst bf16" if bound == "tensor" else " copy"),
                 "ms_per_launch": ms,
-                "note": ("achieved = (16 B fp32 state + 2 B bf16 shard per element) / time of the update kernel" +
-                         ("; it runs underneath the forward + dX kernel, i.e. shares HBM with it" if dom.endswith("ordered") else "")
+                "note": ("achieved = (16 B fp32 state + 2 B bf16 shard per element) / time of the update kernel"
                          if bound == "hbm" else "achieved = algorithmic flops of this kernel / its time (eager pass, alone)")}
     step_tf = 3 * flops_gemm / (ms_per_step * 1e-3) / 1e12         # per GPU: flops_gemm is this rank's share
     line = {
@@ -648,9 +646,7 @@ def main():
         "config": {"workload": cfg["name"] + ", fwd+bwd+" + ("torch SGD step" if not fused else "fused SGD update"),
                    "classes_per_gpu": nl, "active_classes_per_gpu": n_act, "local_batch": b,
                    "parallelism": f"class-sharded x{world}", "mode": mode,
-                   "update": ("lazy: step t's SGD update runs at the start of step t+1 underneath its forward + dX kernel; "
-                              "every timed step applies exactly one update" if mode == "lazy" else
-                              "in-step" if fused else "torch.optim.SGD"),
+                   "update": "in-step (fused into the backward)" if fused else "torch.optim.SGD",
                    "launch": ("cuda-graph replay (GraphedHeadStep" + (")" if args.autograd else ", no autograd)")
                               if gstep is not None else "eager"),
                    "dx_side_stream": True,
@@ -668,8 +664,9 @@ def main():
                           "work": "6*B*n*D per step and GPU (3 GEMMs, no recompute credited); the HBM-bound update is inside the step",
                           "peak_source": pk["kind"] + " burst bf16"},
         "kernels_ms": {k: round(v["ms_avg"], 4) for k, v in kern.items()} if kern else None,
-        "kernels_ms_note": ("instrumented eager pass, each call alone on its stream (the lazy update and the forward + dX kernel "
-                            "overlap)" if kern else "per-kernel times are reported on one GPU only"),
+        "kernels_ms_note": ("instrumented eager pass, CUDA events around each call on the stream it is made on (calls on "
+                            "the side streams overlap the main stream's)" if kern else
+                            "per-kernel times are reported on one GPU only"),
         "parity_check": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * EMB * 4 + b * 8,
                 "d2h_bytes_per_step": 4 + b * EMB * 4, "steps": e2e_steps, "timing": "host wall clock, max over ranks" +

@@ -52,13 +52,6 @@ _SIGS = {
     "pfc_l2norm_rows_localize": (c_int, [p, c_int, c_int, p, p, p, c_int64, c_int, p, p]),
     "pfc_dx_splits": (c_int, [c_int, c_int, c_int]),
     "pfc_dx_max_splits": (c_int, [c_int, c_int]),
-    "pfc_fx_splits": (c_int, [c_int, c_int, c_int]),
-    "pfc_fx_max_splits": (c_int, [c_int, c_int]),
-    "pfc_fx_counter_words": (c_int, [c_int, c_int, c_int]),
-    "pfc_fx_tile_order": (c_int, [c_int, c_int, c_int, p]),
-    "pfc_forward_dx": (c_int, [p, p, p, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float, p, c_int, p, p,
-                               p, p, p, c_int, p, c_int, p]),
-    "pfc_dw_sgd_ordered": (c_int, [p, p, p, p, c_int, c_int, c_float, c_float, c_float, p, p, p, c_int, p, p, p]),
     "pfc_l2norm_rows": (c_int, [p, p, c_int, c_int, p, p, p]),
     "pfc_localize_labels": (c_int, [p, c_int, c_int64, c_int, p, p]),
     "pfc_sample_workspace_bytes": (c_size_t, [c_int]),
@@ -72,8 +65,7 @@ _SIGS = {
     "pfc_loss": (c_int, [p, c_int, p, p, p]),
     "pfc_backward_prepare": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, c_int, p]),
     "pfc_backward_prepare_deferred": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, p, c_int,
-                                              p, p]),
-    "pfc_apply_target_patch": (c_int, [p, c_int, c_int, p, p, p, p]),
+                                              p]),
     "pfc_dx_finalize_patched": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p, p, p, p]),
     "pfc_backward_dx": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dx_finalize": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p]),

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
+#include <cooperative_groups.h>
 #include "pfc_internal.h"
 
 namespace pfc {
@@ -106,9 +107,11 @@ struct RocOut {
     int th_at[16];         // -1 when never recorded
 };
 
-// key for "minimum value, first from the top": smaller value wins, then larger threshold
+// key for "minimum value, first from the top": smaller value wins, then larger threshold; `aux` rides along (the EER
+// value of the winning threshold)
 struct Best {
     double v;
+    double aux;
     int th;
 };
 __device__ __forceinline__ Best better(Best a, Best b) {
@@ -122,107 +125,143 @@ __device__ __forceinline__ Best warp_best(Best x) {
     for (int o = 16; o > 0; o >>= 1) {
         Best y;
         y.v = __shfl_xor_sync(0xffffffffu, x.v, o);
+        y.aux = __shfl_xor_sync(0xffffffffu, x.aux, o);
         y.th = __shfl_xor_sync(0xffffffffu, x.th, o);
         x = better(x, y);
     }
     return x;
 }
 
-// One CTA.  Thread t owns a contiguous block of thresholds; cumulative counts above each threshold come from a
-// two-level suffix scan, so far/frr are the same integer ratios the reference forms, divided in fp64.
-__global__ void __launch_bounds__(1024)
+// performance_roc as ONE cluster of 8 CTAs (8 SMs): CTA c stages bins [c S, (c+1) S) of both histograms into shared
+// memory with coalesced loads (200 KB), thread t owns 13 consecutive thresholds of the slice.  The counts above each
+// thread's run come from a warp-shuffle suffix scan inside the CTA plus the CTA totals exchanged through distributed
+// shared memory, so far / frr are the same integer ratios the reference forms, divided in fp64; the sweep for the EER
+// and for every FAR level then runs out of shared memory.  The per-CTA winners go to CTA 0 through DSMEM.
+// (Round 1: one CTA, per-thread strided global loads, 1 + levels passes over global memory: 767 us.)
+__constant__ double ROC_LIT[17] = {1e0, 1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8, 1e-9, 1e-10, 1e-11, 1e-12,
+                                   1e-13, 1e-14, 1e-15, 1e-16};   // the doubles float('1e-k') parses to
+constexpr int ROC_CLUSTER = 8;
+constexpr int ROC_THREADS = 1024;
+constexpr int ROC_SLICE = (HIST_BINS + ROC_CLUSTER - 1) / ROC_CLUSTER;      // 12501 bins per CTA
+constexpr int ROC_PER = (ROC_SLICE + ROC_THREADS - 1) / ROC_THREADS;        // 13 bins per thread
+constexpr int ROC_SMEM = 2 * ROC_SLICE * 8;
+
+__device__ __forceinline__ unsigned long long warp_suffix_excl(unsigned long long v, int lane, unsigned long long* total) {
+    // exclusive suffix sum over the warp (sum of the lanes ABOVE this one); *total = sum over the warp
+    unsigned long long s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_down_sync(0xffffffffu, s, o);
+        if (lane + o < 32) s += y;
+    }
+    *total = __shfl_sync(0xffffffffu, s, 0);
+    return s - v;
+}
+
+__global__ void __cluster_dims__(ROC_CLUSTER, 1, 1) __launch_bounds__(ROC_THREADS)
 roc_kernel(const unsigned long long* __restrict__ hist_g, const unsigned long long* __restrict__ hist_i, int min_level,
            int max_level, RocOut* __restrict__ out) {
-    __shared__ unsigned long long sg[1024], si[1024];
-    __shared__ Best sb[32];
-    const int T = threadIdx.x;
-    constexpr int PER = (HIST_BINS + 1023) / 1024;   // 98
-    const int lo = T * PER, hi = min(lo + PER, HIST_BINS);   // bins [lo, hi)
-    unsigned long long tg = 0, ti = 0;
-    for (int b = lo; b < hi; ++b) { tg += hist_g[b]; ti += hist_i[b]; }
-    sg[T] = tg; si[T] = ti;
-    __syncthreads();
-    // suffix sums over threads (serial by thread 0: 1024 adds)
-    __shared__ unsigned long long tot_g, tot_i;
-    if (T == 0) {
-        unsigned long long ag = 0, ai = 0;
-        for (int k = 1023; k >= 0; --k) {
-            const unsigned long long g = sg[k], i2 = si[k];
-            sg[k] = ag; si[k] = ai;       // counts in bins strictly above thread k's block
-            ag += g; ai += i2;
-        }
-        tot_g = ag; tot_i = ai;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char roc_smem[];
+    unsigned long long* sg = reinterpret_cast<unsigned long long*>(roc_smem);
+    unsigned long long* si = sg + ROC_SLICE;
+    __shared__ unsigned long long wtot_g[32], wtot_i[32];
+    __shared__ unsigned long long cta_g[ROC_CLUSTER], cta_i[ROC_CLUSTER];     // every CTA's totals (written by the peers)
+    __shared__ Best wbest[32];
+    __shared__ Best cand[ROC_CLUSTER][17];                                    // CTA 0: per-CTA winners (EER, levels)
+
+    const int T = threadIdx.x, lane = T & 31, warp = T >> 5;
+    const int c = static_cast<int>(cluster.block_rank());
+    const int base = c * ROC_SLICE;
+    const int len = max(0, min(ROC_SLICE, HIST_BINS - base));
+    for (int k = T; k < len; k += ROC_THREADS) {
+        sg[k] = hist_g[base + k];
+        si[k] = hist_i[base + k];
     }
     __syncthreads();
+    const int lo = min(T * ROC_PER, len), hi = min(lo + ROC_PER, len);        // local bins [lo, hi)
+    unsigned long long tg = 0, ti = 0;
+    for (int b = lo; b < hi; ++b) { tg += sg[b]; ti += si[b]; }
+    unsigned long long wg, wi;
+    unsigned long long ag = warp_suffix_excl(tg, lane, &wg);                  // in-warp counts above this thread's run
+    unsigned long long ai = warp_suffix_excl(ti, lane, &wi);
+    if (lane == 0) { wtot_g[warp] = wg; wtot_i[warp] = wi; }
+    __syncthreads();
+    if (warp == 0) {
+        unsigned long long tw_g, tw_i;
+        const unsigned long long vg = wtot_g[lane], vi = wtot_i[lane];
+        const unsigned long long eg = warp_suffix_excl(vg, lane, &tw_g);
+        const unsigned long long ei = warp_suffix_excl(vi, lane, &tw_i);
+        wtot_g[lane] = eg; wtot_i[lane] = ei;                                 // now: counts in the warps above
+        if (lane < ROC_CLUSTER) {                                             // lane r publishes this CTA's totals to CTA r
+            *cluster.map_shared_rank(&cta_g[c], lane) = tw_g;
+            *cluster.map_shared_rank(&cta_i[c], lane) = tw_i;
+        }
+    }
+    cluster.sync();
+    unsigned long long tot_g = 0, tot_i = 0, up_g = 0, up_i = 0;
+#pragma unroll
+    for (int r = 0; r < ROC_CLUSTER; ++r) {
+        tot_g += cta_g[r]; tot_i += cta_i[r];
+        if (r > c) { up_g += cta_g[r]; up_i += cta_i[r]; }
+    }
+    const unsigned long long cg0 = up_g + wtot_g[warp] + ag;                  // counts in bins strictly above this run
+    const unsigned long long ci0 = up_i + wtot_i[warp] + ai;
     const double total_g = (double)(long long)tot_g, total_i = (double)(long long)tot_i;
     const int levels = max_level - min_level + 1;
-    __shared__ double s_eer[1024];
-    // ---- EER: minimum |far - frr|, first from the top (strict <, starting from 1)
-    {
-        Best best; best.v = 0; best.th = -1;
-        double eer_val = 0;
-        unsigned long long cg = sg[T], ci = si[T];
-        for (int th = hi - 1; th >= lo; --th) {
+    // q = 0: EER (minimum |far - frr| below 1, first from the top); q = 1 + l: minimum frr with far <= 1e-(min_level + l)
+    for (int q = 0; q <= levels; ++q) {
+        const double lim = q ? ROC_LIT[q - 1 + min_level] : 0.0;
+        Best best; best.v = 0; best.aux = 0; best.th = -1;
+        unsigned long long cgv = cg0, civ = ci0;
+        for (int b = hi - 1; b >= lo; --b) {
+            const int th = base + b;
+            const unsigned long long hgb = sg[b], hib = si[b];
             if (th >= 1) {
-                const double far = (double)(long long)(ci + hist_i[th]) / total_i;
-                const double frr = (double)(long long)(tot_g - cg) / total_g;
-                const double diff = fabs(far - frr);
-                if (diff < 1.0) {
-                    Best c; c.v = diff; c.th = th;
-                    const Best nb = better(best, c);
-                    if (nb.th == th) eer_val = (far + frr) / 2;
-                    best = nb;
+                const double far = (double)(long long)(civ + hib) / total_i;
+                const double frr = (double)(long long)(tot_g - cgv) / total_g;
+                Best cnd; cnd.th = th;
+                if (q == 0) {
+                    cnd.v = fabs(far - frr); cnd.aux = (far + frr) / 2;
+                    if (cnd.v < 1.0) best = better(best, cnd);
+                } else if (far <= lim) {
+                    cnd.v = frr; cnd.aux = 0;
+                    best = better(best, cnd);
                 }
             }
-            cg += hist_g[th];
-            ci += hist_i[th];
+            cgv += hgb; civ += hib;
         }
-        s_eer[T] = eer_val;
         const Best w = warp_best(best);
-        if ((T & 31) == 0) sb[T >> 5] = w;
+        if (lane == 0) wbest[warp] = w;
         __syncthreads();
-        if (T < 32) {
-            const Best x = warp_best(sb[T]);
-            if (T == 0) {
+        if (warp == 0) {
+            const Best x = warp_best(wbest[lane]);
+            if (lane == 0) *cluster.map_shared_rank(&cand[c][q], 0) = x;
+        }
+        __syncthreads();
+    }
+    cluster.sync();
+    if (c == 0 && warp == 0) {
+        for (int q = lane; q < 17; q += 32) {
+            if (q > levels) {
+                out->frr_at[q - 1] = nan(""); out->th_at[q - 1] = -1;
+                continue;
+            }
+            Best x = cand[0][q];
+            for (int r = 1; r < ROC_CLUSTER; ++r) x = better(x, cand[r][q]);
+            if (q == 0) {
                 out->eer_threshold = x.th < 0 ? 100000 : x.th;
+                out->pad = 0;
+                out->eer = x.th < 0 ? nan("") : x.aux;
                 out->total_genuine = total_g;
                 out->total_imposter = total_i;
-                out->eer = x.th < 0 ? nan("") : s_eer[x.th / PER];   // owner thread of the winning threshold
+            } else {
+                out->frr_at[q - 1] = x.th < 0 ? nan("") : x.v;
+                out->th_at[q - 1] = x.th;
             }
         }
     }
-    // ---- FRR @ FAR <= 1e-k: minimum frr among thresholds with far <= 1e-k, first from the top
-    const double lit[17] = {1e0, 1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8, 1e-9, 1e-10, 1e-11, 1e-12,
-                            1e-13, 1e-14, 1e-15, 1e-16};   // the doubles float('1e-k') parses to
-    for (int l = 0; l < levels; ++l) {
-        const double lim = lit[l + min_level];
-        Best best; best.v = 0; best.th = -1;
-        unsigned long long cg = sg[T], ci = si[T];
-        for (int th = hi - 1; th >= lo; --th) {
-            if (th >= 1) {
-                const double far = (double)(long long)(ci + hist_i[th]) / total_i;
-                if (far <= lim) {
-                    Best c; c.v = (double)(long long)(tot_g - cg) / total_g; c.th = th;
-                    best = better(best, c);
-                }
-            }
-            cg += hist_g[th];
-            ci += hist_i[th];
-        }
-        __syncthreads();
-        const Best w = warp_best(best);
-        if ((T & 31) == 0) sb[T >> 5] = w;
-        __syncthreads();
-        if (T < 32) {
-            const Best x = warp_best(sb[T]);
-            if (T == 0) {
-                out->frr_at[l] = x.th < 0 ? nan("") : x.v;
-                out->th_at[l] = x.th;
-            }
-        }
-    }
-    for (int l = levels; l < 16; ++l)
-        if (T == 0) { out->frr_at[l] = nan(""); out->th_at[l] = -1; }
 }
 
 __global__ void __launch_bounds__(256)
@@ -243,50 +282,101 @@ acc_kernel(const double* __restrict__ scores, const uint8_t* __restrict__ labels
     }
 }
 
-// correct[f][t] = #pairs of fold f classified correctly by "dist < t*step"
-__global__ void __launch_bounds__(256)
-kfold_count_kernel(const double* __restrict__ dist, const uint8_t* __restrict__ labels, int N, int folds, int n_thr,
-                   double step, unsigned int* __restrict__ correct) {
-    const int t = blockIdx.x;
-    if (t >= n_thr) return;
-    __shared__ unsigned int c[64];
-    if (threadIdx.x < 64) c[threadIdx.x] = 0;
-    __syncthreads();
-    const double thr = t * step;          // np.arange(0, 4, 0.01)[t]
-    const int base = N / folds, rem = N % folds;   // sklearn KFold: first `rem` folds get one extra
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const int cut = rem * (base + 1);
-        const int f = i < cut ? i / (base + 1) : rem + (i - cut) / base;
-        const bool pred = dist[i] < thr;
-        if (pred == (labels[i] != 0)) atomicAdd(&c[f], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < folds) correct[threadIdx.x * n_thr + t] = c[threadIdx.x];
-}
+// Standard LFW k-fold protocol in ONE single-CTA launch.  A pair is classified "same" by threshold t iff
+// dist < t*step, so its verdict flips exactly once along the sweep: tmin = the first t with dist < t*step (n_thr when
+// there is none).  A genuine pair is counted correct for t >= tmin, an imposter pair for t < tmin -- one shared-memory
+// histogram entry per pair and fold instead of n_thr CTAs each re-reading every distance (round 1: 226 us):
+//   correct[f][t] = sum_{u <= t} Hg[f][u] + sum_{u > t} Hi[f][u].
+// The comparison that decides tmin is the very `dist < t*step` in fp64 (t*step is monotone in t), so the counts are
+// the ones a threshold-by-threshold sweep would produce.
+constexpr int KF_THREADS = 1024;
 
-__global__ void kfold_pick_kernel(const unsigned int* __restrict__ correct, int N, int folds, int n_thr,
-                                  double* __restrict__ acc, int* __restrict__ best_idx) {
-    const int f = threadIdx.x;
-    if (f >= folds) return;
-    const int base = N / folds, rem = N % folds;
-    const int test_n = base + (f < rem ? 1 : 0);
-    const int train_n = N - test_n;
-    double best = -1.0;
-    int bi = 0;
-    for (int t = 0; t < n_thr; ++t) {
-        unsigned int tot = 0;
-        for (int g = 0; g < folds; ++g)
-            if (g != f) tot += correct[g * n_thr + t];
-        const double a = (double)tot / (double)train_n;
-        if (a > best) { best = a; bi = t; }   // np.argmax: first maximum
+__global__ void __launch_bounds__(KF_THREADS)
+kfold_kernel(const double* __restrict__ dist, const uint8_t* __restrict__ labels, int N, int folds, int n_thr, double step,
+             unsigned int* __restrict__ correct, double* __restrict__ acc, int* __restrict__ best_idx) {
+    extern __shared__ unsigned int kf_smem[];
+    const int S = n_thr + 1;
+    unsigned int* hg = kf_smem;                 // [folds][S]  -> inclusive prefix -> correct[f][t]
+    unsigned int* hi = hg + folds * S;          // [folds][S]
+    unsigned int* tot = hi + folds * S;         // [n_thr] correct pairs over all folds
+    const int T = threadIdx.x, lane = T & 31, warp = T >> 5, warps = KF_THREADS / 32;
+    for (int k = T; k < 2 * folds * S + n_thr; k += KF_THREADS) kf_smem[k] = 0;
+    __syncthreads();
+    const int base = N / folds, rem = N % folds;   // sklearn KFold: first `rem` folds get one extra
+    const int cut = rem * (base + 1);
+    for (int i = T; i < N; i += KF_THREADS) {
+        const int f = i < cut ? i / (base + 1) : rem + (i - cut) / base;
+        const double dv = dist[i];
+        int t = n_thr;
+        if (dv == dv) {
+            const double q = floor(dv / step);
+            t = q < 0.0 ? 0 : (q > (double)n_thr ? n_thr : (int)q);
+            while (t > 0 && dv < (double)(t - 1) * step) --t;
+            while (t < n_thr && !(dv < (double)t * step)) ++t;
+        }
+        atomicAdd((labels[i] != 0 ? hg : hi) + f * S + t, 1u);
     }
-    best_idx[f] = bi;
-    acc[f] = (double)correct[f * n_thr + bi] / (double)test_n;
+    __syncthreads();
+    // per fold: inclusive prefix sums of both histograms (one warp per fold, 32 thresholds per trip)
+    for (int f = warp; f < folds; f += warps) {
+        unsigned int cg = 0, ci = 0;
+        for (int t0 = 0; t0 < S; t0 += 32) {
+            const int t = t0 + lane;
+            unsigned int vg = t < S ? hg[f * S + t] : 0u, vi = t < S ? hi[f * S + t] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int yg = __shfl_up_sync(0xffffffffu, vg, o), yi = __shfl_up_sync(0xffffffffu, vi, o);
+                if (lane >= o) { vg += yg; vi += yi; }
+            }
+            vg += cg; vi += ci;
+            if (t < S) { hg[f * S + t] = vg; hi[f * S + t] = vi; }
+            cg = __shfl_sync(0xffffffffu, vg, 31);
+            ci = __shfl_sync(0xffffffffu, vi, 31);
+        }
+        // cg / ci: pairs of the fold by label; correct[f][t] = prefix_g[t] + (ci - prefix_i[t])
+        for (int t = lane; t < n_thr; t += 32) {
+            const unsigned int cr = hg[f * S + t] + (ci - hi[f * S + t]);
+            hg[f * S + t] = cr;
+            if (correct) correct[f * n_thr + t] = cr;
+            atomicAdd(&tot[t], cr);
+        }
+    }
+    __syncthreads();
+    // per fold: best training threshold (np.argmax: the first maximum), applied to the held-out fold
+    for (int f = warp; f < folds; f += warps) {
+        const int test_n = base + (f < rem ? 1 : 0);
+        const int train_n = N - test_n;
+        double best = -1.0;
+        int bi = 0x7fffffff;
+        for (int t = lane; t < n_thr; t += 32) {
+            const double a = (double)(tot[t] - hg[f * S + t]) / (double)train_n;
+            if (a > best) { best = a; bi = t; }        // ascending t per lane: keeps the first maximum
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+            if (bi == 0x7fffffff) bi = 0;
+            best_idx[f] = bi;
+            acc[f] = (double)hg[f * S + bi] / (double)test_n;
+        }
+    }
 }
 
 }  // namespace pfc
 
 using namespace pfc;
+
+// both histograms zeroed by one memset node when the caller laid them out back to back (eval.py does)
+static int zero_histograms(unsigned long long* hist_g, unsigned long long* hist_i, cudaStream_t stream) {
+    const size_t bytes = sizeof(unsigned long long) * HIST_BINS;
+    if (hist_i == hist_g + HIST_BINS)
+        return cudaMemsetAsync(hist_g, 0, 2 * bytes, stream) != cudaSuccess;
+    return cudaMemsetAsync(hist_g, 0, bytes, stream) != cudaSuccess || cudaMemsetAsync(hist_i, 0, bytes, stream) != cudaSuccess;
+}
 
 extern "C" {
 
@@ -296,8 +386,7 @@ int fr_pair_score(const float* e1, const float* e2, const uint8_t* labels, int N
                   unsigned long long* hist_g, unsigned long long* hist_i, void* stream_) {
     if (N < 0 || d <= 0) return PFC_ERR_SHAPE;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (cudaMemsetAsync(hist_g, 0, sizeof(unsigned long long) * HIST_BINS, stream) != cudaSuccess) return PFC_ERR_CUDA;
-    if (cudaMemsetAsync(hist_i, 0, sizeof(unsigned long long) * HIST_BINS, stream) != cudaSuccess) return PFC_ERR_CUDA;
+    if (zero_histograms(hist_g, hist_i, stream)) return PFC_ERR_CUDA;
     if (N == 0) return PFC_OK;
     pair_score_kernel<<<(N + 7) / 8, 256, 0, stream>>>(e1, e2, labels, N, d, scores, dist, hist_g, hist_i);
     return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
@@ -308,8 +397,15 @@ int fr_roc(const unsigned long long* hist_g, const unsigned long long* hist_i, i
            void* stream_) {
     if (max_level < min_level || max_level - min_level + 1 > 16 || min_level < 0 || max_level > 16)
         return PFC_ERR_SHAPE;
-    roc_kernel<<<1, 1024, 0, (cudaStream_t)stream_>>>(hist_g, hist_i, min_level, max_level,
-                                                     reinterpret_cast<RocOut*>(out));
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(roc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ROC_SMEM) != cudaSuccess)
+            return PFC_ERR_CUDA;
+        attr_set = true;
+    }
+    // one cluster of ROC_CLUSTER CTAs (compile-time __cluster_dims__)
+    roc_kernel<<<ROC_CLUSTER, ROC_THREADS, ROC_SMEM, (cudaStream_t)stream_>>>(hist_g, hist_i, min_level, max_level,
+                                                                            reinterpret_cast<RocOut*>(out));
     return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 
@@ -329,8 +425,15 @@ int fr_kfold_acc(const double* dist, const uint8_t* labels, int N, int folds, in
                  unsigned int* correct_ws, double* acc, int* best_idx, void* stream_) {
     if (N <= 0 || folds < 2 || folds > 64 || n_thr <= 0 || N < folds) return PFC_ERR_SHAPE;
     cudaStream_t stream = (cudaStream_t)stream_;
-    kfold_count_kernel<<<n_thr, 256, 0, stream>>>(dist, labels, N, folds, n_thr, step, correct_ws);
-    kfold_pick_kernel<<<1, 64, 0, stream>>>(correct_ws, N, folds, n_thr, acc, best_idx);
+    const size_t smem = (static_cast<size_t>(2) * folds * (n_thr + 1) + n_thr) * sizeof(unsigned int);
+    if (smem > 227 * 1024) return PFC_ERR_SHAPE;          // folds x thresholds beyond one CTA's shared memory
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(kfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+            return PFC_ERR_CUDA;
+        attr_set = true;
+    }
+    kfold_kernel<<<1, KF_THREADS, smem, stream>>>(dist, labels, N, folds, n_thr, step, correct_ws, acc, best_idx);
     return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 
@@ -338,8 +441,7 @@ int fr_cross_score(const float* e, const long long* labels, int N, int d, double
                    unsigned long long* hist_g, unsigned long long* hist_i, void* stream_) {
     if (N < 0 || d <= 0) return PFC_ERR_SHAPE;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (cudaMemsetAsync(hist_g, 0, sizeof(unsigned long long) * HIST_BINS, stream) != cudaSuccess) return PFC_ERR_CUDA;
-    if (cudaMemsetAsync(hist_i, 0, sizeof(unsigned long long) * HIST_BINS, stream) != cudaSuccess) return PFC_ERR_CUDA;
+    if (zero_histograms(hist_g, hist_i, stream)) return PFC_ERR_CUDA;
     if (N < 2) return PFC_OK;
     const int t = (N + 31) / 32;
     cross_score_kernel<<<dim3(t, t), 1024, 0, stream>>>(e, labels, N, d, scores, label_list, hist_g, hist_i);

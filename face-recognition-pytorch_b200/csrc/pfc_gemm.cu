@@ -265,10 +265,6 @@ struct StorePolicy {
     }
 };
 
-}  // namespace pfc
-#include "pfc_fx.cuh"
-namespace pfc {
-
 // ============================================================================ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -594,114 +590,6 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     if (dwn_bf16 == 1 && pfc_l2_grad_enabled())   // 2: bf16 without the L2 hints (consumed a step later: lazy update)
         return launch_gemm<StorePolicy<true, true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
     return launch_gemm<StorePolicy<true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// FX: forward GEMM + dX GEMM in one persistent kernel (pfc_fx.cuh)
-static void fx_geometry(int B, int n, int d, int* R, int* H, int* G, int* CT) {
-    const int sms = num_sms() > 0 ? num_sms() : 148;
-    *R = (B + 2 * BM - 1) / (2 * BM);
-    *H = (d + BN - 1) / BN;
-    *CT = (n + BN - 1) / BN;
-    int g = (sms / 2) / (*R * *H);
-    if (g < 1) g = 1;
-    if (g > *CT) g = *CT;
-    *G = g;
-}
-
-// class groups = slabs of the dX partial buffer [G][B][d] pfc_forward_dx writes
-int pfc_fx_splits(int B, int n, int d) {
-    int R, H, G, CT;
-    fx_geometry(B, n, d, &R, &H, &G, &CT);
-    return G;
-}
-int pfc_fx_max_splits(int B, int d) {
-    const int sms = num_sms() > 0 ? num_sms() : 148;
-    const int g = (sms / 2) / (((B + 2 * BM - 1) / (2 * BM)) * ((d + BN - 1) / BN));
-    return g > 1 ? g : 1;
-}
-// int32 words of the per-step counter array: [CT] wn_ready, [R * CT] e_ready (zeroed by the caller before every step)
-int pfc_fx_counter_words(int B, int n, int d) {
-    int R, H, G, CT;
-    fx_geometry(B, n, d, &R, &H, &G, &CT);
-    return CT + R * CT;
-}
-// order[i] = i-th class tile (256 classes) the FX kernel asks for: round p of every group before round p + 1.  The
-// update kernel of the lazy mode rewrites the shard in this order (host array of ceil(n / 256) ints).
-int pfc_fx_tile_order(int B, int n, int d, int32_t* order) {
-    int R, H, G, CT;
-    fx_geometry(B, n, d, &R, &H, &G, &CT);
-    int k = 0, longest = 0;
-    for (int g = 0; g < G; ++g) {
-        const int L = (int)(((long long)(g + 1) * CT) / G) - (int)(((long long)g * CT) / G);
-        if (L > longest) longest = L;
-    }
-    for (int i = 0; i < longest; ++i)
-        for (int g = 0; g < G; ++g) {
-            const int c0 = (int)(((long long)g * CT) / G), L = (int)(((long long)(g + 1) * CT) / G) - c0;
-            if (i < L) order[k++] = c0 + i;
-        }
-    return k == CT ? PFC_OK : PFC_ERR_SHAPE;
-}
-
-// pfc_forward (with the target column of E' left at 0) and pfc_backward_dx on that spill, fused: see pfc_fx.cuh.
-// partial: [pfc_fx_splits(B, n, d)][B][d] fp32; counters: pfc_fx_counter_words ints, ZERO on entry; wn_gate != 0: wait
-// for counters[ct] == rows of class tile ct (pfc_dw_sgd_ordered) before reading that tile of wn.
-int pfc_forward_dx(const void* xn, const void* wn, const int32_t* labels_local, int B, int n, int d, float s,
-                   int margin_kind, float m2, float m3, float filter_thr, void* E, int n_pad, float* part_sum,
-                   float* tgt_raw, float* tgt_e, float* tgt_z, float* partial, int splits, int* counters, int wn_gate,
-                   void* stream) {
-    if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 64 || n_pad < n || !counters || !partial) return PFC_ERR_SHAPE;
-    const float log2e = 1.4426950408889634f;
-    if (!(s > 0.f) || 2.f * s * log2e > PFC_EXP_TOP + 126.f) return PFC_ERR_SCALE_RANGE;
-    FxParams p;
-    fx_geometry(B, n, d, &p.R, &p.H, &p.G, &p.CT);
-    if (splits != p.G) return PFC_ERR_SHAPE;
-    CUtensorMap t_xn, t_wnk, t_est, t_eld, t_wnmn, t_dx;
-    int rc = make_tmap(&t_xn, xn, d, B, d, BK, BM);
-    if (rc) return rc;
-    rc = make_tmap(&t_wnk, wn, d, n, d, BK, BN / 2);
-    if (rc) return rc;
-    rc = make_store_tmap(&t_est, E, true, 64, B, n_pad / 64, 64, static_cast<uint64_t>(B) * 64);
-    if (rc) return rc;
-    rc = make_blocked_tmap(&t_eld, E, B, n_pad, BM);
-    if (rc) return rc;
-    rc = make_tmap(&t_wnmn, wn, d, n, d, 64, BK);
-    if (rc) return rc;
-    rc = make_store_tmap(&t_dx, partial, false, d, B, p.G, d, static_cast<uint64_t>(B) * d);
-    if (rc) return rc;
-    fill_fwd_params(p.f, B, n, n_pad, d, 2 * p.R, s, margin_kind, m2, m3, filter_thr, labels_local, E, part_sum, tgt_raw,
-                    tgt_e, tgt_z);
-    p.x = StoreParams{};
-    p.x.rows_valid = B; p.x.cols_valid = d; p.x.ld = d;
-    p.x.split_stride = static_cast<size_t>(B) * d;
-    p.x.out = partial;
-    p.x.out_bf16 = 0;
-    p.kf_stages = (d + BK - 1) / BK;
-    p.n_pad = n_pad;
-    p.n = n;
-    p.wn_ready = wn_gate ? counters : nullptr;
-    p.e_ready = counters + p.CT;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_SMEM) != cudaSuccess)
-            return PFC_ERR_CUDA;
-        attr_set = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * p.R * p.H * p.G);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = FX_SMEM;
-    cfg.stream = reinterpret_cast<cudaStream_t>(stream);
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fx_kernel, t_xn, t_wnk, t_est, t_eld, t_wnmn, t_dx, p);
-    return e == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 
 }  // extern "C"

@@ -213,8 +213,9 @@ loss_kernel(const float* __restrict__ stats, int B, float* __restrict__ row_L, f
 //   c_i = g * s / (B * L_i);  Xs_i = c_i * Xn_i (bf16);  E'[i, y_i] = -dm_i * mask_i * Lothers_i
 //   dm_i = d(margin)/dt = cos m + sin m * t / sqrt(1 - t^2)  if t > cos(pi - m) else 1   (CosFace: 1)
 //   mask_i = 1 if -1 <= raw <= 1 (clamp backward) else 0
-// kDefer: leave E' alone (a dX GEMM launched early may still be reading it) and hand the target value out as patch[i]
-// (0 for rows whose class lives on another rank); pfc_apply_target_patch writes it into E' later.
+// kDefer (early dX, see pfc_backward_prepare_deferred): the dX GEMM has already run on the spill with its target column
+// still 0, so besides patching E' for the dW GEMM the target value is handed out as patch[i] (0 for rows whose class
+// lives on another rank) for the rank-1 fix-up of dX.
 template <bool kDefer>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict__ row_L,
@@ -222,10 +223,9 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
                         const int32_t* __restrict__ labels, const float* __restrict__ tgt_raw, int margin_kind,
                         float cos_m, float sin_m, float theta, const __nv_bfloat16* __restrict__ xn,
                         __nv_bfloat16* __restrict__ xs, float* __restrict__ coef, __nv_bfloat16* __restrict__ E,
-                        int n_pad, float* __restrict__ patch, int* __restrict__ pending) {
+                        int n_pad, float* __restrict__ patch) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (kDefer && pending != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *pending = 1;   // see apply_target_patch
     if (row >= B) return;
     const float g = grad_loss ? grad_loss[0] : 1.f;
     const float c = g * s / (static_cast<float>(B) * row_L[row]);
@@ -248,24 +248,11 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
             const __nv_bfloat16 pv = __float2bfloat16_rn(-dm * mask * stats[2 * row]);
             // class-blocked spill: E'[class / 64][row][class % 64]
             if constexpr (kDefer) patch[row] = __bfloat162float(pv);
-            // kDefer with E given: the dX partials of the unpatched spill exist already (pfc_forward_dx), so the spill
-            // can take its target values for the dW GEMM right away
-            if (!kDefer || E != nullptr) E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = pv;
+            E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = pv;
         } else if constexpr (kDefer) {
             patch[row] = 0.f;
         }
     }
-}
-
-// E'[i, y_i] = patch[i] for the rows whose class lives on this rank (the deferred half of backward_prepare)
-// pending (lazy update, may be null): set to 1 -- the dW GEMM that follows leaves a gradient the next step applies
-__global__ void apply_target_patch_kernel(__nv_bfloat16* __restrict__ E, int B, const int32_t* __restrict__ labels,
-                                          const float* __restrict__ patch, int* __restrict__ pending) {
-    const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row == 0 && pending != nullptr) *pending = 1;
-    if (row >= B) return;
-    const int lbl = labels[row];
-    if (lbl >= 0) E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = __float2bfloat16_rn(patch[row]);
 }
 
 // d = 512 fast path of dx_finalize_kernel: FOUR warps per row (one float4 per lane and slab), two rows per CTA -- the
@@ -437,9 +424,10 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
     const float gs = inv * opt_inv_grad_scale(opt.grad_scale);
     float bc1 = opt.bc1, bc2_sqrt = opt.bc2_sqrt;
     if (opt.step_dev != nullptr) {                   // CUDA-graph replay: the step count lives on the device
-        const float t = static_cast<float>(opt.step_dev[0] + 1);
-        bc1 = 1.f - powf(opt.beta1, t);
-        bc2_sqrt = sqrtf(1.f - powf(opt.beta2, t));
+        // in double, like the host computes the same two numbers for an eager step (pfc_dw_adam)
+        const double t = static_cast<double>(opt.step_dev[0] + 1);
+        bc1 = static_cast<float>(1.0 - pow(static_cast<double>(opt.beta1), t));
+        bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(opt.beta2), t)));
     }
     float ss = 0.f;
 #pragma unroll
@@ -611,96 +599,6 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
     }
 }
 
-// Lazy mode: the SAME update as dw_sgd_rows_kernel, applied at the START of the next step, co-resident with the FX
-// kernel (pfc_fx.cuh) that consumes the rewritten bf16 shard tile by tile.  Persistent (one CTA per SM, 4 warps, 64
-// registers, no shared memory: fits next to FX's one CTA per SM), rows taken in the order FX asks for its class tiles
-// (tile_order, pfc_fx_tile_order), one row per warp and trip.  wn_ready[tile] counts finished rows; a row is
-// published one trip late, behind the fence that the NEXT row's loads have to wait for anyway, so the release costs
-// the streaming warp nothing.  *pending == 0 (nothing to apply: first step, or after a flush): only the counters move.
-// grad_scale (device scalar or nullptr): the loss scale the gradient carries (GradScaler flow), divided out here.
-template <int NV>
-__global__ void __launch_bounds__(128)
-dw_sgd_ordered_kernel(const __nv_bfloat16* __restrict__ dwn, float* __restrict__ w, float* __restrict__ mom,
-                      float* inv_norm_w, int rows, float lr, float momentum, float wd, const float* __restrict__ grad_scale,
-                      __nv_bfloat16* __restrict__ wn, const int* __restrict__ tile_order, int num_tiles,
-                      int* wn_ready, const int* __restrict__ pending) {
-    constexpr int d = 128 * NV;
-    constexpr int TILE = 256;
-    const int lane = threadIdx.x & 31;
-    const int warps = blockDim.x >> 5;
-    const int wid = threadIdx.x >> 5;
-    const int blocks_per_tile = TILE / warps;
-    const int total = num_tiles * blocks_per_tile;
-    const bool apply = pending == nullptr || *pending != 0;
-    const float igs = grad_scale ? 1.f / grad_scale[0] : 1.f;
-    int publish = -1;                                    // tile of the row this warp finished in the previous trip
-    for (int vb = blockIdx.x; vb < total; vb += gridDim.x) {
-        const int tile = tile_order[vb / blocks_per_tile];
-        const int row = tile * TILE + (vb % blocks_per_tile) * warps + wid;
-        if (row >= rows) continue;                       // warp-uniform
-        if (!apply) {
-            if (lane == 0) atomicAdd(wn_ready + tile, 1);
-            continue;
-        }
-        const size_t base = static_cast<size_t>(row) * d;
-        float4 g[NV], wv[NV], mv[NV];
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            uint2 r;
-            const __nv_bfloat16* gp = dwn + base + 4 * (lane + 32 * j);
-            asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(gp));
-            g[j] = unpack4_bf16(r);
-        }
-#pragma unroll
-        for (int j = 0; j < NV; ++j) wv[j] = ld4(w + base + 4 * (lane + 32 * j));
-#pragma unroll
-        for (int j = 0; j < NV; ++j) mv[j] = ld4(mom + base + 4 * (lane + 32 * j));
-        const float inv = inv_norm_w[row];
-        if (publish >= 0) {                              // previous row: its stores were issued a whole trip ago
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) atomicAdd(wn_ready + publish, 1);
-        }
-        float dot = 0.f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j)
-            dot += wv[j].x * g[j].x + wv[j].y * g[j].y + wv[j].z * g[j].z + wv[j].w * g[j].w;
-        dot = warp_sum(dot) * inv;
-        const float wscale = dot * inv;
-        const float gs = inv * igs;
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            float4 a, b = mv[j], q = wv[j];
-            a.x = (g[j].x - q.x * wscale) * gs + wd * q.x;
-            a.y = (g[j].y - q.y * wscale) * gs + wd * q.y;
-            a.z = (g[j].z - q.z * wscale) * gs + wd * q.z;
-            a.w = (g[j].w - q.w * wscale) * gs + wd * q.w;
-            b.x = momentum * b.x + a.x; b.y = momentum * b.y + a.y;
-            b.z = momentum * b.z + a.z; b.w = momentum * b.w + a.w;
-            q.x -= lr * b.x; q.y -= lr * b.y; q.z -= lr * b.z; q.w -= lr * b.w;
-            st4(mom + base + 4 * (lane + 32 * j), b);
-            st4(w + base + 4 * (lane + 32 * j), q);
-            wv[j] = q;
-            ss += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
-        }
-        ss = warp_sum(ss);
-        const float denom = fmaxf(sqrtf(ss), 1e-12f);
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            const float4 q = make_float4(wv[j].x / denom, wv[j].y / denom, wv[j].z / denom, wv[j].w / denom);
-            *reinterpret_cast<uint2*>(wn + base + 4 * (lane + 32 * j)) = pack4_bf16(q);
-        }
-        if (lane == 0) inv_norm_w[row] = 1.f / denom;
-        publish = tile;
-    }
-    if (publish >= 0) {
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(wn_ready + publish, 1);
-    }
-}
-
 static int g_sgd_persistent_warps = 0;   // 0: one row per warp, full grid; > 0: that many warps per SM, grid-stride
 
 template <int NV>
@@ -849,28 +747,20 @@ int pfc_backward_prepare(const float* stats, const float* row_L, const float* gr
     launch_step_kernel(PDL_PREPARE, backward_prepare_kernel<false>, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
         (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
-        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, nullptr, nullptr);
+        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, nullptr);
     return check_launch();
 }
 
 int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
                                   const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                                  const void* xn, void* xs, float* coef, float* patch, void* E, int n_pad, int* pending,
+                                  const void* xn, void* xs, float* coef, float* patch, void* E, int n_pad,
                                   void* stream) {
-    if (B <= 0 || bad_d(d) || !patch || (E && n_pad % 64)) return PFC_ERR_SHAPE;
+    if (B <= 0 || bad_d(d) || !patch || !E || n_pad % 64) return PFC_ERR_SHAPE;
     const double pi = 3.14159265358979323846;
     launch_step_kernel(PDL_PREPARE, backward_prepare_kernel<true>, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
         (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
-        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, patch, pending);
-    return check_launch();
-}
-
-int pfc_apply_target_patch(void* E, int n_pad, int B, const int32_t* labels_local, const float* patch, int* pending,
-                           void* stream) {
-    if (B <= 0 || n_pad % 64 || !patch) return PFC_ERR_SHAPE;
-    launch_step_kernel(PDL_PREPARE, apply_target_patch_kernel, (B + 255) / 256, 256, 0, (cudaStream_t)stream,
-        reinterpret_cast<__nv_bfloat16*>(E), B, labels_local, patch, pending);
+        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, patch);
     return check_launch();
 }
 
@@ -950,36 +840,6 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         static_cast<const float*>(dwn), w, inv_norm_w, rows, d, o, nullptr, mom, nullptr,
         reinterpret_cast<__nv_bfloat16*>(wn_next), inv_norm_next);
-    return check_launch();
-}
-
-// The fused SGD update of pfc_dw_sgd as a persistent, ordered kernel that publishes its progress per class tile
-// (lazy mode, see dw_sgd_ordered_kernel).  d must be a multiple of 128 (<= 1024); dwn is the bf16 gradient spill.
-int pfc_dw_sgd_ordered(const void* dwn_bf16, float* w, float* mom, float* inv_norm_w, int rows, int d, float lr,
-                       float momentum, float weight_decay, const float* grad_scale, void* wn, const int32_t* tile_order,
-                       int num_tiles, int* wn_ready, const int* pending, void* stream) {
-    if (rows <= 0 || d <= 0 || d % 128 || d > 128 * MAXV || num_tiles != (rows + 255) / 256) return PFC_ERR_SHAPE;
-    if (!dwn_bf16 || !w || !mom || !inv_norm_w || !wn || !tile_order || !wn_ready) return PFC_ERR_SHAPE;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const __nv_bfloat16* g = reinterpret_cast<const __nv_bfloat16*>(dwn_bf16);
-    __nv_bfloat16* wnp = reinterpret_cast<__nv_bfloat16*>(wn);
-    cudaStream_t st = (cudaStream_t)stream;
-#define PFC_ORD_CASE(NV) \
-    dw_sgd_ordered_kernel<NV><<<sms, 128, 0, st>>>(g, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, grad_scale, \
-                                                   wnp, tile_order, num_tiles, wn_ready, pending)
-    switch (d / 128) {
-        case 1: PFC_ORD_CASE(1); break;
-        case 2: PFC_ORD_CASE(2); break;
-        case 3: PFC_ORD_CASE(3); break;
-        case 4: PFC_ORD_CASE(4); break;
-        case 5: PFC_ORD_CASE(5); break;
-        case 6: PFC_ORD_CASE(6); break;
-        case 7: PFC_ORD_CASE(7); break;
-        default: PFC_ORD_CASE(8); break;
-    }
-#undef PFC_ORD_CASE
     return check_launch();
 }
 

@@ -23,6 +23,12 @@ def _to_dev(a, dtype):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(_dev(), non_blocking=True).contiguous()
 
 
+def _histograms(bins, dev):
+    """Genuine / imposter histograms laid out back to back: the library then zeroes both with one memset."""
+    h = torch.empty(2, bins, dtype=torch.int64, device=dev)
+    return h[0], h[1]
+
+
 def pair_score(embedding_1, embedding_2, labels, metric="euclidean", min_level=3, max_level=9, return_dist=False):
     """utils/eval.py:68-99 -> (hist_genuine[100001] f64, hist_imposter[100001] f64, score_list[N] f64)."""
     assert metric in ["euclidean", "cosine"], "Invalid metric !!!"
@@ -33,8 +39,7 @@ def pair_score(embedding_1, embedding_2, labels, metric="euclidean", min_level=3
     bins = K.hist_bins()
     scores = torch.empty(N, dtype=torch.float64, device=e1.device)
     dist = torch.empty(N, dtype=torch.float64, device=e1.device)
-    hg = torch.empty(bins, dtype=torch.int64, device=e1.device)
-    hi = torch.empty(bins, dtype=torch.int64, device=e1.device)
+    hg, hi = _histograms(bins, e1.device)
     if metric == "euclidean":       # 'cosine' is accepted but has no code path in the reference either (:80-81)
         K.pair_score(e1, e2, lab, scores, dist, hg, hi)
     else:
@@ -55,8 +60,7 @@ def cross_score(embeddings, labels, metric="euclidean"):
     bins = K.hist_bins()
     scores = torch.zeros(npairs, dtype=torch.float64, device=e.device)
     label_list = torch.zeros(npairs, dtype=torch.float64, device=e.device)
-    hg = torch.empty(bins, dtype=torch.int64, device=e.device)
-    hi = torch.empty(bins, dtype=torch.int64, device=e.device)
+    hg, hi = _histograms(bins, e.device)
     if metric == "euclidean":
         K.cross_score(e, lab, scores, label_list, hg, hi)
     else:
@@ -112,8 +116,7 @@ def kfold_accuracy(embedding_1, embedding_2, labels, folds=10, n_thr=400, step=0
     bins = K.hist_bins()
     scores = torch.empty(N, dtype=torch.float64, device=e1.device)
     dist = torch.empty(N, dtype=torch.float64, device=e1.device)
-    hg = torch.empty(bins, dtype=torch.int64, device=e1.device)
-    hi = torch.empty(bins, dtype=torch.int64, device=e1.device)
+    hg, hi = _histograms(bins, e1.device)
     K.pair_score(e1, e2, lab, scores, dist, hg, hi)
     ws = torch.zeros(folds * n_thr, dtype=torch.int32, device=e1.device)
     acc = torch.zeros(folds, dtype=torch.float64, device=e1.device)

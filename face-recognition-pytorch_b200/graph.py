@@ -13,7 +13,7 @@ collectives included -- NCCL or the peer-memory exchanges) and replays it:
 `loss` and `dx` are static device buffers that the next call overwrites.  Requirements (checked): the head runs with
 conf.fused_optimizer (the update is part of the captured backward), sample_rate == 1 (sampling patches the optimizer on
 the host every step) and a constant batch size -- the configuration of BASELINE configs[1].  Both heads are supported:
-PartialFC (SGD, also with conf.lazy_update) and PartialFCAdamW (the bias-correction step count lives in a device scalar
+PartialFC (SGD) and PartialFCAdamW (the bias-correction step count lives in a device scalar
 that every replay advances).  Hyper-parameters (lr, momentum / betas, weight decay) are kernel arguments and therefore
 part of the graph: every call compares optimizer.param_groups[-1] and the storage of weight_activated with what was
 captured and re-captures when the scheduler (utils/scheduler.py:87-88) or load_state_dict() changed them.  Capturing
@@ -76,7 +76,6 @@ class GraphedHeadStep:
     def recapture(self):
         """(Re)build the graph from the head's current state and the optimizer's current hyper-parameters."""
         head = self.head
-        head.flush()                                   # conf.lazy_update: start from weights that owe nothing
         torch.cuda.synchronize(self.device)
         w = head.weight_activated.data
         saved_w = w.clone()
@@ -98,8 +97,8 @@ class GraphedHeadStep:
             self._loss = self._eager()
         torch.cuda.synchronize(self.device)
         self._graph = g
-        # undo the warm-up steps: weights, optimizer state, step count, the pending lazy update and the normalised bf16
-        # shard the graph's first replay will read
+        # undo the warm-up steps: weights, optimizer state, step count and the normalised bf16 shard the graph's first
+        # replay will read
         w.copy_(saved_w)
         if had_state:
             for t, s in zip(self._optimizer_state(), saved_state):
@@ -109,8 +108,6 @@ class GraphedHeadStep:
                 t.zero_()
         head.step = saved_step
         ws.adam_step.fill_(saved_step)
-        ws.pending.zero_()
-        head._pending, head._pending_opt = False, None
         K.l2norm_rows(w, None, head._n, ws.wn, ws.inv_w)
         head._wn_valid = True
         torch.cuda.synchronize(self.device)
@@ -123,9 +120,7 @@ class GraphedHeadStep:
         self._x.data.copy_(feat, non_blocking=True)
         self._labels.copy_(labels.reshape(-1), non_blocking=True)
         self._graph.replay()
-        # host mirrors of what the replayed step did on the device
-        if head.lazy_update:
-            head._pending = True
+        # host mirror of what the replayed step did on the device
         if head._optimizer_kind != "sgd":
             head.step += 1
         return self._loss, (self._x.grad if self._autograd else self._dx)

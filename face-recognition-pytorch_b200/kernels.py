@@ -83,17 +83,6 @@ num_class_tiles = lib.pfc_num_class_tiles
 part_sum_cols = lib.pfc_part_sum_cols
 dx_splits = lib.pfc_dx_splits
 dx_max_splits = lib.pfc_dx_max_splits
-fx_splits = lib.pfc_fx_splits
-fx_max_splits = lib.pfc_fx_max_splits
-fx_counter_words = lib.pfc_fx_counter_words
-
-
-def fx_tile_order(B, n, d):
-    """int32 [ceil(n / 256)] host tensor: the order in which pfc_forward_dx asks for the 256-class tiles of the shard."""
-    ct = (n + 255) // 256
-    out = torch.empty(ct, dtype=torch.int32)
-    check(lib.pfc_fx_tile_order(B, n, d, ctypes.c_void_p(out.data_ptr())), "pfc_fx_tile_order")
-    return out
 sample_workspace_bytes = lib.pfc_sample_workspace_bytes
 hist_bins = lib.pfc_eval_hist_bins
 
@@ -162,17 +151,6 @@ def forward(xn, wn, labels_local, B, n, d, s, margin_kind, m2, m3, filter_thr, E
                           _p(tgt_z, F32), _stream()), "pfc_forward")
 
 
-@_timed("pfc_forward_dx")
-def forward_dx(xn, wn, labels_local, B, n, d, s, margin_kind, m2, m3, filter_thr, E, n_pad, part_sum, tgt_raw, tgt_e,
-               tgt_z, partial, splits, counters, wn_gate):
-    """pfc_forward with the target column of E' left at 0, plus the dX partials of that spill (csrc/pfc_fx.cuh).
-    counters must be zero on entry; wn_gate: wait for pfc_dw_sgd_ordered's per-tile progress before reading wn."""
-    check(lib.pfc_forward_dx(_p(xn, BF16), _p(wn, BF16), _p(labels_local, I32), B, n, d, s, margin_kind, m2, m3,
-                             filter_thr, _p(E, BF16), n_pad, _p(part_sum, F32), _p(tgt_raw, F32), _p(tgt_e, F32),
-                             _p(tgt_z, F32), _p(partial, F32), splits, _p(counters, I32), int(bool(wn_gate)), _stream()),
-          "pfc_forward_dx")
-
-
 @_timed("pfc_margin_apply")
 def margin_apply(logits, labels, margin_kind, s, m2, m3, filter_thr, out, gate):
     B, n = logits.shape
@@ -207,19 +185,13 @@ def backward_prepare(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, ma
 
 @_timed("pfc_backward_prepare_deferred")
 def backward_prepare_deferred(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef,
-                              patch, E=None, n_pad=0, pending=None):
-    """E given: the target values also go into the spill (no separate apply_target_patch); pending: set to 1."""
+                              patch, E, n_pad):
+    """pfc_backward_prepare for a step whose dX GEMM already ran on the unpatched spill: also hands the target values out
+    as patch[B] for pfc_dx_finalize_patched / pfc_peer_dx_scatter_patched."""
     check(lib.pfc_backward_prepare_deferred(_p(stats, F32), _p(row_L, F32), _p(grad_loss, F32), s, B, d,
                                             _p(labels_local, I32), _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16),
-                                            _p(xs, BF16), _p(coef, F32), _p(patch, F32), _p(E, BF16), n_pad,
-                                            _p(pending, I32), _stream()),
+                                            _p(xs, BF16), _p(coef, F32), _p(patch, F32), _p(E, BF16), n_pad, _stream()),
           "pfc_backward_prepare_deferred")
-
-
-@_timed("pfc_apply_target_patch")
-def apply_target_patch(E, n_pad, B, labels_local, patch, pending=None):
-    check(lib.pfc_apply_target_patch(_p(E, BF16), n_pad, B, _p(labels_local, I32), _p(patch, F32), _p(pending, I32),
-                                     _stream()), "pfc_apply_target_patch")
 
 
 @_timed("pfc_dx_finalize_patched")
@@ -262,17 +234,6 @@ def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_sc
     check(lib.pfc_dw_sgd(_p(dwn, BF16 if is_bf16 else F32), int(is_bf16), _p(w, F32), _p(mom, F32),
                          _p(inv_norm_w, F32), rows, d, lr, momentum, weight_decay, _p(grad_scale, F32),
                          _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()), "pfc_dw_sgd")
-
-
-@_timed("pfc_dw_sgd_ordered")
-def dw_sgd_ordered(dwn_bf16, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_scale, wn, tile_order,
-                   counters, pending):
-    """pfc_dw_sgd as a persistent kernel that rewrites the shard in pfc_forward_dx's tile order and publishes its
-    progress in counters[0 : ceil(rows / 256)]; *pending == 0: only the counters move."""
-    check(lib.pfc_dw_sgd_ordered(_p(dwn_bf16, BF16), _p(w, F32), _p(mom, F32), _p(inv_norm_w, F32), rows, d, lr, momentum,
-                                 weight_decay, _p(grad_scale, F32), _p(wn, BF16), _p(tile_order, I32),
-                                 tile_order.numel(), _p(counters, I32), _p(pending, I32), _stream()),
-          "pfc_dw_sgd_ordered")
 
 
 @_timed("pfc_dw_adam")

@@ -20,19 +20,15 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       optimizer.param_groups[-1] every step (the scheduler mutates lr, utils/scheduler.py:87-88).  A scaled loss
       (GradScaler flow, model/FR_PartialFC.py:178-184) is honoured: dX keeps the scale autograd expects and the fused
       update divides it out on the device; the scaler's inf-skipping cannot be (bf16 operands do not need a scaler).
-  conf.fx (bool, default True): compute the dX partials inside the forward kernel (pfc_forward_dx, csrc/pfc_fx.cuh)
-      whenever local_embeddings needs a gradient -- the spill E' and the normalised shard are then read from L2
-      instead of HBM and the two contractions share the tensor pipe.  False: separate forward / dX GEMMs.
-  conf.lazy_update (bool, default False; needs fused_optimizer, SGD, sample_rate == 1, emd_size % 128 == 0): backward
-      stops after the dW GEMM; the SGD / momentum update it feeds is applied at the START of the next forward by a
-      persistent kernel that runs underneath the forward + dX kernel (HBM-bound next to tensor-bound, same SMs) and
-      feeds it the rewritten shard tile by tile.  Same arithmetic, same order of updates; only `weight_activated` (and
-      the momentum) lag by one pending update between steps -- `flush()` applies it, and `state_dict()`,
-      `load_state_dict()` and forward passes that do not train call flush() themselves.
+  conf.early_dx (bool, default True): launch the dX contraction right behind the forward GEMM on its own stream, next to
+      the softmax statistics, their exchange between ranks and the loss, whenever local_embeddings needs a gradient.
+      The forward leaves 0 in the target column of the spill and dX needs neither the softmax denominator nor the target
+      value: both are applied when the partials are summed (pfc_dx_finalize_patched).  False: dX after the coefficients
+      are known (backward order of the reference).
   conf.device_sampling (bool, default False): draw the PartialFC sampling scores with the CUDA generator on the device
       instead of `torch.rand` on the CPU generator + H2D copy (nets/PartialFC.py:110).  Removes a host round trip per
       step; the sampled index set is then NOT the reference's for the same seed (same distribution, other stream).
-  conf.dx_side_stream (True / False / "auto", default "auto" = on when world_size > 1 or conf.fx): after the dX
+  conf.dx_side_stream (True / False / "auto", default "auto" = on): after the dX
       partials exist the step forks -- the peer scatter + barrier + normalise-backward of dX (one GPU: just the
       normalise-backward) on a side stream, the rank-local dW GEMM / update on the main one -- and joins before
       backward returns.  The branches share no buffer; in a CUDA graph they become parallel branches.
@@ -88,17 +84,13 @@ class _Workspace:
         self.coef = z(B)
         self.patch = z(B)                         # target values of E' kept aside while the spill's target column is 0
         self.xs = z(B, d, dt=bf16)
-        self.max_splits = max(1, K.dx_max_splits(B, d), K.fx_max_splits(B, d))
+        self.max_splits = max(1, K.dx_max_splits(B, d))
         self.dx_partial = z(self.max_splits * B * d)
         self.dxn_all = z(B, d) if W > 1 else None
         self.dxn_local = z(b, d) if W > 1 else None
         self.dwn = None                           # fp32 un-normalised dW (un-fused / AdamW), allocated on first use
         self.dwn_bf16 = None                      # bf16 spill of it (fused SGD), allocated on first use
-        # FX kernel (pfc_forward_dx): per-step tile counters; lazy update: tile order, pending flag, loss scale
-        self.counters = z(K.fx_counter_words(B, n_max, d) + 4, dt=i32)
-        self.tile_order = None
-        self.pending = z(1, dt=i32)
-        self.gscale = torch.ones(1, dtype=f32, device=dev)
+        self.gscale = torch.ones(1, dtype=f32, device=dev)     # loss scale the gradient carries (fused update)
         self.adam_step = z(1, dt=i32)
         if sampled:
             self.perm = z(nl)
@@ -151,10 +143,8 @@ class _PartialFCBase(torch.nn.Module):
         self.fp16 = conf.mixed_precision           # kept for interface parity; the kernels always run bf16-in / fp32-acc
         self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
         self.device_sampling = bool(getattr(conf, "device_sampling", False))
-        # forward + dX partials in one kernel (csrc/pfc_fx.cuh) whenever the embeddings need a gradient
-        self.fx = bool(getattr(conf, "fx", True))
-        # apply the fused SGD update at the start of the NEXT forward, underneath the forward + dX kernel
-        self.lazy_update = bool(getattr(conf, "lazy_update", False))
+        # dX contraction launched right behind the forward GEMM, next to the statistics / exchange / loss
+        self.early_dx = bool(getattr(conf, "early_dx", True))
         # run the tail of the dX path (finalize / peer scatter + finalize) on a side stream next to the rank-local
         # dW GEMM + update, which it does not depend on; may be flipped between steps (before a graph capture)
         self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto"
@@ -193,17 +183,10 @@ class _PartialFCBase(torch.nn.Module):
         self._n = self.num_local        # active classes this step
         self._opt_args = None
         self._side_stream = None        # dX tail
-        self._upd_stream = None         # lazy update
-        self._fx_splits = None          # slabs of dX partials the forward of this step left in ws.dx_partial
-        self._pending = False           # lazy update: ws.dwn_bf16 holds a gradient that has not been applied yet
-        self._pending_opt = None        # ... and the hyper-parameters of the step that produced it
+        self._dx_stream = None          # early dX GEMM
+        self._early_splits = None       # slabs of dX partials (of the UNPATCHED spill) this step's forward left behind
         self._gscale_is_one = True
         self._graph_steps = False       # AdamW: take the bias-correction step count from ws.adam_step (graph replay)
-        if self.lazy_update:
-            if not (self.fused_optimizer and self._optimizer_kind == "sgd" and self.sample_rate >= 1
-                    and self.embedding_size % 128 == 0 and self.embedding_size <= 1024 and self.fx):
-                raise RuntimeError("conf.lazy_update needs conf.fused_optimizer, conf.fx, the SGD head (PartialFC), "
-                                   "sample_rate == 1 and emd_size a multiple of 128 (<= 1024)")
         # True / False / "auto": exchange the batch, the softmax statistics and dX through peer (NVLink) memory with
         # the stores fused into the producing kernels (csrc/pfc_peer.cu) instead of three NCCL collectives
         self.peer_collectives = getattr(conf, "peer_collectives", "auto")
@@ -384,72 +367,35 @@ class _PartialFCBase(torch.nn.Module):
         else:
             self._n = self.num_local
 
-    # ---- lazy update (conf.lazy_update)
-    def _launch_lazy_update(self):
-        """The pending SGD step as the ordered, progress-publishing kernel (pfc_dw_sgd_ordered) on the CURRENT stream;
-        ws.counters must be zero.  With nothing pending on the device only the counters move."""
-        ws, d = self._ws, self.embedding_size
-        n = self.num_local
-        w = self.weight_activated.data
-        if ws.tile_order is None:
-            ws.tile_order = K.fx_tile_order(ws.B, n, d).to(w.device)
-        o = self._pending_opt or self._opt_args or self._read_optimizer(self._optimizer)
-        K.dw_sgd_ordered(ws.grad_buffer(True, d), w, self._momentum(w), ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"],
-                         ws.gscale, ws.wn, ws.tile_order, ws.counters, ws.pending)
-
-    @torch.no_grad()
-    def flush(self):
-        """Apply the update a lazy head still owes (conf.lazy_update); a no-op otherwise."""
-        if not (self.lazy_update and self._pending):
-            return
-        ws = self._ws
-        ws.counters.zero_()
-        self._launch_lazy_update()
-        ws.pending.zero_()
-        self._pending = False
-        self._pending_opt = None
-
     def _forward_impl(self, local_embeddings, clone_loss=True, need_dx=False):
         ws, W, d = self._ws, self.world_size, self.embedding_size
         b, B = ws.b, ws.B
         n = self._n
         w = self.weight_activated.data
-        use_fx = self.fx and need_dx
         if self.fused_optimizer:
             self._opt_args = self._read_optimizer(self._optimizer)
-        lazy = self.lazy_update and use_fx
-        if self.lazy_update and not lazy:
-            self.flush()                # a forward that does not train sees the up-to-date shard
+        if self._dx_stream is not None:
+            # an early dX GEMM whose backward never ran may still be reading the spill this forward overwrites
+            torch.cuda.current_stream().wait_stream(self._dx_stream)
         if not self._wn_valid:
             K.l2norm_rows(w, None, n, ws.wn, ws.inv_w)                            # :200
             self._wn_valid = True
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
         self._n_pad = K.padded_classes(n)
-        self._fx_splits = None
-        if use_fx:
-            # :201-207 plus the dX contraction on the same tiles (target column of E' = 0, fixed up in backward)
-            splits = K.fx_splits(B, n, d)
-            ws.counters.zero_()
-            upd = None
-            if lazy:
-                # the update of the previous step's gradient runs NEXT TO the kernel below and feeds it the shard
-                if w.is_cuda:
-                    if self._upd_stream is None:
-                        self._upd_stream = torch.cuda.Stream(device=w.device)
-                    upd = self._upd_stream
-                    upd.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(upd) if upd is not None else contextlib.nullcontext():
-                    self._launch_lazy_update()
-            K.forward_dx(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
-                         ws.tgt_raw, ws.tgt_e, ws.tgt_z, ws.dx_partial, splits, ws.counters, lazy)
-            if upd is not None:
-                torch.cuda.current_stream().wait_stream(upd)
-            if lazy:
-                self._pending, self._pending_opt = False, None      # consumed (the device flag is set again by backward)
-            self._fx_splits = splits
-        else:
-            K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
-                      ws.tgt_raw, ws.tgt_e, ws.tgt_z)                             # :201-207
+        K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
+                  ws.tgt_raw, ws.tgt_e, ws.tgt_z)                                 # :201-207
+        self._early_splits = None
+        if need_dx and self.early_dx:
+            # the forward leaves 0 in the target column of the spill: dXn_i = c_i (sum_c E'_ic Wn_c + patch_i Wn_{y_i}), so
+            # the contraction can start now and run next to the statistics, their exchange and the loss
+            if w.is_cuda:
+                if self._dx_stream is None:
+                    self._dx_stream = torch.cuda.Stream(device=w.device)
+                self._dx_stream.wait_stream(torch.cuda.current_stream())
+            splits = K.dx_splits(B, n, d)
+            with torch.cuda.stream(self._dx_stream) if w.is_cuda else contextlib.nullcontext():
+                K.backward_dx(ws.E, self._n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
+            self._early_splits = splits
         peer = self._peer
         if peer is not None:
             # statistics straight into every peer's slot, then a rank-ordered local sum (identical bits on all ranks)
@@ -475,39 +421,41 @@ class _PartialFCBase(torch.nn.Module):
         g = None if grad_loss is None else grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         w = self.weight_activated.data
         peer = self._peer
-        patched = self._fx_splits is not None      # the forward left the dX partials of the UNPATCHED spill behind
-        lazy = self.lazy_update and patched
+        early = self._early_splits is not None     # the dX GEMM of the UNPATCHED spill is running / has run
         if self.fused_optimizer:
             if g is not None:
                 ws.gscale.copy_(g)                 # the fused update divides the loss scale out again
             elif not self._gscale_is_one:
                 ws.gscale.fill_(1.0)
             self._gscale_is_one = g is None
-        if patched:
-            # keep the target values aside for the rank-1 fix-up of dX, then write them into the spill for dW
+        if early:
+            # the dX GEMM must have finished READING the spill before its target column is written for the dW GEMM; the
+            # target values are also kept aside (ws.patch) for the rank-1 fix-up of dX
+            if self._dx_stream is not None:
+                torch.cuda.current_stream().wait_stream(self._dx_stream)
             K.backward_prepare_deferred(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all,
-                                        ws.xs, ws.coef, ws.patch, ws.E, n_pad, ws.pending if lazy else None)
+                                        ws.xs, ws.coef, ws.patch, ws.E, n_pad)
         else:
             K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
                                ws.coef, ws.E, n_pad)
         spill_bf16 = self.fused_optimizer and self._optimizer_kind == "sgd" and d % 128 == 0
         dwn = ws.grad_buffer(spill_bf16, d)
         dw = None
-        # Order without FX.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the
+        # Order without early dX.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the
         # reduce-scatter / peer stores have the whole dW + update to complete.  N = 1: dW GEMM first (it walks the class
         # tiles from the end, where the forward's spill is still in L2), then dX, then the update.
-        dw_first = W == 1 and not patched
+        dw_first = W == 1 and not early
         if dw_first:
             K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         dx, rs_work = None, None
         # fork: the tail of the dX path runs on a side stream next to the dW GEMM / update (see conf.dx_side_stream)
-        want_fork = (W > 1 or patched) if self.dx_side_stream == "auto" else bool(self.dx_side_stream)
+        want_fork = True if self.dx_side_stream == "auto" else bool(self.dx_side_stream)
         fork = want_fork and w.is_cuda and need_dx and (W == 1 or peer is not None)
         tail = None
         wn_read_done = None       # fork: the tail's patched kernel reads wn, which the fused update rewrites in place
         if need_dx:
-            if patched:
-                splits = self._fx_splits
+            if early:
+                splits = self._early_splits
             else:
                 splits = K.dx_splits(B, n, d)
                 K.backward_dx(ws.E, n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
@@ -519,7 +467,7 @@ class _PartialFCBase(torch.nn.Module):
                 tail.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():
                 if W == 1:
-                    if patched:
+                    if early:
                         K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx,
                                               ws.patch, ws.labels_act, ws.wn)
                     else:
@@ -527,7 +475,7 @@ class _PartialFCBase(torch.nn.Module):
                 elif peer is not None:
                     # :505-522 -- every rank stores its scaled partial of row i into the owner's slot; the owner sums
                     # the W slots in rank order inside the normalise-backward kernel (x W, :521)
-                    if patched:
+                    if early:
                         K.peer_dx_scatter_patched(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W,
                                                   peer.ptrs("dx_slots"), ws.patch, ws.labels_act, ws.wn)
                     else:
@@ -538,7 +486,7 @@ class _PartialFCBase(torch.nn.Module):
                         K.peer_dx_finalize(peer.ptrs("flags"), peer.counter, self.rank, W, peer.dx_slots,
                                            self._x_local, ws.inv_x, float(W), b, d, dx)
                 else:
-                    if patched:
+                    if early:
                         K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all,
                                               ws.patch, ws.labels_act, ws.wn)
                     else:
@@ -546,14 +494,12 @@ class _PartialFCBase(torch.nn.Module):
                     # :505-519 -- asynchronous: it overlaps the rank-local dW GEMM / update below
                     rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
                                                                 async_op=True)
-                if patched and tail is not None and self.fused_optimizer and not lazy:
+                if early and tail is not None and self.fused_optimizer:
                     wn_read_done = torch.cuda.Event()
                     wn_read_done.record()                     # on the tail stream
         if not dw_first:
-            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn, keep_in_l2=not lazy)
-        if lazy:
-            self._pending, self._pending_opt = True, self._opt_args   # applied by the next forward / flush()
-        elif self.fused_optimizer:
+            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
+        if self.fused_optimizer:
             if wn_read_done is not None:
                 torch.cuda.current_stream().wait_event(wn_read_done)
             self._fused_step(w, n, d, dwn, ws.wn)         # in place, after the last reader of this step's shard
@@ -573,7 +519,7 @@ class _PartialFCBase(torch.nn.Module):
                 K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
         if tail is not None:
             torch.cuda.current_stream().wait_stream(tail)                          # join
-        self._fx_splits = None
+        self._early_splits = None
         return dx, dw
 
     def _fused_step(self, w, n, d, dwn, wn_out):
@@ -581,7 +527,6 @@ class _PartialFCBase(torch.nn.Module):
 
     # ------------------------------------------------------------------ checkpoint layout (nets/PartialFC.py:210-232)
     def state_dict(self, destination=None, prefix="", keep_vars=False):
-        self.flush()                    # conf.lazy_update: the checkpoint holds the weights AFTER the last step
         if destination is None:
             destination = collections.OrderedDict()
             destination._metadata = collections.OrderedDict()
@@ -595,7 +540,6 @@ class _PartialFCBase(torch.nn.Module):
         return destination
 
     def load_state_dict(self, state_dict, strict: bool = True):
-        self.flush()                    # a pending lazy update belongs to the weights that are being replaced
         self._wn_valid = False
         if self.sample_rate < 1:
             self.weight = state_dict["weight"].to(self.weight.device)

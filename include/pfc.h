@@ -43,11 +43,6 @@ int pfc_num_class_tiles(int n);                   /* number of part_sum slabs (c
 int pfc_part_sum_cols(void);                      /* classes per part_sum slab (64) */
 int pfc_dx_splits(int B, int n, int d);           /* class splits pfc_backward_dx will use for this shape */
 int pfc_dx_max_splits(int B, int d);              /* upper bound of pfc_dx_splits over all n (sizes `partial`) */
-int pfc_fx_splits(int B, int n, int d);           /* slabs of dX partials pfc_forward_dx writes (its class groups) */
-int pfc_fx_max_splits(int B, int d);              /* upper bound of pfc_fx_splits over all n */
-int pfc_fx_counter_words(int B, int n, int d);    /* int32 words of pfc_forward_dx's per-step counter array */
-int pfc_fx_tile_order(int B, int n, int d, int32_t* order);   /* HOST array [ceil(n/256)]: order in which
-                                                      pfc_forward_dx asks for the 256-class tiles of the shard */
 
 /* ---- (1) fused L2 normalise: F.normalize of embeddings / of the classifier shard, nets/PartialFC.py:199-200.
  * xn[r,:] = bf16(x[src,:] / max(||x[src,:]||, 1e-12)), inv_norm[r] = 1/max(||.||, 1e-12), src = index ? index[r] : r
@@ -130,30 +125,18 @@ int pfc_backward_dx(const void* E_bf16, int n_pad, const void* wn_bf16, int B, i
                     int splits, void* stream);
 int pfc_dx_finalize(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
                     float scale, int rows, int rows_total, int d, float* out, void* stream);
-/* Forward + dX in one kernel (csrc/pfc_fx.cuh; replaces pfc_forward followed by pfc_backward_dx on the same step).
- * pfc_forward_dx = pfc_forward -- same outputs, E's target column left at 0 -- plus partial[g] = E[:, group g] . Wn[group g, :]
- * for the G = pfc_fx_splits(B,n,d) class groups, contracted tile by tile while the spill and the shard are still in
- * L2.  dX needs neither the softmax denominator nor the target patch: those are applied when the partials are summed:
- * pfc_backward_prepare_deferred = pfc_backward_prepare that writes the target value to patch[i] (the bf16-rounded
- * -dm_i*mask_i*stats[i][0]; 0 for rows whose class is on another rank) and, when E_bf16 != NULL, into E as well (the dX
- * partials exist already, the dW GEMM comes next); pending != NULL: also sets *pending = 1 (lazy update);
- * pfc_apply_target_patch writes patch[] into E as a separate step (before pfc_backward_dw);
+/* Early dX (the host launches pfc_backward_dx right behind pfc_forward, next to the softmax statistics / their exchange /
+ * the loss): the forward leaves 0 in the target column of E, and the dX contraction needs neither the softmax denominator
+ * nor the target value -- both are applied when the partials are summed:
+ * pfc_backward_prepare_deferred = pfc_backward_prepare (run once the dX GEMM has finished reading E) that ALSO hands the
+ * target value out as patch[i] (the bf16-rounded -dm_i*mask_i*stats[i][0]; 0 for rows whose class is on another rank);
  * pfc_dx_finalize_patched / pfc_peer_dx_scatter_patched add the missing rank-1 term patch[i] * Wn[labels_local[i], :]
- * to row i of the summed partials before scaling (bf16 x bf16 products are exact in fp32: the result differs from the
- * patched GEMM only by the position of that term in the sum).
- * counters: pfc_fx_counter_words ints, ZERO on entry (per step).  wn_gate != 0 (lazy update): the kernel asks for the
- * 256-class tile t of wn only once counters[t] == rows of that tile, which pfc_dw_sgd_ordered -- launched on another
- * stream, co-resident on the same SMs -- counts up as it rewrites the shard with the PREVIOUS step's gradient. */
-int pfc_forward_dx(const void* xn_bf16, const void* wn_bf16, const int32_t* labels_local, int B, int n, int d, float s,
-                   int margin_kind, float m2, float m3, float interclass_filtering_threshold, void* E_bf16, int n_pad,
-                   float* part_sum, float* tgt_raw, float* tgt_e, float* tgt_z, float* partial, int splits,
-                   int* counters, int wn_gate, void* stream);
+ * to row i of the summed partials before scaling (bf16 x bf16 products are exact in fp32: the result differs from a
+ * GEMM over the patched spill only by the position of that term in the sum). */
 int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
                                   const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
                                   const void* xn_bf16, void* xs_bf16, float* coef, float* patch, void* E_bf16, int n_pad,
-                                  int* pending, void* stream);
-int pfc_apply_target_patch(void* E_bf16, int n_pad, int B, const int32_t* labels_local, const float* patch,
-                           int* pending, void* stream);
+                                  void* stream);
 int pfc_dx_finalize_patched(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
                             float scale, int rows, int rows_total, int d, float* out, const float* patch,
                             const int32_t* labels_local, const void* wn_bf16, void* stream);
@@ -173,14 +156,6 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* momentum_buf, con
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                 const float* grad_scale, void* wn_next_bf16, float* inv_norm_next, const int* step_dev, void* stream);
-/* pfc_dw_sgd (bf16 gradient, d % 128 == 0) as a persistent kernel -- one small CTA per SM, no shared memory, so that it
- * runs NEXT TO pfc_forward_dx on the same SMs -- that rewrites the shard in pfc_fx_tile_order's order and counts the
- * finished rows of 256-class tile t in wn_ready[t] (zero on entry).  inv_norm_w is read (old norm) and rewritten (new
- * norm) in place.  pending (device int, may be NULL = 1): 0 = nothing to apply, only the counters move. */
-int pfc_dw_sgd_ordered(const void* dwn_bf16, float* w, float* momentum_buf, float* inv_norm_w, int rows, int d, float lr,
-                       float momentum, float weight_decay, const float* grad_scale, void* wn_bf16,
-                       const int32_t* tile_order, int num_tiles, int* wn_ready, const int* pending, void* stream);
-
 /* ---- (5b) the three exchanges of the step over peer memory (NVLink / NVSwitch), fused into the producing kernels.
  * They replace all_gather (nets/PartialFC.py:182-186), the softmax all_reduces (:448, :453, :459) and the dX
  * reduce (:505-522).  peer_* arguments are HOST arrays of W device pointers: entry q is rank q's symmetric buffer as

@@ -21,8 +21,7 @@ class FakeKernels:
         self._real = real
         # host-only helpers come from the real library (no GPU needed)
         for name in ("exp_top", "padded_classes", "padded_batch", "num_class_tiles", "part_sum_cols", "dx_splits",
-                     "dx_max_splits", "fx_splits", "fx_max_splits", "fx_counter_words", "fx_tile_order",
-                     "sample_workspace_bytes", "hist_bins"):
+                     "dx_max_splits", "sample_workspace_bytes", "hist_bins"):
             setattr(self, name, getattr(real, name))
 
     # ---- rows
@@ -122,34 +121,11 @@ class FakeKernels:
         Ev[rows, labels[rows].long()] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16)
 
     def backward_prepare_deferred(self, stats, row_L, grad_loss, s, B, d, labels, tgt_raw, kind, m2, xn, xs, coef,
-                                  patch, E=None, n_pad=0, pending=None):
-        g = float(grad_loss[0]) if grad_loss is not None else 1.0
-        c = g * s / (B * row_L)
-        coef.copy_(c)
-        xs[:B] = (xn[:B].float() * c.reshape(-1, 1)).to(torch.bfloat16)
+                                  patch, E, n_pad):
+        self.backward_prepare(stats, row_L, grad_loss, s, B, d, labels, tgt_raw, kind, m2, xn, xs, coef, E, n_pad)
         rows = torch.nonzero(labels[:B] >= 0).reshape(-1)
-        raw = tgt_raw[rows]
-        _, dm = self._margin(kind, raw.clamp(-1, 1), m2, 0.0)
-        mask = (raw.abs() <= 1).float()
         patch.zero_()
-        patch[rows] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16).float()
-        if E is not None:
-            self.apply_target_patch(E, n_pad, B, labels, patch, pending)
-
-    def forward_dx(self, xn, wn, labels, B, n, d, s, kind, m2, m3, thr, E, n_pad, part_sum, tgt_raw, tgt_e, tgt_z,
-                   partial, splits, counters, wn_gate):
-        if wn_gate:      # the ordered update must have published every tile of the shard
-            tiles = (n + 255) // 256
-            want = torch.tensor([min(256, n - 256 * t) for t in range(tiles)], dtype=counters.dtype)
-            assert torch.equal(counters[:tiles], want), "pfc_forward_dx gate: shard tiles not published"
-        self.forward(xn, wn, labels, B, n, d, s, kind, m2, m3, thr, E, n_pad, part_sum, tgt_raw, tgt_e, tgt_z)
-        self.backward_dx(E, n_pad, wn, B, n, d, partial, splits)       # target column of E' is 0 here
-
-    def apply_target_patch(self, E, n_pad, B, labels, patch, pending=None):
-        if pending is not None:
-            pending[0] = 1
-        rows = torch.nonzero(labels[:B] >= 0).reshape(-1)
-        E[: B * n_pad].view(B, n_pad)[rows, labels[rows].long()] = patch[rows].to(torch.bfloat16)
+        patch[rows] = E[: B * n_pad].view(B, n_pad)[rows, labels[rows].long()].float()
 
     def dx_finalize_patched(self, partial, splits, coef, x, inv_norm, scale, rows, rows_total, d, out, patch, labels, wn):
         p = partial.reshape(-1)[: splits * rows_total * d].view(splits, rows_total, d)
@@ -188,15 +164,6 @@ class FakeKernels:
         w[:rows] = w_new
         mom[:rows] = m_new
         self.l2norm_rows(w, None, rows, wn_next, inv_norm_next)
-
-    def dw_sgd_ordered(self, dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn, tile_order, counters,
-                       pending):
-        tiles = (rows + 255) // 256
-        assert sorted(tile_order.tolist()) == list(range(tiles))
-        if pending is None or int(pending[0]) != 0:
-            self.dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn, inv_norm_w)
-        for t in range(tiles):
-            counters[t] += min(256, rows - 256 * t)
 
     def dw_adam(self, dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, wd, step, decoupled,
                 grad_scale, wn_next, inv_norm_next, step_dev=None):

@@ -15,20 +15,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-# (name, fused, direct = PartialFC.fused_step instead of autograd, mode): mode "" = defaults (conf.fx: forward + dX
-# partials in one kernel, target term fixed up when they are summed), "nofx" = separate forward / dX GEMMs,
-# "lazy" = conf.lazy_update (the fused SGD step applied at the start of the next forward)
+# (name, fused, direct = PartialFC.fused_step instead of autograd, mode): mode "" = defaults (conf.early_dx: the dX GEMM runs
+# on the spill before its target column is written, the target term is fixed up when the partials are summed),
+# "late_dx" = dX after the coefficients (the reference's backward order)
 SGD_CASES = [("head_w2_full", False, False, ""), ("head_w2_sampled", False, False, ""),
              ("head_w2_full", True, False, ""), ("head_w2_sampled", True, False, ""),
              ("head_w2_sampled", False, True, ""), ("head_w2_full", True, True, ""),
              # one rank: CombinedMarginLoss with inter-class filtering
              ("head_w1_filter_wide", False, False, ""), ("head_w1_filter_wide", True, True, ""),
-             ("head_w2_sampled", False, False, "nofx"), ("head_w2_full", True, True, "nofx"),
-             ("head_w1_full", True, False, "nofx"),
+             ("head_w2_sampled", False, False, "late_dx"), ("head_w2_full", True, True, "late_dx"),
+             ("head_w1_full", True, False, "late_dx"),
              # d = 128, several 256-class tiles per rank
              ("head_w2_d128", True, False, ""), ("head_w1_d128", False, False, ""),
-             ("head_w2_d128", True, False, "lazy"), ("head_w2_d128", True, True, "lazy"),
-             ("head_w1_d128", True, True, "lazy")]
+             ("head_w2_d128", True, True, "late_dx")]
 # (name, fused)
 ADAM_CASES = [("head_w2_adamw_sampled", False), ("head_w2_adamw_sampled", True), ("head_w1_adamw_full", True),
               ("head_w1_adam_sampled", True), ("head_w1_adam_sampled", False)]
@@ -100,8 +99,8 @@ def _run_sgd_case(rank, W, name, fused, direct, mode):
     weights, xs, ls = case_inputs(cfg)
     b = cfg["b"]
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
-                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused, fx=mode != "nofx",
-                                 lazy_update=mode == "lazy")
+                                 loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused,
+                                 early_dx=mode != "late_dx")
     if cfg["margin"] == "combined_filter":
         thr = cfg["filter_thr"]
         margin = lambda s_, m_: pfc.CombinedMarginLoss(s_, 1.0, m_, 0.0, interclass_filtering_threshold=thr)  # noqa: E731
@@ -136,7 +135,6 @@ def _run_sgd_case(rank, W, name, fused, direct, mode):
         head.update()
         out["weight_final"] = head.weight.numpy().copy()
     else:
-        head.flush()                                  # conf.lazy_update: the last step's update is still owed
         out["weight_final"] = head.weight_activated.detach().numpy().copy()
     out["state_dict_shape"] = tuple(head.state_dict()["weight"].shape)
     out["state_dict_keys"] = list(head.state_dict().keys())

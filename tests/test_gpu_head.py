@@ -45,17 +45,16 @@ def _make_head(pfc, cfg, weights, fused=False, adam=False, **extra):
     return head
 
 
-# mode: "unfused" (dW to torch.optim.SGD), "fused" (conf.fused_optimizer), "nofx" (fused, separate forward / dX GEMMs
-# instead of the forward + dX kernel), "lazy" (conf.lazy_update: the fused step applied under the next forward)
+# mode: "unfused" (dW to torch.optim.SGD), "fused" (conf.fused_optimizer), "late_dx" (fused, conf.early_dx off: the dX GEMM
+# runs on the patched spill after the coefficients, the reference's backward order)
 @pytest.mark.parametrize("name,mode", [(n, m) for n in ["head_w1_full", "head_w1_s30", "head_w1_cosface", "head_w1_sampled",
                                                        "head_w1_manypos", "head_w1_d512", "head_w1_d128"]
-                                       for m in ["unfused", "fused", "nofx"]] +
-                         [("head_w1_d512", "lazy"), ("head_w1_d128", "lazy")])
+                                       for m in ["unfused", "fused", "late_dx"]])
 def test_steps_match_reference_and_oracle(pfc, name, mode):
     cfg, z = load_case(name)
     weights, xs, ls = case_inputs(cfg)
     fused = mode != "unfused"
-    head = _make_head(pfc, cfg, weights, fused=fused, fx=mode != "nofx", lazy_update=mode == "lazy")
+    head = _make_head(pfc, cfg, weights, fused=fused, early_dx=mode != "late_dx")
     dummy = torch.nn.Parameter(torch.zeros(1, device="cuda"))
     opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
                           momentum=cfg["momentum"], weight_decay=cfg["wd"])
@@ -92,7 +91,6 @@ def test_steps_match_reference_and_oracle(pfc, name, mode):
         head.update()
         w_final, m_final = head.weight, head.weight_mom
     else:
-        head.flush()                        # conf.lazy_update: the last step's update is still owed
         w_final = head.weight_activated.data
         m_final = head.weight_activated_mom if fused else opt.state[head.weight_activated]["momentum_buffer"]
     w0 = weights[0].double()
@@ -243,8 +241,8 @@ def test_full_size_properties_cfg2(pfc):
 
 
 def test_fused_update_at_full_size_matches_oracle(pfc):
-    """The fused SGD / momentum step at the BASELINE configs[1] shape against the oracle's fp32 step on the host, for
-    the in-step update and the lazy one (applied under the next forward), two steps so that momentum is exercised."""
+    """The fused SGD / momentum step at the BASELINE configs[1] shape against the oracle's fp32 step on the host, with the
+    dX GEMM launched early (default) and late, two steps so that momentum is exercised."""
     C, d, B = 93431, 512, 1024
     w = torch.normal(0, 0.01, (C, d), generator=torch.Generator().manual_seed(1234))
     batches = []
@@ -259,23 +257,23 @@ def test_fused_update_at_full_size_matches_oracle(pfc):
     w_ref = orc.weight[0].float()
     cfg = dict(C=C, d=d, sample_rate=1.0, s=64.0, m=0.5, margin="arcface")
     finals = {}
-    for mode in ("fused", "lazy"):
-        head = _make_head(pfc, cfg, [w], fused=True, lazy_update=mode == "lazy")
+    for mode in ("fused", "late_dx"):
+        head = _make_head(pfc, cfg, [w], fused=True, early_dx=mode != "late_dx")
         opt = torch.optim.SGD(head.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
         for (x, lab), ref in zip(batches, ref_losses):
             xg = x.clone().cuda().requires_grad_(True)
             loss = head(xg, lab.clone().cuda(), opt)
             loss.backward()
             assert abs(float(loss) - ref) <= LOSS_RTOL * abs(ref), (mode, float(loss), ref)
-        sd = head.state_dict()["weight"].cpu()          # flushes the lazy head
+        sd = head.state_dict()["weight"].cpu()
         assert cosine(sd - w, w_ref - w) >= COS_MIN, mode
         assert abs(float((sd - w).norm()) / float((w_ref - w).norm()) - 1) < 2e-2
         finals[mode] = sd
-    # same arithmetic, same order of updates: the lazy head ends where the eager one does
-    torch.testing.assert_close(finals["lazy"], finals["fused"], rtol=0, atol=1e-6)
+    # dW and the update do not depend on where the dX GEMM runs: identical weights
+    assert torch.equal(finals["late_dx"], finals["fused"])
 
 
-@pytest.mark.parametrize("mode", ["unfused", "fused", "lazy"])
+@pytest.mark.parametrize("mode", ["unfused", "fused", "late_dx"])
 def test_scaled_loss_through_the_kernels(pfc, mode):
     """GradScaler flow (model/FR_PartialFC.py:178-184: amp.scale(loss).backward(), unscale_, step): d loss = 1024 reaches
     pfc_backward_prepare as a device scalar (nets/PartialFC.py:484's `loss_gradient.item()` without the sync); dX and the
@@ -284,7 +282,7 @@ def test_scaled_loss_through_the_kernels(pfc, mode):
     weights, xs, ls = case_inputs(cfg)
     outs = []
     for scale in (1.0, 1024.0):
-        head = _make_head(pfc, cfg, weights, fused=mode != "unfused", lazy_update=mode == "lazy")
+        head = _make_head(pfc, cfg, weights, fused=mode != "unfused", early_dx=mode != "late_dx")
         opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
         rec = []
         for s in range(2):
