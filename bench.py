@@ -264,7 +264,10 @@ def parity_check(cfg, head, opt, x_local, lab_local, perm_local, w_shard, rank, 
     loss.backward()
     if sampled:
         idx = head.weight_index.clone()
-        upd = (head.weight_activated.data - w_shard[idx]) if fused else head.weight_activated.grad.clone()
+        if fused:      # in-place update through the index list (conf.inplace_update), or the gathered rows
+            upd = (head.weight[idx] if head._indexed else head.weight_activated.data) - w_shard[idx]
+        else:
+            upd = head.weight_activated.grad.clone()
     else:
         idx = None
         upd = (head.state_dict()["weight"] - w_shard) if fused else head.weight_activated.grad.clone()
@@ -440,7 +443,7 @@ def main():
 
     # CUDA-graph replay through the package's own public wrapper (face_recognition_pytorch_b200.GraphedHeadStep)
     gstep = None
-    if not args.no_graph and fused and not sampled:
+    if not args.no_graph and fused:
         try:
             gstep = pfc.GraphedHeadStep(head, opt, b, EMB, autograd=args.autograd)
         except Exception as e:   # report, fall back to eager launches (still the CUDA path)
@@ -451,7 +454,10 @@ def main():
 
     def run_step(i):
         if gstep is not None:
-            gstep(x_dev[i % n_data].data, l_dev[i % n_data])
+            if sampled:     # the sampling draw is an input of the step: resident on the device like the batch
+                gstep(x_dev[i % n_data].data, l_dev[i % n_data], perm=perms[i % n_data])
+            else:
+                gstep(x_dev[i % n_data].data, l_dev[i % n_data])
         else:
             step_eager(i)
 
@@ -522,6 +528,7 @@ def main():
 
     def head_call(x, lab, i):
         if gstep is not None:
+            # sampled: perm=None -- the draw is made on the CPU generator and uploaded every step, as in the reference
             return gstep(x, lab)
         xg = x.detach().clone().requires_grad_(True)
         loss = head(xg, lab.clone(), opt, perm=None if perms is None else perms[i % n_data])
@@ -668,7 +675,8 @@ def main():
                             "the side streams overlap the main stream's)" if kern else
                             "per-kernel times are reported on one GPU only"),
         "parity_check": parity,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": b * EMB * 4 + b * 8,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": b * EMB * 4 + b * 8 + (nl * 4 if sampled and gstep is not None else 0),
                 "d2h_bytes_per_step": 4 + b * EMB * 4, "steps": e2e_steps, "timing": "host wall clock, max over ranks" +
                           ("; H2D of step i+1 and D2H of step i's dX + loss on a copy stream, host reads them one step late"
                            if pipelined else "; D2H of step i's dX + loss asynchronous, host reads them one step late"),

@@ -392,6 +392,7 @@ struct OptArgs {
     float beta1, beta2, eps, bc1, bc2_sqrt;   // Adam(W): bc1 = 1-b1^t, bc2_sqrt = sqrt(1-b2^t)
     const float* grad_scale;        // device scalar: the loss scale the gradient carries (divided out first), or null
     const int* step_dev;            // Adam(W): device step counter (the update is step step_dev[0] + 1), or null
+    const int64_t* index;           // sampled shards: row r of (dwn, inv_norm_w, wn_next) is row index[r] of (w, state), or null
 };
 
 __device__ __forceinline__ float opt_inv_grad_scale(const float* grad_scale) {
@@ -408,6 +409,8 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
     const int nv = d >> 2;
     const float inv = inv_norm_w[row];
     const size_t base = static_cast<size_t>(row) * d;
+    // in-place update of a sampled shard: the weights / optimizer state live in the full [num_local, d] arrays
+    const size_t wbase = opt.index ? static_cast<size_t>(opt.index[row]) * d : base;
     float4 g[MAXV], wv[MAXV];
     float dot = 0.f;
 #pragma unroll
@@ -415,7 +418,7 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
         const int k = lane + 32 * j;
         if (k < nv) {
             g[j] = ld4_stream(dwn + base + 4 * k);
-            wv[j] = ld4(w + base + 4 * k);
+            wv[j] = ld4(w + wbase + 4 * k);
             dot += wv[j].x * g[j].x + wv[j].y * g[j].y + wv[j].z * g[j].z + wv[j].w * g[j].w;
         }
     }
@@ -448,10 +451,10 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
                 a.x += opt.wd * wq.x; a.y += opt.wd * wq.y; a.z += opt.wd * wq.z; a.w += opt.wd * wq.w;
                 float4 b = a;
                 if (opt.momentum != 0.f) {
-                    b = ld4(st1 + base + 4 * k);
+                    b = ld4(st1 + wbase + 4 * k);
                     b.x = opt.momentum * b.x + a.x; b.y = opt.momentum * b.y + a.y;
                     b.z = opt.momentum * b.z + a.z; b.w = opt.momentum * b.w + a.w;
-                    st4(st1 + base + 4 * k, b);
+                    st4(st1 + wbase + 4 * k, b);
                 }
                 wq.x -= opt.lr * b.x; wq.y -= opt.lr * b.y; wq.z -= opt.lr * b.z; wq.w -= opt.lr * b.w;
             } else {
@@ -461,21 +464,21 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
                 } else {
                     a.x += opt.wd * wq.x; a.y += opt.wd * wq.y; a.z += opt.wd * wq.z; a.w += opt.wd * wq.w;
                 }
-                float4 m = ld4(st1 + base + 4 * k), v = ld4(st2 + base + 4 * k);
+                float4 m = ld4(st1 + wbase + 4 * k), v = ld4(st2 + wbase + 4 * k);
                 const float b1 = opt.beta1, b2 = opt.beta2;
                 m.x = b1 * m.x + (1.f - b1) * a.x; m.y = b1 * m.y + (1.f - b1) * a.y;
                 m.z = b1 * m.z + (1.f - b1) * a.z; m.w = b1 * m.w + (1.f - b1) * a.w;
                 v.x = b2 * v.x + (1.f - b2) * a.x * a.x; v.y = b2 * v.y + (1.f - b2) * a.y * a.y;
                 v.z = b2 * v.z + (1.f - b2) * a.z * a.z; v.w = b2 * v.w + (1.f - b2) * a.w * a.w;
-                st4(st1 + base + 4 * k, m);
-                st4(st2 + base + 4 * k, v);
+                st4(st1 + wbase + 4 * k, m);
+                st4(st2 + wbase + 4 * k, v);
                 const float step = opt.lr / bc1;
                 wq.x -= step * m.x / (sqrtf(v.x) / bc2_sqrt + opt.eps);
                 wq.y -= step * m.y / (sqrtf(v.y) / bc2_sqrt + opt.eps);
                 wq.z -= step * m.z / (sqrtf(v.z) / bc2_sqrt + opt.eps);
                 wq.w -= step * m.w / (sqrtf(v.w) / bc2_sqrt + opt.eps);
             }
-            st4(w + base + 4 * k, wq);
+            st4(w + wbase + 4 * k, wq);
             wv[j] = wq;
             ss += wq.x * wq.x + wq.y * wq.y + wq.z * wq.z + wq.w * wq.w;
         }
@@ -521,7 +524,8 @@ template <int NV, bool kGradBf16, bool kL2 = false>
 __global__ void __launch_bounds__(128)
 dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* __restrict__ mom,
                    const float* inv_norm_w, int rows, float lr, float momentum, float wd,
-                   const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next) {
+                   const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next,
+                   const int64_t* __restrict__ index) {
     const float inv_grad_scale = opt_inv_grad_scale(grad_scale);
     constexpr int d = 128 * NV;
     const int lane = threadIdx.x & 31;
@@ -530,6 +534,8 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
     // (a few CTAs per SM, see pfc_debug_sgd_persistent) loops so that the kernel can share SMs with a GEMM
     for (int row = blockIdx.x * warps + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps) {
     const size_t base = static_cast<size_t>(row) * d;
+    // sampled shard updated in place: w / momentum rows live at index[row] of the full arrays
+    const size_t wbase = index ? static_cast<size_t>(index[row]) * d : base;
     float4 g[NV], wv[NV], mv[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -546,10 +552,10 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
     if constexpr (kL2) pol = l2_evict_first_policy();
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        wv[j] = kL2 ? ld4_hint(w + base + 4 * (lane + 32 * j), pol) : ld4(w + base + 4 * (lane + 32 * j));
+        wv[j] = kL2 ? ld4_hint(w + wbase + 4 * (lane + 32 * j), pol) : ld4(w + wbase + 4 * (lane + 32 * j));
 #pragma unroll
     for (int j = 0; j < NV; ++j)
-        mv[j] = kL2 ? ld4_hint(mom + base + 4 * (lane + 32 * j), pol) : ld4(mom + base + 4 * (lane + 32 * j));
+        mv[j] = kL2 ? ld4_hint(mom + wbase + 4 * (lane + 32 * j), pol) : ld4(mom + wbase + 4 * (lane + 32 * j));
     const float inv = inv_norm_w[row];
     float dot = 0.f;
 #pragma unroll
@@ -570,11 +576,11 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
         b.z = momentum * b.z + a.z; b.w = momentum * b.w + a.w;
         q.x -= lr * b.x; q.y -= lr * b.y; q.z -= lr * b.z; q.w -= lr * b.w;
         if constexpr (kL2) {
-            st4_hint(mom + base + 4 * (lane + 32 * j), b, pol);
-            st4_hint(w + base + 4 * (lane + 32 * j), q, pol);
+            st4_hint(mom + wbase + 4 * (lane + 32 * j), b, pol);
+            st4_hint(w + wbase + 4 * (lane + 32 * j), q, pol);
         } else {
-            st4(mom + base + 4 * (lane + 32 * j), b);
-            st4(w + base + 4 * (lane + 32 * j), q);
+            st4(mom + wbase + 4 * (lane + 32 * j), b);
+            st4(w + wbase + 4 * (lane + 32 * j), q);
         }
         wv[j] = q;
         ss += q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w;
@@ -604,7 +610,7 @@ static int g_sgd_persistent_warps = 0;   // 0: one row per warp, full grid; > 0:
 template <int NV>
 static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom, const float* inv_norm_w, int rows,
                                float lr, float momentum, float wd, const float* igs, __nv_bfloat16* wn_next,
-                               float* inv_next, cudaStream_t st) {
+                               float* inv_next, const int64_t* index, cudaStream_t st) {
     int grid = (rows + 3) / 4, block = 128;
     if (g_sgd_persistent_warps > 0) {
         int dev = 0, sms = 148;
@@ -619,13 +625,13 @@ static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom,
     }
     if (bf16 && pfc_l2_grad_enabled())
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr,
-                           momentum, wd, igs, wn_next, inv_next);
+                           momentum, wd, igs, wn_next, inv_next, index);
     else if (bf16)
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
-                           wd, igs, wn_next, inv_next);
+                           wd, igs, wn_next, inv_next, index);
     else
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, false>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
-                           wd, igs, wn_next, inv_next);
+                           wd, igs, wn_next, inv_next, index);
 }
 
 // dst[r] = src[index[r]]  /  dst[index[r]] = src[r]   (nets/PartialFC.py:120-121, :142-143), up to 3 tensors at once
@@ -811,7 +817,7 @@ int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, i
 
 int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float* inv_norm_w, int rows, int d, float lr,
                float momentum, float weight_decay, const float* grad_scale, void* wn_next, float* inv_norm_next,
-               void* stream) {
+               const int64_t* index, void* stream) {
     if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
     if (d % 128 == 0 && mom != nullptr) {
         cudaStream_t st = (cudaStream_t)stream;
@@ -819,7 +825,7 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
         const bool bf = dwn_bf16 != 0;
 #define PFC_SGD_CASE(NV) \
     launch_dw_sgd_rows<NV>(dwn, bf, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, grad_scale, wnn, \
-                           inv_norm_next, st)
+                           inv_norm_next, index, st)
         switch (d / 128) {
             case 1: PFC_SGD_CASE(1); break;
             case 2: PFC_SGD_CASE(2); break;
@@ -837,6 +843,7 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
     OptArgs o = {};
     o.kind = OPT_SGD;
     o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.grad_scale = grad_scale;
+    o.index = index;
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         static_cast<const float*>(dwn), w, inv_norm_w, rows, d, o, nullptr, mom, nullptr,
         reinterpret_cast<__nv_bfloat16*>(wn_next), inv_norm_next);
@@ -845,7 +852,8 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
 
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
-                const float* grad_scale, void* wn_next, float* inv_norm_next, const int* step_dev, void* stream) {
+                const float* grad_scale, void* wn_next, float* inv_norm_next, const int* step_dev,
+                const int64_t* index, void* stream) {
     if (rows <= 0 || bad_d(d) || (step <= 0 && !step_dev)) return PFC_ERR_SHAPE;
     if (step <= 0) step = 1;
     OptArgs o = {};
@@ -855,6 +863,7 @@ int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, c
     o.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     o.grad_scale = grad_scale;
     o.step_dev = step_dev;
+    o.index = index;
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         dwn, w, inv_norm_w, rows, d, o, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(wn_next),
         inv_norm_next);

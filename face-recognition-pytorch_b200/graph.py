@@ -11,8 +11,12 @@ collectives included -- NCCL or the peer-memory exchanges) and replays it:
 
 `feat` / `labels` may be device tensors or PINNED host tensors (copied with non_blocking=True on the current stream);
 `loss` and `dx` are static device buffers that the next call overwrites.  Requirements (checked): the head runs with
-conf.fused_optimizer (the update is part of the captured backward), sample_rate == 1 (sampling patches the optimizer on
-the host every step) and a constant batch size -- the configuration of BASELINE configs[1].  Both heads are supported:
+conf.fused_optimizer (the update is part of the captured backward) and a constant batch size.  sample_rate < 1 (BASELINE
+configs[2], [3]) is captured too: the sampler, the row normalisation through the index list and the in-place update
+(conf.inplace_update) are ordinary kernels; what stays on the host is the random draw -- `torch.rand(num_local)` on the CPU
+generator exactly like the reference (nets/PartialFC.py:110), uploaded from a pinned ring before each replay (or
+conf.device_sampling: drawn on the device) -- and it needs num_sample >= global batch, so that the number of active classes
+is not data dependent (:114-115 would otherwise need a host read).  Both heads are supported:
 PartialFC (SGD) and PartialFCAdamW (the bias-correction step count lives in a device scalar
 that every replay advances).  Hyper-parameters (lr, momentum / betas, weight decay) are kernel arguments and therefore
 part of the graph: every call compares optimizer.param_groups[-1] and the storage of weight_activated with what was
@@ -32,10 +36,15 @@ class GraphedHeadStep:
         results (tests/test_gpu_modes.py)."""
         if not head.fused_optimizer:
             raise RuntimeError("GraphedHeadStep needs conf.fused_optimizer = True (the update is part of the graph)")
-        if head.sample_rate < 1:
-            raise RuntimeError("GraphedHeadStep needs sample_rate == 1 (sampling patches the optimizer on the host)")
+        self._sampled = head.sample_rate < 1
+        if self._sampled:
+            if not head._indexed:
+                raise RuntimeError("GraphedHeadStep with sample_rate < 1 needs conf.inplace_update (the default)")
+            if head.num_sample < batch * head.world_size:
+                raise RuntimeError("GraphedHeadStep with sample_rate < 1 needs num_sample >= global batch: with fewer, the "
+                                   "number of active classes depends on the labels (nets/PartialFC.py:114-115)")
         self.head, self.optimizer = head, optimizer
-        dev = device if device is not None else head.weight_activated.device
+        dev = device if device is not None else (head.weight if self._sampled else head.weight_activated).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedHeadStep needs a CUDA head")
         self.device = dev
@@ -47,15 +56,37 @@ class GraphedHeadStep:
         self._graph = None
         self._warmup = warmup
         self._captured = None
+        self._perm = None                  # sample_rate < 1: the workspace's draw buffer [num_local] (static)
+        self._perm_host, self._perm_ev, self._perm_k = None, None, 0
+        if self._sampled:
+            self._perm = head._ensure_workspace(batch, dev).perm
+            self._perm_host = [torch.empty(head.num_local, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._perm_ev = [torch.cuda.Event() for _ in range(2)]
+            self._draw()
         self.recapture()
 
     # ------------------------------------------------------------------
+    def _draw(self, perm=None):
+        """Next step's sampling scores into the static device buffer: the caller's, the CUDA generator's
+        (conf.device_sampling) or -- the reference's semantics -- torch.rand on the CPU generator (nets/PartialFC.py:110)."""
+        if perm is not None:
+            self._perm.copy_(perm.reshape(-1), non_blocking=True)
+        elif self.head.device_sampling:
+            self._perm.uniform_()
+        else:
+            k = self._perm_k
+            self._perm_ev[k].synchronize()             # the upload that last used this pinned buffer has finished
+            torch.rand(self.head.num_local, out=self._perm_host[k])
+            self._perm.copy_(self._perm_host[k], non_blocking=True)
+            self._perm_ev[k].record()
+            self._perm_k = 1 - k
+
     def _eager(self):
         if not self._autograd:
-            loss, self._dx = self.head.fused_step(self._x.detach(), self._labels, self.optimizer)
+            loss, self._dx = self.head.fused_step(self._x.detach(), self._labels, self.optimizer, perm=self._perm)
             return loss
         self._x.grad = None
-        loss = self.head(self._x, self._labels, self.optimizer)
+        loss = self.head(self._x, self._labels, self.optimizer, perm=self._perm)
         loss.backward()
         self._dx = self._x.grad
         return loss
@@ -64,10 +95,12 @@ class GraphedHeadStep:
         """What the captured kernels have baked in: the head's hyper-parameters and the storage they update."""
         g = self.optimizer.param_groups[-1]
         hp = tuple((k, g[k]) for k in ("lr", "momentum", "weight_decay", "betas", "eps") if k in g)
-        return hp, self.head.weight_activated.data_ptr()
+        return hp, (self.head.weight if self._sampled else self.head.weight_activated).data_ptr()
 
     def _optimizer_state(self):
         head = self.head
+        if self._sampled:
+            return [getattr(head, "weight_" + nm) for nm in head._state_names]
         st = head._fused_state
         if st is None:
             return []
@@ -77,9 +110,9 @@ class GraphedHeadStep:
         """(Re)build the graph from the head's current state and the optimizer's current hyper-parameters."""
         head = self.head
         torch.cuda.synchronize(self.device)
-        w = head.weight_activated.data
+        w = head.weight if self._sampled else head.weight_activated.data
         saved_w = w.clone()
-        had_state = head._fused_state is not None
+        had_state = self._sampled or head._fused_state is not None
         saved_state = [t.clone() for t in self._optimizer_state()]
         saved_step = head.step
         head._graph_steps = head._optimizer_kind != "sgd"
@@ -107,16 +140,22 @@ class GraphedHeadStep:
             for t in self._optimizer_state():
                 t.zero_()
         head.step = saved_step
-        ws.adam_step.fill_(saved_step)
-        K.l2norm_rows(w, None, head._n, ws.wn, ws.inv_w)
-        head._wn_valid = True
+        # Adam(W): the kernels use adam_step[0] + 1; a sampled shard is bias-corrected one step ahead (PartialFCAdamW)
+        ws.adam_step.fill_(saved_step + (1 if self._sampled else 0))
+        if not self._sampled:
+            K.l2norm_rows(w, None, head._n, ws.wn, ws.inv_w)
+            head._wn_valid = True
         torch.cuda.synchronize(self.device)
         self._captured = self._signature()
 
-    def __call__(self, feat, labels):
+    def __call__(self, feat, labels, perm=None):
+        """perm (sample_rate < 1, optional): this step's sampling scores [num_local] (host or device); default: drawn as
+        the reference draws them."""
         if self._signature() != self._captured:
             self.recapture()               # the scheduler changed lr, or load_state_dict() rebound the weights
         head = self.head
+        if self._sampled:
+            self._draw(perm)
         self._x.data.copy_(feat, non_blocking=True)
         self._labels.copy_(labels.reshape(-1), non_blocking=True)
         self._graph.replay()

@@ -228,21 +228,24 @@ def dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, dw):
 
 
 @_timed("pfc_dw_sgd")
-def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_scale, wn_next, inv_norm_next):
-    """grad_scale: device scalar holding the loss scale the gradient carries (divided out first), or None."""
+def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_scale, wn_next, inv_norm_next, index=None):
+    """grad_scale: device scalar holding the loss scale the gradient carries (divided out first), or None.
+    index (int64 [rows], ascending): w / mom are the FULL shard arrays and row r of dwn updates row index[r] in place."""
     is_bf16 = dwn.dtype == BF16
     check(lib.pfc_dw_sgd(_p(dwn, BF16 if is_bf16 else F32), int(is_bf16), _p(w, F32), _p(mom, F32),
                          _p(inv_norm_w, F32), rows, d, lr, momentum, weight_decay, _p(grad_scale, F32),
-                         _p(wn_next, BF16), _p(inv_norm_next, F32), _stream()), "pfc_dw_sgd")
+                         _p(wn_next, BF16), _p(inv_norm_next, F32), _p(index, I64), _stream()), "pfc_dw_sgd")
 
 
 @_timed("pfc_dw_adam")
 def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, weight_decay, step, decoupled,
-            grad_scale, wn_next, inv_norm_next, step_dev=None):
-    """step_dev (int32 device scalar): the update is step step_dev[0] + 1 (CUDA-graph replay), `step` is ignored."""
+            grad_scale, wn_next, inv_norm_next, step_dev=None, index=None):
+    """step_dev (int32 device scalar): the update is step step_dev[0] + 1 (CUDA-graph replay), `step` is ignored.
+    index: as in dw_sgd (in-place update of a sampled shard)."""
     check(lib.pfc_dw_adam(_p(dwn, F32), _p(w, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), _p(inv_norm_w, F32), rows,
                           d, lr, beta1, beta2, eps, weight_decay, step, int(decoupled), _p(grad_scale, F32),
-                          _p(wn_next, BF16), _p(inv_norm_next, F32), _p(step_dev, I32), _stream()), "pfc_dw_adam")
+                          _p(wn_next, BF16), _p(inv_norm_next, F32), _p(step_dev, I32), _p(index, I64), _stream()),
+          "pfc_dw_adam")
 
 
 # ---- peer-memory exchanges (peer_* are ctypes arrays of W mapped device pointers, see partial_fc._PeerExchange)

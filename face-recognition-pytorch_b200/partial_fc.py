@@ -20,6 +20,12 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       optimizer.param_groups[-1] every step (the scheduler mutates lr, utils/scheduler.py:87-88).  A scaled loss
       (GradScaler flow, model/FR_PartialFC.py:178-184) is honoured: dX keeps the scale autograd expects and the fused
       update divides it out on the device; the scaler's inf-skipping cannot be (bf16 operands do not need a scaler).
+  conf.inplace_update (bool, default True; only with fused_optimizer and sample_rate < 1): the fused step reads and
+      updates the sampled rows IN PLACE in `weight` / `weight_mom` (or Adam's moments) through the index list, so the
+      row gather before the step (nets/PartialFC.py:120-121) and the scatter after it (:142-143) -- 4 x n x d x 4 bytes
+      of HBM traffic each -- disappear; `weight_activated` then stays the reference's initial (0, 0) placeholder and
+      `weight`, `weight_mom`, `weight_index`, state_dict() are always current.  False: gather / scatter like the
+      reference (what the un-fused path always does, because torch.optim steps on `weight_activated`).
   conf.early_dx (bool, default True): launch the dX contraction right behind the forward GEMM on its own stream, next to
       the softmax statistics, their exchange between ranks and the loss, whenever local_embeddings needs a gradient.
       The forward leaves 0 in the target column of the spill and dX needs neither the softmax denominator nor the target
@@ -148,6 +154,8 @@ class _PartialFCBase(torch.nn.Module):
         # run the tail of the dX path (finalize / peer scatter + finalize) on a side stream next to the rank-local
         # dW GEMM + update, which it does not depend on; may be flipped between steps (before a graph capture)
         self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto"
+        # fused update of a sampled shard in place through the index list (no gather / scatter of the active rows)
+        self._indexed = (self.fused_optimizer and self.sample_rate < 1 and bool(getattr(conf, "inplace_update", True)))
         self._num_classes = int(num_classes)
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
@@ -184,6 +192,7 @@ class _PartialFCBase(torch.nn.Module):
         self._opt_args = None
         self._side_stream = None        # dX tail
         self._dx_stream = None          # early dX GEMM
+        self._dx_unjoined = False       # ... launched and not yet waited for by a backward
         self._early_splits = None       # slabs of dX partials (of the UNPATCHED spill) this step's forward left behind
         self._gscale_is_one = True
         self._graph_steps = False       # AdamW: take the bias-correction step count from ws.adam_step (graph replay)
@@ -207,7 +216,9 @@ class _PartialFCBase(torch.nn.Module):
         is implied by it and only kept for signature parity).  `perm` defaults to torch.rand on the CPU generator exactly like the reference
         (:110) -- one H2D copy per step; pass a device tensor to replay a recorded draw."""
         ws = self._ws
-        if perm is None and self.device_sampling and ws.perm.is_cuda:
+        if perm is ws.perm:
+            pass                                     # the caller filled the workspace's draw buffer (GraphedHeadStep)
+        elif perm is None and self.device_sampling and ws.perm.is_cuda:
             ws.perm.uniform_()                       # [0, 1) from the CUDA generator, no host round trip
         else:
             if perm is None:
@@ -221,6 +232,9 @@ class _PartialFCBase(torch.nn.Module):
             n = int(ws.n_out.item())                 # data-dependent: more positives than num_sample (:114-115)
         self._n = n
         self.weight_index = ws.index[:n]
+        self._wn_valid = False
+        if self._indexed:
+            return                 # rows are normalised (forward) and updated (backward) in place through weight_index
         names = self._state_names
         srcs = [self.weight] + [getattr(self, "weight_" + nm) for nm in names]
         dsts = [self._act_store[0][:n]] + [self._act_store[1 + i][:n] for i in range(len(names))]
@@ -237,7 +251,7 @@ class _PartialFCBase(torch.nn.Module):
         if self.init_weight_update:
             self.init_weight_update = False
             return
-        if self.sample_rate < 1:
+        if self.sample_rate < 1 and not self._indexed:
             names = self._state_names
             n = self.weight_activated.shape[0]
             if n == 0:
@@ -255,7 +269,7 @@ class _PartialFCBase(torch.nn.Module):
         if self._ws is None or self._ws.b != b or self._ws.xn_local.device != dev:
             self._ws = _Workspace(dev, b, self.world_size, n_max, self.num_local, d, sampled)
             self._wn_valid = False
-            if sampled:
+            if sampled and not self._indexed:
                 k = 1 + len(self._state_names)
                 self._act_store = [torch.zeros(n_max, d, device=dev) for _ in range(k)]
             self._peer = None
@@ -371,14 +385,15 @@ class _PartialFCBase(torch.nn.Module):
         ws, W, d = self._ws, self.world_size, self.embedding_size
         b, B = ws.b, ws.B
         n = self._n
-        w = self.weight_activated.data
+        w = self.weight if self._indexed else self.weight_activated.data
         if self.fused_optimizer:
             self._opt_args = self._read_optimizer(self._optimizer)
-        if self._dx_stream is not None:
+        if self._dx_unjoined:
             # an early dX GEMM whose backward never ran may still be reading the spill this forward overwrites
             torch.cuda.current_stream().wait_stream(self._dx_stream)
+            self._dx_unjoined = False
         if not self._wn_valid:
-            K.l2norm_rows(w, None, n, ws.wn, ws.inv_w)                            # :200
+            K.l2norm_rows(w, ws.index if self._indexed else None, n, ws.wn, ws.inv_w)   # :200 (+ :120 when indexed)
             self._wn_valid = True
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
         self._n_pad = K.padded_classes(n)
@@ -396,6 +411,7 @@ class _PartialFCBase(torch.nn.Module):
             with torch.cuda.stream(self._dx_stream) if w.is_cuda else contextlib.nullcontext():
                 K.backward_dx(ws.E, self._n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
             self._early_splits = splits
+            self._dx_unjoined = w.is_cuda
         peer = self._peer
         if peer is not None:
             # statistics straight into every peer's slot, then a rank-ordered local sum (identical bits on all ranks)
@@ -419,7 +435,7 @@ class _PartialFCBase(torch.nn.Module):
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
         need_dx = x_in.requires_grad if need_dx is None else bool(need_dx)
         g = None if grad_loss is None else grad_loss.detach().to(torch.float32).reshape(1).contiguous()
-        w = self.weight_activated.data
+        w = self.weight if self._indexed else self.weight_activated.data
         peer = self._peer
         early = self._early_splits is not None     # the dX GEMM of the UNPATCHED spill is running / has run
         if self.fused_optimizer:
@@ -431,8 +447,9 @@ class _PartialFCBase(torch.nn.Module):
         if early:
             # the dX GEMM must have finished READING the spill before its target column is written for the dW GEMM; the
             # target values are also kept aside (ws.patch) for the rank-1 fix-up of dX
-            if self._dx_stream is not None:
+            if self._dx_unjoined:
                 torch.cuda.current_stream().wait_stream(self._dx_stream)
+                self._dx_unjoined = False
             K.backward_prepare_deferred(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all,
                                         ws.xs, ws.coef, ws.patch, ws.E, n_pad)
         else:
@@ -588,6 +605,11 @@ class PartialFC(_PartialFCBase):
 
     def _fused_step(self, w, n, d, dwn, wn_out):
         ws, o = self._ws, self._opt_args
+        if self._indexed:
+            # rows weight_index of the full shard / momentum, in place; the next step samples other rows, so no bf16 shard
+            K.dw_sgd(dwn, self.weight, self.weight_mom, ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], ws.gscale, None,
+                     None, index=ws.index)
+            return
         K.dw_sgd(dwn, w, self._momentum(w), ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], ws.gscale, wn_out, ws.inv_w)
         self._wn_valid = True             # the update wrote next step's normalised bf16 rows and 1/norm in place
 
@@ -628,8 +650,12 @@ class PartialFCAdamW(_PartialFCBase):
 
     def _fused_step(self, w, n, d, dwn, wn_out):
         ws, o = self._ws, self._opt_args
+        index = None
         if self.sample_rate < 1:
-            m, v = self.weight_activated_exp_avg, self.weight_activated_exp_avg_sq
+            if self._indexed:
+                w, m, v, index, wn_out = self.weight, self.weight_exp_avg, self.weight_exp_avg_sq, ws.index, None
+            else:
+                m, v = self.weight_activated_exp_avg, self.weight_activated_exp_avg_sq
             # The reference hands torch.optim.AdamW state["step"] = self.step BEFORE optimizer.step(), which increments it
             # once more: forward call t is bias-corrected with t + 1 (nets/PartialFC.py:306, :327; pinned by
             # tests/golden/head_w*_adamw_sampled.npz).  The un-fused path inherits that from torch; mirror it here.
@@ -640,10 +666,12 @@ class PartialFCAdamW(_PartialFCBase):
             m, v = self._fused_state
             self.step += 1
             step = self.step
-        # under GraphedHeadStep the step count comes from a device scalar that every replay advances
-        graphed = self._graph_steps and self.sample_rate >= 1
+        # under GraphedHeadStep the step count comes from a device scalar that every replay advances (the kernel uses
+        # adam_step[0] + 1; for a sampled shard the scalar runs one ahead, see the quirk above)
+        graphed = self._graph_steps
         K.dw_adam(dwn, w, m, v, ws.inv_w, n, d, o["lr"], o["beta1"], o["beta2"], o["eps"], o["wd"], step,
-                  o["decoupled"], ws.gscale, wn_out, ws.inv_w, ws.adam_step if graphed else None)
+                  o["decoupled"], ws.gscale, wn_out, None if wn_out is None else ws.inv_w,
+                  ws.adam_step if graphed else None, index=index)
         if graphed:
             ws.adam_step.add_(1)
-        self._wn_valid = True
+        self._wn_valid = wn_out is not None

@@ -149,13 +149,18 @@ int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, i
                     float* dw, void* stream);
 /* grad_scale: device scalar with the loss scale the gradient carries (g = d loss of pfc_backward_prepare), divided out
  * before the step; NULL = 1.  step_dev (Adam): int32 device scalar, the update is step step_dev[0] + 1 and `step` is
- * ignored (CUDA-graph replay; the caller increments it); NULL: `step` (host, >= 1). */
+ * ignored (CUDA-graph replay; the caller increments it); NULL: `step` (host, >= 1).
+ * index (sampled shards, nets/PartialFC.py:120-121 + :142-143 without the copies): NULL, or the ascending list of active
+ * classes -- row r of dwn / inv_norm_w (/ wn_next) then belongs to row index[r] of w and of the optimizer state, which
+ * are the FULL [num_local, d] arrays and are updated in place: no gather of the active rows before the step and no
+ * scatter back after it. */
 int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* momentum_buf, const float* inv_norm_w, int rows, int d,
                float lr, float momentum, float weight_decay, const float* grad_scale, void* wn_next_bf16,
-               float* inv_norm_next, void* stream);
+               float* inv_norm_next, const int64_t* index, void* stream);
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
-                const float* grad_scale, void* wn_next_bf16, float* inv_norm_next, const int* step_dev, void* stream);
+                const float* grad_scale, void* wn_next_bf16, float* inv_norm_next, const int* step_dev,
+                const int64_t* index, void* stream);
 /* ---- (5b) the three exchanges of the step over peer memory (NVLink / NVSwitch), fused into the producing kernels.
  * They replace all_gather (nets/PartialFC.py:182-186), the softmax all_reduces (:448, :453, :459) and the dX
  * reduce (:505-522).  peer_* arguments are HOST arrays of W device pointers: entry q is rank q's symmetric buffer as

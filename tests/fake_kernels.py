@@ -156,25 +156,29 @@ class FakeKernels:
         g = dwn[:rows]
         dw[:rows] = (g - wn * (wn * g).sum(1, keepdim=True)) * inv_norm_w[:rows].reshape(-1, 1) * inv_grad_scale
 
-    def dw_sgd(self, dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn_next, inv_norm_next):
+    def dw_sgd(self, dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn_next, inv_norm_next, index=None):
+        sel = slice(0, rows) if index is None else index[:rows].long()
         g = torch.empty(rows, d)
         inv_grad_scale = 1.0 if grad_scale is None else 1.0 / float(grad_scale[0])
-        self.dw_finalize(dwn.float(), w, inv_norm_w, rows, d, inv_grad_scale, g)
-        w_new, m_new = ho.sgd_update(w[:rows], mom[:rows], g, lr, momentum, wd)
-        w[:rows] = w_new
-        mom[:rows] = m_new
-        self.l2norm_rows(w, None, rows, wn_next, inv_norm_next)
+        self.dw_finalize(dwn.float(), w[sel], inv_norm_w, rows, d, inv_grad_scale, g)
+        w_new, m_new = ho.sgd_update(w[sel], mom[sel], g, lr, momentum, wd)
+        w[sel] = w_new
+        mom[sel] = m_new
+        if wn_next is not None:
+            self.l2norm_rows(w_new, None, rows, wn_next, inv_norm_next)
 
     def dw_adam(self, dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, wd, step, decoupled,
-                grad_scale, wn_next, inv_norm_next, step_dev=None):
+                grad_scale, wn_next, inv_norm_next, step_dev=None, index=None):
+        sel = slice(0, rows) if index is None else index[:rows].long()
         if step_dev is not None:
             step = int(step_dev[0]) + 1
         inv_grad_scale = 1.0 if grad_scale is None else 1.0 / float(grad_scale[0])
         g = torch.empty(rows, d)
-        self.dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, g)
-        w_new, m_new, v_new = ho.adamw_update(w[:rows], exp_avg[:rows], exp_avg_sq[:rows], g, step, lr, beta1, beta2,
+        self.dw_finalize(dwn, w[sel], inv_norm_w, rows, d, inv_grad_scale, g)
+        w_new, m_new, v_new = ho.adamw_update(w[sel], exp_avg[sel], exp_avg_sq[sel], g, step, lr, beta1, beta2,
                                               eps, wd, decoupled=bool(decoupled))
-        w[:rows] = w_new
-        exp_avg[:rows] = m_new
-        exp_avg_sq[:rows] = v_new
-        self.l2norm_rows(w, None, rows, wn_next, inv_norm_next)
+        w[sel] = w_new
+        exp_avg[sel] = m_new
+        exp_avg_sq[sel] = v_new
+        if wn_next is not None:
+            self.l2norm_rows(w_new, None, rows, wn_next, inv_norm_next)

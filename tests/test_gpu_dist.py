@@ -68,25 +68,87 @@ def _cos(a, b):
 
 
 # peer = False: the three NCCL collectives; peer = True: the same exchanges through NVLink peer memory, fused into the
-# producing kernels (csrc/pfc_peer.cu) -- must raise rather than fall back if symmetric memory is unavailable
-@pytest.mark.parametrize("name,fused,port,peer", [
-    ("head_w2_full", False, 29841, False), ("head_w2_sampled", False, 29842, False),
-    ("head_w2_full", True, 29843, False), ("head_w2_sampled", True, 29844, False),
-    ("head_w2_full", False, 29845, True), ("head_w2_sampled", True, 29846, True),
-    ("head_w2_full", True, 29847, True)])
-def test_two_rank_nccl_matches_reference(name, fused, port, peer):
-    _run_case(name, fused, port, peer, None)
-
-
-# features written after the round's GPU budget was spent (see tests/test_gpu_experimental.py): opt-in
-@pytest.mark.skipif(os.environ.get("PFC_EXPERIMENTAL") != "1", reason="opt-in: PFC_EXPERIMENTAL=1")
+# producing kernels (csrc/pfc_peer.cu) -- must raise rather than fall back if symmetric memory is unavailable.
+# extra: conf switches -- early_dx off = dX GEMM on the patched spill after the statistics exchange (the reference's
+# backward order); dx_side_stream off = no fork of the dX tail.
 @pytest.mark.parametrize("name,fused,port,peer,extra", [
-    ("head_w2_full", False, 29851, True, {"early_dx": True}),
-    ("head_w2_sampled", True, 29852, True, {"early_dx": True}),
-    ("head_w2_full", True, 29853, False, {"early_dx": True}),
-    ("head_w2_full", True, 29854, True, {"early_dx": True, "dx_side_priority": True})])
-def test_two_rank_experimental_variants(name, fused, port, peer, extra):
+    ("head_w2_full", False, 29841, False, None), ("head_w2_sampled", False, 29842, False, None),
+    ("head_w2_full", True, 29843, False, None), ("head_w2_sampled", True, 29844, False, None),
+    ("head_w2_full", False, 29845, True, None), ("head_w2_sampled", True, 29846, True, None),
+    ("head_w2_full", True, 29847, True, None),
+    ("head_w2_d128", True, 29848, True, None), ("head_w2_d128", False, 29849, False, None),
+    ("head_w2_full", False, 29851, True, {"early_dx": False}),
+    ("head_w2_sampled", True, 29852, True, {"early_dx": False}),
+    ("head_w2_full", True, 29853, False, {"early_dx": False}),
+    ("head_w2_full", True, 29854, True, {"dx_side_stream": False})])
+def test_two_rank_matches_reference(name, fused, port, peer, extra):
     _run_case(name, fused, port, peer, extra)
+
+
+def _fence_main(rank, W, port, q):
+    """Forward-only steps (no backward, hence no trailing dX barrier) between training steps, 40 steps back to back with no
+    host synchronisation: the flag barriers alone must keep a fast rank's next gather / statistics out of the buffers a
+    slow rank still reads.  Every step's loss is compared with an un-pipelined recomputation by the NCCL path."""
+    for p in (ROOT, HERE, os.path.join(HERE, "golden")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from helpers import load_case, case_inputs
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=W, device_id=dev)
+    import face_recognition_pytorch_b200 as pfc
+    cfg, z = load_case("head_w2_d128")
+    weights, xs, ls = case_inputs(cfg)
+    b = cfg["b"]
+    losses = {}
+    for peer in (True, False):
+        conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=1.0, mixed_precision=False, loss_s=cfg["s"],
+                                     loss_m=cfg["m"], fused_optimizer=True, peer_collectives=peer)
+        head = pfc.PartialFC(conf, cfg["C"])
+        head.load_state_dict({"weight": weights[rank].clone()})
+        head = head.train().cuda()
+        opt = torch.optim.SGD(head.parameters(), lr=cfg["lr"], momentum=cfg["momentum"], weight_decay=cfg["wd"])
+        out = []
+        for it in range(40):
+            s = it % cfg["steps"]
+            x = xs[s][rank * b:(rank + 1) * b].clone().to(dev)
+            lab = ls[s][rank * b:(rank + 1) * b].clone().to(dev)
+            if it % 3 == 2:                                  # a training step
+                x.requires_grad_(True)
+                loss = head(x, lab, opt)
+                loss.backward()
+            else:                                            # forward only
+                with torch.no_grad():
+                    loss = head(x, lab, opt)
+            out.append(loss.detach().reshape(1))
+            if rank == 1 and it % 5 == 0 and peer:
+                torch.cuda._sleep(2_000_000)                 # ~1 ms of skew on one rank
+        losses[peer] = torch.cat(out).cpu()
+        assert (head._peer is not None) == peer
+    q.put((rank, losses[True].numpy(), losses[False].numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_forward_only_steps_keep_the_fence():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fence_main, args=(r, 2, 29861, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        r, a, b = q.get(timeout=300)
+        res[r] = (a, b)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0][0], res[1][0])                 # both ranks see the same loss, every step
+    np.testing.assert_allclose(res[0][0], res[0][1], rtol=1e-5)  # peer exchange == NCCL exchange
+    assert np.isfinite(res[0][0]).all()
 
 
 def _run_case(name, fused, port, peer, extra):

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=15)
     ap.add_argument("--classes", type=int, default=93431)
     ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--l2-only", action="store_true", help="only the variants with the L2 hints on")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -139,7 +140,7 @@ def main():
         return run
 
     print(f"B={B} n={n} d={d} splits={splits}")
-    for pw in (0, 8, 16):
+    for pw in (() if args.l2_only else (0, 8, 16)):
         lib.pfc_debug_sgd_persistent(pw)
         tag = "full grid" if pw == 0 else f"persistent {pw} warps/SM"
         print(f"--- update kernel: {tag}")
@@ -176,6 +177,24 @@ def main():
         return run
     for ch in (3, 4, 6):
         timed(f"serial chunks+L2: {ch} x [dW chunk, update chunk], dX", serial_chunks(ch))
+    # the update with evict_first streams next to dX (which lives on L2 reuse of its operand stages)
+    timed("L2: dW(hint), update, dX (serial)", lambda: (dw(hint=True), upd(), dx()))
+    timed("L2: dX, dW(hint), update (serial, early-dX order)", lambda: (dx(), dw(hint=True), upd()))
+
+    def dw_then_both():
+        dw(hint=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        side_s.wait_event(ev)
+        with torch.cuda.stream(side_s):
+            upd()
+        dx()
+        main_s.wait_stream(side_s)
+    timed("L2: dW(hint), then [update || dX]", dw_then_both)
+    for pw in (8, 12, 16):
+        lib.pfc_debug_sgd_persistent(pw)
+        timed(f"L2: dW(hint), then [update persistent {pw} warps/SM || dX]", dw_then_both)
+    lib.pfc_debug_sgd_persistent(0)
 
 
 if __name__ == "__main__":
