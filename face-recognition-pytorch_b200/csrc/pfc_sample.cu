@@ -9,6 +9,11 @@
 // (the tie rule is ours: torch.topk leaves it implementation-defined), and an ordered stream compaction writes
 // the ascending index list and, for positives, their slot (= searchsorted(index, label), :118).
 //
+// Launches: one memset + six kernels.  Every "pick" / "scan" / "remap" step that needs the result of a whole grid is run by
+// the LAST CTA of the kernel that produces it (atomic ticket + fences), not by a kernel of its own: at the shard sizes of
+// BASELINE configs[2] / [3] (45 k / 250 k classes per rank) each of those kernels was ~2 us of work behind ~3-6 us of launch
+// latency (round 1: 1 + 11 launches, 72 us).
+//
 // The draw itself stays an input (the reference draws on the CPU generator, :110), so the selected set can be
 // compared bit-for-bit with the reference given the same draw.
 #include <cuda_runtime.h>
@@ -30,8 +35,22 @@ struct SelState {
     uint32_t k_rem;       // how many still to take among keys matching the prefix
     uint32_t n_pos;       // number of distinct positive classes
     uint32_t k_eff;       // max(num_sample, n_pos)
+    uint32_t ticket[5];   // CTAs that have finished: hist passes 0..2, count, compact
     uint32_t hist[3][MAX_BINS];
 };
+
+// true in exactly one CTA of the grid: the one whose arrival completes the kernel's global writes (which it may then read
+// through L2).  All threads of the CTA must call it.
+__device__ __forceinline__ bool last_cta_done(uint32_t* ticket) {
+    __shared__ uint32_t last_flag;
+    __threadfence();                       // this thread's global writes / atomics are visible before the ticket is taken
+    __syncthreads();
+    if (threadIdx.x == 0) last_flag = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    const bool last = last_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
 
 __device__ __forceinline__ uint32_t sortable(float f) {
     const uint32_t b = __float_as_uint(f);
@@ -47,8 +66,11 @@ __global__ void mark_positive_kernel(const int32_t* __restrict__ labels, int B, 
 }
 
 template <int PASS>
+__device__ void pick_digit(SelState* st, int num_sample, int nl);
+
+template <int PASS>
 __global__ void __launch_bounds__(SEL_THREADS)
-hist_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, SelState* st) {
+hist_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, SelState* st, int num_sample) {
     __shared__ uint32_t h[MAX_BINS];
     __shared__ uint32_t npos_s;
     for (int b = threadIdx.x; b < MAX_BINS; b += SEL_THREADS) h[b] = 0;
@@ -68,6 +90,7 @@ hist_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, i
     for (int b = threadIdx.x; b < MAX_BINS; b += SEL_THREADS)
         if (h[b]) atomicAdd(&st->hist[PASS][b], h[b]);
     if (PASS == 0 && threadIdx.x == 0 && npos_s) atomicAdd(&st->n_pos, npos_s);
+    if (last_cta_done(&st->ticket[PASS])) pick_digit<PASS>(st, num_sample, nl);     // the histogram is complete
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_tot, uint32_t& total);
@@ -78,8 +101,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
 // reaches k_rem is taken with an atomicMin.  (A single-thread walk, one dependent L2 load per bin, cost 50-100 us of a
 // 190 us sampler in round 1; this is one CTA-wide scan.)
 template <int PASS>
-__global__ void __launch_bounds__(1024)
-pick_parallel_kernel(SelState* st, int num_sample, int nl) {
+__device__ void pick_digit(SelState* st, int num_sample, int nl) {
     constexpr int bins = 1 << radix_bits(PASS);
     constexpr int per = (bins + 1023) / 1024;
     __shared__ uint32_t wt[33];
@@ -88,7 +110,8 @@ pick_parallel_kernel(SelState* st, int num_sample, int nl) {
     __shared__ uint32_t rstar, rem_s;
     if (threadIdx.x == 0) {
         if (PASS == 0) {
-            uint32_t k = st->n_pos > (uint32_t)num_sample ? st->n_pos : (uint32_t)num_sample;
+            const uint32_t np = __ldcg(&st->n_pos);
+            uint32_t k = np > (uint32_t)num_sample ? np : (uint32_t)num_sample;
             if (k > (uint32_t)nl) k = nl;
             st->k_eff = k;
             st->k_rem = k;
@@ -109,7 +132,7 @@ pick_parallel_kernel(SelState* st, int num_sample, int nl) {
 #pragma unroll
     for (int u = 0; u < per; ++u) {
         const int r = threadIdx.x * per + u;  // reversed bin index: r = 0 is the top bin
-        const uint32_t c = r < bins ? st->hist[PASS][bins - 1 - r] : 0u;
+        const uint32_t c = r < bins ? __ldcg(&st->hist[PASS][bins - 1 - r]) : 0u;
         v[u] = c;
         sum += c;
         if (r < bins) hs[r] = c;
@@ -164,8 +187,8 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* warp_t
 
 // per-tile counts of (key > T) and (key == T)
 __global__ void __launch_bounds__(SEL_THREADS)
-count_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, const SelState* st,
-             uint32_t* __restrict__ gt_cnt, uint32_t* __restrict__ eq_cnt) {
+count_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, SelState* st,
+             uint32_t* gt_cnt, uint32_t* eq_cnt, int tiles) {
     __shared__ uint32_t sg, se;
     if (threadIdx.x == 0) { sg = 0; se = 0; }
     __syncthreads();
@@ -187,16 +210,13 @@ count_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, 
     if ((threadIdx.x & 31) == 0) { atomicAdd(&sg, g); atomicAdd(&se, e); }
     __syncthreads();
     if (threadIdx.x == 0) { gt_cnt[blockIdx.x] = sg; eq_cnt[blockIdx.x] = se; }
-}
-
-// exclusive scan of the per-tile counts (tiles <= a few hundred: one CTA, serial chunks of 1024)
-__global__ void __launch_bounds__(SEL_THREADS)
-scan_tiles_kernel(uint32_t* __restrict__ gt_cnt, uint32_t* __restrict__ eq_cnt, int tiles) {
+    if (!last_cta_done(&st->ticket[3])) return;
+    // last CTA: exclusive scan of the per-tile counts (tiles <= a few hundred: serial chunks of 1024)
     __shared__ uint32_t wt[33];
     uint32_t carry_g = 0, carry_e = 0;
     for (int b0 = 0; b0 < tiles; b0 += SEL_THREADS) {
         const int i = b0 + threadIdx.x;
-        const uint32_t g = i < tiles ? gt_cnt[i] : 0, e = i < tiles ? eq_cnt[i] : 0;
+        const uint32_t g = i < tiles ? __ldcg(gt_cnt + i) : 0, e = i < tiles ? __ldcg(eq_cnt + i) : 0;
         uint32_t tg, te;
         const uint32_t xg = block_excl_scan(g, wt, tg);
         const uint32_t xe = block_excl_scan(e, wt, te);
@@ -208,9 +228,10 @@ scan_tiles_kernel(uint32_t* __restrict__ gt_cnt, uint32_t* __restrict__ eq_cnt, 
 
 // ordered compaction: ascending index list + slot of every positive class
 __global__ void __launch_bounds__(SEL_THREADS)
-compact_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, const SelState* st,
+compact_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags, int nl, SelState* st,
                const uint32_t* __restrict__ gt_off, const uint32_t* __restrict__ eq_off,
-               int64_t* __restrict__ index_out, int32_t* __restrict__ slot_of, int32_t* __restrict__ n_out) {
+               int64_t* __restrict__ index_out, int32_t* slot_of, int32_t* __restrict__ n_out,
+               const int32_t* __restrict__ labels, int B, int32_t* __restrict__ labels_out) {
     __shared__ uint32_t wt[33];
     const uint32_t T = st->prefix;
     const uint32_t need_eq = st->k_rem;
@@ -251,14 +272,12 @@ compact_kernel(const float* __restrict__ perm, const uint8_t* __restrict__ flags
             ++pos;
         }
     }
-}
-
-__global__ void remap_labels_kernel(const int32_t* __restrict__ labels, int B, const int32_t* __restrict__ slot_of,
-                                    int32_t* __restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= B) return;
-    const int l = labels[j];
-    out[j] = l >= 0 ? slot_of[l] : -1;
+    if (!last_cta_done(&st->ticket[4])) return;
+    // last CTA: every positive class has its slot -- labels -> position in the index list (= searchsorted, :118)
+    for (int j = threadIdx.x; j < B; j += SEL_THREADS) {
+        const int l = labels[j];
+        labels_out[j] = l >= 0 ? __ldcg(slot_of + l) : -1;
+    }
 }
 
 struct SelLayout {
@@ -304,16 +323,12 @@ int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_lo
     if (cudaMemsetAsync(ws, 0, L.gt, stream) != cudaSuccess) return PFC_ERR_CUDA;
     mark_positive_kernel<<<(B + 255) / 256, 256, 0, stream>>>(labels_local, B, flags);
     int hb = L.tiles;   // one CTA per SEL_TILE keys keeps every SM busy for the big shards, 1 CTA for small ones
-    hist_kernel<0><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    pick_parallel_kernel<0><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
-    hist_kernel<1><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    pick_parallel_kernel<1><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
-    hist_kernel<2><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st);
-    pick_parallel_kernel<2><<<1, 1024, 0, stream>>>(st, num_sample, num_local);
-    count_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq);
-    scan_tiles_kernel<<<1, SEL_THREADS, 0, stream>>>(gt, eq, L.tiles);
-    compact_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq, index_out, slot, n_out);
-    remap_labels_kernel<<<(B + 255) / 256, 256, 0, stream>>>(labels_local, B, slot, labels_remapped);
+    hist_kernel<0><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, num_sample);     // + pick of digit 0
+    hist_kernel<1><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, num_sample);
+    hist_kernel<2><<<hb, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, num_sample);
+    count_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq, L.tiles);   // + tile scan
+    compact_kernel<<<L.tiles, SEL_THREADS, 0, stream>>>(perm, flags, num_local, st, gt, eq, index_out, slot, n_out,
+                                                        labels_local, B, labels_remapped);          // + label remap
     return cudaGetLastError() == cudaSuccess ? PFC_OK : PFC_ERR_LAUNCH;
 }
 

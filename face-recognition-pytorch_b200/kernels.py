@@ -31,7 +31,7 @@ def _stream():
 
 
 # ---- accounting used by bench.py: how many kernels were launched, and (optionally) their device time
-_LAUNCHES_PER_CALL = {"pfc_sample": 11}
+_LAUNCHES_PER_CALL = {"pfc_sample": 6}
 _count = 0
 _timing = None      # name -> list of (start_event, end_event) while enabled
 

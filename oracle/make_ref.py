@@ -17,7 +17,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("PFC_REFERENCE_ROOT", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
-FILES = ["nets/ArcFace.py", "nets/PartialFC.py", "utils/eval.py"]
+# the head (nets/), the scorer (utils/eval.py) and the head's CALL SITE: the trainer's Model with the two small utility modules
+# it imports -- tests/test_gpu_dropin.py drives Model.training_step with the reference head and with this package's head
+FILES = ["nets/ArcFace.py", "nets/PartialFC.py", "utils/eval.py", "model/FR_PartialFC.py", "utils/logger.py",
+         "utils/scheduler.py"]
 
 
 def make_ref(verbose=True):

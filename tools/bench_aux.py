@@ -84,8 +84,8 @@ def main():
         remap = torch.zeros(B, dtype=torch.int32, device=dev)
         wsb = torch.zeros(K.sample_workspace_bytes(nl), dtype=torch.uint8, device=dev)
         timed(f"pfc_sample {nm} (nl={nl}, k={k}, B={B})",
-              lambda: K.sample(perm, lab, nl, k, index, n_out, remap, wsb), nl * 4 + k * 8 + B * 8, launches=11,
-              note="radix select: 3 histogram + pick passes, count, scan, compact, remap")
+              lambda: K.sample(perm, lab, nl, k, index, n_out, remap, wsb), nl * 4 + k * 8 + B * 8, launches=6,
+              note="radix select: mark, 3 x (histogram + pick by the last CTA), count + scan, compact + remap")
         torch.cuda.synchronize()
         n = int(n_out.item())
         w = torch.randn(nl, d, generator=g).to(dev)
@@ -96,7 +96,17 @@ def main():
               lambda: K.gather_rows([w, m], [wa[:n], ma[:n]], index[:n], n), 2 * n * d * 4 * 2)
         timed(f"pfc_scatter_rows {nm} (n={n}, weight + momentum)",
               lambda: K.scatter_rows([wa[:n], ma[:n]], [w, m], index[:n], n), 2 * n * d * 4 * 2)
-        del w, m, wa, ma, perm
+        # what the fused step does instead of gather / scatter (conf.inplace_update): normalise through the index list, and
+        # the SGD step on rows index[r] of the full arrays in place
+        wn = torch.empty(n_max, d, dtype=torch.bfloat16, device=dev)
+        inv = torch.empty(n_max, device=dev)
+        timed(f"pfc_l2norm_rows through the index list {nm} (n={n})",
+              lambda: K.l2norm_rows(w, index, n, wn, inv), n * d * 6 + 12 * n)
+        gbf = torch.zeros(n_max, d, dtype=torch.bfloat16, device=dev)
+        timed(f"pfc_dw_sgd in place through the index list {nm} (n={n})",
+              lambda: K.dw_sgd(gbf, w, m, inv, n, d, 1e-7, 0.9, 5e-4, None, None, None, index=index),
+              n * d * 18 + 12 * n, note="bf16 gradient + fp32 weight / momentum read and written")
+        del w, m, wa, ma, perm, wn, inv, gbf
 
     # ---- verification scorer, cfg-5 (6000 pairs x 512)
     N = 6000
@@ -114,22 +124,22 @@ def main():
     bins = K.hist_bins()
     scores = torch.empty(N, dtype=torch.float64, device=dev)
     dist_ = torch.empty(N, dtype=torch.float64, device=dev)
-    hg = torch.empty(bins, dtype=torch.int64, device=dev)
-    hi = torch.empty(bins, dtype=torch.int64, device=dev)
+    hh = torch.empty(2, bins, dtype=torch.int64, device=dev)      # back to back: one memset zeroes both
+    hg, hi = hh[0], hh[1]
     timed("fr_pair_score cfg-5 (6000 x 512)", lambda: K.pair_score(e1, e2, lab8, scores, dist_, hg, hi), N * 2 * d * 4,
           note="includes zeroing + filling the two 100001-bin histograms")
     import ctypes
     from face_recognition_pytorch_b200 import _lib
     buf = torch.zeros(ctypes.sizeof(_lib.RocOut), dtype=torch.uint8, device=dev)
     timed("fr_roc (100000-threshold sweep, FAR 1e-3..1e-9 + EER)", lambda: K.roc(hg, hi, 3, 9, buf), 2 * bins * 8,
-          note="latency-bound: one CTA scans both histograms")
+          note="one cluster of 8 CTAs, histograms staged in shared memory, DSMEM exchange of the CTA totals / winners")
     out2 = torch.zeros(2, dtype=torch.int64, device=dev)
     timed("fr_acc_counts (6000 scores)", lambda: K.acc_counts(scores, lab8, 0.63399, out2), N * 9)
     ws = torch.zeros(10 * 400, dtype=torch.int32, device=dev)
     acc = torch.zeros(10, dtype=torch.float64, device=dev)
     best = torch.zeros(10, dtype=torch.int32, device=dev)
     timed("fr_kfold_acc (10 folds x 400 thresholds)", lambda: K.kfold_acc(dist_, lab8, 10, 400, 0.01, ws, acc, best),
-          400 * N * 9, launches=2, note="each of the 400 threshold CTAs re-reads the 6000 distances (L2 hits)")
+          N * 9, launches=1, note="one CTA: per-fold flip-threshold histograms in shared memory, prefix sums, argmax")
 
     # ---- the reference-facing call: NumPy in, report out (H2D + kernels + D2H + host formatting), wall clock
     try:
