@@ -3,7 +3,7 @@ global batch 1024 (BASELINE.json configs[1]) on N B200s of one node, with the ro
 reference head's CPU implementation timed on the host cores beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1|2|3|4] [--scaling strong|weak]
-                    [--mode fused|late_dx|unfused] [--no-graph] [--no-parity] [--no-cpu-baseline]
+                    [--mode fused|unfused] [--no-graph] [--no-parity] [--no-cpu-baseline]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
         bench.py --gpus N --steps K --warmup W
 
@@ -346,9 +346,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4], help="BASELINE.json configs[config - 1]")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong: the config's global batch on every N; weak: 128 samples per GPU (global batch 128 N)")
-    ap.add_argument("--mode", default="fused", choices=["fused", "late_dx", "unfused"],
-                    help="fused: SGD update fused into the backward, dX GEMM launched right behind the forward GEMM "
-                         "(conf.early_dx); late_dx: fused, dX after the loss (the round-1 order); unfused: dW handed to "
+    ap.add_argument("--mode", default="fused", choices=["fused", "unfused"],
+                    help="fused: SGD update fused into the backward (conf.fused_optimizer); unfused: dW handed to "
                          "torch.optim.SGD")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--autograd", action="store_true", help="capture forward + loss.backward() instead of head.fused_step")
@@ -396,7 +395,7 @@ def main():
     b = GLOBAL_BATCH // world
     fused = mode != "unfused"
     conf = types.SimpleNamespace(emd_size=EMB, sample_rate=rate, mixed_precision=False, loss_s=S, loss_m=M,
-                                 fused_optimizer=fused, early_dx=mode != "late_dx",
+                                 fused_optimizer=fused,
                                  peer_collectives=False if args.no_peer else "auto")
     head = pfc.PartialFC(conf, C)
     head.load_state_dict({"weight": w_shard.clone()})

@@ -64,9 +64,6 @@ _SIGS = {
     "pfc_row_stats": (c_int, [p, c_int, c_int, p, p, p, p]),
     "pfc_loss": (c_int, [p, c_int, p, p, p]),
     "pfc_backward_prepare": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, c_int, p]),
-    "pfc_backward_prepare_deferred": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, p, c_int,
-                                              p]),
-    "pfc_dx_finalize_patched": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p, p, p, p]),
     "pfc_backward_dx": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dx_finalize": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p]),
     "pfc_backward_dw": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
@@ -83,8 +80,6 @@ _SIGS = {
     "pfc_peer_localize_labels": (c_int, [POINTER(c_void_p), p, c_int, c_int, p, c_int, ctypes.c_int64, c_int, p, p]),
     "pfc_peer_dx_finalize": (c_int, [POINTER(c_void_p), p, c_int, c_int, p, p, p, c_float, c_int, c_int, p, p]),
     "pfc_peer_dx_scatter": (c_int, [p, c_int, p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p), p]),
-    "pfc_peer_dx_scatter_patched": (c_int, [p, c_int, p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p), p, p, p,
-                                            p]),
     "pfc_eval_hist_bins": (c_int, []),
     "fr_pair_score": (c_int, [p, p, p, c_int, c_int, p, p, p, p, p]),
     "fr_cross_score": (c_int, [p, p, c_int, c_int, p, p, p, p, p]),

@@ -229,13 +229,9 @@ peer_loss_kernel(PeerPtrs flags, uint32_t* state, int rank, const float* slots, 
 }
 
 // row i of the global batch belongs to rank i / b; its scaled dXn partial goes to that rank's slot `rank`
-// kPatch: the dX GEMM ran on the spill before its target column was patched (see dx_finalize_d512_kernel, pfc_rows.cu)
-template <bool kPatch>
 __global__ void __launch_bounds__(256)
 peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t split_stride,
-                       const float* __restrict__ coef, int B, int b, int d, int rank, PeerPtrs dx_slots,
-                       const float* __restrict__ patch, const int32_t* __restrict__ labels,
-                       const __nv_bfloat16* __restrict__ wn) {
+                       const float* __restrict__ coef, int B, int b, int d, int rank, PeerPtrs dx_slots) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -253,16 +249,6 @@ peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t spl
                                         : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < 4; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
-        }
-        if constexpr (kPatch) {
-            const int lbl = labels[row];
-            if (lbl >= 0) {
-                const float pv = patch[row];
-                const uint2 raw = *reinterpret_cast<const uint2*>(wn + static_cast<size_t>(lbl) * d + 4 * k);
-                const float2 w01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-                const float2 w23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-                a.x = fmaf(pv, w01.x, a.x); a.y = fmaf(pv, w01.y, a.y); a.z = fmaf(pv, w23.x, a.z); a.w = fmaf(pv, w23.y, a.w);
-            }
         }
         a.x *= c; a.y *= c; a.z *= c; a.w *= c;
         *reinterpret_cast<float4*>(out + 4 * k) = a;
@@ -414,23 +400,8 @@ int pfc_peer_dx_scatter(const float* partial, int splits, const float* coef, int
     PeerPtrs s;
     int rc = fill_peers(&s, peer_dx_slots, W);
     if (rc) return rc;
-    launch_step_kernel(PDL_DX_FINAL, peer_dx_scatter_kernel<false>, (B + 7) / 8, 256, 0, (cudaStream_t)stream,
-                       partial, splits, static_cast<size_t>(B) * d, coef, B, b, d, rank, s, nullptr, nullptr, nullptr);
-    return launched();
-}
-
-// pfc_peer_dx_scatter for a dX GEMM that ran on the unpatched spill (see pfc_dx_finalize_patched)
-int pfc_peer_dx_scatter_patched(const float* partial, int splits, const float* coef, int B, int b, int d, int rank, int W,
-                                void* const* peer_dx_slots, const float* patch, const int32_t* labels_local,
-                                const void* wn, void* stream) {
-    if (B <= 0 || b <= 0 || B != b * W || d <= 0 || (d & 7) || splits <= 0 || !patch || !labels_local || !wn)
-        return PFC_ERR_SHAPE;
-    PeerPtrs s;
-    int rc = fill_peers(&s, peer_dx_slots, W);
-    if (rc) return rc;
-    launch_step_kernel(PDL_DX_FINAL, peer_dx_scatter_kernel<true>, (B + 7) / 8, 256, 0, (cudaStream_t)stream,
-                       partial, splits, static_cast<size_t>(B) * d, coef, B, b, d, rank, s, patch, labels_local,
-                       reinterpret_cast<const __nv_bfloat16*>(wn));
+    launch_step_kernel(PDL_DX_FINAL, peer_dx_scatter_kernel, (B + 7) / 8, 256, 0, (cudaStream_t)stream,
+                       partial, splits, static_cast<size_t>(B) * d, coef, B, b, d, rank, s);
     return launched();
 }
 

@@ -213,17 +213,13 @@ loss_kernel(const float* __restrict__ stats, int B, float* __restrict__ row_L, f
 //   c_i = g * s / (B * L_i);  Xs_i = c_i * Xn_i (bf16);  E'[i, y_i] = -dm_i * mask_i * Lothers_i
 //   dm_i = d(margin)/dt = cos m + sin m * t / sqrt(1 - t^2)  if t > cos(pi - m) else 1   (CosFace: 1)
 //   mask_i = 1 if -1 <= raw <= 1 (clamp backward) else 0
-// kDefer (early dX, see pfc_backward_prepare_deferred): the dX GEMM has already run on the spill with its target column
-// still 0, so besides patching E' for the dW GEMM the target value is handed out as patch[i] (0 for rows whose class
-// lives on another rank) for the rank-1 fix-up of dX.
-template <bool kDefer>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict__ row_L,
                         const float* __restrict__ grad_loss, float s, int B, int d,
                         const int32_t* __restrict__ labels, const float* __restrict__ tgt_raw, int margin_kind,
                         float cos_m, float sin_m, float theta, const __nv_bfloat16* __restrict__ xn,
                         __nv_bfloat16* __restrict__ xs, float* __restrict__ coef, __nv_bfloat16* __restrict__ E,
-                        int n_pad, float* __restrict__ patch) {
+                        int n_pad) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B) return;
@@ -247,25 +243,17 @@ backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict
             if (margin_kind == 0 && t > theta) dm = cos_m + sin_m * t / sqrtf(fmaxf(1.f - t * t, 1e-12f));
             const __nv_bfloat16 pv = __float2bfloat16_rn(-dm * mask * stats[2 * row]);
             // class-blocked spill: E'[class / 64][row][class % 64]
-            if constexpr (kDefer) patch[row] = __bfloat162float(pv);
             E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = pv;
-        } else if constexpr (kDefer) {
-            patch[row] = 0.f;
         }
     }
 }
 
 // d = 512 fast path of dx_finalize_kernel: FOUR warps per row (one float4 per lane and slab), two rows per CTA -- the
 // one-warp-per-row kernel below has only `rows` warps in flight (7 per SM at B = 1024) and ran at 1.9 TB/s.
-// kPatch: the dX GEMM ran on the spill BEFORE its target column was patched (that column holds 0), so the target's
-// rank-1 term patch[i] * Wn[y_i, :] is added here (bf16 x bf16 products are exact in fp32: only the position of the
-// term in the sum differs from the patched GEMM).
-template <bool kPatch>
 __global__ void __launch_bounds__(256)
 dx_finalize_d512_kernel(const float* __restrict__ partial, int splits, size_t split_stride, const float* __restrict__ coef,
                         const float* __restrict__ x, const float* __restrict__ inv_norm, float scale, int rows,
-                        float* __restrict__ out, const float* __restrict__ patch, const int32_t* __restrict__ labels,
-                        const __nv_bfloat16* __restrict__ wn) {
+                        float* __restrict__ out) {
     __shared__ float part[2][4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = warp >> 2, q = warp & 3;
@@ -283,15 +271,6 @@ dx_finalize_d512_kernel(const float* __restrict__ partial, int splits, size_t sp
                 p[u] = (z + u < splits) ? ld4_stream(pp + (z + u) * split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < 8; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
-        }
-        if constexpr (kPatch) {
-            const int lbl = labels[row];
-            if (lbl >= 0) {
-                const float pv = patch[row];
-                const float4 wv = unpack4_bf16(*reinterpret_cast<const uint2*>(wn + static_cast<size_t>(lbl) * 512 +
-                                                                                q * 128 + lane * 4));
-                a.x = fmaf(pv, wv.x, a.x); a.y = fmaf(pv, wv.y, a.y); a.z = fmaf(pv, wv.z, a.z); a.w = fmaf(pv, wv.w, a.w);
-            }
         }
         const float c = coef ? coef[row] : 1.f;
         a.x *= c; a.y *= c; a.z *= c; a.w *= c;
@@ -318,12 +297,10 @@ dx_finalize_d512_kernel(const float* __restrict__ partial, int splits, size_t sp
 // dX: sum the class-split partials, scale by c_i, and (when x is given) apply the normalise backward
 //   dx = scale * (dxn - xn (xn . dxn)) / ||x||,   xn = x * inv_norm          (autograd of F.normalize)
 // scale = world_size reproduces AllGatherFunc.backward's "grad_out *= len(grad_list)" (nets/PartialFC.py:521).
-template <bool kPatch>
 __global__ void __launch_bounds__(ROW_WARPS * 32)
 dx_finalize_kernel(const float* __restrict__ partial, int splits, size_t split_stride, const float* __restrict__ coef,
                    const float* __restrict__ x, const float* __restrict__ inv_norm, float scale, int rows, int d,
-                   float* __restrict__ out, const float* __restrict__ patch, const int32_t* __restrict__ labels,
-                   const __nv_bfloat16* __restrict__ wn) {
+                   float* __restrict__ out) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -345,14 +322,6 @@ dx_finalize_kernel(const float* __restrict__ partial, int splits, size_t split_s
                     p[u] = (z + u < splits) ? ld4_stream(pp + (z + u) * split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { a.x += p[u].x; a.y += p[u].y; a.z += p[u].z; a.w += p[u].w; }
-            }
-            if constexpr (kPatch) {
-                const int lbl = labels[row];
-                if (lbl >= 0) {
-                    const float pv = patch[row];
-                    const float4 wv = unpack4_bf16(*reinterpret_cast<const uint2*>(wn + static_cast<size_t>(lbl) * d + 4 * k));
-                    a.x = fmaf(pv, wv.x, a.x); a.y = fmaf(pv, wv.y, a.y); a.z = fmaf(pv, wv.z, a.z); a.w = fmaf(pv, wv.w, a.w);
-                }
             }
             a.x *= c; a.y *= c; a.z *= c; a.w *= c;
             g[j] = a;
@@ -750,23 +719,10 @@ int pfc_backward_prepare(const float* stats, const float* row_L, const float* gr
                          const void* xn, void* xs, float* coef, void* E, int n_pad, void* stream) {
     if (B <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
     const double pi = 3.14159265358979323846;
-    launch_step_kernel(PDL_PREPARE, backward_prepare_kernel<false>, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
+    launch_step_kernel(PDL_PREPARE, backward_prepare_kernel, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
         (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
-        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, nullptr);
-    return check_launch();
-}
-
-int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
-                                  const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                                  const void* xn, void* xs, float* coef, float* patch, void* E, int n_pad,
-                                  void* stream) {
-    if (B <= 0 || bad_d(d) || !patch || !E || n_pad % 64) return PFC_ERR_SHAPE;
-    const double pi = 3.14159265358979323846;
-    launch_step_kernel(PDL_PREPARE, backward_prepare_kernel<true>, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
-        stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
-        (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
-        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad, patch);
+        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad);
     return check_launch();
 }
 
@@ -774,33 +730,12 @@ int pfc_dx_finalize(const float* partial, int splits, const float* coef, const f
                     float scale, int rows, int rows_total, int d, float* out, void* stream) {
     if (rows <= 0 || bad_d(d) || splits <= 0 || rows_total < rows) return PFC_ERR_SHAPE;
     if (d == 512) {
-        launch_step_kernel(PDL_DX_FINAL, dx_finalize_d512_kernel<false>, (rows + 1) / 2, 256, 0, (cudaStream_t)stream,
-        partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, out, nullptr, nullptr,
-        nullptr);
+        launch_step_kernel(PDL_DX_FINAL, dx_finalize_d512_kernel, (rows + 1) / 2, 256, 0, (cudaStream_t)stream,
+        partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, out);
         return check_launch();
     }
-    launch_step_kernel(PDL_DX_FINAL, dx_finalize_kernel<false>, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
-        partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, d, out, nullptr, nullptr,
-        nullptr);
-    return check_launch();
-}
-
-// pfc_dx_finalize for a dX GEMM that ran on the UNPATCHED spill: adds patch[i] * Wn[labels_local[i], :] to row i
-// before the scaling (rows == rows_total: the variant is for the rank that owns the whole partial, i.e. one GPU).
-int pfc_dx_finalize_patched(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
-                            float scale, int rows, int rows_total, int d, float* out, const float* patch,
-                            const int32_t* labels_local, const void* wn, void* stream) {
-    if (rows <= 0 || bad_d(d) || splits <= 0 || rows_total < rows || !patch || !labels_local || !wn) return PFC_ERR_SHAPE;
-    const __nv_bfloat16* wnp = reinterpret_cast<const __nv_bfloat16*>(wn);
-    if (d == 512) {
-        launch_step_kernel(PDL_DX_FINAL, dx_finalize_d512_kernel<true>, (rows + 1) / 2, 256, 0, (cudaStream_t)stream,
-        partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, out, patch, labels_local,
-        wnp);
-        return check_launch();
-    }
-    launch_step_kernel(PDL_DX_FINAL, dx_finalize_kernel<true>, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
-        partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, d, out, patch, labels_local,
-        wnp);
+    launch_step_kernel(PDL_DX_FINAL, dx_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
+        partial, splits, static_cast<size_t>(rows_total) * d, coef, x, inv_norm, scale, rows, d, out);
     return check_launch();
 }
 

@@ -183,24 +183,6 @@ def backward_prepare(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, ma
                                    _p(E, BF16), n_pad, _stream()), "pfc_backward_prepare")
 
 
-@_timed("pfc_backward_prepare_deferred")
-def backward_prepare_deferred(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef,
-                              patch, E, n_pad):
-    """pfc_backward_prepare for a step whose dX GEMM already ran on the unpatched spill: also hands the target values out
-    as patch[B] for pfc_dx_finalize_patched / pfc_peer_dx_scatter_patched."""
-    check(lib.pfc_backward_prepare_deferred(_p(stats, F32), _p(row_L, F32), _p(grad_loss, F32), s, B, d,
-                                            _p(labels_local, I32), _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16),
-                                            _p(xs, BF16), _p(coef, F32), _p(patch, F32), _p(E, BF16), n_pad, _stream()),
-          "pfc_backward_prepare_deferred")
-
-
-@_timed("pfc_dx_finalize_patched")
-def dx_finalize_patched(partial, splits, coef, x, inv_norm, scale, rows, rows_total, d, out, patch, labels_local, wn):
-    check(lib.pfc_dx_finalize_patched(_p(partial, F32), splits, _p(coef, F32), _p(x, F32), _p(inv_norm, F32), scale,
-                                      rows, rows_total, d, _p(out, F32), _p(patch, F32), _p(labels_local, I32),
-                                      _p(wn, BF16), _stream()), "pfc_dx_finalize_patched")
-
-
 @_timed("pfc_backward_dx")
 def backward_dx(E, n_pad, wn, B, n, d, partial, splits):
     check(lib.pfc_backward_dx(_p(E, BF16), n_pad, _p(wn, BF16), B, n, d, _p(partial, F32), splits, _stream()),
@@ -290,13 +272,6 @@ def peer_dx_finalize(peer_flags, state, rank, W, dx_slots, x, inv_norm, scale, b
 def peer_dx_scatter(partial, splits, coef, B, b, d, rank, W, peer_dx_slots):
     check(lib.pfc_peer_dx_scatter(_p(partial, F32), splits, _p(coef, F32), B, b, d, rank, W, peer_dx_slots,
                                   _stream()), "pfc_peer_dx_scatter")
-
-
-@_timed("pfc_peer_dx_scatter_patched")
-def peer_dx_scatter_patched(partial, splits, coef, B, b, d, rank, W, peer_dx_slots, patch, labels_local, wn):
-    check(lib.pfc_peer_dx_scatter_patched(_p(partial, F32), splits, _p(coef, F32), B, b, d, rank, W, peer_dx_slots,
-                                          _p(patch, F32), _p(labels_local, I32), _p(wn, BF16), _stream()),
-          "pfc_peer_dx_scatter_patched")
 
 
 # ---- verification scorer

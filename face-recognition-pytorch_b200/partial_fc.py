@@ -26,11 +26,6 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       of HBM traffic each -- disappear; `weight_activated` then stays the reference's initial (0, 0) placeholder and
       `weight`, `weight_mom`, `weight_index`, state_dict() are always current.  False: gather / scatter like the
       reference (what the un-fused path always does, because torch.optim steps on `weight_activated`).
-  conf.early_dx (bool, default True): launch the dX contraction right behind the forward GEMM on its own stream, next to
-      the softmax statistics, their exchange between ranks and the loss, whenever local_embeddings needs a gradient.
-      The forward leaves 0 in the target column of the spill and dX needs neither the softmax denominator nor the target
-      value: both are applied when the partials are summed (pfc_dx_finalize_patched).  False: dX after the coefficients
-      are known (backward order of the reference).
   conf.device_sampling (bool, default False): draw the PartialFC sampling scores with the CUDA generator on the device
       instead of `torch.rand` on the CPU generator + H2D copy (nets/PartialFC.py:110).  Removes a host round trip per
       step; the sampled index set is then NOT the reference's for the same seed (same distribution, other stream).
@@ -88,7 +83,6 @@ class _Workspace:
         self.loss = z(1)
         self.ticket = z(1, dt=i32)
         self.coef = z(B)
-        self.patch = z(B)                         # target values of E' kept aside while the spill's target column is 0
         self.xs = z(B, d, dt=bf16)
         self.max_splits = max(1, K.dx_max_splits(B, d))
         self.dx_partial = z(self.max_splits * B * d)
@@ -149,8 +143,6 @@ class _PartialFCBase(torch.nn.Module):
         self.fp16 = conf.mixed_precision           # kept for interface parity; the kernels always run bf16-in / fp32-acc
         self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
         self.device_sampling = bool(getattr(conf, "device_sampling", False))
-        # dX contraction launched right behind the forward GEMM, next to the statistics / exchange / loss
-        self.early_dx = bool(getattr(conf, "early_dx", True))
         # run the tail of the dX path (finalize / peer scatter + finalize) on a side stream next to the rank-local
         # dW GEMM + update, which it does not depend on; may be flipped between steps (before a graph capture)
         self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto"
@@ -191,9 +183,6 @@ class _PartialFCBase(torch.nn.Module):
         self._n = self.num_local        # active classes this step
         self._opt_args = None
         self._side_stream = None        # dX tail
-        self._dx_stream = None          # early dX GEMM
-        self._dx_unjoined = False       # ... launched and not yet waited for by a backward
-        self._early_splits = None       # slabs of dX partials (of the UNPATCHED spill) this step's forward left behind
         self._gscale_is_one = True
         self._graph_steps = False       # AdamW: take the bias-correction step count from ws.adam_step (graph replay)
         # True / False / "auto": exchange the batch, the softmax statistics and dX through peer (NVLink) memory with
@@ -388,10 +377,6 @@ class _PartialFCBase(torch.nn.Module):
         w = self.weight if self._indexed else self.weight_activated.data
         if self.fused_optimizer:
             self._opt_args = self._read_optimizer(self._optimizer)
-        if self._dx_unjoined:
-            # an early dX GEMM whose backward never ran may still be reading the spill this forward overwrites
-            torch.cuda.current_stream().wait_stream(self._dx_stream)
-            self._dx_unjoined = False
         if not self._wn_valid:
             K.l2norm_rows(w, ws.index if self._indexed else None, n, ws.wn, ws.inv_w)   # :200 (+ :120 when indexed)
             self._wn_valid = True
@@ -399,19 +384,6 @@ class _PartialFCBase(torch.nn.Module):
         self._n_pad = K.padded_classes(n)
         K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
                   ws.tgt_raw, ws.tgt_e, ws.tgt_z)                                 # :201-207
-        self._early_splits = None
-        if need_dx and self.early_dx:
-            # the forward leaves 0 in the target column of the spill: dXn_i = c_i (sum_c E'_ic Wn_c + patch_i Wn_{y_i}), so
-            # the contraction can start now and run next to the statistics, their exchange and the loss
-            if w.is_cuda:
-                if self._dx_stream is None:
-                    self._dx_stream = torch.cuda.Stream(device=w.device)
-                self._dx_stream.wait_stream(torch.cuda.current_stream())
-            splits = K.dx_splits(B, n, d)
-            with torch.cuda.stream(self._dx_stream) if w.is_cuda else contextlib.nullcontext():
-                K.backward_dx(ws.E, self._n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
-            self._early_splits = splits
-            self._dx_unjoined = w.is_cuda
         peer = self._peer
         if peer is not None:
             # statistics straight into every peer's slot, then a rank-ordered local sum (identical bits on all ranks)
@@ -437,31 +409,21 @@ class _PartialFCBase(torch.nn.Module):
         g = None if grad_loss is None else grad_loss.detach().to(torch.float32).reshape(1).contiguous()
         w = self.weight if self._indexed else self.weight_activated.data
         peer = self._peer
-        early = self._early_splits is not None     # the dX GEMM of the UNPATCHED spill is running / has run
         if self.fused_optimizer:
             if g is not None:
                 ws.gscale.copy_(g)                 # the fused update divides the loss scale out again
             elif not self._gscale_is_one:
                 ws.gscale.fill_(1.0)
             self._gscale_is_one = g is None
-        if early:
-            # the dX GEMM must have finished READING the spill before its target column is written for the dW GEMM; the
-            # target values are also kept aside (ws.patch) for the rank-1 fix-up of dX
-            if self._dx_unjoined:
-                torch.cuda.current_stream().wait_stream(self._dx_stream)
-                self._dx_unjoined = False
-            K.backward_prepare_deferred(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all,
-                                        ws.xs, ws.coef, ws.patch, ws.E, n_pad)
-        else:
-            K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
-                               ws.coef, ws.E, n_pad)
+        K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs, ws.coef,
+                           ws.E, n_pad)
         spill_bf16 = self.fused_optimizer and self._optimizer_kind == "sgd" and d % 128 == 0
         dwn = ws.grad_buffer(spill_bf16, d)
         dw = None
-        # Order without early dX.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the
+        # Order.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the
         # reduce-scatter / peer stores have the whole dW + update to complete.  N = 1: dW GEMM first (it walks the class
         # tiles from the end, where the forward's spill is still in L2), then dX, then the update.
-        dw_first = W == 1 and not early
+        dw_first = W == 1
         if dw_first:
             K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         dx, rs_work = None, None
@@ -469,13 +431,9 @@ class _PartialFCBase(torch.nn.Module):
         want_fork = True if self.dx_side_stream == "auto" else bool(self.dx_side_stream)
         fork = want_fork and w.is_cuda and need_dx and (W == 1 or peer is not None)
         tail = None
-        wn_read_done = None       # fork: the tail's patched kernel reads wn, which the fused update rewrites in place
         if need_dx:
-            if early:
-                splits = self._early_splits
-            else:
-                splits = K.dx_splits(B, n, d)
-                K.backward_dx(ws.E, n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
+            splits = K.dx_splits(B, n, d)
+            K.backward_dx(ws.E, n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
             if fork:
                 if self._side_stream is None:
@@ -484,41 +442,24 @@ class _PartialFCBase(torch.nn.Module):
                 tail.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():
                 if W == 1:
-                    if early:
-                        K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx,
-                                              ws.patch, ws.labels_act, ws.wn)
-                    else:
-                        K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
+                    K.dx_finalize(ws.dx_partial, splits, ws.coef, self._x_local, ws.inv_x, 1.0, B, B, d, dx)
                 elif peer is not None:
                     # :505-522 -- every rank stores its scaled partial of row i into the owner's slot; the owner sums
                     # the W slots in rank order inside the normalise-backward kernel (x W, :521)
-                    if early:
-                        K.peer_dx_scatter_patched(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W,
-                                                  peer.ptrs("dx_slots"), ws.patch, ws.labels_act, ws.wn)
-                    else:
-                        K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
+                    K.peer_dx_scatter(ws.dx_partial, splits, ws.coef, B, b, d, self.rank, W, peer.ptrs("dx_slots"))
                     if tail is not None:
                         # barrier + :521; also the fence that keeps a fast rank's NEXT gather out of xn_all while a
                         # slow rank still reads it (this rank signals after its last read of the gathered batch)
                         K.peer_dx_finalize(peer.ptrs("flags"), peer.counter, self.rank, W, peer.dx_slots,
                                            self._x_local, ws.inv_x, float(W), b, d, dx)
                 else:
-                    if early:
-                        K.dx_finalize_patched(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all,
-                                              ws.patch, ws.labels_act, ws.wn)
-                    else:
-                        K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
+                    K.dx_finalize(ws.dx_partial, splits, ws.coef, None, None, 1.0, B, B, d, ws.dxn_all)
                     # :505-519 -- asynchronous: it overlaps the rank-local dW GEMM / update below
                     rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
                                                                 async_op=True)
-                if early and tail is not None and self.fused_optimizer:
-                    wn_read_done = torch.cuda.Event()
-                    wn_read_done.record()                     # on the tail stream
         if not dw_first:
             K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         if self.fused_optimizer:
-            if wn_read_done is not None:
-                torch.cuda.current_stream().wait_event(wn_read_done)
             self._fused_step(w, n, d, dwn, ws.wn)         # in place, after the last reader of this step's shard
         else:
             dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
@@ -536,7 +477,6 @@ class _PartialFCBase(torch.nn.Module):
                 K.peer_barrier(peer.ptrs("flags"), peer.counter, self.rank, W)
         if tail is not None:
             torch.cuda.current_stream().wait_stream(tail)                          # join
-        self._early_splits = None
         return dx, dw
 
     def _fused_step(self, w, n, d, dwn, wn_out):

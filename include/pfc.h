@@ -125,21 +125,6 @@ int pfc_backward_dx(const void* E_bf16, int n_pad, const void* wn_bf16, int B, i
                     int splits, void* stream);
 int pfc_dx_finalize(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
                     float scale, int rows, int rows_total, int d, float* out, void* stream);
-/* Early dX (the host launches pfc_backward_dx right behind pfc_forward, next to the softmax statistics / their exchange /
- * the loss): the forward leaves 0 in the target column of E, and the dX contraction needs neither the softmax denominator
- * nor the target value -- both are applied when the partials are summed:
- * pfc_backward_prepare_deferred = pfc_backward_prepare (run once the dX GEMM has finished reading E) that ALSO hands the
- * target value out as patch[i] (the bf16-rounded -dm_i*mask_i*stats[i][0]; 0 for rows whose class is on another rank);
- * pfc_dx_finalize_patched / pfc_peer_dx_scatter_patched add the missing rank-1 term patch[i] * Wn[labels_local[i], :]
- * to row i of the summed partials before scaling (bf16 x bf16 products are exact in fp32: the result differs from a
- * GEMM over the patched spill only by the position of that term in the sum). */
-int pfc_backward_prepare_deferred(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
-                                  const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                                  const void* xn_bf16, void* xs_bf16, float* coef, float* patch, void* E_bf16, int n_pad,
-                                  void* stream);
-int pfc_dx_finalize_patched(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
-                            float scale, int rows, int rows_total, int d, float* out, const float* patch,
-                            const int32_t* labels_local, const void* wn_bf16, void* stream);
 /* dwn_bf16 != 0: dwn is a bf16 [n,d] matrix (halves the spill that pfc_dw_sgd re-reads; fused-SGD mode only);
  * 1: stored with L2 evict_last hints for a pfc_dw_sgd that runs right behind it, 2: plain stores. */
 int pfc_backward_dw(const void* E_bf16, int n_pad, const void* xs_bf16, int B, int n, int d, void* dwn, int dwn_bf16,
@@ -194,10 +179,6 @@ int pfc_peer_dx_finalize(void* const* peer_flags, uint32_t* barrier_state, int r
                          const float* x, const float* inv_norm, float scale, int b, int d, float* out, void* stream);
 int pfc_peer_dx_scatter(const float* partial, int splits, const float* coef, int B, int b, int d, int rank, int W,
                         void* const* peer_dx_slots, void* stream);
-int pfc_peer_dx_scatter_patched(const float* partial, int splits, const float* coef, int B, int b, int d, int rank, int W,
-                                void* const* peer_dx_slots, const float* patch, const int32_t* labels_local,
-                                const void* wn_bf16, void* stream);
-
 /* ---- (6) pair verification, utils/eval.py.
  * fr_pair_score  (:68-99): scores[i] = 1 - ||e1_i - e2_i||^2/4 (fp32 difference, fp64 accumulation), optional
  *   dist[i] = ||.||^2, and the 100001-bin genuine / imposter histograms (uint64 counts; zeroed by the call).

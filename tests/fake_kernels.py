@@ -120,20 +120,6 @@ class FakeKernels:
         Ev = E[: B * n_pad].view(B, n_pad)
         Ev[rows, labels[rows].long()] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16)
 
-    def backward_prepare_deferred(self, stats, row_L, grad_loss, s, B, d, labels, tgt_raw, kind, m2, xn, xs, coef,
-                                  patch, E, n_pad):
-        self.backward_prepare(stats, row_L, grad_loss, s, B, d, labels, tgt_raw, kind, m2, xn, xs, coef, E, n_pad)
-        rows = torch.nonzero(labels[:B] >= 0).reshape(-1)
-        patch.zero_()
-        patch[rows] = E[: B * n_pad].view(B, n_pad)[rows, labels[rows].long()].float()
-
-    def dx_finalize_patched(self, partial, splits, coef, x, inv_norm, scale, rows, rows_total, d, out, patch, labels, wn):
-        p = partial.reshape(-1)[: splits * rows_total * d].view(splits, rows_total, d)
-        own = torch.nonzero(labels[:rows_total] >= 0).reshape(-1)
-        fixed = p.clone()
-        fixed[0, own] += patch[own].reshape(-1, 1) * wn[labels[own].long()].float()
-        self.dx_finalize(fixed, splits, coef, x, inv_norm, scale, rows, rows_total, d, out)
-
     def backward_dx(self, E, n_pad, wn, B, n, d, partial, splits):
         p = partial[: splits * B * d].view(splits, B, d)
         p.zero_()

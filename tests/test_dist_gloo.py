@@ -15,19 +15,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-# (name, fused, direct = PartialFC.fused_step instead of autograd, mode): mode "" = defaults (conf.early_dx: the dX GEMM runs
-# on the spill before its target column is written, the target term is fixed up when the partials are summed),
-# "late_dx" = dX after the coefficients (the reference's backward order)
+# (name, fused, direct = PartialFC.fused_step instead of autograd, mode): mode "" = defaults, "gather" = conf.inplace_update
+# off (sampled + fused: gather / scatter of the active rows like the reference instead of the in-place indexed update)
 SGD_CASES = [("head_w2_full", False, False, ""), ("head_w2_sampled", False, False, ""),
              ("head_w2_full", True, False, ""), ("head_w2_sampled", True, False, ""),
              ("head_w2_sampled", False, True, ""), ("head_w2_full", True, True, ""),
              # one rank: CombinedMarginLoss with inter-class filtering
              ("head_w1_filter_wide", False, False, ""), ("head_w1_filter_wide", True, True, ""),
-             ("head_w2_sampled", False, False, "late_dx"), ("head_w2_full", True, True, "late_dx"),
-             ("head_w1_full", True, False, "late_dx"),
+             ("head_w2_sampled", True, False, "gather"), ("head_w2_sampled", True, True, "gather"),
              # d = 128, several 256-class tiles per rank
              ("head_w2_d128", True, False, ""), ("head_w1_d128", False, False, ""),
-             ("head_w2_d128", True, True, "late_dx")]
+             ("head_w2_d128", True, True, "")]
 # (name, fused)
 ADAM_CASES = [("head_w2_adamw_sampled", False), ("head_w2_adamw_sampled", True), ("head_w1_adamw_full", True),
               ("head_w1_adam_sampled", True), ("head_w1_adam_sampled", False)]
@@ -100,7 +98,7 @@ def _run_sgd_case(rank, W, name, fused, direct, mode):
     b = cfg["b"]
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
                                  loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused,
-                                 early_dx=mode != "late_dx")
+                                 inplace_update=mode != "gather")
     if cfg["margin"] == "combined_filter":
         thr = cfg["filter_thr"]
         margin = lambda s_, m_: pfc.CombinedMarginLoss(s_, 1.0, m_, 0.0, interclass_filtering_threshold=thr)  # noqa: E731

@@ -69,17 +69,16 @@ def _cos(a, b):
 
 # peer = False: the three NCCL collectives; peer = True: the same exchanges through NVLink peer memory, fused into the
 # producing kernels (csrc/pfc_peer.cu) -- must raise rather than fall back if symmetric memory is unavailable.
-# extra: conf switches -- early_dx off = dX GEMM on the patched spill after the statistics exchange (the reference's
-# backward order); dx_side_stream off = no fork of the dX tail.
+# extra: conf switches -- dx_side_stream off = no fork of the dX tail; inplace_update off = gather / scatter of the sampled
+# rows like the reference instead of the in-place indexed update.
 @pytest.mark.parametrize("name,fused,port,peer,extra", [
     ("head_w2_full", False, 29841, False, None), ("head_w2_sampled", False, 29842, False, None),
     ("head_w2_full", True, 29843, False, None), ("head_w2_sampled", True, 29844, False, None),
     ("head_w2_full", False, 29845, True, None), ("head_w2_sampled", True, 29846, True, None),
     ("head_w2_full", True, 29847, True, None),
     ("head_w2_d128", True, 29848, True, None), ("head_w2_d128", False, 29849, False, None),
-    ("head_w2_full", False, 29851, True, {"early_dx": False}),
-    ("head_w2_sampled", True, 29852, True, {"early_dx": False}),
-    ("head_w2_full", True, 29853, False, {"early_dx": False}),
+    ("head_w2_sampled", True, 29852, True, {"inplace_update": False}),
+    ("head_w2_sampled", True, 29853, False, {"inplace_update": False}),
     ("head_w2_full", True, 29854, True, {"dx_side_stream": False})])
 def test_two_rank_matches_reference(name, fused, port, peer, extra):
     _run_case(name, fused, port, peer, extra)

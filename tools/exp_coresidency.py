@@ -24,7 +24,7 @@ def main():
     cfg = dict(bench.CONFIGS[2])
     w_shard, xs, ls = bench.synth(cfg, 0, 1, 2, dev)
     conf = types.SimpleNamespace(emd_size=512, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5,
-                                 fused_optimizer=True, early_dx=False)
+                                 fused_optimizer=True)
     head = pfc.PartialFC(conf, cfg["C"])
     head.load_state_dict({"weight": w_shard})
     head = head.train().cuda()

@@ -1,7 +1,7 @@
 """EXPERIMENT (one GPU, no exchange): the head step at the per-GPU shard shapes of BASELINE configs[1] on 1 / 2 / 4 / 8 GPUs
 (global batch 1024 against 93 431 / 46 716 / 23 358 / 11 679 classes), graph-replayed, for each step variant -- what the
 strong-scaling curve would be if the exchanges were free, and where the fixed per-launch costs are.
-    python tools/exp_shard_shapes.py [--modes late_dx,early_dx] [--kernels]"""
+    python tools/exp_shard_shapes.py  [--kernels]"""
 import argparse
 import os
 import statistics
@@ -16,7 +16,6 @@ import torch.distributed as dist  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--modes", default="late_dx,early_dx")
     ap.add_argument("--shards", default="93431,46716,23358,11679")
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=30)
@@ -32,9 +31,9 @@ def main():
     for C in (int(v) for v in args.shards.split(",")):
         cfg = dict(bench.CONFIGS[2], C=C, B=args.batch)
         w_shard, xs, ls = bench.synth(cfg, 0, 1, 4, dev)
-        for mode in args.modes.split(","):
+        for mode in ("fused",):
             conf = types.SimpleNamespace(emd_size=512, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5,
-                                         fused_optimizer=True, early_dx=mode == "early_dx")
+                                         fused_optimizer=True)
             head = pfc.PartialFC(conf, C)
             head.load_state_dict({"weight": w_shard.clone()})
             head = head.train().cuda()

@@ -1,5 +1,6 @@
 """Condense `ncu --page raw --csv` output into the per-kernel metrics the design discussion uses (first launch of each
-kernel name).  python tools/ncu_summary.py raw.csv"""
+kernel name; --all: the LAST launch of each distinct (kernel name, grid size), i.e. warmed-up launches of every shape).
+python tools/ncu_summary.py raw.csv [--all]"""
 import csv
 import sys
 
@@ -23,11 +24,22 @@ for i, r in enumerate(rows):
 if hdr is None:
     sys.exit("no header row found")
 ki = hdr.index("Kernel Name")
-seen = set()
-for r in data:
-    if len(r) != len(hdr) or r[ki] in seen:
-        continue
-    seen.add(r[ki])
+rows_sel = []
+if "--all" in sys.argv:
+    gi = hdr.index("launch__grid_size") if "launch__grid_size" in hdr else None
+    last = {}
+    for r in data:
+        if len(r) == len(hdr):
+            last[(r[ki], r[gi] if gi is not None else "")] = r
+    rows_sel = list(last.values())
+else:
+    seen = set()
+    for r in data:
+        if len(r) != len(hdr) or r[ki] in seen:
+            continue
+        seen.add(r[ki])
+        rows_sel.append(r)
+for r in rows_sel:
     print("----", r[ki][:110])
     for m in KEEP:
         if m in hdr:

@@ -6,12 +6,11 @@ TAG=${2:-c11}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29621"
 run() { name=$1; shift; timeout 300 $TR bench.py --gpus $N "$@" > gpurun_out/${TAG}_n${N}_$name.json 2> gpurun_out/${TAG}_n${N}_$name.err; echo "$name exit $?"; }
 run cfg2 --steps 50 --warmup 5
-run cfg2_late --steps 50 --warmup 5 --mode late_dx
 run cfg2_nccl --steps 50 --warmup 5 --no-peer
 run cfg2_weak --steps 50 --warmup 5 --scaling weak
 run cfg3 --steps 30 --warmup 5 --config 3
 run cfg4 --steps 20 --warmup 3 --config 4
-for f in cfg2 cfg2_late cfg2_nccl cfg2_weak cfg3 cfg4; do python - <<PY
+for f in cfg2 cfg2_nccl cfg2_weak cfg3 cfg4; do python - <<PY
 import json
 try:
     j = json.load(open('gpurun_out/${TAG}_n${N}_$f.json'))
