@@ -356,6 +356,8 @@ def main():
     ap.add_argument("--gemm-mode", type=int, default=0, help="0 auto, 1 single CTA, 2 multicast pair, 3 cta_group::2")
     ap.add_argument("--no-flush-l2", dest="flush_l2", action="store_false",
                     help="skip the 256 MB write between timed steps (one step streams > 1 GB through the 126 MB L2 anyway)")
+    ap.add_argument("--dw-first", default="auto", choices=["auto", "0", "1"],
+                    help="order of the gradient GEMMs: 1 = dW, dX, update; 0 = dX, dW, update; auto = 1 on one GPU")
     ap.add_argument("--no-peer", action="store_true",
                     help="N>1: NCCL collectives instead of the peer-memory (NVLink) exchanges fused into the kernels")
     args = ap.parse_args()
@@ -396,6 +398,7 @@ def main():
     fused = mode != "unfused"
     conf = types.SimpleNamespace(emd_size=EMB, sample_rate=rate, mixed_precision=False, loss_s=S, loss_m=M,
                                  fused_optimizer=fused,
+                                 dw_first="auto" if args.dw_first == "auto" else bool(int(args.dw_first)),
                                  peer_collectives=False if args.no_peer else "auto")
     head = pfc.PartialFC(conf, C)
     head.load_state_dict({"weight": w_shard.clone()})

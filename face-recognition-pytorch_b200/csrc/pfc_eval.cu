@@ -133,18 +133,23 @@ __device__ __forceinline__ Best warp_best(Best x) {
 }
 
 // performance_roc as ONE cluster of 8 CTAs (8 SMs): CTA c stages bins [c S, (c+1) S) of both histograms into shared
-// memory with coalesced loads (200 KB), thread t owns 13 consecutive thresholds of the slice.  The counts above each
+// memory with coalesced loads (200 KB), thread t owns 49 consecutive thresholds of the slice.  The counts above each
 // thread's run come from a warp-shuffle suffix scan inside the CTA plus the CTA totals exchanged through distributed
-// shared memory, so far / frr are the same integer ratios the reference forms, divided in fp64; the sweep for the EER
-// and for every FAR level then runs out of shared memory.  The per-CTA winners go to CTA 0 through DSMEM.
-// (Round 1: one CTA, per-thread strided global loads, 1 + levels passes over global memory: 767 us.)
+// shared memory, so far / frr are the same integer ratios the reference forms, divided in fp64.  ONE sweep over the
+// thread's bins serves the EER and every FAR level: far and frr are divided once per threshold (fp64 divisions are the
+// cost of this kernel); for "minimum frr with far <= 1e-k" the candidates are compared by their integer numerators
+// (frr = num / total_genuine is strictly monotone in num) and only the winner is divided.  The per-CTA winners go to
+// CTA 0 through DSMEM.  (Round 1: one CTA, strided global loads, 1 + levels passes over global memory: 767 us.)
 __constant__ double ROC_LIT[17] = {1e0, 1e-1, 1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1e-7, 1e-8, 1e-9, 1e-10, 1e-11, 1e-12,
                                    1e-13, 1e-14, 1e-15, 1e-16};   // the doubles float('1e-k') parses to
 constexpr int ROC_CLUSTER = 8;
-constexpr int ROC_THREADS = 1024;
+constexpr int ROC_THREADS = 256;
+constexpr int ROC_WARPS = ROC_THREADS / 32;
 constexpr int ROC_SLICE = (HIST_BINS + ROC_CLUSTER - 1) / ROC_CLUSTER;      // 12501 bins per CTA
-constexpr int ROC_PER = (ROC_SLICE + ROC_THREADS - 1) / ROC_THREADS;        // 13 bins per thread
+constexpr int ROC_PER = (ROC_SLICE + ROC_THREADS - 1) / ROC_THREADS;        // 49 bins per thread (256 threads: the 16 level candidates stay in registers)
 constexpr int ROC_SMEM = 2 * ROC_SLICE * 8;
+constexpr int ROC_LEVELS = 16;
+constexpr unsigned long long ROC_NONE = ~0ull;
 
 __device__ __forceinline__ unsigned long long warp_suffix_excl(unsigned long long v, int lane, unsigned long long* total) {
     // exclusive suffix sum over the warp (sum of the lanes ABOVE this one); *total = sum over the warp
@@ -158,6 +163,26 @@ __device__ __forceinline__ unsigned long long warp_suffix_excl(unsigned long lon
     return s - v;
 }
 
+// candidate for one FAR level: smallest genuine count at or below the threshold (= frr numerator), then larger threshold
+struct LevelBest {
+    unsigned long long num;     // ROC_NONE: none
+    int th;
+};
+__device__ __forceinline__ LevelBest level_better(LevelBest a, LevelBest b) {
+    if (b.num < a.num || (b.num == a.num && b.num != ROC_NONE && b.th > a.th)) return b;
+    return a;
+}
+__device__ __forceinline__ LevelBest warp_level_best(LevelBest x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        LevelBest y;
+        y.num = __shfl_xor_sync(0xffffffffu, x.num, o);
+        y.th = __shfl_xor_sync(0xffffffffu, x.th, o);
+        x = level_better(x, y);
+    }
+    return x;
+}
+
 __global__ void __cluster_dims__(ROC_CLUSTER, 1, 1) __launch_bounds__(ROC_THREADS)
 roc_kernel(const unsigned long long* __restrict__ hist_g, const unsigned long long* __restrict__ hist_i, int min_level,
            int max_level, RocOut* __restrict__ out) {
@@ -168,8 +193,10 @@ roc_kernel(const unsigned long long* __restrict__ hist_g, const unsigned long lo
     unsigned long long* si = sg + ROC_SLICE;
     __shared__ unsigned long long wtot_g[32], wtot_i[32];
     __shared__ unsigned long long cta_g[ROC_CLUSTER], cta_i[ROC_CLUSTER];     // every CTA's totals (written by the peers)
-    __shared__ Best wbest[32];
-    __shared__ Best cand[ROC_CLUSTER][17];                                    // CTA 0: per-CTA winners (EER, levels)
+    __shared__ Best wbest[ROC_WARPS];
+    __shared__ LevelBest wlevel[ROC_LEVELS][ROC_WARPS];
+    __shared__ Best cand_eer[ROC_CLUSTER];                                    // CTA 0: per-CTA winners
+    __shared__ LevelBest cand_level[ROC_CLUSTER][ROC_LEVELS];
 
     const int T = threadIdx.x, lane = T & 31, warp = T >> 5;
     const int c = static_cast<int>(cluster.block_rank());
@@ -179,18 +206,19 @@ roc_kernel(const unsigned long long* __restrict__ hist_g, const unsigned long lo
         sg[k] = hist_g[base + k];
         si[k] = hist_i[base + k];
     }
+    if (T < 32) { wtot_g[T] = 0; wtot_i[T] = 0; }
     __syncthreads();
     const int lo = min(T * ROC_PER, len), hi = min(lo + ROC_PER, len);        // local bins [lo, hi)
     unsigned long long tg = 0, ti = 0;
     for (int b = lo; b < hi; ++b) { tg += sg[b]; ti += si[b]; }
     unsigned long long wg, wi;
-    unsigned long long ag = warp_suffix_excl(tg, lane, &wg);                  // in-warp counts above this thread's run
-    unsigned long long ai = warp_suffix_excl(ti, lane, &wi);
+    const unsigned long long ag = warp_suffix_excl(tg, lane, &wg);            // in-warp counts above this thread's run
+    const unsigned long long ai = warp_suffix_excl(ti, lane, &wi);
     if (lane == 0) { wtot_g[warp] = wg; wtot_i[warp] = wi; }
     __syncthreads();
     if (warp == 0) {
         unsigned long long tw_g, tw_i;
-        const unsigned long long vg = wtot_g[lane], vi = wtot_i[lane];
+        const unsigned long long vg = wtot_g[lane], vi = wtot_i[lane];        // zero beyond the CTA's warps
         const unsigned long long eg = warp_suffix_excl(vg, lane, &tw_g);
         const unsigned long long ei = warp_suffix_excl(vi, lane, &tw_i);
         wtot_g[lane] = eg; wtot_i[lane] = ei;                                 // now: counts in the warps above
@@ -206,60 +234,77 @@ roc_kernel(const unsigned long long* __restrict__ hist_g, const unsigned long lo
         tot_g += cta_g[r]; tot_i += cta_i[r];
         if (r > c) { up_g += cta_g[r]; up_i += cta_i[r]; }
     }
-    const unsigned long long cg0 = up_g + wtot_g[warp] + ag;                  // counts in bins strictly above this run
-    const unsigned long long ci0 = up_i + wtot_i[warp] + ai;
+    unsigned long long cgv = up_g + wtot_g[warp] + ag;                        // counts in bins strictly above this run
+    unsigned long long civ = up_i + wtot_i[warp] + ai;
     const double total_g = (double)(long long)tot_g, total_i = (double)(long long)tot_i;
     const int levels = max_level - min_level + 1;
-    // q = 0: EER (minimum |far - frr| below 1, first from the top); q = 1 + l: minimum frr with far <= 1e-(min_level + l)
-    for (int q = 0; q <= levels; ++q) {
-        const double lim = q ? ROC_LIT[q - 1 + min_level] : 0.0;
-        Best best; best.v = 0; best.aux = 0; best.th = -1;
-        unsigned long long cgv = cg0, civ = ci0;
-        for (int b = hi - 1; b >= lo; --b) {
-            const int th = base + b;
-            const unsigned long long hgb = sg[b], hib = si[b];
-            if (th >= 1) {
-                const double far = (double)(long long)(civ + hib) / total_i;
-                const double frr = (double)(long long)(tot_g - cgv) / total_g;
-                Best cnd; cnd.th = th;
-                if (q == 0) {
-                    cnd.v = fabs(far - frr); cnd.aux = (far + frr) / 2;
-                    if (cnd.v < 1.0) best = better(best, cnd);
-                } else if (far <= lim) {
-                    cnd.v = frr; cnd.aux = 0;
-                    best = better(best, cnd);
+    double lim[ROC_LEVELS];
+#pragma unroll
+    for (int l = 0; l < ROC_LEVELS; ++l) lim[l] = l < levels ? ROC_LIT[l + min_level] : -1.0;   // far >= 0: never met
+    Best eer; eer.v = 0; eer.aux = 0; eer.th = -1;
+    LevelBest lb[ROC_LEVELS];
+#pragma unroll
+    for (int l = 0; l < ROC_LEVELS; ++l) { lb[l].num = ROC_NONE; lb[l].th = -1; }
+    for (int b = hi - 1; b >= lo; --b) {                                      // thresholds from the top down
+        const int th = base + b;
+        const unsigned long long hgb = sg[b], hib = si[b];
+        if (th >= 1) {
+            const unsigned long long num = tot_g - cgv;                      // genuine pairs at or below th
+            const double far = (double)(long long)(civ + hib) / total_i;
+            const double frr = (double)(long long)num / total_g;
+            Best cnd; cnd.th = th; cnd.v = fabs(far - frr); cnd.aux = (far + frr) / 2;
+            if (cnd.v < 1.0) eer = better(eer, cnd);                          // strict '<' from the top: first minimum
+#pragma unroll
+            for (int l = 0; l < ROC_LEVELS; ++l) {
+                if (far <= lim[l]) {
+                    LevelBest q; q.num = num; q.th = th;
+                    lb[l] = level_better(lb[l], q);
                 }
             }
-            cgv += hgb; civ += hib;
         }
-        const Best w = warp_best(best);
+        cgv += hgb; civ += hib;
+    }
+    {
+        const Best w = warp_best(eer);
         if (lane == 0) wbest[warp] = w;
-        __syncthreads();
-        if (warp == 0) {
-            const Best x = warp_best(wbest[lane]);
-            if (lane == 0) *cluster.map_shared_rank(&cand[c][q], 0) = x;
+#pragma unroll
+        for (int l = 0; l < ROC_LEVELS; ++l) {
+            const LevelBest x = warp_level_best(lb[l]);
+            if (lane == 0) wlevel[l][warp] = x;
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        Best x; x.v = 0; x.aux = 0; x.th = -1;
+        if (lane < ROC_WARPS) x = wbest[lane];
+        x = warp_best(x);
+        if (lane == 0) *cluster.map_shared_rank(&cand_eer[c], 0) = x;
+        for (int l = 0; l < levels; ++l) {
+            LevelBest y; y.num = ROC_NONE; y.th = -1;
+            if (lane < ROC_WARPS) y = wlevel[l][lane];
+            y = warp_level_best(y);
+            if (lane == 0) *cluster.map_shared_rank(&cand_level[c][l], 0) = y;
+        }
     }
     cluster.sync();
     if (c == 0 && warp == 0) {
-        for (int q = lane; q < 17; q += 32) {
-            if (q > levels) {
-                out->frr_at[q - 1] = nan(""); out->th_at[q - 1] = -1;
-                continue;
+        if (lane == 0) {
+            Best x = cand_eer[0];
+            for (int r = 1; r < ROC_CLUSTER; ++r) x = better(x, cand_eer[r]);
+            out->eer_threshold = x.th < 0 ? 100000 : x.th;
+            out->pad = 0;
+            out->eer = x.th < 0 ? nan("") : x.aux;
+            out->total_genuine = total_g;
+            out->total_imposter = total_i;
+        }
+        if (lane < ROC_LEVELS) {
+            LevelBest y; y.num = ROC_NONE; y.th = -1;
+            if (lane < levels) {
+                y = cand_level[0][lane];
+                for (int r = 1; r < ROC_CLUSTER; ++r) y = level_better(y, cand_level[r][lane]);
             }
-            Best x = cand[0][q];
-            for (int r = 1; r < ROC_CLUSTER; ++r) x = better(x, cand[r][q]);
-            if (q == 0) {
-                out->eer_threshold = x.th < 0 ? 100000 : x.th;
-                out->pad = 0;
-                out->eer = x.th < 0 ? nan("") : x.aux;
-                out->total_genuine = total_g;
-                out->total_imposter = total_i;
-            } else {
-                out->frr_at[q - 1] = x.th < 0 ? nan("") : x.v;
-                out->th_at[q - 1] = x.th;
-            }
+            out->frr_at[lane] = y.num == ROC_NONE ? nan("") : (double)(long long)y.num / total_g;
+            out->th_at[lane] = y.num == ROC_NONE ? -1 : y.th;
         }
     }
 }

@@ -148,6 +148,7 @@ class _PartialFCBase(torch.nn.Module):
         self.dx_side_stream = getattr(conf, "dx_side_stream", "auto")    # True / False / "auto"
         # fused update of a sampled shard in place through the index list (no gather / scatter of the active rows)
         self._indexed = (self.fused_optimizer and self.sample_rate < 1 and bool(getattr(conf, "inplace_update", True)))
+        self.dw_first = getattr(conf, "dw_first", "auto")     # order of the two gradient GEMMs (see _backward_impl)
         self._num_classes = int(num_classes)
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
@@ -423,7 +424,7 @@ class _PartialFCBase(torch.nn.Module):
         # Order.  N > 1: dX GEMM and its exchange first, THEN the rank-local dW GEMM and the update, so the
         # reduce-scatter / peer stores have the whole dW + update to complete.  N = 1: dW GEMM first (it walks the class
         # tiles from the end, where the forward's spill is still in L2), then dX, then the update.
-        dw_first = W == 1
+        dw_first = (W == 1) if self.dw_first == "auto" else bool(self.dw_first)
         if dw_first:
             K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         dx, rs_work = None, None

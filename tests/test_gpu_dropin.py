@@ -133,18 +133,25 @@ def test_training_step_with_the_head_swapped_in(tmp_path, optimizer, sample_rate
         with open(path, "w") as fh:
             fh.write(textwrap.dedent(body))
     C, b, d, img, steps = 2000, 64, 512, 8, 3
-    ref = _run_model(stub_dir, False, optimizer, sample_rate, amp, steps, C, b, d, img)
     ours = _run_model(stub_dir, True, optimizer, sample_rate, amp, steps, C, b, d, img)
-    # fp32 reference: the north-star's 1e-3; under the reference's fp16 autocast its own logits carry ~1e-3 of rounding
-    tol = 5e-3 if amp else 1e-3
+    # The comparator is the reference in fp32.  With conf.mixed_precision the reference rounds its logits to fp16 and its
+    # GradScaler may skip steps; mathematically the loss scale is a no-op, and this package's head computes the same numbers
+    # with and without it -- so the GradScaler flow through our head must reproduce the reference's fp32 run.  The
+    # reference's own mixed-precision run is only compared on the loss (its fp16 rounding: 1e-2).
+    ref = _run_model(stub_dir, False, optimizer, sample_rate, False, steps, C, b, d, img)
     for s, (lr, lo) in enumerate(zip(ref[0], ours[0])):
-        assert np.isfinite(lo) and abs(lo - lr) <= tol * abs(lr), (s, lo, lr)
+        assert np.isfinite(lo) and abs(lo - lr) <= 1e-3 * abs(lr), (s, lo, lr)
+    if amp:
+        ref_amp = _run_model(stub_dir, False, optimizer, sample_rate, True, steps, C, b, d, img)
+        assert abs(ours[0][0] - ref_amp[0][0]) <= 1e-2 * abs(ref_amp[0][0])
+        print("reference fp16-AMP vs reference fp32: losses", ref_amp[0], ref[0], "head-update cosine",
+              _cos(ref_amp[2] - ref_amp[3], ref[2] - ref[3]))
     # the head moved like the reference's: direction and size of the total update of the class centres
     w0 = ref[3]
     assert torch.equal(w0, ours[3])
     du_ref, du_ours = ref[2] - w0, ours[2] - w0
     # (Adam divides by sqrt(v): where a gradient entry is ~0 its sign, hence that entry's step, is rounding noise)
-    cos_min = 0.97 if optimizer == "AdamW" else (0.99 if amp else 0.999)
+    cos_min = 0.97 if optimizer == "AdamW" else 0.999
     assert _cos(du_ours, du_ref) >= cos_min
     assert abs(float(du_ours.norm() / du_ref.norm()) - 1) < 5e-2
     # ... and so did the encoder, which only sees the head through dX (same initial weights, compare the updates)

@@ -12,10 +12,13 @@ ncu --set full --clock-control none --import-source on --launch-skip 60 \
     -k regex:'umma_gemm|dw_sgd|row_stats|prepare|finalize|l2norm' -c 12 -o gpurun_out/${tag}_full -f \
     python bench.py --no-graph --no-parity --no-cpu-baseline --steps 3 --warmup 3 "$@" > gpurun_out/${tag}_ncu2.log 2>&1
 ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
+ncu -i gpurun_out/${tag}_full.ncu-rep --page details --csv > gpurun_out/${tag}_full_details.csv 2>/dev/null
+rm -f gpurun_out/${tag}_full.ncu-rep        # gpurun_out/ travels back only below 64 MiB: keep the CSV exports
 python tools/ncu_summary.py gpurun_out/${tag}_full_raw.csv > gpurun_out/${tag}_ncu_full_summary.txt 2>&1
 ncu --set full --clock-control none --import-source on \
     -k regex:'hist_kernel|count_kernel|compact_kernel|mark_positive|roc_kernel|kfold_kernel|pair_score_kernel|acc_kernel|move_rows|l2norm_rows_kernel|dw_sgd_rows' \
     -c 60 -o gpurun_out/${tag}_aux -f python tools/bench_aux.py --iters 1 --out gpurun_out/${tag}_aux_under_ncu.json > gpurun_out/${tag}_ncu3.log 2>&1
 ncu -i gpurun_out/${tag}_aux.ncu-rep --page raw --csv > gpurun_out/${tag}_aux_raw.csv 2>/dev/null
+rm -f gpurun_out/${tag}_aux.ncu-rep
 python tools/ncu_summary.py gpurun_out/${tag}_aux_raw.csv --all > gpurun_out/${tag}_ncu_aux_summary.txt 2>&1
-tail -3 gpurun_out/${tag}_ncu2.log gpurun_out/${tag}_ncu3.log
+tail -n 3 gpurun_out/${tag}_ncu2.log; tail -n 3 gpurun_out/${tag}_ncu3.log; du -sh gpurun_out
