@@ -31,7 +31,7 @@ def _stream():
 
 
 # ---- accounting used by bench.py: how many kernels were launched, and (optionally) their device time
-_LAUNCHES_PER_CALL = {"pfc_sample": 6}
+_LAUNCHES_PER_CALL = {}
 _count = 0
 _timing = None      # name -> list of (start_event, end_event) while enabled
 
@@ -84,6 +84,7 @@ part_sum_cols = lib.pfc_part_sum_cols
 dx_splits = lib.pfc_dx_splits
 dx_max_splits = lib.pfc_dx_max_splits
 sample_workspace_bytes = lib.pfc_sample_workspace_bytes
+sample_launches = lib.pfc_sample_launches
 hist_bins = lib.pfc_eval_hist_bins
 
 
@@ -122,6 +123,8 @@ def localize_labels(labels, class_start, num_local, out):
 
 @_timed("pfc_sample")
 def sample(perm, labels_local, num_local, num_sample, index_out, n_out, labels_remapped, workspace):
+    global _count
+    _count += lib.pfc_sample_launches(num_local) - 1        # one cluster kernel, or six tiled ones for huge shards
     check(lib.pfc_sample(_p(perm, F32), _p(labels_local, I32), labels_local.numel(), num_local, num_sample,
                          _p(index_out, I64), _p(n_out, I32), _p(labels_remapped, I32), _p(workspace, U8),
                          workspace.numel(), _stream()), "pfc_sample")

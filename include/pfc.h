@@ -58,8 +58,13 @@ int pfc_localize_labels(const int64_t* labels, int B, int64_t class_start, int n
  * perm: the rank's uniform draw [num_local] (the reference draws it with torch.rand on the CPU generator, :110).
  * index_out [max(num_sample, #positives)] ascending int64 (== self.weight_index), n_out[0] its length,
  * labels_remapped[i] = searchsorted(index_out, labels_local[i]) for owned rows, -1 otherwise (:118).
- * Ties at the k-th value are resolved lowest-index-first. */
+ * Ties at the k-th value are resolved lowest-index-first.  One launch (a thread-block cluster of 16 CTAs, 8 for
+ * small shards or where 16 cannot be co-scheduled) for shards of up to ~750 k classes per rank; larger shards take
+ * one memset + six launches (pfc_sample_launches tells which).  pfc_sample_debug_cluster: 0 = automatic, 8 / 16 =
+ * that cluster size where it fits, -1 = always the tiled six-launch path (tests, A/B measurements). */
 size_t pfc_sample_workspace_bytes(int num_local);
+int pfc_sample_launches(int num_local);
+int pfc_sample_debug_cluster(int mode);
 int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_local, int num_sample,
                int64_t* index_out, int32_t* n_out, int32_t* labels_remapped, void* workspace,
                size_t workspace_bytes, void* stream);

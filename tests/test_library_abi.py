@@ -44,7 +44,9 @@ def test_shape_helpers():
         k_total = (n + 63) // 64
         per = (k_total + s - 1) // s
         assert (s - 1) * per < k_total          # no empty split
-    assert K.sample_workspace_bytes(45029) > 45029 * 5
+    # one cluster kernel (slot table only) up to ~376 k classes per rank, the tiled six-launch path beyond
+    assert K.sample_workspace_bytes(45029) >= 45029 * 4
+    assert K.sample_workspace_bytes(2000000) > 2000000 * 5
 
 
 def test_kernels_refuse_cpu_tensors():

@@ -84,8 +84,9 @@ def main():
         remap = torch.zeros(B, dtype=torch.int32, device=dev)
         wsb = torch.zeros(K.sample_workspace_bytes(nl), dtype=torch.uint8, device=dev)
         timed(f"pfc_sample {nm} (nl={nl}, k={k}, B={B})",
-              lambda: K.sample(perm, lab, nl, k, index, n_out, remap, wsb), nl * 4 + k * 8 + B * 8, launches=6,
-              note="radix select: mark, 3 x (histogram + pick by the last CTA), count + scan, compact + remap")
+              lambda: K.sample(perm, lab, nl, k, index, n_out, remap, wsb), nl * 4 + k * 8 + B * 8, launches=1,
+              note="radix select in ONE cluster of 8 CTAs: bitmap of the positives + 3 histogram passes in shared memory, "
+                   "merged through DSMEM, ordered compaction + label remap")
         torch.cuda.synchronize()
         n = int(n_out.item())
         w = torch.randn(nl, d, generator=g).to(dev)

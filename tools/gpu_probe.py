@@ -191,26 +191,41 @@ def case_sample():
 
 
 def _case_sample_once():
+    """Every path of pfc_sample: the cluster kernel with 16 and with 8 CTAs, the tiled six-launch path, and the automatic
+    choice."""
     import torch
     from face_recognition_pytorch_b200 import kernels as K
+    from face_recognition_pytorch_b200._lib import lib
     from oracle import head_oracle as ho
     ok = True
-    for nl, ns, B, seed in [(400, 100, 32, 1), (45029, 4502, 1024, 2), (257489, 51497, 4096, 3), (64, 16, 32, 4),
-                            (5000, 0, 16, 5), (1000, 1000, 8, 6)]:
-        g = torch.Generator().manual_seed(seed)
-        perm = torch.rand(nl, generator=g)
-        perm = torch.floor(perm * 4096) / 4096                                   # force plenty of ties
-        lab = torch.randint(-1, nl, (B,), generator=g).to(torch.int32)
-        idx_ref, lab_ref = ho.sample_indices(perm, lab.long(), ns)
-        ws = torch.zeros(K.sample_workspace_bytes(nl), dtype=torch.uint8, device="cuda")
-        idx = torch.zeros(max(ns, B), dtype=torch.int64, device="cuda")
-        n_out = torch.zeros(1, dtype=torch.int32, device="cuda")
-        rem = torch.zeros(B, dtype=torch.int32, device="cuda")
-        K.sample(perm.cuda(), lab.cuda(), nl, ns, idx, n_out, rem, ws)
-        n = int(n_out.item())
-        good = n == idx_ref.numel() and torch.equal(idx[:n].cpu(), idx_ref) and torch.equal(rem.cpu().long(), lab_ref)
-        print(f"  sample nl={nl} ns={ns} B={B}: n={n} ref_n={idx_ref.numel()} {'OK' if good else 'MISMATCH'}", flush=True)
-        ok &= good
+    cases = [(400, 100, 32, 1), (45029, 4502, 1024, 2), (257489, 51497, 4096, 3), (64, 16, 32, 4), (5000, 0, 16, 5),
+             (1000, 1000, 8, 6), (2000000, 400000, 4096, 7), (400000, 3, 4096, 8)]
+    refs = {}
+    try:
+        for mode in (0, 16, 8, -1):
+            lib.pfc_sample_debug_cluster(mode)
+            for nl, ns, B, seed in cases:
+                g = torch.Generator().manual_seed(seed)
+                perm = torch.rand(nl, generator=g)
+                perm = torch.floor(perm * 4096) / 4096                               # force plenty of ties
+                lab = torch.randint(-1, nl, (B,), generator=g).to(torch.int32)
+                if seed not in refs:
+                    refs[seed] = ho.sample_indices(perm, lab.long(), ns)
+                idx_ref, lab_ref = refs[seed]
+                ws = torch.zeros(K.sample_workspace_bytes(nl), dtype=torch.uint8, device="cuda")
+                idx = torch.zeros(max(ns, B), dtype=torch.int64, device="cuda")
+                n_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+                rem = torch.zeros(B, dtype=torch.int32, device="cuda")
+                for _ in range(2):                                                    # the second call reuses the workspace
+                    K.sample(perm.cuda(), lab.cuda(), nl, ns, idx, n_out, rem, ws)
+                n = int(n_out.item())
+                good = (n == idx_ref.numel() and torch.equal(idx[:n].cpu(), idx_ref)
+                        and torch.equal(rem.cpu().long(), lab_ref))
+                print(f"  sample mode={mode} launches={K.sample_launches(nl)} nl={nl} ns={ns} B={B}: n={n} "
+                      f"ref_n={idx_ref.numel()} {'OK' if good else 'MISMATCH'}", flush=True)
+                ok &= good
+    finally:
+        lib.pfc_sample_debug_cluster(0)
     return ok
 
 
