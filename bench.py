@@ -485,6 +485,8 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     t_wall = time.perf_counter() - t_wall0
+    if gstep is not None:
+        launches_per_step = gstep.launches_per_replay          # the captured (no-autograd) step
     launches = launches_per_step * args.steps      # kernels of libpfc_b200 per step (replayed from the graph or eager)
     ms_steps = [a.elapsed_time(bb) for a, bb in ev]
     t = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)

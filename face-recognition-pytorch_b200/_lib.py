@@ -49,6 +49,8 @@ _SIGS = {
     "pfc_num_class_tiles": (c_int, [c_int]),
     "pfc_part_sum_cols": (c_int, []),
     "pfc_row_stats_loss": (c_int, [p, c_int, c_int, p, p, p, p, p, p, p]),
+    "pfc_row_stats_loss_prepare": (c_int, [p, c_int, c_int, p, p, p, p, p, p, p, c_float, c_int, p, c_int, c_float, p, p,
+                                           p, p, c_int, p]),
     "pfc_l2norm_rows_localize": (c_int, [p, c_int, c_int, p, p, p, c_int64, c_int, p, p]),
     "pfc_dx_splits": (c_int, [c_int, c_int, c_int]),
     "pfc_dx_max_splits": (c_int, [c_int, c_int]),
@@ -79,6 +81,8 @@ _SIGS = {
     "pfc_peer_l2norm_gather": (c_int, [p, p, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), p, p]),
     "pfc_peer_row_stats": (c_int, [p, c_int, c_int, p, p, c_int, c_int, POINTER(c_void_p), p]),
     "pfc_peer_loss": (c_int, [POINTER(c_void_p), p, c_int, p, c_int, c_int, p, p, p, p]),
+    "pfc_peer_loss_prepare": (c_int, [POINTER(c_void_p), p, c_int, p, c_int, c_int, p, p, p, p, p, c_float, c_int, p, p,
+                                      c_int, c_float, p, p, p, p, c_int, p]),
     "pfc_peer_localize_labels": (c_int, [POINTER(c_void_p), p, c_int, c_int, p, c_int, ctypes.c_int64, c_int, p, p]),
     "pfc_peer_dx_finalize": (c_int, [POINTER(c_void_p), p, c_int, c_int, p, p, p, c_float, c_int, c_int, p, p]),
     "pfc_peer_dx_scatter": (c_int, [p, c_int, p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p), p]),

@@ -21,8 +21,10 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <math.h>
 #include "pfc_internal.h"
 #include "pfc_launch.cuh"
+#include "pfc_prepare.cuh"
 
 namespace pfc {
 
@@ -228,6 +230,46 @@ peer_loss_kernel(PeerPtrs flags, uint32_t* state, int rank, const float* slots, 
     }
 }
 
+// The no-autograd step's "barrier -> loss -> coefficients" in one launch: every CTA takes the entry barrier, then one warp
+// per row sums the W slots of its row in rank order (identical bits on all ranks), writes stats / row_L and forms the
+// backward coefficients of the row (pfc_backward_prepare); the last CTA through (ticket) reduces the loss from the finished
+// statistics in loss_kernel's order.  Replaces pfc_peer_loss (one 1024-thread CTA) + pfc_backward_prepare.
+constexpr int PLP_WARPS = 8;
+__global__ void __launch_bounds__(PLP_WARPS * 32)
+peer_loss_prepare_kernel(PeerPtrs flags, uint32_t* state, int rank, const float* slots, int W, int B, float* stats,
+                         float* __restrict__ row_L, float* __restrict__ loss, unsigned int* ticket, PrepArgs pa) {
+    __shared__ bool last;
+    peer_entry_barrier(flags, state, rank, W);
+    const int row = blockIdx.x * PLP_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row < B) {
+        float2 v = make_float2(0.f, 0.f);
+        if (lane < W)      // peers wrote the slots: plain (not read-only-cache) loads, one rank per lane
+            asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];"
+                         : "=f"(v.x), "=f"(v.y) : "l"(slots + (static_cast<size_t>(lane) * B + row) * 2));
+        float others = 0.f, te = 0.f;
+        for (int r = 0; r < W; ++r) {                       // rank order, like peer_loss_kernel
+            others += __shfl_sync(0xffffffffu, v.x, r);
+            te += __shfl_sync(0xffffffffu, v.y, r);
+        }
+        const float L = others + te;
+        if (lane == 0) {
+            stats[2 * row] = others;
+            stats[2 * row + 1] = te;
+            row_L[row] = L;
+        }
+        prepare_row(pa, row, L, others, lane, 32);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    loss_from_stats<PLP_WARPS * 32>(stats, B, row_L, loss);
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
 // row i of the global batch belongs to rank i / b; its scaled dXn partial goes to that rank's slot `rank`
 __global__ void __launch_bounds__(256)
 peer_dx_scatter_kernel(const float* __restrict__ partial, int splits, size_t split_stride,
@@ -369,6 +411,26 @@ int pfc_peer_loss(void* const* peer_flags, uint32_t* barrier_state, int rank, co
         launch_step_kernel(PDL_STATS, peer_loss_kernel<false>, 1, 1024, 0, (cudaStream_t)stream,
                        f, nullptr, rank, slots, W, B, stats, row_L, loss);
     }
+    return launched();
+}
+
+int pfc_peer_loss_prepare(void* const* peer_flags, uint32_t* barrier_state, int rank, const float* slots, int W, int B,
+                          float* stats, float* row_L, float* loss, unsigned int* ticket, const float* grad_loss, float s,
+                          int d, const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
+                          const void* xn, void* xs, float* coef, void* E, int n_pad, void* stream) {
+    if (B <= 0 || W < 1 || W > 32 || !barrier_state || !ticket || d <= 0 || (d & 7) || d > 1024) return PFC_ERR_SHAPE;
+    PeerPtrs f;
+    int rc = fill_peers(&f, peer_flags, W);
+    if (rc) return rc;
+    const double pi = 3.14159265358979323846;
+    PrepArgs a;
+    a.grad_loss = grad_loss; a.s = s; a.B = B; a.d = d; a.labels = labels_local; a.tgt_raw = tgt_raw;
+    a.margin_kind = margin_kind;
+    a.cos_m = (float)cos((double)m2); a.sin_m = (float)sin((double)m2); a.theta = (float)cos(pi - (double)m2);
+    a.xn = reinterpret_cast<const __nv_bfloat16*>(xn); a.xs = reinterpret_cast<__nv_bfloat16*>(xs);
+    a.coef = coef; a.E = reinterpret_cast<__nv_bfloat16*>(E); a.n_pad = n_pad;
+    launch_step_kernel(PDL_STATS, peer_loss_prepare_kernel, (B + PLP_WARPS - 1) / PLP_WARPS, PLP_WARPS * 32, 0,
+                       (cudaStream_t)stream, f, barrier_state, rank, slots, W, B, stats, row_L, loss, ticket, a);
     return launched();
 }
 

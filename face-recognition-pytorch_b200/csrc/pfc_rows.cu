@@ -11,6 +11,7 @@
 #include <math.h>
 #include "pfc_internal.h"
 #include "pfc_launch.cuh"
+#include "pfc_prepare.cuh"
 
 namespace pfc {
 
@@ -141,17 +142,34 @@ row_stats_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_p
 // Single-GPU step: row statistics AND the loss in one launch.  Every CTA writes the stats of its rows, then takes a
 // ticket; the last CTA through sees all of them (threadfence + L2 loads) and forms row_L and the loss exactly like
 // loss_kernel (same per-thread row assignment and reduction tree -> same bits as the two-kernel path).
+// kPrepare: the CTA also forms the backward coefficients of its 8 rows (pfc_backward_prepare: on one GPU the row sum is
+// final as soon as the CTA has it) -- two warps per row -- so the no-autograd step has one launch fewer.
+template <bool kPrepare>
 __global__ void __launch_bounds__(RS_ROWS * RS_GROUPS)
 row_stats_loss_kernel(const float* __restrict__ part_sum, int n_tiles, int B, int B_pad,
                       const int32_t* __restrict__ labels, const float* __restrict__ tgt_e, float* stats,
-                      float* __restrict__ row_L, float* __restrict__ loss, unsigned int* ticket) {
+                      float* __restrict__ row_L, float* __restrict__ loss, unsigned int* ticket, PrepArgs pa) {
     __shared__ float red[RS_GROUPS][RS_ROWS + 1];
+    __shared__ float row_o[RS_ROWS], row_t[RS_ROWS];
     __shared__ bool last;
     const float tot = row_stats_sum(part_sum, n_tiles, B, B_pad, red);
     const int row = blockIdx.x * RS_ROWS + (threadIdx.x & (RS_ROWS - 1));
     if (threadIdx.x < RS_ROWS && row < B) {
+        const float te = (labels[row] >= 0) ? tgt_e[row] : 0.f;
         stats[2 * row] = tot;
-        stats[2 * row + 1] = (labels[row] >= 0) ? tgt_e[row] : 0.f;
+        stats[2 * row + 1] = te;
+        if (kPrepare) { row_o[threadIdx.x] = tot; row_t[threadIdx.x] = te; }
+    }
+    if (kPrepare) {
+        __syncthreads();
+        constexpr int kWarpsPerRow = (RS_ROWS * RS_GROUPS / 32) / RS_ROWS;    // 16 warps, 8 rows: two warps per row
+        const int w = threadIdx.x >> 5, r = w / kWarpsPerRow;
+        const int prow = blockIdx.x * RS_ROWS + r;
+        if (prow < B) {
+            const float L = row_o[r] + row_t[r];
+            row_L[prow] = L;
+            prepare_row(pa, prow, L, row_o[r], (w % kWarpsPerRow) * 32 + (threadIdx.x & 31), kWarpsPerRow * 32);
+        }
     }
     __threadfence();
     __syncthreads();
@@ -159,31 +177,8 @@ row_stats_loss_kernel(const float* __restrict__ part_sum, int n_tiles, int B, in
     __syncthreads();
     if (!last) return;
     __threadfence();
-    // this CTA's threads stand in for loss_kernel's 1024: thread t covers the rows of loss_kernel's threads t,
-    // t + blockDim, ... in the same order, and the partial sums are combined in loss_kernel's order (warp tree, then
-    // 32 warp sums)
-    __shared__ float wsum[32];
-    constexpr int kThreads = RS_ROWS * RS_GROUPS;
-    for (int v = 0; v < 1024 / kThreads; ++v) {
-        const int vt = threadIdx.x + kThreads * v;       // virtual thread id of loss_kernel
-        float acc = 0.f;
-        for (int i = vt; i < B; i += 1024) {
-            const float others = __ldcg(stats + 2 * i), te = __ldcg(stats + 2 * i + 1);
-            const float L = others + te;
-            row_L[i] = L;
-            acc -= logf(fmaxf(te / L, 1e-30f));
-        }
-        acc = warp_sum(acc);
-        if ((threadIdx.x & 31) == 0) wsum[vt >> 5] = acc;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = warp_sum(wsum[threadIdx.x]);
-        if (threadIdx.x == 0) {
-            loss[0] = v / static_cast<float>(B);
-            *ticket = 0;
-        }
-    }
+    loss_from_stats<RS_ROWS * RS_GROUPS>(stats, B, row_L, loss);
+    if (threadIdx.x == 0) *ticket = 0;
 }
 
 // loss = -mean_i log(max(p_i, 1e-30)),  p_i = target e / row sum             (nets/PartialFC.py:454-461)
@@ -209,43 +204,12 @@ loss_kernel(const float* __restrict__ stats, int B, float* __restrict__ row_L, f
     }
 }
 
-// Backward coefficients (nets/PartialFC.py:464-484 and the autograd of nets/ArcFace.py:80-91, :204):
-//   c_i = g * s / (B * L_i);  Xs_i = c_i * Xn_i (bf16);  E'[i, y_i] = -dm_i * mask_i * Lothers_i
-//   dm_i = d(margin)/dt = cos m + sin m * t / sqrt(1 - t^2)  if t > cos(pi - m) else 1   (CosFace: 1)
-//   mask_i = 1 if -1 <= raw <= 1 (clamp backward) else 0
+// Backward coefficients of every row: prepare_row (pfc_prepare.cuh), one warp per row.
 __global__ void __launch_bounds__(ROW_WARPS * 32)
-backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict__ row_L,
-                        const float* __restrict__ grad_loss, float s, int B, int d,
-                        const int32_t* __restrict__ labels, const float* __restrict__ tgt_raw, int margin_kind,
-                        float cos_m, float sin_m, float theta, const __nv_bfloat16* __restrict__ xn,
-                        __nv_bfloat16* __restrict__ xs, float* __restrict__ coef, __nv_bfloat16* __restrict__ E,
-                        int n_pad) {
+backward_prepare_kernel(const float* __restrict__ stats, const float* __restrict__ row_L, PrepArgs pa) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= B) return;
-    const float g = grad_loss ? grad_loss[0] : 1.f;
-    const float c = g * s / (static_cast<float>(B) * row_L[row]);
-    const int nv = d >> 2;
-    for (int k = lane; k < nv; k += 32) {
-        const uint2 raw = *reinterpret_cast<const uint2*>(xn + static_cast<size_t>(row) * d + 4 * k);
-        float4 v = unpack4_bf16(raw);
-        v.x *= c; v.y *= c; v.z *= c; v.w *= c;
-        *reinterpret_cast<uint2*>(xs + static_cast<size_t>(row) * d + 4 * k) = pack4_bf16(v);
-    }
-    if (lane == 0) {
-        coef[row] = c;
-        const int lbl = labels[row];
-        if (lbl >= 0) {
-            const float raw = tgt_raw[row];
-            const float mask = (fabsf(raw) <= 1.f) ? 1.f : 0.f;
-            const float t = fminf(fmaxf(raw, -1.f), 1.f);
-            float dm = 1.f;
-            if (margin_kind == 0 && t > theta) dm = cos_m + sin_m * t / sqrtf(fmaxf(1.f - t * t, 1e-12f));
-            const __nv_bfloat16 pv = __float2bfloat16_rn(-dm * mask * stats[2 * row]);
-            // class-blocked spill: E'[class / 64][row][class % 64]
-            E[(static_cast<size_t>(lbl >> 6) * B + row) * 64 + (lbl & 63)] = pv;
-        }
-    }
+    if (row >= pa.B) return;
+    prepare_row(pa, row, row_L[row], stats[2 * row], threadIdx.x & 31, 32);
 }
 
 // d = 512 fast path of dx_finalize_kernel: FOUR warps per row (one float4 per lane and slab), two rows per CTA -- the
@@ -698,12 +662,36 @@ int pfc_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labe
     return check_launch();
 }
 
+static PrepArgs prep_args(const float* grad_loss, float s, int B, int d, const int32_t* labels_local, const float* tgt_raw,
+                          int margin_kind, float m2, const void* xn, void* xs, float* coef, void* E, int n_pad) {
+    const double pi = 3.14159265358979323846;
+    PrepArgs a;
+    a.grad_loss = grad_loss; a.s = s; a.B = B; a.d = d; a.labels = labels_local; a.tgt_raw = tgt_raw;
+    a.margin_kind = margin_kind;
+    a.cos_m = (float)cos((double)m2); a.sin_m = (float)sin((double)m2); a.theta = (float)cos(pi - (double)m2);
+    a.xn = reinterpret_cast<const __nv_bfloat16*>(xn); a.xs = reinterpret_cast<__nv_bfloat16*>(xs);
+    a.coef = coef; a.E = reinterpret_cast<__nv_bfloat16*>(E); a.n_pad = n_pad;
+    return a;
+}
+
 int pfc_row_stats_loss(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
                        float* stats, float* row_L, float* loss, unsigned int* ticket, void* stream) {
     if (B <= 0 || n_tiles <= 0 || !ticket) return PFC_ERR_SHAPE;
     const int B_pad = (B + 127) / 128 * 128;
-    launch_step_kernel(PDL_STATS, row_stats_loss_kernel, (B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0, (cudaStream_t)stream,
-        part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats, row_L, loss, ticket);
+    launch_step_kernel(PDL_STATS, row_stats_loss_kernel<false>, (B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0,
+        (cudaStream_t)stream, part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats, row_L, loss, ticket, PrepArgs{});
+    return check_launch();
+}
+
+int pfc_row_stats_loss_prepare(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
+                               float* stats, float* row_L, float* loss, unsigned int* ticket, const float* grad_loss,
+                               float s, int d, const float* tgt_raw, int margin_kind, float m2, const void* xn, void* xs,
+                               float* coef, void* E, int n_pad, void* stream) {
+    if (B <= 0 || n_tiles <= 0 || !ticket || bad_d(d)) return PFC_ERR_SHAPE;
+    const int B_pad = (B + 127) / 128 * 128;
+    launch_step_kernel(PDL_STATS, row_stats_loss_kernel<true>, (B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0,
+        (cudaStream_t)stream, part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats, row_L, loss, ticket,
+        prep_args(grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E, n_pad));
     return check_launch();
 }
 
@@ -718,11 +706,8 @@ int pfc_backward_prepare(const float* stats, const float* row_L, const float* gr
                          const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
                          const void* xn, void* xs, float* coef, void* E, int n_pad, void* stream) {
     if (B <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
-    const double pi = 3.14159265358979323846;
     launch_step_kernel(PDL_PREPARE, backward_prepare_kernel, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
-        stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, (float)cos((double)m2),
-        (float)sin((double)m2), (float)cos(pi - (double)m2), reinterpret_cast<const __nv_bfloat16*>(xn),
-        reinterpret_cast<__nv_bfloat16*>(xs), coef, reinterpret_cast<__nv_bfloat16*>(E), n_pad);
+        stats, row_L, prep_args(grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E, n_pad));
     return check_launch();
 }
 

@@ -126,8 +126,10 @@ class GraphedHeadStep:
         ws = head._ws
         g = torch.cuda.CUDAGraph()
         self._x.grad = None
+        l0 = K.launch_count()
         with torch.cuda.graph(g):
             self._loss = self._eager()
+        self.launches_per_replay = K.launch_count() - l0      # libpfc_b200 kernels inside the captured step
         torch.cuda.synchronize(self.device)
         self._graph = g
         # undo the warm-up steps: weights, optimizer state, step count and the normalised bf16 shard the graph's first

@@ -173,6 +173,17 @@ def row_stats_loss(part_sum, n_tiles, B, labels_local, tgt_e, stats, row_L, out,
                                  _p(row_L, F32), _p(out, F32), _p(ticket, I32), _stream()), "pfc_row_stats_loss")
 
 
+@_timed("pfc_row_stats_loss_prepare")
+def row_stats_loss_prepare(part_sum, n_tiles, B, labels_local, tgt_e, stats, row_L, out, ticket, grad_loss, s, d, tgt_raw,
+                           margin_kind, m2, xn, xs, coef, E, n_pad):
+    """row_stats_loss + backward_prepare in one launch (one GPU, no-autograd step)."""
+    check(lib.pfc_row_stats_loss_prepare(_p(part_sum, F32), n_tiles, B, _p(labels_local, I32), _p(tgt_e, F32),
+                                         _p(stats, F32), _p(row_L, F32), _p(out, F32), _p(ticket, I32),
+                                         _p(grad_loss, F32), s, d, _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16),
+                                         _p(xs, BF16), _p(coef, F32), _p(E, BF16), n_pad, _stream()),
+          "pfc_row_stats_loss_prepare")
+
+
 @_timed("pfc_loss")
 def loss(stats, B, row_L, out):
     check(lib.pfc_loss(_p(stats, F32), B, _p(row_L, F32), _p(out, F32), _stream()), "pfc_loss")
@@ -257,6 +268,16 @@ def peer_loss(peer_flags, state, rank, slots, W, B, stats, row_L, out):
     """peer_flags / state None: no barrier (the caller ran pfc_peer_barrier); else the kernel takes it at its start."""
     check(lib.pfc_peer_loss(peer_flags, _p(state, I32), rank, _p(slots, F32), W, B, _p(stats, F32), _p(row_L, F32),
                             _p(out, F32), _stream()), "pfc_peer_loss")
+
+
+@_timed("pfc_peer_loss_prepare")
+def peer_loss_prepare(peer_flags, state, rank, slots, W, B, stats, row_L, out, ticket, grad_loss, s, d, labels_local,
+                      tgt_raw, margin_kind, m2, xn, xs, coef, E, n_pad):
+    """barrier + peer_loss + backward_prepare in one launch (no-autograd step)."""
+    check(lib.pfc_peer_loss_prepare(peer_flags, _p(state, I32), rank, _p(slots, F32), W, B, _p(stats, F32),
+                                    _p(row_L, F32), _p(out, F32), _p(ticket, I32), _p(grad_loss, F32), s, d,
+                                    _p(labels_local, I32), _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16), _p(xs, BF16),
+                                    _p(coef, F32), _p(E, BF16), n_pad, _stream()), "pfc_peer_loss_prepare")
 
 
 @_timed("pfc_peer_localize_labels")

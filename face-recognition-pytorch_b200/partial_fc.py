@@ -33,6 +33,9 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       partials exist the step forks -- the peer scatter + barrier + normalise-backward of dX (one GPU: just the
       normalise-backward) on a side stream, the rank-local dW GEMM / update on the main one -- and joins before
       backward returns.  The branches share no buffer; in a CUDA graph they become parallel branches.
+  conf.fuse_prepare (bool, default True; only `fused_step`, i.e. the no-autograd step, where d loss = 1 is known when the
+      forward ends): the kernel that forms the loss also forms the backward coefficients (c_i, the scaled bf16 rows and
+      the patched target column), so the step has one launch fewer; False: the two launches of the autograd path.
   conf.peer_collectives (True / False / "auto"): exchange the batch, the softmax statistics and dX through peer
       (NVLink) memory with the stores fused into the producing kernels instead of three NCCL collectives.
   conf.peer_timeout_ms (float, default 600 000 = NCCL's watchdog default; 0 = wait forever): how long a flag barrier of
@@ -149,6 +152,9 @@ class _PartialFCBase(torch.nn.Module):
         # fused update of a sampled shard in place through the index list (no gather / scatter of the active rows)
         self._indexed = (self.fused_optimizer and self.sample_rate < 1 and bool(getattr(conf, "inplace_update", True)))
         self.dw_first = getattr(conf, "dw_first", "auto")     # order of the two gradient GEMMs (see _backward_impl)
+        # fused_step: form the backward coefficients in the kernel that forms the loss (one launch fewer)
+        self.fuse_prepare = bool(getattr(conf, "fuse_prepare", True))
+        self._prepared = False
         self._num_classes = int(num_classes)
         self.num_local, self.class_start = shard_range(num_classes, self.rank, self.world_size)
         self.num_sample: int = int(self.sample_rate * self.num_local)
@@ -324,7 +330,8 @@ class _PartialFCBase(torch.nn.Module):
         self._optimizer = optimizer
         self._step_id += 1
         self._prepare(local_embeddings, local_labels.contiguous(), optimizer, perm)
-        loss = self._forward_impl(local_embeddings, clone_loss=False, need_dx=True)
+        # d loss = 1 is known here, so the backward coefficients are formed by the kernel that forms the loss
+        loss = self._forward_impl(local_embeddings, clone_loss=False, need_dx=True, fuse_prepare=self.fuse_prepare)
         dx, dw = self._backward_impl(local_embeddings, None, need_dx=True)
         if dw is not None:
             self.weight_activated.grad = dw
@@ -371,8 +378,9 @@ class _PartialFCBase(torch.nn.Module):
         else:
             self._n = self.num_local
 
-    def _forward_impl(self, local_embeddings, clone_loss=True, need_dx=False):
+    def _forward_impl(self, local_embeddings, clone_loss=True, need_dx=False, fuse_prepare=False):
         ws, W, d = self._ws, self.world_size, self.embedding_size
+        self._prepared = False
         b, B = ws.b, ws.B
         n = self._n
         w = self.weight if self._indexed else self.weight_activated.data
@@ -390,8 +398,19 @@ class _PartialFCBase(torch.nn.Module):
             # statistics straight into every peer's slot, then a rank-ordered local sum (identical bits on all ranks)
             K.peer_row_stats(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, self.rank, W,
                              peer.ptrs("slots"))
-            K.peer_loss(peer.ptrs("flags"), peer.counter, self.rank, peer.slots, W, B, ws.stats, ws.row_L,
-                        ws.loss)                                                  # barrier + :448, :453, :459, :461
+            if fuse_prepare:                                                      # + :464-484 (d loss = 1)
+                K.peer_loss_prepare(peer.ptrs("flags"), peer.counter, self.rank, peer.slots, W, B, ws.stats, ws.row_L,
+                                    ws.loss, ws.ticket, None, s, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all,
+                                    ws.xs, ws.coef, ws.E, self._n_pad)
+                self._prepared = True
+            else:
+                K.peer_loss(peer.ptrs("flags"), peer.counter, self.rank, peer.slots, W, B, ws.stats, ws.row_L,
+                            ws.loss)                                              # barrier + :448, :453, :459, :461
+        elif W == 1 and fuse_prepare:
+            K.row_stats_loss_prepare(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats, ws.row_L,
+                                     ws.loss, ws.ticket, None, s, d, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs, ws.coef,
+                                     ws.E, self._n_pad)                           # :446-461 + :464-484 in one launch
+            self._prepared = True
         elif W == 1:
             K.row_stats_loss(ws.part_sum, K.num_class_tiles(n), B, ws.labels_act, ws.tgt_e, ws.stats, ws.row_L,
                              ws.loss, ws.ticket)                                  # :446-461 in one launch
@@ -416,8 +435,10 @@ class _PartialFCBase(torch.nn.Module):
             elif not self._gscale_is_one:
                 ws.gscale.fill_(1.0)
             self._gscale_is_one = g is None
-        K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs, ws.coef,
-                           ws.E, n_pad)
+        if not (self._prepared and g is None):
+            K.backward_prepare(ws.stats, ws.row_L, g, s, B, d, ws.labels_act, ws.tgt_raw, kind, m2, ws.xn_all, ws.xs,
+                               ws.coef, ws.E, n_pad)
+        self._prepared = False
         spill_bf16 = self.fused_optimizer and self._optimizer_kind == "sgd" and d % 128 == 0
         dwn = ws.grad_buffer(spill_bf16, d)
         dw = None

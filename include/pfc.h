@@ -112,6 +112,12 @@ int pfc_row_stats_loss(const float* part_sum, int n_tiles, int B, const int32_t*
                        float* stats, float* row_L, float* loss, unsigned int* ticket, void* stream);
 int pfc_l2norm_rows_localize(const float* x, int rows, int d, void* xn_bf16, float* inv_norm, const int64_t* labels,
                              int64_t class_start, int num_local, int32_t* labels_local, void* stream);
+/* pfc_row_stats_loss + pfc_backward_prepare (below) in one launch, for a step driven without autograd (d loss known when
+ * the forward ends; model/FR_PartialFC.py:175-184 as one call): every CTA forms the coefficients of the rows it summed. */
+int pfc_row_stats_loss_prepare(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
+                               float* stats, float* row_L, float* loss, unsigned int* ticket, const float* grad_loss,
+                               float s, int d, const float* tgt_raw, int margin_kind, float m2, const void* xn_bf16,
+                               void* xs_bf16, float* coef, void* E_bf16, int n_pad, void* stream);
 
 /* ---- (5) backward, nets/PartialFC.py:464-484 (DistCrossEntropyFunc.backward) + autograd of :199-206.
  * pfc_backward_prepare: coef[i] = g*s/(B*row_L[i]) (g = grad_loss[0], device scalar, NULL = 1), xs = bf16(coef*xn),
@@ -178,6 +184,12 @@ int pfc_peer_row_stats(const float* part_sum, int n_tiles, int B, const int32_t*
                        int rank, int W, void* const* peer_slots, void* stream);
 int pfc_peer_loss(void* const* peer_flags, uint32_t* barrier_state, int rank, const float* slots, int W, int B,
                   float* stats, float* row_L, float* loss, void* stream);
+/* barrier + pfc_peer_loss + pfc_backward_prepare in one multi-CTA launch (no-autograd step): one warp per row sums the W
+ * slots in rank order and forms the row's coefficients; the last CTA (ticket: uint32, zeroed once) reduces the loss. */
+int pfc_peer_loss_prepare(void* const* peer_flags, uint32_t* barrier_state, int rank, const float* slots, int W, int B,
+                          float* stats, float* row_L, float* loss, unsigned int* ticket, const float* grad_loss, float s,
+                          int d, const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
+                          const void* xn_bf16, void* xs_bf16, float* coef, void* E_bf16, int n_pad, void* stream);
 int pfc_peer_localize_labels(void* const* peer_flags, uint32_t* barrier_state, int rank, int W, const int64_t* labels,
                              int B, int64_t class_start, int num_local, int32_t* labels_local, void* stream);
 int pfc_peer_dx_finalize(void* const* peer_flags, uint32_t* barrier_state, int rank, int W, const float* dx_slots,

@@ -39,6 +39,11 @@ class FakeKernels:
         self.row_stats(part_sum, n_tiles, B, labels, tgt_e, stats)
         self.loss(stats, B, row_L, out)
 
+    def row_stats_loss_prepare(self, part_sum, n_tiles, B, labels, tgt_e, stats, row_L, out, ticket, grad_loss, s, d,
+                               tgt_raw, kind, m2, xn, xs, coef, E, n_pad):
+        self.row_stats_loss(part_sum, n_tiles, B, labels, tgt_e, stats, row_L, out, ticket)
+        self.backward_prepare(stats, row_L, grad_loss, s, B, d, labels, tgt_raw, kind, m2, xn, xs, coef, E, n_pad)
+
     def localize_labels(self, labels, class_start, num_local, out):
         out.copy_(ho.localize_labels(labels, class_start, num_local).to(torch.int32))
 

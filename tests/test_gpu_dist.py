@@ -27,6 +27,8 @@ def _rank_main(rank, W, port, name, fused, peer, q, extra=None):
     cfg, z = load_case(name)
     weights, xs, ls = case_inputs(cfg)
     b = cfg["b"]
+    extra = dict(extra or {})
+    no_autograd = extra.pop("no_autograd", False)      # head.fused_step: barrier + loss + coefficients in one launch
     conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
                                  loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused,
                                  peer_collectives=peer, **(extra or {}))
@@ -42,8 +44,12 @@ def _rank_main(rank, W, port, name, fused, peer, q, extra=None):
         lab = ls[s][rank * b:(rank + 1) * b].clone().to(dev)
         perms = case_perms(cfg, z, s)
         opt.zero_grad()
-        loss = head(x, lab, opt, perm=None if perms is None else perms[rank].to(dev))
-        loss.backward()
+        if no_autograd:
+            loss, dx = head.fused_step(x.detach(), lab, opt, perm=None if perms is None else perms[rank].to(dev))
+            x.grad = dx.clone()
+        else:
+            loss = head(x, lab, opt, perm=None if perms is None else perms[rank].to(dev))
+            loss.backward()
         out[f"loss_{s}"] = float(loss.detach())
         out[f"dx_{s}"] = x.grad.cpu().numpy().copy()
         if not fused:
@@ -79,7 +85,9 @@ def _cos(a, b):
     ("head_w2_d128", True, 29848, True, None), ("head_w2_d128", False, 29849, False, None),
     ("head_w2_sampled", True, 29852, True, {"inplace_update": False}),
     ("head_w2_sampled", True, 29853, False, {"inplace_update": False}),
-    ("head_w2_full", True, 29854, True, {"dx_side_stream": False})])
+    ("head_w2_full", True, 29854, True, {"dx_side_stream": False}),
+    ("head_w2_full", True, 29855, True, {"no_autograd": True}), ("head_w2_sampled", True, 29856, True, {"no_autograd": True}),
+    ("head_w2_full", True, 29857, True, {"no_autograd": True, "fuse_prepare": False})])
 def test_two_rank_matches_reference(name, fused, port, peer, extra):
     _run_case(name, fused, port, peer, extra)
 

@@ -58,6 +58,16 @@ def test_graph_without_autograd_is_bit_identical(pfc):
         assert torch.equal(u, v), f"output {i} differs without autograd"
 
 
+@pytest.mark.parametrize("B,C,d", [(1024, 20000, 512), (320, 3100, 512), (96, 1500, 64)])
+def test_loss_and_coefficients_in_one_launch_is_bit_identical(pfc, B, C, d):
+    """conf.fuse_prepare (row statistics + loss + backward coefficients in ONE kernel on the no-autograd path) against
+    the two launches of the autograd path, ragged batch / class tails included."""
+    a = _graph_run(pfc, False, B=B, C=C, d=d, fuse_prepare=True)
+    b = _graph_run(pfc, False, B=B, C=C, d=d, fuse_prepare=False)
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert torch.equal(u, v), f"output {i} differs with the fused loss + coefficient kernel"
+
+
 def test_fused_step_eager_matches_autograd(pfc):
     d, B, C = 512, 320, 3100
     g = torch.Generator().manual_seed(5)
