@@ -3,7 +3,7 @@ global batch 1024 (BASELINE.json configs[1]) on N B200s of one node, with the ro
 reference head's CPU implementation timed on the host cores beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1|2|3|4] [--scaling strong|weak]
-                    [--mode fused|unfused] [--no-graph] [--no-parity] [--no-cpu-baseline]
+                    [--mode fused|unfused] [--amp] [--no-graph] [--no-parity] [--no-cpu-baseline]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \\
         bench.py --gpus N --steps K --warmup W
 
@@ -362,6 +362,8 @@ def main():
                     help="skip the 256 MB write between timed steps (one step streams > 1 GB through the 126 MB L2 anyway)")
     ap.add_argument("--dw-first", default="auto", choices=["auto", "0", "1"],
                     help="order of the gradient GEMMs: 1 = dW, dX, update; 0 = dX, dW, update; auto = 1 on one GPU")
+    ap.add_argument("--amp", action="store_true",
+                    help="conf.mixed_precision = True: fp16 GEMM operands like the reference's autocast (default: bf16)")
     ap.add_argument("--no-peer", action="store_true",
                     help="N>1: NCCL collectives instead of the peer-memory (NVLink) exchanges fused into the kernels")
     args = ap.parse_args()
@@ -400,7 +402,7 @@ def main():
     w_shard, xs, ls = synth(cfg, rank, world, n_data, dev)
     b = GLOBAL_BATCH // world
     fused = mode != "unfused"
-    conf = types.SimpleNamespace(emd_size=EMB, sample_rate=rate, mixed_precision=False, loss_s=S, loss_m=M,
+    conf = types.SimpleNamespace(emd_size=EMB, sample_rate=rate, mixed_precision=bool(args.amp), loss_s=S, loss_m=M,
                                  fused_optimizer=fused,
                                  dw_first="auto" if args.dw_first == "auto" else bool(int(args.dw_first)),
                                  peer_collectives=False if args.no_peer else "auto")
@@ -657,7 +659,7 @@ def main():
         "metric": METRIC if args.config == 2 else "PartialFC ArcFace fwd+bwd samples/sec", "value": value, "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
+        "dtype": "fp16" if args.amp else "bf16", "data": "synthetic",
         "config": {"workload": cfg["name"] + ", fwd+bwd+SGD step",
                    "classes_per_gpu": nl, "active_classes_per_gpu": n_act, "local_batch": b,
                    "parallelism": f"class-sharded x{world}", "mode": mode,

@@ -49,12 +49,12 @@ _SIGS = {
     "pfc_num_class_tiles": (c_int, [c_int]),
     "pfc_part_sum_cols": (c_int, []),
     "pfc_row_stats_loss": (c_int, [p, c_int, c_int, p, p, p, p, p, p, p]),
-    "pfc_row_stats_loss_prepare": (c_int, [p, c_int, c_int, p, p, p, p, p, p, p, c_float, c_int, p, c_int, c_float, p, p,
-                                           p, p, c_int, p]),
-    "pfc_l2norm_rows_localize": (c_int, [p, c_int, c_int, p, p, p, c_int64, c_int, p, p]),
+    "pfc_row_stats_loss_prepare": (c_int, [p, c_int, c_int, p, p, p, p, p, p, p, c_float, c_int, p, c_int, c_float, p, p, p, p, c_int, c_int, p]),
+    "pfc_l2norm_rows_localize": (c_int, [p, c_int, c_int, p, p, p, c_int64, c_int, p, c_int, p]),
     "pfc_dx_splits": (c_int, [c_int, c_int, c_int]),
     "pfc_dx_max_splits": (c_int, [c_int, c_int]),
-    "pfc_l2norm_rows": (c_int, [p, p, c_int, c_int, p, p, p]),
+    "pfc_cast_f16_to_bf16": (c_int, [p, p, c_size_t, p]),
+    "pfc_l2norm_rows": (c_int, [p, p, c_int, c_int, p, p, c_int, p]),
     "pfc_localize_labels": (c_int, [p, c_int, c_int64, c_int, p, p]),
     "pfc_sample_workspace_bytes": (c_size_t, [c_int]),
     "pfc_sample": (c_int, [p, p, c_int, c_int, c_int, p, p, p, p, c_size_t, p]),
@@ -62,27 +62,24 @@ _SIGS = {
     "pfc_sample_debug_cluster": (c_int, [c_int]),
     "pfc_gather_rows": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, p, c_int, c_int, p]),
     "pfc_scatter_rows": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, p, c_int, c_int, p]),
-    "pfc_forward": (c_int, [p, p, p, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float, p, c_int, p, p,
-                            p, p, p]),
+    "pfc_forward": (c_int, [p, p, p, c_int, c_int, c_int, c_float, c_int, c_float, c_float, c_float, p, c_int, p, p, p, p, c_int, p]),
     "pfc_margin_apply": (c_int, [p, p, c_int, c_int, c_int, c_float, c_float, c_float, c_float, p, p, p]),
     "pfc_row_stats": (c_int, [p, c_int, c_int, p, p, p, p]),
     "pfc_loss": (c_int, [p, c_int, p, p, p]),
-    "pfc_backward_prepare": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, c_int, p]),
+    "pfc_backward_prepare": (c_int, [p, p, p, c_float, c_int, c_int, p, p, c_int, c_float, p, p, p, p, c_int, c_int, p]),
     "pfc_backward_dx": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dx_finalize": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p]),
     "pfc_backward_dw": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dw_finalize": (c_int, [p, p, p, c_int, c_int, c_float, p, p]),
-    "pfc_dw_sgd": (c_int, [p, c_int, p, p, p, c_int, c_int, c_float, c_float, c_float, p, p, p, p, p]),
-    "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int,
-                            p, p, p, p, p, p]),
+    "pfc_dw_sgd": (c_int, [p, c_int, p, p, p, c_int, c_int, c_float, c_float, c_float, p, p, p, p, c_int, p]),
+    "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int, p, p, p, p, p, c_int, p]),
     "pfc_peer_max_ranks": (c_int, []),
     "pfc_peer_set_timeout_ms": (c_int, [c_double]),
     "pfc_peer_barrier": (c_int, [POINTER(c_void_p), p, c_int, c_int, p]),
-    "pfc_peer_l2norm_gather": (c_int, [p, p, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), p, p]),
+    "pfc_peer_l2norm_gather": (c_int, [p, p, c_int, c_int, c_int, c_int, POINTER(c_void_p), POINTER(c_void_p), p, c_int, p]),
     "pfc_peer_row_stats": (c_int, [p, c_int, c_int, p, p, c_int, c_int, POINTER(c_void_p), p]),
     "pfc_peer_loss": (c_int, [POINTER(c_void_p), p, c_int, p, c_int, c_int, p, p, p, p]),
-    "pfc_peer_loss_prepare": (c_int, [POINTER(c_void_p), p, c_int, p, c_int, c_int, p, p, p, p, p, c_float, c_int, p, p,
-                                      c_int, c_float, p, p, p, p, c_int, p]),
+    "pfc_peer_loss_prepare": (c_int, [POINTER(c_void_p), p, c_int, p, c_int, c_int, p, p, p, p, p, c_float, c_int, p, p, c_int, c_float, p, p, p, p, c_int, c_int, p]),
     "pfc_peer_localize_labels": (c_int, [POINTER(c_void_p), p, c_int, c_int, p, c_int, ctypes.c_int64, c_int, p, p]),
     "pfc_peer_dx_finalize": (c_int, [POINTER(c_void_p), p, c_int, c_int, p, p, p, c_float, c_int, c_int, p, p]),
     "pfc_peer_dx_scatter": (c_int, [p, c_int, p, c_int, c_int, c_int, c_int, c_int, POINTER(c_void_p), p]),

@@ -46,6 +46,7 @@ struct FwdPolicy {
         float* tgt_e;            // [B] e of the margin-adjusted target logit
         float* tgt_z;            // [B] margin-adjusted target logit (already * s)
         float s;
+        uint32_t idesc_xor;      // flips the operand formats of the bf16 instruction descriptor (fp16 operands)
     };
     __device__ static __forceinline__ DescCfg desc(const Params&) { return default_desc_cfg(false, false); }
     __device__ static __forceinline__ TileCoord tile(const Params& p, int t) {
@@ -186,6 +187,7 @@ struct StoreParams {
     float* out;
     int out_bf16;           // 1: `out` is a bf16 matrix (same ld in elements); used for the dWn spill in fused mode
     DescCfg dc;             // descriptor geometry (runtime so that tools/gpu_probe.py can try alternatives)
+    uint32_t idesc_xor;     // flips BOTH operand formats of the bf16 instruction descriptor (0 for the gradient GEMMs)
 };
 
 // kKeep (dW GEMM only, PFC_L2_GRAD): the bf16 gradient tiles are stored with an L2 evict_last hint so that the update
@@ -480,7 +482,7 @@ int pfc_padded_batch(int B) { return (B + BM - 1) / BM * BM; }
 
 int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int B, int n, int d, float s,
                 int margin_kind, float m2, float m3, float filter_thr, void* E, int n_pad, float* part_sum,
-                float* tgt_raw, float* tgt_e, float* tgt_z, void* stream) {
+                float* tgt_raw, float* tgt_e, float* tgt_z, int fp16_operands, void* stream) {
     if (B <= 0 || n <= 0 || d <= 0 || d % 8 || n_pad % 8 || n_pad < n) return PFC_ERR_SHAPE;
     const float log2e = 1.4426950408889634f;
     // every representable term must stay a normal bf16/fp32 number: 2*s*log2e <= TOP + 126
@@ -499,6 +501,7 @@ int pfc_forward(const void* xn, const void* wn, const int32_t* labels_local, int
     FwdPolicy::Params p;
     fill_fwd_params(p, B, n, n_pad, d, mode == MODE_PAIR ? even_up(m_tiles) : m_tiles, s, margin_kind, m2, m3, filter_thr,
                     labels_local, E, part_sum, tgt_raw, tgt_e, tgt_z);
+    p.idesc_xor = fp16_operands ? (UMMA_IDESC_A_BF16 | UMMA_IDESC_B_BF16) : 0u;     // Xn and Wn are fp16
     return launch_gemm<FwdPolicy>(PDL_FORWARD, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -548,6 +551,9 @@ int pfc_backward_dx(const void* E, int n_pad, const void* wn, int B, int n, int 
     p.out = partial;
     p.out_bf16 = 0;
     p.dc = store_desc_cfg(false);
+    // both operands bf16 in every mode: E' needs the bf16 exponent range and tcgen05 kind::f16 rejects mixed operand
+    // formats (bf16 x fp16 raises an illegal-instruction error on sm_100a), so an fp16 shard is cast first (pfc_cast_...)
+    p.idesc_xor = 0;
     CUtensorMap tc;
     rc = make_store_tmap(&tc, partial, false, d, B, p.splits, d, static_cast<uint64_t>(B) * d);
     if (rc) return rc;
@@ -584,6 +590,7 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     p.out = reinterpret_cast<float*>(dwn);
     p.out_bf16 = dwn_bf16 ? 1 : 0;
     p.dc = store_desc_cfg(true);
+    p.idesc_xor = 0;                                            // E'^T and Xs are bf16 in both modes
     CUtensorMap tc;
     rc = make_store_tmap(&tc, dwn, dwn_bf16 != 0, d, n, 1, d, 0);
     if (rc) return rc;

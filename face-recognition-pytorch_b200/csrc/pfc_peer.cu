@@ -19,6 +19,7 @@
 // same launch sequence can be replayed from a CUDA graph.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
@@ -124,7 +125,7 @@ peer_localize_labels_kernel(PeerPtrs flags, uint32_t* state, int rank, int W, co
 // warp per row; lane l handles float4 #l, #l+32, ... (d <= 1024)
 __global__ void __launch_bounds__(256)
 peer_l2norm_gather_kernel(const float* __restrict__ x, const int64_t* __restrict__ labels, int b, int d, int rank, int W,
-                          PeerPtrs xn_all, PeerPtrs labels_all, float* __restrict__ inv_norm) {
+                          PeerPtrs xn_all, PeerPtrs labels_all, float* __restrict__ inv_norm, int f16) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= b) return;
@@ -147,11 +148,18 @@ peer_l2norm_gather_kernel(const float* __restrict__ x, const int64_t* __restrict
     for (int j = 0; j < 8; ++j) {
         const int c = lane + 32 * j;
         if (c < nv) {
-            __nv_bfloat162 a = __floats2bfloat162_rn(v[j].x / denom, v[j].y / denom);
-            __nv_bfloat162 bb = __floats2bfloat162_rn(v[j].z / denom, v[j].w / denom);
             uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&a);
-            pk.y = *reinterpret_cast<uint32_t*>(&bb);
+            if (f16) {       // the reference's AMP operands (nets/PartialFC.py:198)
+                __half2 a = __floats2half2_rn(v[j].x / denom, v[j].y / denom);
+                __half2 bb = __floats2half2_rn(v[j].z / denom, v[j].w / denom);
+                pk.x = *reinterpret_cast<uint32_t*>(&a);
+                pk.y = *reinterpret_cast<uint32_t*>(&bb);
+            } else {
+                __nv_bfloat162 a = __floats2bfloat162_rn(v[j].x / denom, v[j].y / denom);
+                __nv_bfloat162 bb = __floats2bfloat162_rn(v[j].z / denom, v[j].w / denom);
+                pk.x = *reinterpret_cast<uint32_t*>(&a);
+                pk.y = *reinterpret_cast<uint32_t*>(&bb);
+            }
             for (int q = 0; q < W; ++q)
                 *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(xn_all.p[q]) + grow * d + 4 * c) = pk;
         }
@@ -373,7 +381,8 @@ int pfc_peer_barrier(void* const* peer_flags, uint32_t* epoch_counter, int rank,
 }
 
 int pfc_peer_l2norm_gather(const float* x, const int64_t* labels, int b, int d, int rank, int W,
-                           void* const* peer_xn_all, void* const* peer_labels_all, float* inv_norm, void* stream) {
+                           void* const* peer_xn_all, void* const* peer_labels_all, float* inv_norm, int fp16_operands,
+                           void* stream) {
     if (b <= 0 || d <= 0 || (d & 7) || d > 1024) return PFC_ERR_SHAPE;
     PeerPtrs xa, la;
     int rc = fill_peers(&xa, peer_xn_all, W);
@@ -381,7 +390,7 @@ int pfc_peer_l2norm_gather(const float* x, const int64_t* labels, int b, int d, 
     rc = fill_peers(&la, peer_labels_all, W);
     if (rc) return rc;
     launch_step_kernel(PDL_NORMALISE, peer_l2norm_gather_kernel, (b + 7) / 8, 256, 0, (cudaStream_t)stream,
-                       x, labels, b, d, rank, W, xa, la, inv_norm);
+                       x, labels, b, d, rank, W, xa, la, inv_norm, fp16_operands);
     return launched();
 }
 
@@ -417,7 +426,7 @@ int pfc_peer_loss(void* const* peer_flags, uint32_t* barrier_state, int rank, co
 int pfc_peer_loss_prepare(void* const* peer_flags, uint32_t* barrier_state, int rank, const float* slots, int W, int B,
                           float* stats, float* row_L, float* loss, unsigned int* ticket, const float* grad_loss, float s,
                           int d, const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                          const void* xn, void* xs, float* coef, void* E, int n_pad, void* stream) {
+                          const void* xn, void* xs, float* coef, void* E, int n_pad, int fp16_operands, void* stream) {
     if (B <= 0 || W < 1 || W > 32 || !barrier_state || !ticket || d <= 0 || (d & 7) || d > 1024) return PFC_ERR_SHAPE;
     PeerPtrs f;
     int rc = fill_peers(&f, peer_flags, W);
@@ -429,6 +438,7 @@ int pfc_peer_loss_prepare(void* const* peer_flags, uint32_t* barrier_state, int 
     a.cos_m = (float)cos((double)m2); a.sin_m = (float)sin((double)m2); a.theta = (float)cos(pi - (double)m2);
     a.xn = reinterpret_cast<const __nv_bfloat16*>(xn); a.xs = reinterpret_cast<__nv_bfloat16*>(xs);
     a.coef = coef; a.E = reinterpret_cast<__nv_bfloat16*>(E); a.n_pad = n_pad;
+    a.xn_f16 = fp16_operands;
     launch_step_kernel(PDL_STATS, peer_loss_prepare_kernel, (B + PLP_WARPS - 1) / PLP_WARPS, PLP_WARPS * 32, 0,
                        (cudaStream_t)stream, f, barrier_state, rank, slots, W, B, stats, row_L, loss, ticket, a);
     return launched();

@@ -3,6 +3,7 @@
 // produce the same bits as the separate launches.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -16,8 +17,9 @@ struct PrepArgs {
     const float* tgt_raw;
     int margin_kind;
     float cos_m, sin_m, theta;
-    const __nv_bfloat16* xn;
-    __nv_bfloat16* xs;
+    const __nv_bfloat16* xn;    // bf16, or fp16 bits when xn_f16 (the reference's AMP operands)
+    int xn_f16;
+    __nv_bfloat16* xs;          // always bf16: c_i can be far below the fp16 range
     float* coef;
     __nv_bfloat16* E;
     int n_pad;
@@ -34,8 +36,14 @@ __device__ __forceinline__ void prepare_row(const PrepArgs& a, int row, float L,
     const int nv = a.d >> 2;
     for (int k = vlane; k < nv; k += vlanes) {
         const uint2 raw = *reinterpret_cast<const uint2*>(a.xn + static_cast<size_t>(row) * a.d + 4 * k);
-        __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x), p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-        float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+        float2 f0, f1;
+        if (a.xn_f16) {
+            f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+            f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        } else {
+            f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+            f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        }
         __nv_bfloat162 q0 = __floats2bfloat162_rn(f0.x * c, f0.y * c), q1 = __floats2bfloat162_rn(f1.x * c, f1.y * c);
         uint2 out;
         out.x = *reinterpret_cast<uint32_t*>(&q0);

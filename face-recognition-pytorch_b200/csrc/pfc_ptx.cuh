@@ -325,6 +325,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32.
 //   [4,6) c_format=1 (f32)  [7,10) a_format=1 (bf16)  [10,13) b_format=1 (bf16)
 //   [15] a_major (0=K, 1=MN)  [16] b_major  [17,23) N>>3  [24,29) M>>4
+// a_format / b_format: 0 = f16, 1 = bf16; xor-ing BOTH bits into a bf16 descriptor gives the fp16 x fp16 instruction (the
+// fields are separate, but sm_100a raises an illegal-instruction error for a mixed bf16 x fp16 pair -- measured)
+constexpr uint32_t UMMA_IDESC_A_BF16 = 1u << 7;
+constexpr uint32_t UMMA_IDESC_B_BF16 = 1u << 10;
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
            (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |

@@ -7,6 +7,7 @@
 // with 16-byte loads (lane l handles float4 #l, #l+32, ...), reductions are warp shuffles.
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <math.h>
 #include "pfc_internal.h"
@@ -39,6 +40,15 @@ __device__ __forceinline__ uint2 pack4_bf16(float4 v) {
     r.y = *reinterpret_cast<uint32_t*>(&b);
     return r;
 }
+// the GEMM operands are bf16 by default and fp16 in the reference's AMP mode (conf.mixed_precision, nets/PartialFC.py:198)
+__device__ __forceinline__ uint2 pack4_op(float4 v, int f16) {
+    if (!f16) return pack4_bf16(v);
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    return r;
+}
 __device__ __forceinline__ float4 unpack4_bf16(uint2 r) {
     __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x), b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
     float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
@@ -53,7 +63,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32)
 l2norm_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ index, int rows, int d,
                    __nv_bfloat16* __restrict__ xn, float* __restrict__ inv_norm,
                    const int64_t* __restrict__ labels, int64_t class_start, int num_local,
-                   int32_t* __restrict__ labels_local) {
+                   int32_t* __restrict__ labels_local, int f16) {
     const int row = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -82,10 +92,29 @@ l2norm_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ inde
         const int c = lane + 32 * j;
         if (c < nv) {
             const float4 q = make_float4(v[j].x / denom, v[j].y / denom, v[j].z / denom, v[j].w / denom);
-            *reinterpret_cast<uint2*>(o + 4 * c) = pack4_bf16(q);
+            *reinterpret_cast<uint2*>(o + 4 * c) = pack4_op(q, f16);
         }
     }
     if (lane == 0) inv_norm[row] = 1.f / denom;
+}
+
+// fp16 -> bf16, 8 elements per thread: the dX contraction needs the shard in the spill's format (AMP mode only)
+__global__ void __launch_bounds__(256)
+cast_f16_bf16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t n8) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n8) return;
+    const uint4 v = src[i];
+    uint4 o;
+    const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+    uint32_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[k]));
+        __nv_bfloat162 b = __floats2bfloat162_rn(f.x, f.y);
+        out[k] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    o.x = out[0]; o.y = out[1]; o.z = out[2]; o.w = out[3];
+    dst[i] = o;
 }
 
 // labels -> shard-local ids, -1 for classes owned by another rank           (nets/PartialFC.py:188-193)
@@ -326,6 +355,7 @@ struct OptArgs {
     const float* grad_scale;        // device scalar: the loss scale the gradient carries (divided out first), or null
     const int* step_dev;            // Adam(W): device step counter (the update is step step_dev[0] + 1), or null
     const int64_t* index;           // sampled shards: row r of (dwn, inv_norm_w, wn_next) is row index[r] of (w, state), or null
+    int wn_f16;                     // wn_next is written as fp16 instead of bf16
 };
 
 __device__ __forceinline__ float opt_inv_grad_scale(const float* grad_scale) {
@@ -425,7 +455,7 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
         const int k = lane + 32 * j;
         if (k < nv) {
             const float4 q = make_float4(wv[j].x / denom, wv[j].y / denom, wv[j].z / denom, wv[j].w / denom);
-            *reinterpret_cast<uint2*>(wn_next + base + 4 * k) = pack4_bf16(q);
+            *reinterpret_cast<uint2*>(wn_next + base + 4 * k) = pack4_op(q, opt.wn_f16);
         }
     }
     if (lane == 0) inv_norm_next[row] = 1.f / denom;
@@ -458,7 +488,7 @@ __global__ void __launch_bounds__(128)
 dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* __restrict__ mom,
                    const float* inv_norm_w, int rows, float lr, float momentum, float wd,
                    const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next,
-                   const int64_t* __restrict__ index) {
+                   const int64_t* __restrict__ index, int wn_f16) {
     const float inv_grad_scale = opt_inv_grad_scale(grad_scale);
     constexpr int d = 128 * NV;
     const int lane = threadIdx.x & 31;
@@ -532,7 +562,7 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
         const float4 q = make_float4(wv[j].x / denom, wv[j].y / denom, wv[j].z / denom, wv[j].w / denom);
-        *reinterpret_cast<uint2*>(wn_next + base + 4 * (lane + 32 * j)) = pack4_bf16(q);
+        *reinterpret_cast<uint2*>(wn_next + base + 4 * (lane + 32 * j)) = pack4_op(q, wn_f16);
     }
     if (lane == 0) inv_norm_next[row] = 1.f / denom;
     }
@@ -543,7 +573,7 @@ static int g_sgd_persistent_warps = 0;   // 0: one row per warp, full grid; > 0:
 template <int NV>
 static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom, const float* inv_norm_w, int rows,
                                float lr, float momentum, float wd, const float* igs, __nv_bfloat16* wn_next,
-                               float* inv_next, const int64_t* index, cudaStream_t st) {
+                               float* inv_next, const int64_t* index, int wn_f16, cudaStream_t st) {
     int grid = (rows + 3) / 4, block = 128;
     if (g_sgd_persistent_warps > 0) {
         int dev = 0, sms = 148;
@@ -558,13 +588,13 @@ static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom,
     }
     if (bf16 && pfc_l2_grad_enabled())
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr,
-                           momentum, wd, igs, wn_next, inv_next, index);
+                           momentum, wd, igs, wn_next, inv_next, index, wn_f16);
     else if (bf16)
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
-                           wd, igs, wn_next, inv_next, index);
+                           wd, igs, wn_next, inv_next, index, wn_f16);
     else
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, false>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
-                           wd, igs, wn_next, inv_next, index);
+                           wd, igs, wn_next, inv_next, index, wn_f16);
 }
 
 // dst[r] = src[index[r]]  /  dst[index[r]] = src[r]   (nets/PartialFC.py:120-121, :142-143), up to 3 tensors at once
@@ -628,20 +658,32 @@ extern "C" {
 // (used when it is overlapped with a GEMM on another stream), 0 restores the full grid
 void pfc_debug_sgd_persistent(int warps_per_sm) { g_sgd_persistent_warps = warps_per_sm; }
 
-int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void* xn, float* inv_norm, void* stream) {
+int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void* xn, float* inv_norm, int fp16_operands,
+                    void* stream) {
     if (rows < 0 || bad_d(d)) return PFC_ERR_SHAPE;
     if (rows == 0) return PFC_OK;
     launch_step_kernel(PDL_NORMALISE, l2norm_rows_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
-        x, index, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm, nullptr, 0, 0, nullptr);
+        x, index, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm, nullptr, 0, 0, nullptr, fp16_operands);
     return check_launch();
 }
 
 int pfc_l2norm_rows_localize(const float* x, int rows, int d, void* xn, float* inv_norm, const int64_t* labels,
-                             int64_t class_start, int num_local, int32_t* labels_local, void* stream) {
+                             int64_t class_start, int num_local, int32_t* labels_local, int fp16_operands,
+                             void* stream) {
     if (rows <= 0 || bad_d(d) || !labels || !labels_local) return PFC_ERR_SHAPE;
     launch_step_kernel(PDL_NORMALISE, l2norm_rows_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         x, nullptr, rows, d, reinterpret_cast<__nv_bfloat16*>(xn), inv_norm, labels, class_start, num_local,
-        labels_local);
+        labels_local, fp16_operands);
+    return check_launch();
+}
+
+int pfc_cast_f16_to_bf16(const void* src_f16, void* dst_bf16, size_t elems, void* stream) {
+    if (elems == 0) return PFC_OK;
+    if (elems % 8 || (reinterpret_cast<uintptr_t>(src_f16) & 15) || (reinterpret_cast<uintptr_t>(dst_bf16) & 15))
+        return PFC_ERR_ALIGNMENT;
+    const size_t n8 = elems / 8;
+    cast_f16_bf16_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint4*>(src_f16), static_cast<uint4*>(dst_bf16), n8);
     return check_launch();
 }
 
@@ -663,7 +705,8 @@ int pfc_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labe
 }
 
 static PrepArgs prep_args(const float* grad_loss, float s, int B, int d, const int32_t* labels_local, const float* tgt_raw,
-                          int margin_kind, float m2, const void* xn, void* xs, float* coef, void* E, int n_pad) {
+                          int margin_kind, float m2, const void* xn, void* xs, float* coef, void* E, int n_pad,
+                          int fp16_operands) {
     const double pi = 3.14159265358979323846;
     PrepArgs a;
     a.grad_loss = grad_loss; a.s = s; a.B = B; a.d = d; a.labels = labels_local; a.tgt_raw = tgt_raw;
@@ -671,6 +714,7 @@ static PrepArgs prep_args(const float* grad_loss, float s, int B, int d, const i
     a.cos_m = (float)cos((double)m2); a.sin_m = (float)sin((double)m2); a.theta = (float)cos(pi - (double)m2);
     a.xn = reinterpret_cast<const __nv_bfloat16*>(xn); a.xs = reinterpret_cast<__nv_bfloat16*>(xs);
     a.coef = coef; a.E = reinterpret_cast<__nv_bfloat16*>(E); a.n_pad = n_pad;
+    a.xn_f16 = fp16_operands;
     return a;
 }
 
@@ -686,12 +730,12 @@ int pfc_row_stats_loss(const float* part_sum, int n_tiles, int B, const int32_t*
 int pfc_row_stats_loss_prepare(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
                                float* stats, float* row_L, float* loss, unsigned int* ticket, const float* grad_loss,
                                float s, int d, const float* tgt_raw, int margin_kind, float m2, const void* xn, void* xs,
-                               float* coef, void* E, int n_pad, void* stream) {
+                               float* coef, void* E, int n_pad, int fp16_operands, void* stream) {
     if (B <= 0 || n_tiles <= 0 || !ticket || bad_d(d)) return PFC_ERR_SHAPE;
     const int B_pad = (B + 127) / 128 * 128;
     launch_step_kernel(PDL_STATS, row_stats_loss_kernel<true>, (B + RS_ROWS - 1) / RS_ROWS, RS_ROWS * RS_GROUPS, 0,
         (cudaStream_t)stream, part_sum, n_tiles, B, B_pad, labels_local, tgt_e, stats, row_L, loss, ticket,
-        prep_args(grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E, n_pad));
+        prep_args(grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E, n_pad, fp16_operands));
     return check_launch();
 }
 
@@ -704,10 +748,11 @@ int pfc_loss(const float* stats, int B, float* row_L, float* loss, void* stream)
 
 int pfc_backward_prepare(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
                          const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                         const void* xn, void* xs, float* coef, void* E, int n_pad, void* stream) {
+                         const void* xn, void* xs, float* coef, void* E, int n_pad, int fp16_operands, void* stream) {
     if (B <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
     launch_step_kernel(PDL_PREPARE, backward_prepare_kernel, row_grid(B), ROW_WARPS * 32, 0, (cudaStream_t)stream,
-        stats, row_L, prep_args(grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E, n_pad));
+        stats, row_L, prep_args(grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E, n_pad,
+                                fp16_operands));
     return check_launch();
 }
 
@@ -737,7 +782,7 @@ int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, i
 
 int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float* inv_norm_w, int rows, int d, float lr,
                float momentum, float weight_decay, const float* grad_scale, void* wn_next, float* inv_norm_next,
-               const int64_t* index, void* stream) {
+               const int64_t* index, int fp16_operands, void* stream) {
     if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
     if (d % 128 == 0 && mom != nullptr) {
         cudaStream_t st = (cudaStream_t)stream;
@@ -745,7 +790,7 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
         const bool bf = dwn_bf16 != 0;
 #define PFC_SGD_CASE(NV) \
     launch_dw_sgd_rows<NV>(dwn, bf, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, grad_scale, wnn, \
-                           inv_norm_next, index, st)
+                           inv_norm_next, index, fp16_operands, st)
         switch (d / 128) {
             case 1: PFC_SGD_CASE(1); break;
             case 2: PFC_SGD_CASE(2); break;
@@ -764,6 +809,7 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
     o.kind = OPT_SGD;
     o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.grad_scale = grad_scale;
     o.index = index;
+    o.wn_f16 = fp16_operands;
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         static_cast<const float*>(dwn), w, inv_norm_w, rows, d, o, nullptr, mom, nullptr,
         reinterpret_cast<__nv_bfloat16*>(wn_next), inv_norm_next);
@@ -773,7 +819,7 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                 const float* grad_scale, void* wn_next, float* inv_norm_next, const int* step_dev,
-                const int64_t* index, void* stream) {
+                const int64_t* index, int fp16_operands, void* stream) {
     if (rows <= 0 || bad_d(d) || (step <= 0 && !step_dev)) return PFC_ERR_SHAPE;
     if (step <= 0) step = 1;
     OptArgs o = {};
@@ -784,6 +830,7 @@ int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, c
     o.grad_scale = grad_scale;
     o.step_dev = step_dev;
     o.index = index;
+    o.wn_f16 = fp16_operands;
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         dwn, w, inv_norm_w, rows, d, o, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(wn_next),
         inv_norm_next);

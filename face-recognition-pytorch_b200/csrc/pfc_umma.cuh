@@ -243,7 +243,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         // K-major : rows of 128 B, 8-row swizzle atoms 1024 B apart; +32 B per 16-element K step.
         // MN-major: 64(MN) x 8(K) atoms of 1024 B; next 64-wide MN block one box (8 KB) further,
         //           next 8 K rows 1024 B further; +2048 B per 16-row K step.
-        constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
+        const uint32_t idesc = umma_idesc_bf16(BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0) ^ prm.idesc_xor;
         const DescCfg dc = P::desc(prm);
         const uint64_t a_tmpl = umma_smem_desc_sw128(smem_u32(sA), dc.a_lbo, dc.a_sbo);
         const uint64_t b_tmpl = umma_smem_desc_sw128(smem_u32(sB), dc.b_lbo, dc.b_sbo);

@@ -112,7 +112,7 @@ umma_gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         // ------------------------------------------------------------------ MMA issuer (leader CTA only; the whole
         // warp walks the loops, one elected lane issues; descriptors = template + start address, see pfc_umma.cuh)
         if (leader) {
-            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0);
+            const uint32_t idesc = umma_idesc_bf16(2 * BM, BN, P::A_MN ? 1 : 0, P::B_MN ? 1 : 0) ^ prm.idesc_xor;
             const DescCfg dc = P::desc(prm);
             const uint64_t a_tmpl = umma_smem_desc_sw128(smem_u32(sA), dc.a_lbo, dc.a_sbo);
             const uint64_t b_tmpl = umma_smem_desc_sw128(smem_u32(sB), dc.b_lbo, dc.b_sbo);

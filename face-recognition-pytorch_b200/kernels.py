@@ -26,6 +26,15 @@ def _p(t, dtype=None):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _op(t):
+    """A normalised GEMM operand (Xn / Wn): bf16 by default, fp16 in the reference's AMP mode; -> (pointer, fp16 flag)."""
+    if t is None:
+        return None, 0
+    if t.dtype not in (BF16, F16):
+        raise TypeError(f"expected a bf16 or fp16 operand, got {t.dtype}")
+    return _p(t), int(t.dtype == F16)
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -75,6 +84,7 @@ def _timed(name):
 
 
 F32, BF16, I32, I64, U8, F64 = torch.float32, torch.bfloat16, torch.int32, torch.int64, torch.uint8, torch.float64
+F16 = torch.float16
 
 exp_top = lib.pfc_exp_top
 padded_classes = lib.pfc_padded_classes
@@ -100,18 +110,26 @@ def spill_from_rowmajor(M):
     return M.view(B, n_pad // 64, 64).permute(1, 0, 2).contiguous().reshape(-1)
 
 
+@_timed("pfc_cast_f16_to_bf16")
+def cast_f16_to_bf16(src, dst, elems):
+    """AMP mode: bf16 copy of the fp16 shard for the dX contraction (tcgen05 takes no mixed bf16 x fp16 operands)."""
+    check(lib.pfc_cast_f16_to_bf16(_p(src, F16), _p(dst, BF16), elems, _stream()), "pfc_cast_f16_to_bf16")
+
+
 @_timed("pfc_l2norm_rows")
 def l2norm_rows(x, index, rows, xn, inv_norm):
     d = x.shape[1]
-    check(lib.pfc_l2norm_rows(_p(x, F32), _p(index, I64), rows, d, _p(xn, BF16), _p(inv_norm, F32), _stream()),
+    xp, f16 = _op(xn)
+    check(lib.pfc_l2norm_rows(_p(x, F32), _p(index, I64), rows, d, xp, _p(inv_norm, F32), f16, _stream()),
           "pfc_l2norm_rows")
 
 
 @_timed("pfc_l2norm_rows_localize")
 def l2norm_rows_localize(x, rows, xn, inv_norm, labels, class_start, num_local, labels_local):
     d = x.shape[1]
-    check(lib.pfc_l2norm_rows_localize(_p(x, F32), rows, d, _p(xn, BF16), _p(inv_norm, F32), _p(labels, I64),
-                                       class_start, num_local, _p(labels_local, I32), _stream()),
+    xp, f16 = _op(xn)
+    check(lib.pfc_l2norm_rows_localize(_p(x, F32), rows, d, xp, _p(inv_norm, F32), _p(labels, I64),
+                                       class_start, num_local, _p(labels_local, I32), f16, _stream()),
           "pfc_l2norm_rows_localize")
 
 
@@ -149,9 +167,12 @@ def scatter_rows(srcs, dsts, index, rows):
 @_timed("pfc_forward")
 def forward(xn, wn, labels_local, B, n, d, s, margin_kind, m2, m3, filter_thr, E, n_pad, part_sum, tgt_raw, tgt_e,
             tgt_z):
-    check(lib.pfc_forward(_p(xn, BF16), _p(wn, BF16), _p(labels_local, I32), B, n, d, s, margin_kind, m2, m3,
+    (xp, f16), (wp, wf16) = _op(xn), _op(wn)
+    if f16 != wf16:
+        raise TypeError("pfc_forward: Xn and Wn must have the same operand format")
+    check(lib.pfc_forward(xp, wp, _p(labels_local, I32), B, n, d, s, margin_kind, m2, m3,
                           filter_thr, _p(E, BF16), n_pad, _p(part_sum, F32), _p(tgt_raw, F32), _p(tgt_e, F32),
-                          _p(tgt_z, F32), _stream()), "pfc_forward")
+                          _p(tgt_z, F32), f16, _stream()), "pfc_forward")
 
 
 @_timed("pfc_margin_apply")
@@ -177,10 +198,11 @@ def row_stats_loss(part_sum, n_tiles, B, labels_local, tgt_e, stats, row_L, out,
 def row_stats_loss_prepare(part_sum, n_tiles, B, labels_local, tgt_e, stats, row_L, out, ticket, grad_loss, s, d, tgt_raw,
                            margin_kind, m2, xn, xs, coef, E, n_pad):
     """row_stats_loss + backward_prepare in one launch (one GPU, no-autograd step)."""
+    xp, f16 = _op(xn)
     check(lib.pfc_row_stats_loss_prepare(_p(part_sum, F32), n_tiles, B, _p(labels_local, I32), _p(tgt_e, F32),
                                          _p(stats, F32), _p(row_L, F32), _p(out, F32), _p(ticket, I32),
-                                         _p(grad_loss, F32), s, d, _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16),
-                                         _p(xs, BF16), _p(coef, F32), _p(E, BF16), n_pad, _stream()),
+                                         _p(grad_loss, F32), s, d, _p(tgt_raw, F32), margin_kind, m2, xp,
+                                         _p(xs, BF16), _p(coef, F32), _p(E, BF16), n_pad, f16, _stream()),
           "pfc_row_stats_loss_prepare")
 
 
@@ -192,9 +214,10 @@ def loss(stats, B, row_L, out):
 @_timed("pfc_backward_prepare")
 def backward_prepare(stats, row_L, grad_loss, s, B, d, labels_local, tgt_raw, margin_kind, m2, xn, xs, coef, E,
                      n_pad):
+    xp, f16 = _op(xn)
     check(lib.pfc_backward_prepare(_p(stats, F32), _p(row_L, F32), _p(grad_loss, F32), s, B, d, _p(labels_local, I32),
-                                   _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16), _p(xs, BF16), _p(coef, F32),
-                                   _p(E, BF16), n_pad, _stream()), "pfc_backward_prepare")
+                                   _p(tgt_raw, F32), margin_kind, m2, xp, _p(xs, BF16), _p(coef, F32),
+                                   _p(E, BF16), n_pad, f16, _stream()), "pfc_backward_prepare")
 
 
 @_timed("pfc_backward_dx")
@@ -228,9 +251,10 @@ def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_sc
     """grad_scale: device scalar holding the loss scale the gradient carries (divided out first), or None.
     index (int64 [rows], ascending): w / mom are the FULL shard arrays and row r of dwn updates row index[r] in place."""
     is_bf16 = dwn.dtype == BF16
+    wp, f16 = _op(wn_next)
     check(lib.pfc_dw_sgd(_p(dwn, BF16 if is_bf16 else F32), int(is_bf16), _p(w, F32), _p(mom, F32),
                          _p(inv_norm_w, F32), rows, d, lr, momentum, weight_decay, _p(grad_scale, F32),
-                         _p(wn_next, BF16), _p(inv_norm_next, F32), _p(index, I64), _stream()), "pfc_dw_sgd")
+                         wp, _p(inv_norm_next, F32), _p(index, I64), f16, _stream()), "pfc_dw_sgd")
 
 
 @_timed("pfc_dw_adam")
@@ -238,9 +262,10 @@ def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, 
             grad_scale, wn_next, inv_norm_next, step_dev=None, index=None):
     """step_dev (int32 device scalar): the update is step step_dev[0] + 1 (CUDA-graph replay), `step` is ignored.
     index: as in dw_sgd (in-place update of a sampled shard)."""
+    wp, f16 = _op(wn_next)
     check(lib.pfc_dw_adam(_p(dwn, F32), _p(w, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), _p(inv_norm_w, F32), rows,
                           d, lr, beta1, beta2, eps, weight_decay, step, int(decoupled), _p(grad_scale, F32),
-                          _p(wn_next, BF16), _p(inv_norm_next, F32), _p(step_dev, I32), _p(index, I64), _stream()),
+                          wp, _p(inv_norm_next, F32), _p(step_dev, I32), _p(index, I64), f16, _stream()),
           "pfc_dw_adam")
 
 
@@ -251,10 +276,11 @@ def peer_barrier(peer_flags, counter, rank, W):
 
 
 @_timed("pfc_peer_l2norm_gather")
-def peer_l2norm_gather(x, labels, rank, W, peer_xn_all, peer_labels_all, inv_norm):
+def peer_l2norm_gather(x, labels, rank, W, peer_xn_all, peer_labels_all, inv_norm, fp16=False):
+    """fp16: the peers' xn_all buffers hold fp16 instead of bf16 rows (the reference's AMP operands)."""
     b, d = x.shape
     check(lib.pfc_peer_l2norm_gather(_p(x, F32), _p(labels, I64), b, d, rank, W, peer_xn_all, peer_labels_all,
-                                     _p(inv_norm, F32), _stream()), "pfc_peer_l2norm_gather")
+                                     _p(inv_norm, F32), int(bool(fp16)), _stream()), "pfc_peer_l2norm_gather")
 
 
 @_timed("pfc_peer_row_stats")
@@ -274,10 +300,11 @@ def peer_loss(peer_flags, state, rank, slots, W, B, stats, row_L, out):
 def peer_loss_prepare(peer_flags, state, rank, slots, W, B, stats, row_L, out, ticket, grad_loss, s, d, labels_local,
                       tgt_raw, margin_kind, m2, xn, xs, coef, E, n_pad):
     """barrier + peer_loss + backward_prepare in one launch (no-autograd step)."""
+    xp, f16 = _op(xn)
     check(lib.pfc_peer_loss_prepare(peer_flags, _p(state, I32), rank, _p(slots, F32), W, B, _p(stats, F32),
                                     _p(row_L, F32), _p(out, F32), _p(ticket, I32), _p(grad_loss, F32), s, d,
-                                    _p(labels_local, I32), _p(tgt_raw, F32), margin_kind, m2, _p(xn, BF16), _p(xs, BF16),
-                                    _p(coef, F32), _p(E, BF16), n_pad, _stream()), "pfc_peer_loss_prepare")
+                                    _p(labels_local, I32), _p(tgt_raw, F32), margin_kind, m2, xp, _p(xs, BF16),
+                                    _p(coef, F32), _p(E, BF16), n_pad, f16, _stream()), "pfc_peer_loss_prepare")
 
 
 @_timed("pfc_peer_localize_labels")

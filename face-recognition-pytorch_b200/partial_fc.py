@@ -63,20 +63,23 @@ class _Workspace:
     """Persistent device buffers for one (global batch, max active classes, d) shape -- allocated once so that the
     whole step is CUDA-graph capturable and nothing is allocated in the hot loop."""
 
-    def __init__(self, dev, b, W, n_max, nl, d, sampled):
+    def __init__(self, dev, b, W, n_max, nl, d, sampled, op_dtype=torch.bfloat16):
         B = b * W
         f32, bf16, i32, i64 = torch.float32, torch.bfloat16, torch.int32, torch.int64
+        self.op_dtype = op_dtype                  # Xn / Wn: bf16, or fp16 in the reference's AMP mode
         z = lambda *s, dt=f32: torch.zeros(*s, dtype=dt, device=dev)   # noqa: E731
         self.B, self.b, self.n_max = B, b, n_max
         self.n_pad_max = K.padded_classes(n_max)
         self.B_pad = K.padded_batch(B)
-        self.xn_local = z(b, d, dt=bf16)
+        self.xn_local = z(b, d, dt=op_dtype)
         self.inv_x = z(b)
-        self.xn_all = z(B, d, dt=bf16) if W > 1 else self.xn_local
+        self.xn_all = z(B, d, dt=op_dtype) if W > 1 else self.xn_local
         self.labels_all = z(B, dt=i64)
         self.labels_local = z(B, dt=i32)
         self.labels_act = z(B, dt=i32) if sampled else self.labels_local
-        self.wn = z(n_max, d, dt=bf16)
+        self.wn = z(n_max, d, dt=op_dtype)
+        # AMP mode: the dX contraction multiplies the bf16 spill with a bf16 copy of the fp16 shard
+        self.wn_b = z(n_max, d, dt=bf16) if op_dtype != bf16 else self.wn
         self.inv_w = z(n_max)
         self.E = z(B * self.n_pad_max, dt=bf16)
         self.part_sum = z(K.num_class_tiles(n_max) * self.B_pad)
@@ -143,7 +146,10 @@ class _PartialFCBase(torch.nn.Module):
 
         self.embedding_size = conf.emd_size
         self.sample_rate: float = conf.sample_rate
-        self.fp16 = conf.mixed_precision           # kept for interface parity; the kernels always run bf16-in / fp32-acc
+        # nets/PartialFC.py:198 runs the logits GEMM under autocast(fp16) when conf.mixed_precision: the normalised
+        # operands Xn / Wn are then fp16 here as well (fp32 accumulation either way); False: bf16 operands
+        self.fp16 = conf.mixed_precision
+        self._op_dtype = torch.float16 if self.fp16 else torch.bfloat16
         self.fused_optimizer = bool(getattr(conf, "fused_optimizer", False))
         self.device_sampling = bool(getattr(conf, "device_sampling", False))
         # run the tail of the dX path (finalize / peer scatter + finalize) on a side stream next to the rank-local
@@ -263,7 +269,7 @@ class _PartialFCBase(torch.nn.Module):
         B = b * self.world_size
         n_max = self.num_local if not sampled else max(self.num_sample, min(B, self.num_local))
         if self._ws is None or self._ws.b != b or self._ws.xn_local.device != dev:
-            self._ws = _Workspace(dev, b, self.world_size, n_max, self.num_local, d, sampled)
+            self._ws = _Workspace(dev, b, self.world_size, n_max, self.num_local, d, sampled, self._op_dtype)
             self._wn_valid = False
             if sampled and not self._indexed:
                 k = 1 + len(self._state_names)
@@ -272,7 +278,8 @@ class _PartialFCBase(torch.nn.Module):
             if self.world_size > 1 and dev.type == "cuda" and self.peer_collectives in (True, "auto"):
                 try:
                     from .peer import PeerExchange
-                    self._peer = PeerExchange(dev, self.rank, self.world_size, b, d, timeout_ms=self.peer_timeout_ms)
+                    self._peer = PeerExchange(dev, self.rank, self.world_size, b, d, timeout_ms=self.peer_timeout_ms,
+                                              operand_dtype=self._op_dtype)
                     self._ws.xn_all = self._peer.xn_all          # peers store straight into these
                     self._ws.labels_all = self._peer.labels_all
                 except Exception as e:                            # no P2P / symmetric memory: keep the NCCL collectives
@@ -348,7 +355,8 @@ class _PartialFCBase(torch.nn.Module):
         if peer is not None:
             # normalise + all-gather in one kernel: every rank stores its bf16 rows and labels into every peer
             # (the barrier that publishes the rows is taken by the consumer of the labels, below)
-            K.peer_l2norm_gather(x, labels_in, self.rank, W, peer.ptrs("xn_all"), peer.ptrs("labels_all"), ws.inv_x)
+            K.peer_l2norm_gather(x, labels_in, self.rank, W, peer.ptrs("xn_all"), peer.ptrs("labels_all"), ws.inv_x,
+                                 fp16=self._op_dtype == torch.float16)
             labels_all = peer.labels_all
         elif W > 1:
             K.l2norm_rows(x, None, ws.b, ws.xn_local, ws.inv_x)
@@ -455,7 +463,9 @@ class _PartialFCBase(torch.nn.Module):
         tail = None
         if need_dx:
             splits = K.dx_splits(B, n, d)
-            K.backward_dx(ws.E, n_pad, ws.wn, B, n, d, ws.dx_partial, splits)
+            if ws.wn_b is not ws.wn:
+                K.cast_f16_to_bf16(ws.wn, ws.wn_b, n * d)
+            K.backward_dx(ws.E, n_pad, ws.wn_b, B, n, d, ws.dx_partial, splits)
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
             if fork:
                 if self._side_stream is None:

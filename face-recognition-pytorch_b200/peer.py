@@ -2,7 +2,7 @@
 
 One symmetric allocation per rank (torch.distributed._symmetric_memory), carved into
     flags      uint32 [W]            barrier flags, one per sender
-    xn_all     bf16   [W*b, d]       all-gathered normalised batch       (written by every peer)
+    xn_all     bf16   [W*b, d]       all-gathered normalised batch       (written by every peer; fp16 in AMP mode)
     labels_all int64  [W*b]          all-gathered labels
     slots      fp32   [W, B, 2]      softmax statistics, one slot per sender
     dx_slots   fp32   [W, b, d]      scaled dXn rows owned by this rank, one slot per sender
@@ -21,7 +21,7 @@ def _align(v, a=256):
 
 
 class PeerExchange:
-    def __init__(self, device, rank, world, b, d, timeout_ms=None):
+    def __init__(self, device, rank, world, b, d, timeout_ms=None, operand_dtype=torch.bfloat16):
         import torch.distributed._symmetric_memory as symm_mem
         if timeout_ms is not None:      # how long a flag barrier waits for a stalled peer before it traps (default 10 min)
             _lib.check(_lib.lib.pfc_peer_set_timeout_ms(float(timeout_ms)), "pfc_peer_set_timeout_ms")
@@ -47,7 +47,7 @@ class PeerExchange:
         self._ptrs = {name: _lib.ptr_array([base + o for base in bases]) for name, o in off.items()}
         # local typed views
         view = lambda name, dtype, shape: self.buf[off[name]: off[name] + _nbytes(dtype, shape)].view(dtype).view(shape)  # noqa: E731
-        self.xn_all = view("xn_all", torch.bfloat16, (B, d))
+        self.xn_all = view("xn_all", operand_dtype, (B, d))       # bf16, or fp16 (conf.mixed_precision)
         self.labels_all = view("labels_all", torch.int64, (B,))
         self.slots = view("slots", torch.float32, (world, B, 2))
         self.dx_slots = view("dx_slots", torch.float32, (world, b, d))

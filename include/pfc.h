@@ -6,6 +6,14 @@
  * stated otherwise; `stream` is a cudaStream_t (NULL = default stream).  Matrices are row-major with the
  * embedding dimension d contiguous; d must be a multiple of 8 and <= 1024; bf16 buffers are 16-byte aligned.
  *
+ * fp16_operands (the entry points that produce or consume the normalised GEMM operands Xn / Wn): 0 = bf16, the default
+ * of this library (bf16-in / fp32-accumulate); 1 = fp16, what the reference's AMP mode multiplies
+ * (torch.cuda.amp.autocast around the logits, nets/PartialFC.py:198; conf.mixed_precision).  Same buffer sizes, same
+ * kernels: only the element format of the `xn` / `wn` arguments (named *_bf16 below) and the operand formats of the
+ * tcgen05 instruction change.  The spill E' and the scaled rows Xs are bf16 in both modes (their exponent range is
+ * needed), and tcgen05 kind::f16 takes no mixed bf16 x fp16 pair, so pfc_backward_dx wants a bf16 copy of an fp16 shard:
+ * pfc_cast_f16_to_bf16 (elems a multiple of 8, 16-byte aligned buffers).  All calls of one step must agree.
+ *
  * The reference is pure Python (aanna0701/face-recognition-pytorch); each entry point names the reference
  * code it replaces as file:line.  The Python binding a maintainer would add is shown in INTEGRATION.md.
  */
@@ -47,7 +55,8 @@ int pfc_dx_max_splits(int B, int d);              /* upper bound of pfc_dx_split
 /* ---- (1) fused L2 normalise: F.normalize of embeddings / of the classifier shard, nets/PartialFC.py:199-200.
  * xn[r,:] = bf16(x[src,:] / max(||x[src,:]||, 1e-12)), inv_norm[r] = 1/max(||.||, 1e-12), src = index ? index[r] : r
  * (the optional gather is the `self.weight[self.weight_index]` of nets/PartialFC.py:120 fused in). */
-int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void* xn_bf16, float* inv_norm,
+int pfc_cast_f16_to_bf16(const void* src_f16, void* dst_bf16, size_t elems, void* stream);
+int pfc_l2norm_rows(const float* x, const int64_t* index, int rows, int d, void* xn_bf16, float* inv_norm, int fp16_operands,
                     void* stream);
 
 /* ---- label localisation, nets/PartialFC.py:188-193: out[i] = labels[i]-class_start if owned by this rank else -1 */
@@ -90,7 +99,7 @@ int pfc_scatter_rows(const float* const* src, float* const* dst, int count, cons
  * and the target logit.  labels_local: -1 = target on another rank. */
 int pfc_forward(const void* xn_bf16, const void* wn_bf16, const int32_t* labels_local, int B, int n, int d, float s,
                 int margin_kind, float m2, float m3, float interclass_filtering_threshold, void* E_bf16, int n_pad,
-                float* part_sum, float* tgt_raw, float* tgt_e, float* tgt_z, void* stream);
+                float* part_sum, float* tgt_raw, float* tgt_e, float* tgt_z, int fp16_operands, void* stream);
 
 /* ---- stand-alone margin module, nets/ArcFace.py:76-91 (ArcFace.forward), :100-105 (CosFace), :27-61 (Combined):
  * out[i,c] = s * margin(logits[i,c]) on the target column labels[i] (int64, -1 = none), s * logits elsewhere
@@ -111,13 +120,14 @@ int pfc_loss(const float* stats, int B, float* row_L, float* loss, void* stream)
 int pfc_row_stats_loss(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
                        float* stats, float* row_L, float* loss, unsigned int* ticket, void* stream);
 int pfc_l2norm_rows_localize(const float* x, int rows, int d, void* xn_bf16, float* inv_norm, const int64_t* labels,
-                             int64_t class_start, int num_local, int32_t* labels_local, void* stream);
+                             int64_t class_start, int num_local, int32_t* labels_local, int fp16_operands,
+                             void* stream);
 /* pfc_row_stats_loss + pfc_backward_prepare (below) in one launch, for a step driven without autograd (d loss known when
  * the forward ends; model/FR_PartialFC.py:175-184 as one call): every CTA forms the coefficients of the rows it summed. */
 int pfc_row_stats_loss_prepare(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
                                float* stats, float* row_L, float* loss, unsigned int* ticket, const float* grad_loss,
                                float s, int d, const float* tgt_raw, int margin_kind, float m2, const void* xn_bf16,
-                               void* xs_bf16, float* coef, void* E_bf16, int n_pad, void* stream);
+                               void* xs_bf16, float* coef, void* E_bf16, int n_pad, int fp16_operands, void* stream);
 
 /* ---- (5) backward, nets/PartialFC.py:464-484 (DistCrossEntropyFunc.backward) + autograd of :199-206.
  * pfc_backward_prepare: coef[i] = g*s/(B*row_L[i]) (g = grad_loss[0], device scalar, NULL = 1), xs = bf16(coef*xn),
@@ -131,7 +141,8 @@ int pfc_row_stats_loss_prepare(const float* part_sum, int n_tiles, int B, const 
  *   driven from model/FR_PartialFC.py:182-188), also emitting the next step's bf16 normalised shard. */
 int pfc_backward_prepare(const float* stats, const float* row_L, const float* grad_loss, float s, int B, int d,
                          const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                         const void* xn_bf16, void* xs_bf16, float* coef, void* E_bf16, int n_pad, void* stream);
+                         const void* xn_bf16, void* xs_bf16, float* coef, void* E_bf16, int n_pad, int fp16_operands,
+                         void* stream);
 int pfc_backward_dx(const void* E_bf16, int n_pad, const void* wn_bf16, int B, int n, int d, float* partial,
                     int splits, void* stream);
 int pfc_dx_finalize(const float* partial, int splits, const float* coef, const float* x, const float* inv_norm,
@@ -152,11 +163,11 @@ int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, i
  * scatter back after it. */
 int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* momentum_buf, const float* inv_norm_w, int rows, int d,
                float lr, float momentum, float weight_decay, const float* grad_scale, void* wn_next_bf16,
-               float* inv_norm_next, const int64_t* index, void* stream);
+               float* inv_norm_next, const int64_t* index, int fp16_operands, void* stream);
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                 const float* grad_scale, void* wn_next_bf16, float* inv_norm_next, const int* step_dev,
-                const int64_t* index, void* stream);
+                const int64_t* index, int fp16_operands, void* stream);
 /* ---- (5b) the three exchanges of the step over peer memory (NVLink / NVSwitch), fused into the producing kernels.
  * They replace all_gather (nets/PartialFC.py:182-186), the softmax all_reduces (:448, :453, :459) and the dX
  * reduce (:505-522).  peer_* arguments are HOST arrays of W device pointers: entry q is rank q's symmetric buffer as
@@ -179,7 +190,8 @@ int pfc_peer_max_ranks(void);
 int pfc_peer_set_timeout_ms(double ms);
 int pfc_peer_barrier(void* const* peer_flags, uint32_t* epoch_counter, int rank, int W, void* stream);
 int pfc_peer_l2norm_gather(const float* x, const int64_t* labels, int b, int d, int rank, int W,
-                           void* const* peer_xn_all, void* const* peer_labels_all, float* inv_norm, void* stream);
+                           void* const* peer_xn_all, void* const* peer_labels_all, float* inv_norm, int fp16_operands,
+                           void* stream);
 int pfc_peer_row_stats(const float* part_sum, int n_tiles, int B, const int32_t* labels_local, const float* tgt_e,
                        int rank, int W, void* const* peer_slots, void* stream);
 int pfc_peer_loss(void* const* peer_flags, uint32_t* barrier_state, int rank, const float* slots, int W, int B,
@@ -189,7 +201,8 @@ int pfc_peer_loss(void* const* peer_flags, uint32_t* barrier_state, int rank, co
 int pfc_peer_loss_prepare(void* const* peer_flags, uint32_t* barrier_state, int rank, const float* slots, int W, int B,
                           float* stats, float* row_L, float* loss, unsigned int* ticket, const float* grad_loss, float s,
                           int d, const int32_t* labels_local, const float* tgt_raw, int margin_kind, float m2,
-                          const void* xn_bf16, void* xs_bf16, float* coef, void* E_bf16, int n_pad, void* stream);
+                          const void* xn_bf16, void* xs_bf16, float* coef, void* E_bf16, int n_pad, int fp16_operands,
+                          void* stream);
 int pfc_peer_localize_labels(void* const* peer_flags, uint32_t* barrier_state, int rank, int W, const int64_t* labels,
                              int B, int64_t class_start, int num_local, int32_t* labels_local, void* stream);
 int pfc_peer_dx_finalize(void* const* peer_flags, uint32_t* barrier_state, int rank, int W, const float* dx_slots,

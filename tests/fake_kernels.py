@@ -28,7 +28,7 @@ class FakeKernels:
     def l2norm_rows(self, x, index, rows, xn, inv_norm):
         src = x[index[:rows]] if index is not None else x[:rows]
         denom = src.norm(dim=1, keepdim=True).clamp_min(1e-12)
-        xn[:rows] = (src / denom).to(torch.bfloat16)
+        xn[:rows] = (src / denom).to(xn.dtype)
         inv_norm[:rows] = (1.0 / denom).reshape(-1)
 
     def l2norm_rows_localize(self, x, rows, xn, inv_norm, labels, class_start, num_local, labels_local):
@@ -124,6 +124,9 @@ class FakeKernels:
         mask = (raw.abs() <= 1).float()
         Ev = E[: B * n_pad].view(B, n_pad)
         Ev[rows, labels[rows].long()] = (-dm * mask * stats[rows, 0]).to(torch.bfloat16)
+
+    def cast_f16_to_bf16(self, src, dst, elems):
+        dst.reshape(-1)[:elems] = src.reshape(-1)[:elems].to(torch.bfloat16)
 
     def backward_dx(self, E, n_pad, wn, B, n, d, partial, splits):
         p = partial[: splits * B * d].view(splits, B, d)

@@ -29,7 +29,8 @@ def _rank_main(rank, W, port, name, fused, peer, q, extra=None):
     b = cfg["b"]
     extra = dict(extra or {})
     no_autograd = extra.pop("no_autograd", False)      # head.fused_step: barrier + loss + coefficients in one launch
-    conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
+    amp = extra.pop("amp", False)                      # conf.mixed_precision: fp16 operands (nets/PartialFC.py:198)
+    conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=amp,
                                  loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused,
                                  peer_collectives=peer, **(extra or {}))
     head = pfc.PartialFC(conf, cfg["C"])
@@ -87,7 +88,9 @@ def _cos(a, b):
     ("head_w2_sampled", True, 29853, False, {"inplace_update": False}),
     ("head_w2_full", True, 29854, True, {"dx_side_stream": False}),
     ("head_w2_full", True, 29855, True, {"no_autograd": True}), ("head_w2_sampled", True, 29856, True, {"no_autograd": True}),
-    ("head_w2_full", True, 29857, True, {"no_autograd": True, "fuse_prepare": False})])
+    ("head_w2_full", True, 29857, True, {"no_autograd": True, "fuse_prepare": False}),
+    ("head_w2_full", True, 29858, True, {"amp": True}), ("head_w2_sampled", False, 29859, False, {"amp": True}),
+    ("head_w2_full", True, 29860, True, {"amp": True, "no_autograd": True})])
 def test_two_rank_matches_reference(name, fused, port, peer, extra):
     _run_case(name, fused, port, peer, extra)
 
@@ -179,7 +182,8 @@ def _run_case(name, fused, port, peer, extra):
         assert res[0][f"loss_{s}"] == res[1][f"loss_{s}"]
         for r in range(W):
             ref_loss = float(z[f"r{r}_loss_{s}"])
-            assert abs(res[r][f"loss_{s}"] - ref_loss) <= 6e-3 * abs(ref_loss)     # bf16 operands at d = 64
+            rtol = 1e-3 if (extra or {}).get("amp") else 6e-3                        # bf16 operands at d = 64: 6e-3
+            assert abs(res[r][f"loss_{s}"] - ref_loss) <= rtol * abs(ref_loss)
             assert _cos(res[r][f"dx_{s}"], z[f"r{r}_dx_{s}"]) >= 0.999
             assert abs(np.linalg.norm(res[r][f"dx_{s}"]) / np.linalg.norm(z[f"r{r}_dx_{s}"]) - 1) < 2e-2
             if not fused:

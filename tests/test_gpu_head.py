@@ -35,8 +35,8 @@ def _margin_cls(pfc, cfg):
     return {"arcface": pfc.ArcFace, "cosface": pfc.CosFace}[cfg["margin"]]
 
 
-def _make_head(pfc, cfg, weights, fused=False, adam=False, **extra):
-    conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=False,
+def _make_head(pfc, cfg, weights, fused=False, adam=False, amp=False, **extra):
+    conf = types.SimpleNamespace(emd_size=cfg["d"], sample_rate=cfg["sample_rate"], mixed_precision=amp,
                                  loss_s=cfg["s"], loss_m=cfg["m"], fused_optimizer=fused, **extra)
     cls = pfc.PartialFCAdamW if adam else pfc.PartialFC
     head = cls(conf, cfg["C"], margin_loss=_margin_cls(pfc, cfg))
@@ -45,21 +45,25 @@ def _make_head(pfc, cfg, weights, fused=False, adam=False, **extra):
     return head
 
 
-# mode: "unfused" (dW to torch.optim.SGD), "fused" (conf.fused_optimizer)
+# mode: "unfused" (dW to torch.optim.SGD), "fused" (conf.fused_optimizer); "_fp16": conf.mixed_precision = True, i.e. fp16
+# GEMM operands like the reference's autocast (nets/PartialFC.py:198) -- three more mantissa bits than bf16, so the
+# north-star's 1e-3 loss gate holds at d = 64 and d = 128 as well (the fixtures are the reference's fp32 run)
 @pytest.mark.parametrize("name,mode", [(n, m) for n in ["head_w1_full", "head_w1_s30", "head_w1_cosface", "head_w1_sampled",
                                                        "head_w1_manypos", "head_w1_d512", "head_w1_d128"]
-                                       for m in ["unfused", "fused"]])
+                                       for m in ["unfused", "fused", "unfused_fp16", "fused_fp16"]])
 def test_steps_match_reference_and_oracle(pfc, name, mode):
     cfg, z = load_case(name)
     weights, xs, ls = case_inputs(cfg)
-    fused = mode != "unfused"
-    head = _make_head(pfc, cfg, weights, fused=fused)
+    fused = not mode.startswith("unfused")
+    amp = mode.endswith("_fp16")
+    head = _make_head(pfc, cfg, weights, fused=fused, amp=amp)
+    assert head._op_dtype == (torch.float16 if amp else torch.bfloat16)
     dummy = torch.nn.Parameter(torch.zeros(1, device="cuda"))
     opt = torch.optim.SGD([{"params": [dummy]}, {"params": head.parameters()}], lr=cfg["lr"],
                           momentum=cfg["momentum"], weight_decay=cfg["wd"])
     orc = ho.PartialFCOracle(weights, cfg["C"], case_margin(cfg), cfg["sample_rate"], cfg["lr"], cfg["momentum"],
                              cfg["wd"])
-    rtol = LOSS_RTOL if cfg["d"] >= 512 else LOSS_RTOL_D64
+    rtol = LOSS_RTOL if (cfg["d"] >= 512 or amp) else LOSS_RTOL_D64
     for s in range(cfg["steps"]):
         perms = case_perms(cfg, z, s)
         res = orc.step([xs[s]], [ls[s]], perms)

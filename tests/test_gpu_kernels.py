@@ -7,7 +7,7 @@ from tools import gpu_probe
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case", ["rows", "fwd_small", "fwd_mid", "dx", "dw", "sample", "eval", "fwd_big", "dx_big",
+@pytest.mark.parametrize("case", ["rows", "fwd_small", "fwd_mid", "dx", "dw", "sample", "eval", "fp16", "fwd_big", "dx_big",
                                   "dw_big"])
 def test_kernel_case(case):
     ok = getattr(gpu_probe, "case_" + case)()

@@ -16,7 +16,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-CASES = ["rows", "fwd_small", "fwd_mid", "dx", "dw", "sample", "eval", "fwd_big", "dx_big", "dw_big"]
+CASES = ["rows", "fwd_small", "fwd_mid", "dx", "dw", "sample", "eval", "fp16", "fwd_big", "dx_big", "dw_big"]
 
 
 def _stats(name, got, ref):
@@ -30,13 +30,14 @@ def _stats(name, got, ref):
     return float(err.max() / den), cos
 
 
-def _mk(B, n, d, seed=0):
+def _mk(B, n, d, dtype=None, seed=0):
     import torch
     g = torch.Generator(device="cpu").manual_seed(seed)
+    dtype = dtype or torch.bfloat16
     w = torch.nn.functional.normalize(torch.randn(n, d, generator=g)).cuda()
     lab = torch.randint(0, n, (B,), generator=g)
     x = torch.nn.functional.normalize(w[lab].cpu() + 1.0 * torch.randn(B, d, generator=g) / math.sqrt(d)).cuda()
-    return x.to(torch.bfloat16).contiguous(), w.to(torch.bfloat16).contiguous(), lab.cuda()
+    return x.to(dtype).contiguous(), w.to(dtype).contiguous(), lab.cuda()
 
 
 def case_rows():
@@ -52,10 +53,10 @@ def case_rows():
     print("  bf16 bit-equal fraction:", float((xn == ref.to(torch.bfloat16)).float().mean()))
 
 
-def _fwd(B, n, d, s=64.0, m=0.5):
+def _fwd(B, n, d, s=64.0, m=0.5, dtype=None):
     import torch
     from face_recognition_pytorch_b200 import kernels as K
-    xn, wn, lab = _mk(B, n, d)
+    xn, wn, lab = _mk(B, n, d, dtype)
     n_pad = K.padded_classes(n)
     E = torch.zeros(B, n_pad, dtype=torch.bfloat16, device="cuda")
     nt = K.num_class_tiles(n)
@@ -183,6 +184,27 @@ def case_dx_big():
 
 def case_dw_big():
     return _dw(1024, 93431, 512, False)
+
+
+def case_fp16():
+    """fp16 operands (conf.mixed_precision): the forward with fp16 Xn / Wn against an fp32 matmul of the same rounded
+    values, the row kernels' fp16 output against torch's rounding, and the fp16 -> bf16 cast of the shard for the dX
+    contraction (tcgen05 kind::f16 raises an illegal-instruction error for a mixed bf16 x fp16 operand pair)."""
+    import torch
+    from face_recognition_pytorch_b200 import kernels as K
+    ok = _fwd(300, 1000, 512, dtype=torch.float16) and _fwd(128, 256, 64, dtype=torch.float16)
+    x = torch.randn(1000, 512, device="cuda") * 0.3
+    xn = torch.empty(1000, 512, dtype=torch.float16, device="cuda")
+    inv = torch.empty(1000, device="cuda")
+    K.l2norm_rows(x, None, 1000, xn, inv)
+    ref = torch.nn.functional.normalize(x).to(torch.float16)
+    frac = float((xn == ref).float().mean())
+    print("  l2norm fp16 bit-equal fraction:", frac, flush=True)
+    xb = torch.empty(1000, 512, dtype=torch.bfloat16, device="cuda")
+    K.cast_f16_to_bf16(xn, xb, xn.numel())
+    cast_ok = torch.equal(xb, xn.to(torch.bfloat16))
+    print("  fp16 -> bf16 cast bit-equal:", cast_ok, flush=True)
+    return ok and frac > 0.99 and cast_ok
 
 
 def case_sample():
