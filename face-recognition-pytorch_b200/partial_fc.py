@@ -33,6 +33,10 @@ Optional keys read from `conf` beyond the reference's five (emd_size, sample_rat
       partials exist the step forks -- the peer scatter + barrier + normalise-backward of dX (one GPU: just the
       normalise-backward) on a side stream, the rank-local dW GEMM / update on the main one -- and joins before
       backward returns.  The branches share no buffer; in a CUDA graph they become parallel branches.
+  conf.dx_fork_gemm (True / False / "auto", default "auto" = off): move that fork in front of the dX GEMM, so the two
+      gradient GEMMs run side by side (the clusters that run out of tiles in one persistent kernel's last wave pick up the
+      other's); the fused update waits for the dX GEMM's last read of the shard.  Measured -2 us per step at the shard
+      sizes of 2 / 4 / 8 GPUs, nothing on one (profiles/r02c_exp_shard_shapes.txt).
   conf.fuse_prepare (bool, default True; only `fused_step`, i.e. the no-autograd step, where d loss = 1 is known when the
       forward ends): the kernel that forms the loss also forms the backward coefficients (c_i, the scaled bf16 rows and
       the patched target column), so the step has one launch fewer; False: the two launches of the autograd path.
@@ -158,6 +162,8 @@ class _PartialFCBase(torch.nn.Module):
         # fused update of a sampled shard in place through the index list (no gather / scatter of the active rows)
         self._indexed = (self.fused_optimizer and self.sample_rate < 1 and bool(getattr(conf, "inplace_update", True)))
         self.dw_first = getattr(conf, "dw_first", "auto")     # order of the two gradient GEMMs (see _backward_impl)
+        # True / False / "auto": fork the side stream in FRONT of the dX GEMM (both gradient GEMMs side by side)
+        self.dx_fork_gemm = getattr(conf, "dx_fork_gemm", "auto")
         # fused_step: form the backward coefficients in the kernel that forms the loss (one launch fewer)
         self.fuse_prepare = bool(getattr(conf, "fuse_prepare", True))
         self._prepared = False
@@ -454,22 +460,32 @@ class _PartialFCBase(torch.nn.Module):
         # reduce-scatter / peer stores have the whole dW + update to complete.  N = 1: dW GEMM first (it walks the class
         # tiles from the end, where the forward's spill is still in L2), then dX, then the update.
         dw_first = (W == 1) if self.dw_first == "auto" else bool(self.dw_first)
-        if dw_first:
-            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         dx, rs_work = None, None
-        # fork: the tail of the dX path runs on a side stream next to the dW GEMM / update (see conf.dx_side_stream)
+        # fork: the tail of the dX path runs on a side stream next to the dW GEMM / update (see conf.dx_side_stream);
+        # conf.dx_fork_gemm moves the fork in front of the dX GEMM, so the two gradient GEMMs run side by side and the
+        # clusters that run out of tiles in one persistent kernel's last wave pick up the other kernel's tiles
         want_fork = True if self.dx_side_stream == "auto" else bool(self.dx_side_stream)
         fork = want_fork and w.is_cuda and need_dx and (W == 1 or peer is not None)
+        gemm_fork = fork and self._gemm_fork(n)
+        if dw_first and not gemm_fork:
+            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         tail = None
         if need_dx:
             splits = K.dx_splits(B, n, d)
-            if ws.wn_b is not ws.wn:
-                K.cast_f16_to_bf16(ws.wn, ws.wn_b, n * d)
-            K.backward_dx(ws.E, n_pad, ws.wn_b, B, n, d, ws.dx_partial, splits)
+            if fork and self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=w.device)
+            if gemm_fork:
+                tail = self._side_stream
+                tail.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():
+                if ws.wn_b is not ws.wn:
+                    K.cast_f16_to_bf16(ws.wn, ws.wn_b, n * d)
+                K.backward_dx(ws.E, n_pad, ws.wn_b, B, n, d, ws.dx_partial, splits)
+                if gemm_fork:        # the fused update rewrites the shard the dX GEMM is reading: it waits for this
+                    dx_done = torch.cuda.Event()
+                    dx_done.record()
             dx = torch.empty(b, d, dtype=torch.float32, device=x_in.device)
-            if fork:
-                if self._side_stream is None:
-                    self._side_stream = torch.cuda.Stream(device=w.device)
+            if fork and not gemm_fork:
                 tail = self._side_stream
                 tail.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():
@@ -489,9 +505,13 @@ class _PartialFCBase(torch.nn.Module):
                     # :505-519 -- asynchronous: it overlaps the rank-local dW GEMM / update below
                     rs_work = distributed.reduce_scatter_tensor(ws.dxn_local, ws.dxn_all, distributed.ReduceOp.SUM,
                                                                 async_op=True)
+        if dw_first and gemm_fork:
+            K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         if not dw_first:
             K.backward_dw(ws.E, n_pad, ws.xs, B, n, d, dwn)
         if self.fused_optimizer:
+            if gemm_fork and need_dx:
+                torch.cuda.current_stream().wait_event(dx_done)
             self._fused_step(w, n, d, dwn, ws.wn)         # in place, after the last reader of this step's shard
         else:
             dw = torch.empty(n, d, dtype=torch.float32, device=w.device)
@@ -510,6 +530,12 @@ class _PartialFCBase(torch.nn.Module):
         if tail is not None:
             torch.cuda.current_stream().wait_stream(tail)                          # join
         return dx, dw
+
+    def _gemm_fork(self, n):
+        """conf.dx_fork_gemm; "auto": off (see DESIGN.md section 6 for the measurement)."""
+        if self.dx_fork_gemm == "auto":
+            return False
+        return bool(self.dx_fork_gemm)
 
     def _fused_step(self, w, n, d, dwn, wn_out):
         raise NotImplementedError

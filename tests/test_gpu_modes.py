@@ -163,14 +163,16 @@ def test_head_with_interclass_filter_matches_reference(pfc, fused):
 @pytest.mark.parametrize("B,C,d,fused", [(1024, 20000, 512, True), (320, 3100, 512, False), (96, 1500, 64, True),
                                          (200, 777, 128, True), (1024, 300, 512, False)])
 def test_dx_tail_fork_is_bit_identical(pfc, B, C, d, fused):
-    """conf.dx_side_stream: the dX finalize on a side stream next to the dW GEMM / update -- a scheduling change only."""
+    """conf.dx_side_stream: the dX finalize on a side stream next to the dW GEMM / update -- a scheduling change only;
+    conf.dx_fork_gemm: the fork in front of the dX GEMM (both gradient GEMMs side by side, the fused update waiting for
+    the dX GEMM's last read of the shard) -- likewise."""
     g0 = torch.Generator().manual_seed(44)
     w = torch.normal(0, 0.01, (C, d), generator=g0)
     outs = []
-    for fork in (False, True):
+    for fork, gemm in ((False, False), (True, False), (True, True)):
         g = torch.Generator().manual_seed(45)
         conf = types.SimpleNamespace(emd_size=d, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5,
-                                     fused_optimizer=fused, dx_side_stream=fork)
+                                     fused_optimizer=fused, dx_side_stream=fork, dx_fork_gemm=gemm)
         head = pfc.PartialFC(conf, C)
         head.load_state_dict({"weight": w.clone()})
         head = head.train().cuda()
@@ -190,8 +192,9 @@ def test_dx_tail_fork_is_bit_identical(pfc, B, C, d, fused):
         rec.append(head.weight_activated.data.clone())
         torch.cuda.synchronize()
         outs.append(rec)
-    for i, (u, v) in enumerate(zip(*outs)):
+    for i, (u, v, t) in enumerate(zip(*outs)):
         assert torch.equal(u, v), f"output {i} differs with the dX tail forked"
+        assert torch.equal(u, t), f"output {i} differs with the dX GEMM forked"
 
 
 def test_forward_only_and_eval_paths(pfc):

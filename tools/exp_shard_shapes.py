@@ -31,9 +31,9 @@ def main():
     for C in (int(v) for v in args.shards.split(",")):
         cfg = dict(bench.CONFIGS[2], C=C, B=args.batch)
         w_shard, xs, ls = bench.synth(cfg, 0, 1, 4, dev)
-        for mode in ("fused",):
+        for mode in ("serial", "gemm_fork"):     # conf.dx_fork_gemm: dX GEMM on the side stream next to the dW GEMM
             conf = types.SimpleNamespace(emd_size=512, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5,
-                                         fused_optimizer=True)
+                                         fused_optimizer=True, dx_fork_gemm=mode == "gemm_fork")
             head = pfc.PartialFC(conf, C)
             head.load_state_dict({"weight": w_shard.clone()})
             head = head.train().cuda()
@@ -55,7 +55,7 @@ def main():
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1) * 1e3)
-            line = f"n={C:6d} mode={mode:8s} graph step {statistics.median(ts):7.1f} us (min {min(ts):7.1f})"
+            line = f"n={C:6d} mode={mode:9s} graph step {statistics.median(ts):7.1f} us (min {min(ts):7.1f})"
             if args.kernels:
                 K.enable_timing(True)
                 for i in range(6):
