@@ -424,6 +424,8 @@ def main():
 
     def step_eager(i):
         k = i % n_data
+        if fused and not args.autograd:       # the same no-autograd kernel sequence GraphedHeadStep captures
+            return head.fused_step(x_dev[k].detach(), l_dev[k], opt, perm=None if perms is None else perms[k])[0]
         x_dev[k].grad = None
         loss = head(x_dev[k], l_dev[k], opt, perm=None if perms is None else perms[k])
         loss.backward()
@@ -665,7 +667,9 @@ def main():
                    "parallelism": f"class-sharded x{world}", "mode": mode,
                    "update": "in-step (fused into the backward)" if fused else "torch.optim.SGD",
                    "launch": ("cuda-graph replay (GraphedHeadStep" + (")" if args.autograd else ", no autograd)")
-                              if gstep is not None else "eager"),
+                              if gstep is not None else
+                              "eager (head.forward + loss.backward)" if args.autograd or not fused else
+                              "eager (head.fused_step, no autograd)"),
                    "dx_side_stream": True,
                    "exchange": ("none (1 GPU)" if world == 1 else
                                 "peer-memory stores + flag barriers (NVLink)" if head._peer is not None else

@@ -71,8 +71,8 @@ _SIGS = {
     "pfc_dx_finalize": (c_int, [p, c_int, p, p, p, c_float, c_int, c_int, c_int, p, p]),
     "pfc_backward_dw": (c_int, [p, c_int, p, c_int, c_int, c_int, p, c_int, p]),
     "pfc_dw_finalize": (c_int, [p, p, p, c_int, c_int, c_float, p, p]),
-    "pfc_dw_sgd": (c_int, [p, c_int, p, p, p, c_int, c_int, c_float, c_float, c_float, p, p, p, p, c_int, p]),
-    "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int, p, p, p, p, p, c_int, p]),
+    "pfc_dw_sgd": (c_int, [p, c_int, p, p, p, c_int, c_int, c_float, c_float, c_float, p, p, p, p, c_int, p, p]),
+    "pfc_dw_adam": (c_int, [p, p, p, p, p, c_int, c_int, c_float, c_float, c_float, c_float, c_float, c_int, c_int, p, p, p, p, p, c_int, p, p]),
     "pfc_peer_max_ranks": (c_int, []),
     "pfc_peer_set_timeout_ms": (c_int, [c_double]),
     "pfc_peer_barrier": (c_int, [POINTER(c_void_p), p, c_int, c_int, p]),

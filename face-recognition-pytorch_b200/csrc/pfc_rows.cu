@@ -49,6 +49,13 @@ __device__ __forceinline__ uint2 pack4_op(float4 v, int f16) {
     r.y = *reinterpret_cast<uint32_t*>(&b);
     return r;
 }
+// bf16 twin of an fp16 operand row: rounds through fp16 first, i.e. bit for bit what cast_f16_bf16_kernel makes of the
+// fp16 row that pack4_op(v, 1) writes
+__device__ __forceinline__ uint2 pack4_bf16_of_f16(float4 v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    return pack4_bf16(make_float4(fa.x, fa.y, fb.x, fb.y));
+}
 __device__ __forceinline__ float4 unpack4_bf16(uint2 r) {
     __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x), b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
     float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
@@ -356,6 +363,7 @@ struct OptArgs {
     const int* step_dev;            // Adam(W): device step counter (the update is step step_dev[0] + 1), or null
     const int64_t* index;           // sampled shards: row r of (dwn, inv_norm_w, wn_next) is row index[r] of (w, state), or null
     int wn_f16;                     // wn_next is written as fp16 instead of bf16
+    __nv_bfloat16* wn_copy_b;       // wn_f16 only: bf16 twin of wn_next for the next step's dX contraction, or null
 };
 
 __device__ __forceinline__ float opt_inv_grad_scale(const float* grad_scale) {
@@ -456,6 +464,8 @@ dw_finalize_kernel(const float* __restrict__ dwn, float* __restrict__ w, const f
         if (k < nv) {
             const float4 q = make_float4(wv[j].x / denom, wv[j].y / denom, wv[j].z / denom, wv[j].w / denom);
             *reinterpret_cast<uint2*>(wn_next + base + 4 * k) = pack4_op(q, opt.wn_f16);
+            if (opt.wn_copy_b != nullptr)
+                *reinterpret_cast<uint2*>(opt.wn_copy_b + base + 4 * k) = pack4_bf16_of_f16(q);
         }
     }
     if (lane == 0) inv_norm_next[row] = 1.f / denom;
@@ -488,7 +498,7 @@ __global__ void __launch_bounds__(128)
 dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* __restrict__ mom,
                    const float* inv_norm_w, int rows, float lr, float momentum, float wd,
                    const float* __restrict__ grad_scale, __nv_bfloat16* __restrict__ wn_next, float* inv_norm_next,
-                   const int64_t* __restrict__ index, int wn_f16) {
+                   const int64_t* __restrict__ index, int wn_f16, __nv_bfloat16* __restrict__ wn_copy_b) {
     const float inv_grad_scale = opt_inv_grad_scale(grad_scale);
     constexpr int d = 128 * NV;
     const int lane = threadIdx.x & 31;
@@ -563,6 +573,8 @@ dw_sgd_rows_kernel(const void* __restrict__ dwn_, float* __restrict__ w, float* 
     for (int j = 0; j < NV; ++j) {
         const float4 q = make_float4(wv[j].x / denom, wv[j].y / denom, wv[j].z / denom, wv[j].w / denom);
         *reinterpret_cast<uint2*>(wn_next + base + 4 * (lane + 32 * j)) = pack4_op(q, wn_f16);
+        if (wn_copy_b != nullptr)      // AMP mode: the dX contraction reads the shard as bf16 (see pfc_backward_dx)
+            *reinterpret_cast<uint2*>(wn_copy_b + base + 4 * (lane + 32 * j)) = pack4_bf16_of_f16(q);
     }
     if (lane == 0) inv_norm_next[row] = 1.f / denom;
     }
@@ -573,7 +585,8 @@ static int g_sgd_persistent_warps = 0;   // 0: one row per warp, full grid; > 0:
 template <int NV>
 static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom, const float* inv_norm_w, int rows,
                                float lr, float momentum, float wd, const float* igs, __nv_bfloat16* wn_next,
-                               float* inv_next, const int64_t* index, int wn_f16, cudaStream_t st) {
+                               float* inv_next, const int64_t* index, int wn_f16, __nv_bfloat16* wn_copy_b,
+                               cudaStream_t st) {
     int grid = (rows + 3) / 4, block = 128;
     if (g_sgd_persistent_warps > 0) {
         int dev = 0, sms = 148;
@@ -588,13 +601,13 @@ static void launch_dw_sgd_rows(const void* dwn, bool bf16, float* w, float* mom,
     }
     if (bf16 && pfc_l2_grad_enabled())
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr,
-                           momentum, wd, igs, wn_next, inv_next, index, wn_f16);
+                           momentum, wd, igs, wn_next, inv_next, index, wn_f16, wn_copy_b);
     else if (bf16)
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, true>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
-                           wd, igs, wn_next, inv_next, index, wn_f16);
+                           wd, igs, wn_next, inv_next, index, wn_f16, wn_copy_b);
     else
         launch_step_kernel(PDL_UPDATE, dw_sgd_rows_kernel<NV, false>, grid, block, 0, st, dwn, w, mom, inv_norm_w, rows, lr, momentum,
-                           wd, igs, wn_next, inv_next, index, wn_f16);
+                           wd, igs, wn_next, inv_next, index, wn_f16, wn_copy_b);
 }
 
 // dst[r] = src[index[r]]  /  dst[index[r]] = src[r]   (nets/PartialFC.py:120-121, :142-143), up to 3 tensors at once
@@ -782,15 +795,17 @@ int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, i
 
 int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float* inv_norm_w, int rows, int d, float lr,
                float momentum, float weight_decay, const float* grad_scale, void* wn_next, float* inv_norm_next,
-               const int64_t* index, int fp16_operands, void* stream) {
+               const int64_t* index, int fp16_operands, void* wn_next_copy_bf16, void* stream) {
     if (rows <= 0 || bad_d(d)) return PFC_ERR_SHAPE;
+    if (wn_next_copy_bf16 && (!fp16_operands || !wn_next)) return PFC_ERR_SHAPE;   // the twin of an fp16 shard only
+    __nv_bfloat16* wcb = reinterpret_cast<__nv_bfloat16*>(wn_next_copy_bf16);
     if (d % 128 == 0 && mom != nullptr) {
         cudaStream_t st = (cudaStream_t)stream;
         __nv_bfloat16* wnn = reinterpret_cast<__nv_bfloat16*>(wn_next);
         const bool bf = dwn_bf16 != 0;
 #define PFC_SGD_CASE(NV) \
     launch_dw_sgd_rows<NV>(dwn, bf, w, mom, inv_norm_w, rows, lr, momentum, weight_decay, grad_scale, wnn, \
-                           inv_norm_next, index, fp16_operands, st)
+                           inv_norm_next, index, fp16_operands, wcb, st)
         switch (d / 128) {
             case 1: PFC_SGD_CASE(1); break;
             case 2: PFC_SGD_CASE(2); break;
@@ -810,6 +825,7 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
     o.lr = lr; o.momentum = momentum; o.wd = weight_decay; o.grad_scale = grad_scale;
     o.index = index;
     o.wn_f16 = fp16_operands;
+    o.wn_copy_b = wcb;
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         static_cast<const float*>(dwn), w, inv_norm_w, rows, d, o, nullptr, mom, nullptr,
         reinterpret_cast<__nv_bfloat16*>(wn_next), inv_norm_next);
@@ -819,8 +835,9 @@ int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* mom, const float*
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                 const float* grad_scale, void* wn_next, float* inv_norm_next, const int* step_dev,
-                const int64_t* index, int fp16_operands, void* stream) {
+                const int64_t* index, int fp16_operands, void* wn_next_copy_bf16, void* stream) {
     if (rows <= 0 || bad_d(d) || (step <= 0 && !step_dev)) return PFC_ERR_SHAPE;
+    if (wn_next_copy_bf16 && (!fp16_operands || !wn_next)) return PFC_ERR_SHAPE;
     if (step <= 0) step = 1;
     OptArgs o = {};
     o.kind = decoupled ? OPT_ADAMW : OPT_ADAM;
@@ -831,6 +848,7 @@ int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, c
     o.step_dev = step_dev;
     o.index = index;
     o.wn_f16 = fp16_operands;
+    o.wn_copy_b = reinterpret_cast<__nv_bfloat16*>(wn_next_copy_bf16);
     launch_step_kernel(PDL_UPDATE, dw_finalize_kernel, row_grid(rows), ROW_WARPS * 32, 0, (cudaStream_t)stream,
         dwn, w, inv_norm_w, rows, d, o, nullptr, exp_avg, exp_avg_sq, reinterpret_cast<__nv_bfloat16*>(wn_next),
         inv_norm_next);

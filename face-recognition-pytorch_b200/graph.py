@@ -147,6 +147,9 @@ class GraphedHeadStep:
         if not self._sampled:
             K.l2norm_rows(w, None, head._n, ws.wn, ws.inv_w)
             head._wn_valid = True
+            if ws.wn_b is not ws.wn:       # AMP mode: the captured step expects the bf16 twin of the shard as well
+                K.cast_f16_to_bf16(ws.wn, ws.wn_b, head._n * w.shape[1])
+                head._wn_b_valid = True
         torch.cuda.synchronize(self.device)
         self._captured = self._signature()
 

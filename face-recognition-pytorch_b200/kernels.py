@@ -35,6 +35,15 @@ def _op(t):
     return _p(t), int(t.dtype == F16)
 
 
+def _copy_b(wn_next, wn_next_b):
+    """Pointer of the optional bf16 copy of an fp16 `wn_next` (None -> NULL)."""
+    if wn_next_b is None or wn_next_b is wn_next:
+        return None
+    if wn_next is None or wn_next.dtype != F16 or wn_next_b.shape != wn_next.shape:
+        raise TypeError("wn_next_b is the bf16 twin of an fp16 wn_next of the same shape")
+    return _p(wn_next_b, BF16)
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -247,25 +256,29 @@ def dw_finalize(dwn, w, inv_norm_w, rows, d, inv_grad_scale, dw):
 
 
 @_timed("pfc_dw_sgd")
-def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_scale, wn_next, inv_norm_next, index=None):
+def dw_sgd(dwn, w, mom, inv_norm_w, rows, d, lr, momentum, weight_decay, grad_scale, wn_next, inv_norm_next, index=None,
+           wn_next_b=None):
     """grad_scale: device scalar holding the loss scale the gradient carries (divided out first), or None.
-    index (int64 [rows], ascending): w / mom are the FULL shard arrays and row r of dwn updates row index[r] in place."""
+    index (int64 [rows], ascending): w / mom are the FULL shard arrays and row r of dwn updates row index[r] in place.
+    wn_next_b (fp16 wn_next only): bf16 copy of the same rows for the next step's dX contraction."""
     is_bf16 = dwn.dtype == BF16
     wp, f16 = _op(wn_next)
+    wb = _copy_b(wn_next, wn_next_b)
     check(lib.pfc_dw_sgd(_p(dwn, BF16 if is_bf16 else F32), int(is_bf16), _p(w, F32), _p(mom, F32),
                          _p(inv_norm_w, F32), rows, d, lr, momentum, weight_decay, _p(grad_scale, F32),
-                         wp, _p(inv_norm_next, F32), _p(index, I64), f16, _stream()), "pfc_dw_sgd")
+                         wp, _p(inv_norm_next, F32), _p(index, I64), f16, wb, _stream()), "pfc_dw_sgd")
 
 
 @_timed("pfc_dw_adam")
 def dw_adam(dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, weight_decay, step, decoupled,
-            grad_scale, wn_next, inv_norm_next, step_dev=None, index=None):
+            grad_scale, wn_next, inv_norm_next, step_dev=None, index=None, wn_next_b=None):
     """step_dev (int32 device scalar): the update is step step_dev[0] + 1 (CUDA-graph replay), `step` is ignored.
-    index: as in dw_sgd (in-place update of a sampled shard)."""
+    index, wn_next_b: as in dw_sgd (in-place update of a sampled shard; bf16 copy of an fp16 wn_next)."""
     wp, f16 = _op(wn_next)
+    wb = _copy_b(wn_next, wn_next_b)
     check(lib.pfc_dw_adam(_p(dwn, F32), _p(w, F32), _p(exp_avg, F32), _p(exp_avg_sq, F32), _p(inv_norm_w, F32), rows,
                           d, lr, beta1, beta2, eps, weight_decay, step, int(decoupled), _p(grad_scale, F32),
-                          wp, _p(inv_norm_next, F32), _p(step_dev, I32), _p(index, I64), f16, _stream()),
+                          wp, _p(inv_norm_next, F32), _p(step_dev, I32), _p(index, I64), f16, wb, _stream()),
           "pfc_dw_adam")
 
 

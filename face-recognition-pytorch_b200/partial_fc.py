@@ -197,6 +197,7 @@ class _PartialFCBase(torch.nn.Module):
         self._ws = None
         self._step_id = 0
         self._wn_valid = False          # wn / inv_w in the workspace match weight_activated
+        self._wn_b_valid = False        # AMP mode: the bf16 twin of the fp16 shard (ws.wn_b, read by the dX GEMM) matches wn
         self._act_store = None          # persistent storage behind weight_activated / its optimizer state (r < 1)
         self._fused_state = None        # optimizer state for the fused step when sample_rate == 1
         self._n = self.num_local        # active classes this step
@@ -403,6 +404,7 @@ class _PartialFCBase(torch.nn.Module):
         if not self._wn_valid:
             K.l2norm_rows(w, ws.index if self._indexed else None, n, ws.wn, ws.inv_w)   # :200 (+ :120 when indexed)
             self._wn_valid = True
+            self._wn_b_valid = False
         kind, s, m2, m3, thr = self.margin_softmax.margin_spec()
         self._n_pad = K.padded_classes(n)
         K.forward(ws.xn_all, ws.wn, ws.labels_act, B, n, d, s, kind, m2, m3, thr, ws.E, self._n_pad, ws.part_sum,
@@ -478,8 +480,11 @@ class _PartialFCBase(torch.nn.Module):
                 tail = self._side_stream
                 tail.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(tail) if tail is not None else contextlib.nullcontext():
-                if ws.wn_b is not ws.wn:
+                if ws.wn_b is not ws.wn and not self._wn_b_valid:
+                    # AMP mode, first step / after an external optimizer / sampled rows: afterwards the fused update
+                    # writes the bf16 twin next to the fp16 shard
                     K.cast_f16_to_bf16(ws.wn, ws.wn_b, n * d)
+                    self._wn_b_valid = True
                 K.backward_dx(ws.E, n_pad, ws.wn_b, B, n, d, ws.dx_partial, splits)
                 if gemm_fork:        # the fused update rewrites the shard the dX GEMM is reading: it waits for this
                     dx_done = torch.cuda.Event()
@@ -608,8 +613,10 @@ class PartialFC(_PartialFCBase):
             K.dw_sgd(dwn, self.weight, self.weight_mom, ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], ws.gscale, None,
                      None, index=ws.index)
             return
-        K.dw_sgd(dwn, w, self._momentum(w), ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], ws.gscale, wn_out, ws.inv_w)
+        K.dw_sgd(dwn, w, self._momentum(w), ws.inv_w, n, d, o["lr"], o["momentum"], o["wd"], ws.gscale, wn_out, ws.inv_w,
+                 wn_next_b=ws.wn_b)
         self._wn_valid = True             # the update wrote next step's normalised bf16 rows and 1/norm in place
+        self._wn_b_valid = True           # ... and, in AMP mode, their bf16 twin
 
 
 class PartialFCAdamW(_PartialFCBase):
@@ -669,7 +676,7 @@ class PartialFCAdamW(_PartialFCBase):
         graphed = self._graph_steps
         K.dw_adam(dwn, w, m, v, ws.inv_w, n, d, o["lr"], o["beta1"], o["beta2"], o["eps"], o["wd"], step,
                   o["decoupled"], ws.gscale, wn_out, None if wn_out is None else ws.inv_w,
-                  ws.adam_step if graphed else None, index=index)
+                  ws.adam_step if graphed else None, index=index, wn_next_b=None if wn_out is None else ws.wn_b)
         if graphed:
             ws.adam_step.add_(1)
-        self._wn_valid = wn_out is not None
+        self._wn_valid = self._wn_b_valid = wn_out is not None

@@ -160,14 +160,17 @@ int pfc_dw_finalize(const float* dwn, const float* w, const float* inv_norm_w, i
  * index (sampled shards, nets/PartialFC.py:120-121 + :142-143 without the copies): NULL, or the ascending list of active
  * classes -- row r of dwn / inv_norm_w (/ wn_next) then belongs to row index[r] of w and of the optimizer state, which
  * are the FULL [num_local, d] arrays and are updated in place: no gather of the active rows before the step and no
- * scatter back after it. */
+ * scatter back after it.
+ * wn_next_copy_bf16 (fp16_operands only, else NULL): a second [rows, d] matrix that receives the same next-step rows as
+ * bf16 -- bit for bit what pfc_cast_f16_to_bf16(wn_next) would produce -- so that pfc_backward_dx of the next step finds
+ * its bf16 operand without a separate cast pass over the shard. */
 int pfc_dw_sgd(const void* dwn, int dwn_bf16, float* w, float* momentum_buf, const float* inv_norm_w, int rows, int d,
                float lr, float momentum, float weight_decay, const float* grad_scale, void* wn_next_bf16,
-               float* inv_norm_next, const int64_t* index, int fp16_operands, void* stream);
+               float* inv_norm_next, const int64_t* index, int fp16_operands, void* wn_next_copy_bf16, void* stream);
 int pfc_dw_adam(const float* dwn, float* w, float* exp_avg, float* exp_avg_sq, const float* inv_norm_w, int rows,
                 int d, float lr, float beta1, float beta2, float eps, float weight_decay, int step, int decoupled,
                 const float* grad_scale, void* wn_next_bf16, float* inv_norm_next, const int* step_dev,
-                const int64_t* index, int fp16_operands, void* stream);
+                const int64_t* index, int fp16_operands, void* wn_next_copy_bf16, void* stream);
 /* ---- (5b) the three exchanges of the step over peer memory (NVLink / NVSwitch), fused into the producing kernels.
  * They replace all_gather (nets/PartialFC.py:182-186), the softmax all_reduces (:448, :453, :459) and the dX
  * reduce (:505-522).  peer_* arguments are HOST arrays of W device pointers: entry q is rank q's symmetric buffer as

@@ -150,7 +150,14 @@ class FakeKernels:
         g = dwn[:rows]
         dw[:rows] = (g - wn * (wn * g).sum(1, keepdim=True)) * inv_norm_w[:rows].reshape(-1, 1) * inv_grad_scale
 
-    def dw_sgd(self, dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn_next, inv_norm_next, index=None):
+    def _twin(self, wn_next, wn_next_b, rows):
+        """bf16 twin of an fp16 wn_next (what the real update kernels write next to it in AMP mode)."""
+        if wn_next_b is not None and wn_next_b is not wn_next:
+            assert wn_next.dtype == torch.float16 and wn_next_b.dtype == torch.bfloat16
+            wn_next_b[:rows] = wn_next[:rows].to(torch.bfloat16)
+
+    def dw_sgd(self, dwn, w, mom, inv_norm_w, rows, d, lr, momentum, wd, grad_scale, wn_next, inv_norm_next, index=None,
+               wn_next_b=None):
         sel = slice(0, rows) if index is None else index[:rows].long()
         g = torch.empty(rows, d)
         inv_grad_scale = 1.0 if grad_scale is None else 1.0 / float(grad_scale[0])
@@ -160,9 +167,10 @@ class FakeKernels:
         mom[sel] = m_new
         if wn_next is not None:
             self.l2norm_rows(w_new, None, rows, wn_next, inv_norm_next)
+            self._twin(wn_next, wn_next_b, rows)
 
     def dw_adam(self, dwn, w, exp_avg, exp_avg_sq, inv_norm_w, rows, d, lr, beta1, beta2, eps, wd, step, decoupled,
-                grad_scale, wn_next, inv_norm_next, step_dev=None, index=None):
+                grad_scale, wn_next, inv_norm_next, step_dev=None, index=None, wn_next_b=None):
         sel = slice(0, rows) if index is None else index[:rows].long()
         if step_dev is not None:
             step = int(step_dev[0]) + 1
@@ -176,3 +184,4 @@ class FakeKernels:
         exp_avg_sq[sel] = v_new
         if wn_next is not None:
             self.l2norm_rows(w_new, None, rows, wn_next, inv_norm_next)
+            self._twin(wn_next, wn_next_b, rows)

@@ -278,3 +278,48 @@ def test_l2_resident_gradient_is_bit_identical(pfc):
         assert torch.equal(u, v)
     for u, v in zip(c, d):
         assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("adamw", [False, True])
+@pytest.mark.parametrize("B,C,d", [(256, 3100, 512), (96, 1500, 64)])
+def test_amp_update_writes_the_bf16_twin_of_the_shard(pfc, adamw, B, C, d):
+    """conf.mixed_precision (fp16 operands): the dX contraction needs the shard as bf16.  The fused update writes that twin
+    next to the fp16 rows (specialised SGD kernel at d = 512, generic row kernel at d = 64 and for AdamW), bit for bit what
+    pfc_cast_f16_to_bf16 makes of them, so the cast pass runs on the first step only -- and the steps are bit-identical to
+    steps that cast every time."""
+    from face_recognition_pytorch_b200 import partial_fc as PF
+    g = torch.Generator().manual_seed(91)
+    w = torch.normal(0, 0.01, (C, d), generator=g)
+    data = [(torch.nn.functional.normalize(torch.randn(B, d, generator=g)).cuda(),
+             torch.randint(0, C, (B,), generator=g).cuda()) for _ in range(4)]
+    runs = []
+    for always_cast in (False, True):
+        conf = types.SimpleNamespace(emd_size=d, sample_rate=1.0, mixed_precision=True, loss_s=64.0, loss_m=0.5,
+                                     fused_optimizer=True)
+        head = (pfc.PartialFCAdamW if adamw else pfc.PartialFC)(conf, C)
+        head.load_state_dict({"weight": w.clone()})
+        head = head.train().cuda()
+        opt = (torch.optim.AdamW(head.parameters(), lr=1e-3, weight_decay=0.05) if adamw else
+               torch.optim.SGD(head.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4))
+        cast, calls, out = PF.K.cast_f16_to_bf16, [], []
+
+        def counted_cast(*a, **k):
+            calls.append(1)
+            return cast(*a, **k)
+        PF.K.cast_f16_to_bf16 = counted_cast
+        try:
+            for x, lab in data:
+                if always_cast:
+                    head._wn_b_valid = False
+                loss, dx = head.fused_step(x, lab.clone(), opt)
+                ws = head._ws
+                assert ws.wn.dtype == torch.float16 and ws.wn_b.dtype == torch.bfloat16
+                assert torch.equal(ws.wn_b[:C], ws.wn[:C].to(torch.bfloat16)), "twin differs from the cast of the shard"
+                out += [loss.clone(), dx.clone()]
+        finally:
+            PF.K.cast_f16_to_bf16 = cast
+        assert len(calls) == (len(data) if always_cast else 1)
+        out.append(head.weight_activated.data.clone())
+        runs.append(out)
+    for i, (u, v) in enumerate(zip(*runs)):
+        assert torch.equal(u, v), f"output {i}: twin written by the update vs. cast every step"

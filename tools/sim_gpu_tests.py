@@ -35,6 +35,7 @@ RUNS = [
     (te.test_head_with_interclass_filter_matches_reference, [(pfc, False), (pfc, True)]),
     (te.test_dx_tail_fork_is_bit_identical, [(pfc, 320, 3100, 512, False), (pfc, 96, 1500, 64, True)]),
     (te.test_forward_only_and_eval_paths, [(pfc,)]),
+    (te.test_amp_update_writes_the_bf16_twin_of_the_shard, [(pfc, False, 256, 3100, 512), (pfc, True, 96, 1500, 64)]),
     (th.test_steps_match_reference_and_oracle, [(pfc, "head_w1_d128", "fused"),
                                                 (pfc, "head_w1_sampled", "fused"), (pfc, "head_w1_full", "unfused")]),
     (th.test_scaled_loss_through_the_kernels, [(pfc, "unfused"), (pfc, "fused")]),
