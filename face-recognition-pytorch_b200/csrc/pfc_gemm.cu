@@ -447,8 +447,8 @@ static void fill_fwd_params(FwdPolicy::Params& p, int B, int n, int n_pad, int d
 // Keep the bf16 gradient of the dW GEMM in L2 for the update kernel that runs right behind it (evict_last stores here,
 // evict_first streams + discard.global.L2 in dw_sgd_rows_kernel, pfc_rows.cu).  Bit-identical results; measured on B200 at
 // cfg-2: 0.3872 -> 0.3812 ms per step on one GPU, 0.2486 -> 0.2452 on two (profiles/r02a_experimental_n*.log), hence on by
-// default.  PFC_L2_GRAD=0 / pfc_debug_l2_grad(0) switch it off (the A/B test does).  The lazy-update path consumes the
-// gradient a whole step later and does not use the hints.
+// default.  PFC_L2_GRAD=0 / pfc_debug_l2_grad(0) switch it off (the A/B test does); dwn_bf16 = 2 stores without the hints
+// (tools/exp_overlap.py: chunked pipelines in which the update does not run right behind the GEMM).
 static int g_l2_grad = -1;
 
 }  // namespace pfc
@@ -594,7 +594,7 @@ int pfc_backward_dw(const void* E, int n_pad, const void* xs, int B, int n, int 
     CUtensorMap tc;
     rc = make_store_tmap(&tc, dwn, dwn_bf16 != 0, d, n, 1, d, 0);
     if (rc) return rc;
-    if (dwn_bf16 == 1 && pfc_l2_grad_enabled())   // 2: bf16 without the L2 hints (consumed a step later: lazy update)
+    if (dwn_bf16 == 1 && pfc_l2_grad_enabled())   // 2: bf16 without the L2 hints
         return launch_gemm<StorePolicy<true, true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
     return launch_gemm<StorePolicy<true>>(PDL_DW, mode, ta, tb, tc, p, reinterpret_cast<cudaStream_t>(stream));
 }
