@@ -58,6 +58,8 @@ _SIGS = {
     "pfc_localize_labels": (c_int, [p, c_int, c_int64, c_int, p, p]),
     "pfc_sample_workspace_bytes": (c_size_t, [c_int]),
     "pfc_sample": (c_int, [p, p, c_int, c_int, c_int, p, p, p, p, c_size_t, p]),
+    "pfc_host_mt19937_state_bytes": (c_size_t, []),
+    "pfc_host_mt19937_uniform": (c_int, [p, c_size_t, p, c_size_t]),
     "pfc_sample_launches": (c_int, [c_int]),
     "pfc_sample_debug_cluster": (c_int, [c_int]),
     "pfc_gather_rows": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, p, c_int, c_int, p]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpfc_b200.so")
-SOURCES = ["pfc_api.cu", "pfc_gemm.cu", "pfc_rows.cu", "pfc_sample.cu", "pfc_eval.cu", "pfc_peer.cu"]
+SOURCES = ["pfc_api.cu", "pfc_gemm.cu", "pfc_rows.cu", "pfc_sample.cu", "pfc_eval.cu", "pfc_peer.cu", "pfc_hostrng.cu"]
 HEADERS = ["pfc_ptx.cuh", "pfc_umma.cuh", "pfc_umma2.cuh", "pfc_launch.cuh", "pfc_internal.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -27,6 +27,7 @@ them, so constructing / recapturing does not train.
 import torch
 
 from . import kernels as K
+from .hostrng import cpu_rand_
 
 
 class GraphedHeadStep:
@@ -76,7 +77,7 @@ class GraphedHeadStep:
         else:
             k = self._perm_k
             self._perm_ev[k].synchronize()             # the upload that last used this pinned buffer has finished
-            torch.rand(self.head.num_local, out=self._perm_host[k])
+            cpu_rand_(self._perm_host[k])              # = torch.rand(num_local, out=...) on the CPU generator
             self._perm.copy_(self._perm_host[k], non_blocking=True)
             self._perm_ev[k].record()
             self._perm_k = 1 - k

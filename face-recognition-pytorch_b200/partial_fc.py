@@ -53,6 +53,7 @@ import torch
 from torch import distributed
 
 from . import kernels as K
+from .hostrng import cpu_rand
 from .arcface import ArcFace
 
 
@@ -231,7 +232,7 @@ class _PartialFCBase(torch.nn.Module):
             ws.perm.uniform_()                       # [0, 1) from the CUDA generator, no host round trip
         else:
             if perm is None:
-                perm = torch.rand(size=[self.num_local])
+                perm = cpu_rand(self.num_local)      # = torch.rand(size=[num_local]) on the CPU generator, drawn in bulk
             ws.perm.copy_(perm, non_blocking=True)
         K.sample(ws.perm, labels_local, self.num_local, self.num_sample, ws.index, ws.n_out, ws.labels_act,
                  ws.sample_ws)

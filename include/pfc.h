@@ -77,6 +77,13 @@ int pfc_sample_debug_cluster(int mode);
 int pfc_sample(const float* perm, const int32_t* labels_local, int B, int num_local, int num_sample,
                int64_t* index_out, int32_t* n_out, int32_t* labels_remapped, void* workspace,
                size_t workspace_bytes, void* stream);
+/* HOST function (no CUDA call): the next n float32 values `torch.rand(n)` would draw from a CPU torch.Generator, produced
+ * in bulk from the generator's state blob (torch.Generator.get_state(): MT19937, 5056 bytes), which is advanced in place
+ * exactly as torch would leave it -- the sampling draw of nets/PartialFC.py:110 without torch's per-element generator
+ * call.  state and out are HOST pointers (out may be pinned).  PFC_ERR_SHAPE: not a seeded CPU MT19937 state blob. */
+size_t pfc_host_mt19937_state_bytes(void);
+int pfc_host_mt19937_uniform(uint8_t* state, size_t state_bytes, float* out, size_t n);
+
 
 /* rows of up to 3 fp32 matrices at once: dst[t][r,:] = src[t][index[r],:]  (nets/PartialFC.py:120-121)
  * and dst[t][index[r],:] = src[t][r,:] (update(), nets/PartialFC.py:133-143).  src/dst are HOST arrays of device
