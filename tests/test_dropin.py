@@ -70,3 +70,16 @@ def test_constructor_needs_initialised_process_group(dropin_path):
     conf = types.SimpleNamespace(emd_size=64, sample_rate=1.0, mixed_precision=False, loss_s=64.0, loss_m=0.5)
     with pytest.raises(AssertionError):
         mod.PartialFC(conf=conf, num_classes=100)
+
+
+def test_amp_twin_host_logic_on_fake_kernels():
+    """Host logic of the AMP bf16 twin (which step casts, which step lets the fused update write it, bit-identity of the
+    two) with tests/fake_kernels.py standing in for the CUDA kernels: the body of the GPU test, run on the CPU in a
+    separate process (tools/sim_gpu_tests.py patches .cuda() to the identity, which must not leak into this one)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "sim_gpu_tests.py"), "test_amp_update_writes"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok ") == 2 and "FAILED" not in r.stdout, r.stdout

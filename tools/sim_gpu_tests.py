@@ -2,7 +2,7 @@
 kernels and .cuda() patched to the identity.  It catches Python-level mistakes in GPU tests (and in the host logic they
 drive) when no GPU is at hand; it says nothing about the kernels.  Not part of the test-suite.
 
-    python tools/sim_gpu_tests.py
+    python tools/sim_gpu_tests.py [substring of the test names to run]
 """
 import os
 import sys
@@ -41,7 +41,10 @@ RUNS = [
     (th.test_scaled_loss_through_the_kernels, [(pfc, "unfused"), (pfc, "fused")]),
 ]
 failed = 0
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
 for fn, arglists in RUNS:
+    if ONLY not in fn.__name__:
+        continue
     for args in arglists:
         try:
             fn(*args)
