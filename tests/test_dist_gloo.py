@@ -65,8 +65,51 @@ def _group_main(rank, W, port, q):
             q.put((rank, ("scale",), _run_scale_case()))
         except Exception as e:
             q.put((rank, ("scale",), {"error": f"{type(e).__name__}: {e}"}))
+        try:
+            q.put((rank, ("bulk_draw",), _run_bulk_draw_case()))
+        except Exception as e:
+            q.put((rank, ("bulk_draw",), {"error": f"{type(e).__name__}: {e}"}))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def _run_bulk_draw_case():
+    """The head's own sampling draw (no `perm` argument) for a shard big enough for the bulk host generator
+    (hostrng.cpu_rand, >= 4096 classes) against the same head drawing with torch.rand: same seed -> same index sets, same
+    final weights, same generator state afterwards (nets/PartialFC.py:110 semantics)."""
+    import face_recognition_pytorch_b200 as pfc
+    from face_recognition_pytorch_b200 import hostrng
+    C, d, b, steps = 6000, 64, 48, 3
+    g = torch.Generator().manual_seed(11)
+    w0 = torch.normal(0, 0.01, (C, d), generator=g)
+    data = [(torch.nn.functional.normalize(torch.randn(b, d, generator=g)), torch.randint(0, C, (b,), generator=g))
+            for _ in range(steps)]
+    out = {"bulk_available": bool(hostrng.enabled())}
+    for tag, bulk in (("bulk", True), ("torch", False)):
+        saved = hostrng._state["ok"]
+        hostrng._state["ok"] = saved if bulk else False
+        try:
+            conf = types.SimpleNamespace(emd_size=d, sample_rate=0.3, mixed_precision=False, loss_s=64.0, loss_m=0.5)
+            head = pfc.PartialFC(conf, C)
+            head.load_state_dict({"weight": w0.clone()})
+            head.train()
+            opt = torch.optim.SGD(head.parameters(), lr=0.1, momentum=0.9, weight_decay=5e-4)
+            torch.manual_seed(2024)
+            for s, (x, lab) in enumerate(data):
+                x = x.clone().requires_grad_(True)
+                loss = head(x, lab.clone(), opt)
+                loss.backward()
+                opt.step()
+                opt.zero_grad()
+                out[f"{tag}_index_{s}"] = head.weight_index.numpy().copy()
+                out[f"{tag}_loss_{s}"] = float(loss)
+            head.update()
+            out[f"{tag}_weight"] = head.weight.numpy().copy()
+            out[f"{tag}_rng"] = torch.get_rng_state().numpy().copy()
+        finally:
+            hostrng._state["ok"] = saved
+    out["steps"] = steps
+    return out
 
 
 def _run_scale_case():
@@ -189,7 +232,7 @@ def group_results():
         for p in procs:
             p.start()
         n_cases = (sum(_world_of(c[0]) == W for c in SGD_CASES) + sum(_world_of(c[0]) == W for c in ADAM_CASES)
-                   + (1 if W == 1 else 0))
+                   + (2 if W == 1 else 0))            # + the scale and the bulk-draw case
         for _ in range(n_cases * W):
             rank, key, out = q.get(timeout=600)
             results.setdefault(key, {})[rank] = out
@@ -204,6 +247,17 @@ def _case_result(group_results, key):
     for r, out in res.items():
         assert "error" not in out, f"rank {r}: {out.get('error')}"
     return res
+
+
+def test_bulk_host_draw_gives_the_sampling_of_torch_rand(group_results):
+    res = _case_result(group_results, ("bulk_draw",))[0]
+    assert res["bulk_available"]
+    for s in range(res["steps"]):
+        assert np.array_equal(res[f"bulk_index_{s}"], res[f"torch_index_{s}"])
+        assert len(res[f"bulk_index_{s}"]) == 1800                     # int(0.3 * 6000), nets/PartialFC.py:63
+        assert res[f"bulk_loss_{s}"] == res[f"torch_loss_{s}"]
+    assert np.array_equal(res["bulk_weight"], res["torch_weight"])
+    assert np.array_equal(res["bulk_rng"], res["torch_rng"])
 
 
 def test_scaled_loss_scales_the_gradients(group_results):
