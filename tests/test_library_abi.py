@@ -64,3 +64,17 @@ def test_shard_range_matches_oracle():
         for W in (1, 2, 3, 4, 8):
             for r in range(W):
                 assert shard_range(C, r, W) == ho.shard_range(C, r, W)
+
+
+def test_header_is_plain_c_and_cxx():
+    """The drop-in boundary is a C ABI: include/pfc.h must compile on its own as C99 and as C++ (no torch / CUDA types in
+    the signatures, every type it uses declared by the headers it includes)."""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "pfc.h")
+    for cc, lang, std in (("gcc", "c", "-std=c99"), ("g++", "c++", "-std=c++17")):
+        exe = shutil.which(cc)
+        if exe is None:
+            pytest.skip(f"{cc} not installed")
+        r = subprocess.run([exe, "-fsyntax-only", std, "-Wall", "-Werror", "-x", lang, hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
