@@ -81,3 +81,28 @@ def test_env_switch_restores_torch_rand(monkeypatch):
     a = hostrng.cpu_rand(10000)
     torch.manual_seed(9)
     assert torch.equal(a, torch.rand(10000))
+
+
+def test_published_mt19937_known_answers():
+    """Independent of torch: a state blob seeded with the published init_genrand recurrence (seed 5489) must yield the
+    published outputs -- the first is 3499211612, the 10000th is 4123659995 (ISO C++ [rand.predef]) -- as floats of their
+    low 24 bits.  torch.Generator().manual_seed(5489) must be that same state."""
+    import numpy as np
+    s = np.zeros(624, dtype=np.uint64)
+    s[0] = 5489
+    for j in range(1, 624):
+        prev = int(s[j - 1])
+        s[j] = (1812433253 * (prev ^ (prev >> 30)) + j) & 0xFFFFFFFF
+    blob = np.zeros(5056, dtype=np.uint8)
+    blob[0:8] = np.frombuffer(np.uint64(5489).tobytes(), dtype=np.uint8)
+    blob[8:12] = np.frombuffer(np.int32(1).tobytes(), dtype=np.uint8)        # left
+    blob[12:16] = np.frombuffer(np.int32(1).tobytes(), dtype=np.uint8)       # seeded
+    blob[24:24 + 624 * 8] = np.frombuffer(s.tobytes(), dtype=np.uint8)
+    t = torch.from_numpy(blob)
+    out = torch.empty(10000)
+    assert lib.pfc_host_mt19937_uniform(t.data_ptr(), t.numel(), out.data_ptr(), out.numel()) == 0
+    assert float(out[0]) == (3499211612 & 0xFFFFFF) / 2 ** 24
+    assert float(out[9999]) == (4123659995 & 0xFFFFFF) / 2 ** 24
+    g = torch.Generator()
+    g.manual_seed(5489)
+    assert torch.equal(out, torch.rand(10000, generator=g))

@@ -78,3 +78,23 @@ def test_header_is_plain_c_and_cxx():
             pytest.skip(f"{cc} not installed")
         r = subprocess.run([exe, "-fsyntax-only", std, "-Wall", "-Werror", "-x", lang, hdr], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
+
+
+def test_plain_c_client(tmp_path):
+    """tests/c_client/abi_client.c -- a C99 program compiled against include/pfc.h and linked with libpfc_b200.so, as a
+    non-Python binding would be -- loads the library without a GPU and gets the published MT19937 known answers (first
+    and 10000th output of seed 5489) out of the host sampling-draw entry point."""
+    import shutil
+    import subprocess
+    import face_recognition_pytorch_b200  # noqa: F401  (builds the library if it is missing)
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not installed")
+    libdir = os.path.join(ROOT, "face-recognition-pytorch_b200")
+    exe = str(tmp_path / "abi_client")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_client", "abi_client.c"), "-o", exe, "-L", libdir,
+                        "-l:libpfc_b200.so", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "abi_client: ok" in r.stdout, r.stdout + r.stderr
